@@ -1,0 +1,38 @@
+"""pytest wiring: `gpu` marker, import paths, golden-vector loader."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "mg-gan_b200"), os.path.join(ROOT, "oracle"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN_CASES = ["cfg1_g1_tiny", "cfg2_g4_eth_noimg", "cfg3_g8_sdd_masked"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    """npz -> nested dict {group: {key: tensor}} with python seq_start_end."""
+    import torch
+
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    out = {}
+    for key in z.files:
+        grp, _, rest = key.partition("/")
+        v = z[key]
+        scalar = v.ndim == 0 and (grp == "meta" or rest.startswith("metric/") or rest.endswith("/step"))
+        out.setdefault(grp, {})[rest] = v.item() if scalar else torch.from_numpy(np.asarray(v))
+    out["meta"]["seq_start_end"] = [[int(a), int(b)] for a, b in out["meta"]["seq_start_end"].tolist()]
+    return out
+
+
+@pytest.fixture(params=GOLDEN_CASES)
+def golden(request):
+    return load_golden(request.param)

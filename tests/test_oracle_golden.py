@@ -1,0 +1,122 @@
+"""CPU: the oracle restatement reproduces the frozen outputs of the real reference.
+
+Fixtures were produced by `oracle/make_golden.py`, which executes the unmodified
+reference modules and trainer (mggan/model/train.py:23-213,578-658).  Tolerances are
+fp32 round-off only: both sides run the same PyTorch CPU kernels in (slightly)
+different op order.
+"""
+import torch
+
+import mggan_oracle as O
+
+
+def batch_of(g):
+    b = dict(g["batch"])
+    b["seq_start_end"] = g["meta"]["seq_start_end"]
+    return b
+
+
+def close(a, b, rtol=2e-4, atol=2e-6, what=""):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    assert torch.allclose(a, b, rtol=rtol, atol=atol), f"{what}: max abs err {err:.3e}, ref max {b.abs().max().item():.3e}"
+
+
+def test_module_outputs(golden):
+    g = golden
+    b = batch_of(g)
+    ng, k = g["meta"]["num_gens"], g["meta"]["k"]
+    sdG = {n: v.clone() for n, v in g["G0"].items()}
+    sdD = {n: v.clone() for n, v in g["D0"].items()}
+    mask, gt_xy, gt_dxdy = O.OracleTrainer.loss_mask(b)
+    img = b.get("features")
+    m = g["mod"]
+    with torch.no_grad():
+        (rel, ab), logits, _ = O.generator_forward(sdG, ng, b["in_xy"], b["in_dxdy"], b["seq_start_end"],
+                                                   m["all_noise"], True, img, 3, mask,
+                                                   torch.zeros(int(mask.sum()), 3, dtype=torch.long))
+        close(ab, m["all_abs"], what="all_abs")
+        close(rel, m["all_rel"], what="all_rel")
+        close(logits, m["logits"], what="logits")
+        (rel, ab), _, _ = O.generator_forward(sdG, ng, b["in_xy"], b["in_dxdy"], b["seq_start_end"],
+                                              m["sel_noise"], False, img, k, mask, m["sel_idx"])
+        close(ab, m["sel_abs"], what="sel_abs")
+        close(rel, m["sel_rel"], what="sel_rel")
+        for mode in ("scene", "reference"):
+            sd = {n: v.clone() for n, v in sdD.items()}
+            o, br = O.discriminator_forward(sd, b["in_xy"], b["in_dxdy"], m["sel_abs"], m["sel_rel"],
+                                            b["seq_start_end"], img, mask, social_mode=mode)
+            close(o, m["d_fake_out"], what="d_fake_out " + mode)
+            close(br, m["d_fake_branch"], what="d_fake_branch " + mode)
+        o, br = O.discriminator_forward(sdD, b["in_xy"], b["in_dxdy"], m["sel_abs"], m["sel_rel"],
+                                        b["seq_start_end"], img, mask)
+        o, br = O.discriminator_forward(sdD, b["in_xy"], b["in_dxdy"], gt_xy, gt_dxdy, b["seq_start_end"], img, mask)
+        close(o, m["d_real_out"], what="d_real_out")
+        close(br, m["d_real_branch"], what="d_real_branch")
+        (rel, ab), _, _ = O.generator_forward(sdG, ng, b["in_xy"], b["in_dxdy"], b["seq_start_end"],
+                                              m["sel_noise"][:5], False, img, 5, mask, m["sel_idx"][:, :5],
+                                              training=False)
+        close(ab, m["eval_abs"], what="eval_abs")
+    # BatchNorm buffers after the same number of train-mode forwards
+    for n, v in g["Gmod"].items():
+        if "running" in n or "tracked" in n:
+            close(sdG[n].float(), v.float(), what="Gmod " + n)
+    for n, v in g["Dmod"].items():
+        if "running" in n or "tracked" in n:
+            close(sdD[n].float(), v.float(), what="Dmod " + n)
+
+
+def test_training_iterations(golden):
+    g = golden
+    b = batch_of(g)
+    ng, k = g["meta"]["num_gens"], g["meta"]["k"]
+    tr = O.OracleTrainer(g["G0"], g["D0"], ng, num_samples=k)
+    for it in range(g["meta"]["iters"]):
+        r = g[f"it{it}"]
+        lab = r["labels"].tolist()
+        d = tr.discriminator_step(b, r["d_noise"][None], r["d_idx"], lab[0], lab[1])
+        close(d["ce"], r["metric/train/info_mgan_disc_loss"], what="ce")
+        close(d["real"] + d["fake"], r["metric/train/discr_loss"], what="discr_loss")
+        for n, v in r.items():
+            if n.startswith("D_grad/"):
+                close(d["grads"][n[7:]], v, rtol=2e-3, atol=1e-6, what=n)
+        gs = tr.generator_step(b, r["g_noise"], r["g_idx"], lab[2])
+        close(gs["l2"], r["metric/train/L2_loss"], what="l2")
+        close(gs["adv"], r["metric/train/gen_loss"], what="adv")
+        close(gs["clf"], r["metric/train/info_mgan_loss"], what="clf")
+        n_checked = 0
+        for n, v in r.items():
+            if n.startswith("G_grad/"):
+                close(gs["grads"][n[7:]], v, rtol=2e-3, atol=1e-6, what=n)
+                n_checked += 1
+        assert n_checked >= 30
+        assert gs["grads"]["net_chooser.0.weight"] is None
+        pm = tr.net_chooser_step(b, r["pm_noise"][None])
+        close(pm["loss"], r["metric/train/net_chooser_loss"], what="pm loss")
+        for n, v in r.items():
+            if n.startswith("PM_grad/"):
+                close(pm["grads"][n[8:]], v, rtol=2e-3, atol=1e-6, what=n)
+        assert pm["grads"]["gs.0.decoder.weight_hh_l0"] is None
+    # A conv bias that feeds a train-mode BatchNorm has an exactly-zero true gradient; what
+    # reaches AdamW is round-off noise, which Adam normalises to O(lr) steps of random sign.
+    # Those tensors are only required to stay within the lr envelope.
+    iters = g["meta"]["iters"]
+    for tag, sd in (("G1", tr.G), ("D1", tr.D)):
+        for n, v in g[tag].items():
+            if n.endswith("Conv_1.bias"):
+                close(sd[n].detach().float(), v.float(), rtol=0, atol=2.1e-3 * 2 * iters, what=tag + " " + n)
+            elif n.endswith("running_mean"):      # carries the conv bias drift x momentum
+                close(sd[n].detach().float(), v.float(), rtol=1e-3, atol=5e-4 * iters, what=tag + " " + n)
+            else:
+                close(sd[n].detach().float(), v.float(), rtol=1e-3, atol=2e-6, what=tag + " " + n)
+    st = tr.optG.state["gs.0.decoder.weight_hh_l0"]
+    assert st["step"] == g["optG"]["gs.0.decoder.weight_hh_l0/step"] == g["meta"]["iters"]
+    assert tr.optG.state["encoder.embedding.weight"]["step"] == 2 * g["meta"]["iters"]
+    close(st["m"], g["optG"]["gs.0.decoder.weight_hh_l0/exp_avg"], rtol=2e-3, atol=1e-7, what="exp_avg")
+    close(tr.optD.state["discs.0.0.weight"]["v"], g["optD"]["discs.0.0.weight/exp_avg_sq"], rtol=4e-3, atol=1e-10, what="exp_avg_sq")
+
+
+def test_selection_indices():
+    idx = torch.tensor([[1, 2, 3, 1], [0, 0, 0, 0], [2, 1, 2, 1]])
+    assert O.selection_indices(idx).tolist() == [[0, 0, 0, 1], [0, 1, 2, 3], [0, 0, 1, 1]]
