@@ -1,0 +1,161 @@
+/* mggan_b200.h -- C ABI of the B200 (sm_100a) MG-GAN training-step kernels.
+ *
+ * The reference (selflein/MG-GAN) has no FFI: its hot path is Python nn.Modules calling
+ * PyTorch library kernels.  This header is the boundary a maintainer binds
+ * instead: each entry point replaces the reference call sites cited above it.  Conventions:
+ *   - plain pointers to DEVICE memory (fp32 unless noted), explicit sizes, a cudaStream_t;
+ *   - no allocation, no ownership transfer, no stream synchronisation inside;
+ *   - every function returns 0 on success, non-zero on error (1 invalid argument / unsupported
+ *     shape, 2 CUDA launch error, 3 wrong device); mggan_last_error() gives the message
+ *     (thread-local);
+ *   - "accumulated" outputs are added to atomically: the caller zero-fills them first.
+ * Row-major everywhere; weights use the PyTorch (out_features, in_features) layout.
+ */
+#ifndef MGGAN_B200_H
+#define MGGAN_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* mggan_last_error(void);
+int mggan_version(void);
+int mggan_device_check(void);
+
+/* ---- trajectory-encoder LSTM: TrajectoryEncoder.forward, mggan/model/modules/common_modules.py:48-66
+ * x (T,N,2); Wx (4H,2) = W_ih W_emb; b (4H) = W_ih b_emb + b_ih + b_hh; Whh (4H,H); H in {32,64}.
+ * hT (N,H).  acts (T,N,6,H) saves (i,f,g,o,c,tanh c) for the backward, or NULL. */
+int mggan_lstm_seq_fwd(const float* x, int T, int N, int H, const float* Wx, const float* b, const float* Whh,
+                       float* hT, float* acts, cudaStream_t stream);
+/* dWx (4H,2), db (4H), dWhh (4H,H) accumulated. */
+int mggan_lstm_seq_bwd(const float* x, int T, int N, int H, const float* Whh, const float* acts, const float* dhT,
+                       float* dWx, float* db, float* dWhh, cudaStream_t stream);
+
+/* ---- dense layer: nn.Linear (+ activation) call sites standard.py:91-105, discriminators.py:46-56,76-108
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 sigmoid squashed to (1e-7, 1-1e-7) (discriminators.py:203-204). */
+int mggan_linear_fwd(const float* X, int M, int K, const float* W, const float* bias, int O, int act, float slope,
+                     float* Y, cudaStream_t stream);
+/* dX (M,K) overwritten or NULL; dW (O,K), db (O) accumulated or NULL.  Y is the forward output. */
+int mggan_linear_bwd(const float* X, int M, int K, const float* W, int O, int act, float slope, const float* Y,
+                     const float* dY, float* dX, float* dW, float* db, cudaStream_t stream);
+
+/* ---- PM-Net sampling + generator selection: standard.py:217-225, utils.py:234-248, standard.py:190-214 */
+int mggan_gumbel_sample(const float* logits, int n, int k, int G, unsigned long long seed, unsigned long long offset,
+                        long long* idx, cudaStream_t stream);
+int mggan_selection_tiles(int n_seq, int G); /* host helper: tile-table length for n_seq sequences */
+/* idx (n,k) int64 -> work list for the decoder.  scratch: cnt (n*G int32), rank (n*k bytes),
+ * base_row (G+1 int32), err (1 int32, zero-filled by the caller; set to 1 on an out-of-range index).
+ * outputs: totals (G) per-generator draw counts, tile_gen (n_tiles), seq_* (n_tiles*64). */
+int mggan_selection_build(const long long* idx, int n, int k, int G, int n_tiles, int* cnt, unsigned char* rank,
+                          int* base_row, int* err, int* totals, int* tile_gen, int* seq_agent, int* seq_noise,
+                          int* seq_out, cudaStream_t stream);
+/* all generators x k samples (forward_all, standard.py:227-265): G*ceil(n*k/64) tiles. */
+int mggan_selection_all(int n, int k, int G, int* tile_gen, int* seq_agent, int* seq_noise, int* seq_out,
+                        cudaStream_t stream);
+
+/* ---- multi-generator decoder: RelativeDecoder.forward common_modules.py:97-131 x forward_all standard.py:227-265
+ * A (n_agents,32) = enc_h_to_dec_h on the per-agent encoding (bias included), social (n_agents,32),
+ * last_xy/last_dxdy (n_agents,2), noise (rows,Z); Wz (32,Z) noise block of enc_h_to_dec_h;
+ * per generator: Wx (G,128,2), b (G,128), Whh (G,128,32), W1h/W1s (G,16,32) = halves of hidden2pos.0,
+ * b1 (G,16), W2 (G,2,16), b2 (G,2).  out_abs/out_rel (pred_len, n_cols, 2).
+ * acts (pred_len, n_tiles*64, 6, 32), u1save (pred_len, n_tiles*64, 16), h0save (n_tiles*64, 32) or all NULL. */
+int mggan_decoder_fwd(int n_tiles, const int* tile_gen, const int* seq_agent, const int* seq_noise,
+                      const int* seq_out, const float* A, const float* social, const float* last_xy,
+                      const float* last_dxdy, const float* noise, int Z, const float* Wz, const float* Wx,
+                      const float* b, const float* Whh, const float* W1h, const float* W1s, const float* b1,
+                      const float* W2, const float* b2, int pred_len, int n_cols, float* out_abs, float* out_rel,
+                      float* acts, float* u1save, float* h0save, cudaStream_t stream);
+/* d_abs / d_rel (pred_len, n_cols, 2), either may be NULL.  All gradient outputs accumulated. */
+int mggan_decoder_bwd(int n_tiles, const int* tile_gen, const int* seq_agent, const int* seq_noise,
+                      const int* seq_out, const float* social, const float* last_dxdy, const float* noise, int Z,
+                      const float* Wz, const float* Wx, const float* b, const float* Whh, const float* W1h,
+                      const float* W1s, const float* b1, const float* W2, const float* b2, int pred_len, int n_cols,
+                      const float* out_rel, const float* acts, const float* u1save, const float* h0save,
+                      const float* d_abs, const float* d_rel, float* dWz, float* dWx, float* db, float* dWhh,
+                      float* dW1h, float* dW1s, float* db1, float* dW2, float* db2, float* dA, float* dsocial,
+                      cudaStream_t stream);
+
+/* ---- social attention: SocialAttention / AttentionPooling, mggan/model/modules/social.py:7-123
+ * x4 (N,4) = (xy_T, dxdy_T); h (N,HD), HD in {32,64}; Us (N,65) = per-agent folded (u_j, s_j);
+ * scene_off (S+1) agent ranges, pair_off (S+1) prefix of n_s^2; W1 (32,3), b1, W2 (64,32), b2.
+ * S (N,HD); att (sum n_s^2) attention weights (saved for the backward). */
+int mggan_social_attn_fwd(const float* x4, const float* h, int HD, const float* Us, const int* scene_off,
+                          const int* pair_off, int n_scenes, const float* W1, const float* b1, const float* W2,
+                          const float* b2, float* S, float* att, cudaStream_t stream);
+/* dsig (sum n_s^2) scratch; dh (N,HD), dUs (N,65) zero-filled by the caller; dW1, db1, dW2, db2 accumulated. */
+int mggan_social_attn_bwd(const float* x4, const float* h, int HD, const float* Us, const int* scene_off,
+                          const int* pair_off, int n_scenes, const float* W1, const float* b1, const float* W2,
+                          const float* b2, const float* att, const float* dS, float* dsig, float* dh, float* dUs,
+                          float* dW1, float* db1, float* dW2, float* db2, cudaStream_t stream);
+
+/* ---- physical attention: AttentionGlobal / CNN / Conv_Blocks, mggan/model/modules/cnn.py:101-116,119-282
+ * img (.,4,33,33); rows (N) optional int32 gather of image rows (mask compaction) or NULL; C in {8,16}.
+ * x1 (N,C,33,33), x2 (N,C,16,16) pre-BatchNorm conv outputs; stats (2C doubles: sum, sum of squares)
+ * accumulated or NULL (eval mode). */
+int mggan_scene_conv1_fwd(const float* img, const int* rows, int N, int C, const float* W, const float* bias,
+                          float* x1, double* stats, cudaStream_t stream);
+/* training != 0: batch statistics (count = elements per channel) + running-stat update (momentum,
+ * unbiased variance) + num_batches_tracked += 1; else running statistics.
+ * ab (2C) = BN as y = a x + b; mean_istd (2C). */
+int mggan_scene_bn_finalize(const double* stats, double count, int C, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                            float eps, int training, float* ab, float* mean_istd, cudaStream_t stream);
+int mggan_scene_block2_fwd(const float* x1, int N, int C, const float* ab1, const float* W, const float* bias,
+                           float* x2, double* stats, cudaStream_t stream);
+/* Wa1 (32,C), ba1 (32), Wa2 (C,32), ba2 (C) = cnn_attention; out (N,64). */
+int mggan_scene_attn_fwd(const float* x2, int N, int C, const float* ab2, const float* Wa1, const float* ba1,
+                         const float* Wa2, const float* ba2, float* out, cudaStream_t stream);
+/* dy2 (N,C,64) + idx2 (N,C,64 bytes): sparse gradient at BatchNorm-2 output; sums2 (2C doubles) accumulated. */
+int mggan_scene_attn_bwd(const float* x2, int N, int C, const float* ab2, const float* mean_istd2, const float* Wa1,
+                         const float* ba1, const float* Wa2, const float* ba2, const float* dout, float* dWa1,
+                         float* dba1, float* dWa2, float* dba2, float* dy2, unsigned char* idx2, double* sums2,
+                         cudaStream_t stream);
+/* sums (2C doubles) -> m12 (2C) means for the BatchNorm backward; dgamma, dbeta (C) accumulated. */
+int mggan_scene_bn_bwd_finalize(const double* sums, double count, int C, float* m12, float* dgamma, float* dbeta,
+                                cudaStream_t stream);
+int mggan_scene_block2_bwd(const float* x1, const float* x2, int N, int C, const float* ab1, const float* mean_istd1,
+                           const float* ab2, const float* mean_istd2, const float* m12_2, const float* W,
+                           const float* dy2, const unsigned char* idx2, float* dW, float* dbias, float* dy1,
+                           unsigned char* idx1, double* sums1, cudaStream_t stream);
+int mggan_scene_conv1_bwd(const float* img, const int* rows, const float* x1, int N, int C, const float* ab1,
+                          const float* mean_istd1, const float* m12_1, const float* dy1, const unsigned char* idx1,
+                          float* dW, float* dbias, cudaStream_t stream);
+
+/* ---- losses: mggan/model/train.py:55-113 (G step), :148-200 (D step), :626-639 (PM step) */
+/* abs (T,k,n,2), gt (T,n,2); loss += sum_scenes min_s sum_{i in scene} sum_t |abs-gt| * inv_norm;
+ * best (S) argmin sample; d_abs (T,k,n,2) zero-filled by the caller, or NULL. */
+int mggan_l2_scene_min(const float* abs_, const float* gt, int T, int k, int n, const int* scene_off, int n_scenes,
+                       float inv_norm, float* loss, int* best, float* d_abs, cudaStream_t stream);
+/* loss += inv_denom * sum_i w_i BCE(p_i, label), w_i = 1/counts[gen_idx[i]] or 1; dp (n) or NULL. */
+int mggan_bce_scalar_label(const float* p, int n, float label, const long long* gen_idx, const int* counts,
+                           float inv_denom, float* loss, float* dp, cudaStream_t stream);
+int mggan_ce_generators(const float* logits, int n, int G, const long long* target, const int* counts,
+                        float inv_denom, float* loss, float* dlogits, cudaStream_t stream);
+int mggan_pm_ml_loss(const float* abs_all, const float* gt, int T, int ks, int G, int n, const float* logits,
+                     float sigma, float weight, float inv_n, float* loss, float* dlogits, float* target_out,
+                     cudaStream_t stream);
+
+/* ---- optimiser: clip_grad_norm_ + AdamW, train.py:131-135,209-213,656-658; abstract_train.py:45-57 */
+#define MGGAN_TABLE_MAX 64
+typedef struct MgganTensorTable {
+    float* p[MGGAN_TABLE_MAX];
+    const float* g[MGGAN_TABLE_MAX];
+    float* m[MGGAN_TABLE_MAX];
+    float* v[MGGAN_TABLE_MAX];
+    int n[MGGAN_TABLE_MAX];
+    float bc1[MGGAN_TABLE_MAX];      /* 1 - beta1^step */
+    float bc2_sqrt[MGGAN_TABLE_MAX]; /* sqrt(1 - beta2^step) */
+} MgganTensorTable;
+/* table is a HOST pointer (copied into kernel-parameter space). */
+int mggan_grad_sqnorm(const MgganTensorTable* table, int count, double* sqnorm_accum, cudaStream_t stream);
+int mggan_clip_adamw(const MgganTensorTable* table, int count, const double* sqnorm, float max_norm,
+                     float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     cudaStream_t stream);
+int mggan_multi_copy(const MgganTensorTable* table, int count, cudaStream_t stream); /* p[t] <- g[t] */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGGAN_B200_H */

@@ -1,0 +1,143 @@
+// Shared device helpers for the MG-GAN training-step kernels (sm_100a, fp32).
+//
+// Every kernel in this directory follows the same pattern: one CTA of 256 threads owns a tile
+// of independent rows (agents, sampled sequences or in-scene pairs), stages the small weight
+// matrices of the layer it runs in shared memory, and expresses each dense layer as a
+// register-blocked tile product over shared memory (float4 loads, broadcast-friendly lane
+// mapping: a warp is 4 row-lanes x 8 column-lanes so that one LDS.128 wavefront feeds 32 FMAs).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MGGAN_THREADS 256
+
+// ---- error plumbing (api.cu) -------------------------------------------------------------
+extern "C" const char* mggan_last_error(void);
+int mggan_set_error(int code, const char* fmt, ...);
+int mggan_check_launch(const char* what);
+
+#define MGGAN_OK 0
+#define MGGAN_ERR_INVALID 1     // bad argument / unsupported shape
+#define MGGAN_ERR_CUDA 2        // CUDA runtime error at launch
+#define MGGAN_ERR_DEVICE 3      // not an sm_100 device
+
+#define MGGAN_REQUIRE(cond, ...)                                    \
+    do {                                                            \
+        if (!(cond)) return mggan_set_error(MGGAN_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+// ---- scalar math -------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// tanh via exp; |abs err| ~1e-7, saturates cleanly for large |x|.
+__device__ __forceinline__ float tanhf_(float x) {
+    float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
+__device__ __forceinline__ float lrelu_(float x, float a) { return x > 0.f ? x : a * x; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---- shared-memory tile products ---------------------------------------------------------
+// acc[i][j] += sum_k A[(r0 + i*RS)*lda + k] * W[(o0 + j*OS)*ldw + k],  k in [0, K), K % 4 == 0.
+// lda / ldw are in floats, multiples of 4 (16-byte aligned rows).
+template <int TR, int TO, int K>
+__device__ __forceinline__ void tile_rowdot(float (&acc)[TR][TO], const float* __restrict__ A, int lda, int r0,
+                                            int RS, const float* __restrict__ W, int ldw, int o0, int OS) {
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+        float4 a[TR], w[TO];
+#pragma unroll
+        for (int i = 0; i < TR; ++i) a[i] = ld4(A + (r0 + i * RS) * lda + k);
+#pragma unroll
+        for (int j = 0; j < TO; ++j) w[j] = ld4(W + (o0 + j * OS) * ldw + k);
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int j = 0; j < TO; ++j) {
+                acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
+                acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
+                acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
+                acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
+            }
+    }
+}
+
+// Input gradient of a dense layer: acc[i][c] += sum_o G[(r0+i*RS)*ldg + o] * W[o*ldw + k0 + c],
+// o in [0, O), O % 4 == 0, c in 0..3 (the thread owns 4 consecutive input columns k0..k0+3).
+template <int TR, int O>
+__device__ __forceinline__ void tile_dgrad(float (&acc)[TR][4], const float* __restrict__ G, int ldg, int r0, int RS,
+                                           const float* __restrict__ W, int ldw, int k0) {
+#pragma unroll 2
+    for (int o = 0; o < O; o += 4) {
+        float4 g[TR], w[4];
+#pragma unroll
+        for (int i = 0; i < TR; ++i) g[i] = ld4(G + (r0 + i * RS) * ldg + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = ld4(W + (o + j) * ldw + k0);
+#pragma unroll
+        for (int i = 0; i < TR; ++i) {
+            acc[i][0] = fmaf(g[i].x, w[0].x, acc[i][0]); acc[i][1] = fmaf(g[i].x, w[0].y, acc[i][1]);
+            acc[i][2] = fmaf(g[i].x, w[0].z, acc[i][2]); acc[i][3] = fmaf(g[i].x, w[0].w, acc[i][3]);
+            acc[i][0] = fmaf(g[i].y, w[1].x, acc[i][0]); acc[i][1] = fmaf(g[i].y, w[1].y, acc[i][1]);
+            acc[i][2] = fmaf(g[i].y, w[1].z, acc[i][2]); acc[i][3] = fmaf(g[i].y, w[1].w, acc[i][3]);
+            acc[i][0] = fmaf(g[i].z, w[2].x, acc[i][0]); acc[i][1] = fmaf(g[i].z, w[2].y, acc[i][1]);
+            acc[i][2] = fmaf(g[i].z, w[2].z, acc[i][2]); acc[i][3] = fmaf(g[i].z, w[2].w, acc[i][3]);
+            acc[i][0] = fmaf(g[i].w, w[3].x, acc[i][0]); acc[i][1] = fmaf(g[i].w, w[3].y, acc[i][1]);
+            acc[i][2] = fmaf(g[i].w, w[3].z, acc[i][2]); acc[i][3] = fmaf(g[i].w, w[3].w, acc[i][3]);
+        }
+    }
+}
+
+// Weight gradient: acc[a][b] += sum_r G[r*ldg + o0 + a] * X[r*ldx + k0 + b], r in [0, R).
+// Rows that do not exist must hold zeros in G.
+template <int R>
+__device__ __forceinline__ void tile_wgrad(float (&acc)[4][4], const float* __restrict__ G, int ldg, int o0,
+                                           const float* __restrict__ X, int ldx, int k0) {
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+        float4 g = ld4(G + r * ldg + o0);
+        float4 x = ld4(X + r * ldx + k0);
+        acc[0][0] = fmaf(g.x, x.x, acc[0][0]); acc[0][1] = fmaf(g.x, x.y, acc[0][1]);
+        acc[0][2] = fmaf(g.x, x.z, acc[0][2]); acc[0][3] = fmaf(g.x, x.w, acc[0][3]);
+        acc[1][0] = fmaf(g.y, x.x, acc[1][0]); acc[1][1] = fmaf(g.y, x.y, acc[1][1]);
+        acc[1][2] = fmaf(g.y, x.z, acc[1][2]); acc[1][3] = fmaf(g.y, x.w, acc[1][3]);
+        acc[2][0] = fmaf(g.z, x.x, acc[2][0]); acc[2][1] = fmaf(g.z, x.y, acc[2][1]);
+        acc[2][2] = fmaf(g.z, x.z, acc[2][2]); acc[2][3] = fmaf(g.z, x.w, acc[2][3]);
+        acc[3][0] = fmaf(g.w, x.x, acc[3][0]); acc[3][1] = fmaf(g.w, x.y, acc[3][1]);
+        acc[3][2] = fmaf(g.w, x.z, acc[3][2]); acc[3][3] = fmaf(g.w, x.w, acc[3][3]);
+    }
+}
+
+// Copy a dense (rows x cols) fp32 matrix from global into shared with a padded leading dimension.
+__device__ __forceinline__ void stage_matrix(float* __restrict__ dst, int ldd, const float* __restrict__ src, int rows,
+                                             int cols) {
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+        int r = i / cols, c = i - r * cols;
+        dst[r * ldd + c] = __ldg(src + i);
+    }
+}
+
+// atomicAdd a 4x4 register block into a dense row-major matrix.
+__device__ __forceinline__ void atomic_block44(float* __restrict__ dst, int ld, int o0, int k0, const float (&acc)[4][4]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) atomicAdd(dst + (o0 + a) * ld + k0 + b, acc[a][b]);
+}

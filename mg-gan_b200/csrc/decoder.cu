@@ -1,0 +1,546 @@
+// Fused multi-generator trajectory decoder (reference: RelativeDecoder.forward
+// mggan/model/modules/common_modules.py:97-131, called once per generator and per sample
+// multiplicity by MultiGenerator.forward_all mggan/model/modules/standard.py:227-265, followed
+// by the (sample, generator) gather of standard.py:190-214).
+//
+// The reference decodes G * M * N sequences with 12 * G separate LSTM-step launches and then
+// gathers k * N of them.  Here the *selected* sequences are the unit of work: rows are
+// sequences sorted by generator (select.cu builds the order), a CTA owns 64 rows of one
+// generator for all pred_len autoregressive steps, and results are written straight to their
+// (t, sample, agent) slot.  Per step and row:
+//     gates = Wx dxdy_{t-1} + b + W_hh h_{t-1}      (Wx = W_ih W_s folded on the host, 128 x 2)
+//     (i, f, g, o) -> c_t, h_t
+//     u = LReLU_0.01(W_1h h_t + [W_1s social + b_1])   (social half hoisted out of the time loop)
+//     dxdy_t = W_2 u + b_2 ;  xy_t = xy_{t-1} + dxdy_t
+// h_0 = A[agent] + Wz z   where A = enc_h_to_dec_h applied to the per-agent encoding (hoisted;
+// computed once per agent by the caller) and Wz is the noise block of that layer.
+#include "common.cuh"
+
+namespace {
+
+constexpr int H = 32;        // decoder hidden size (config.decoder_h_dim default)
+constexpr int M1 = 16;       // hidden2pos mid width = H / 2
+constexpr int ROWS = 64;
+constexpr int LDH = H + 4;   // 36
+constexpr int LDG = 4 * H + 4;
+constexpr int LDU = M1 + 4;  // 20
+constexpr int ZMAX = 16;
+
+struct DecWeights {
+    const float* Wz;    // (H, Z)            shared by all generators
+    const float* Wx;    // (G, 4H, 2)
+    const float* b;     // (G, 4H)
+    const float* Whh;   // (G, 4H, H)
+    const float* W1h;   // (G, M1, H)
+    const float* W1s;   // (G, M1, H)
+    const float* b1;    // (G, M1)
+    const float* W2;    // (G, 2, M1)
+    const float* b2;    // (G, 2)
+};
+
+struct DecGrads {
+    float* dWz; float* dWx; float* db; float* dWhh; float* dW1h; float* dW1s; float* db1; float* dW2; float* db2;
+    float* dA;        // (n_agents, H)
+    float* dsocial;   // (n_agents, H)
+};
+
+struct DecSeq {
+    const int* tile_gen;    // (n_tiles) generator of each 64-row tile, -1 = unused tile
+    const int* seq_agent;   // (n_tiles*64) agent index of the row, -1 = padding
+    const int* seq_noise;   // row into noise (.., Z)
+    const int* seq_out;     // output column
+};
+
+__global__ void __launch_bounds__(MGGAN_THREADS)
+decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const float* __restrict__ social,
+                   const float* __restrict__ last_xy, const float* __restrict__ last_dxdy,
+                   const float* __restrict__ noise, int Z, DecWeights w, int T, int n_cols,
+                   float* __restrict__ out_abs, float* __restrict__ out_rel, float* __restrict__ acts,
+                   float* __restrict__ u1save, float* __restrict__ h0save) {
+    extern __shared__ __align__(16) float smem[];
+    float* sW = smem;                       // [4H][LDH]
+    float* sW1 = sW + 4 * H * LDH;          // [M1][LDH]   W1h
+    float* sW1s = sW1 + M1 * LDH;           // [M1][LDH]   W1s
+    float* sH = sW1s + M1 * LDH;            // [2][ROWS][LDH]
+    float* sBs = sH + 2 * ROWS * LDH;       // [ROWS][LDU]
+    float* sD = sBs + ROWS * LDU;           // [ROWS][2]
+    float* sWz = sD + ROWS * 2;             // [H][ZMAX+1]
+    __shared__ int sAgent[ROWS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = (warp & 3) * 8 + (lane & 7);
+    const int rl = (warp >> 2) * 32 + (lane >> 3);
+    const int prow = threadIdx.x >> 2, mq = threadIdx.x & 3;     // hidden2pos mapping
+    const size_t Rpad = (size_t)n_tiles * ROWS;
+
+    for (int i = threadIdx.x; i < H * Z; i += MGGAN_THREADS) sWz[(i / Z) * (ZMAX + 1) + (i % Z)] = __ldg(w.Wz + i);
+
+    const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * per, t_end = min(n_tiles, t_begin + per);
+    int cur_g = -1;
+    float wx0[4], wx1[4], bb[4], w2a[4], w2b[4], b2a = 0.f, b2b = 0.f;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const int g = sq.tile_gen[tile];
+        if (g < 0) continue;
+        __syncthreads();                       // previous tile finished with all shared buffers
+        if (g != cur_g) {
+            cur_g = g;
+            stage_matrix(sW, LDH, w.Whh + (size_t)g * 4 * H * H, 4 * H, H);
+            stage_matrix(sW1, LDH, w.W1h + (size_t)g * M1 * H, M1, H);
+            stage_matrix(sW1s, LDH, w.W1s + (size_t)g * M1 * H, M1, H);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                wx0[q] = __ldg(w.Wx + ((size_t)g * 4 * H + q * H + u) * 2);
+                wx1[q] = __ldg(w.Wx + ((size_t)g * 4 * H + q * H + u) * 2 + 1);
+                bb[q] = __ldg(w.b + (size_t)g * 4 * H + q * H + u);
+                w2a[q] = __ldg(w.W2 + (size_t)g * 2 * M1 + mq + 4 * q);
+                w2b[q] = __ldg(w.W2 + (size_t)g * 2 * M1 + M1 + mq + 4 * q);
+            }
+            b2a = __ldg(w.b2 + g * 2);
+            b2b = __ldg(w.b2 + g * 2 + 1);
+        }
+        const int row0 = tile * ROWS;
+        if (threadIdx.x < ROWS) sAgent[threadIdx.x] = sq.seq_agent[row0 + threadIdx.x];
+        __syncthreads();
+        // ---- per-row constants: Bs = b1 + W1s social ; xy, dxdy of the last observation
+        const int pag = sAgent[prow];
+        float xy0 = 0.f, xy1 = 0.f;
+        {
+            float bs[1][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bs[0][j] = __ldg(w.b1 + (size_t)g * M1 + mq + 4 * j);
+            if (pag >= 0) {
+                const float* sp = social + (size_t)pag * H;
+#pragma unroll
+                for (int k = 0; k < H; k += 4) {
+                    float4 s4 = __ldg(reinterpret_cast<const float4*>(sp + k));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 w4 = ld4(sW1s + (mq + 4 * j) * LDH + k);
+                        bs[0][j] = fmaf(s4.x, w4.x, fmaf(s4.y, w4.y, fmaf(s4.z, w4.z, fmaf(s4.w, w4.w, bs[0][j]))));
+                    }
+                }
+                xy0 = __ldg(last_xy + (size_t)pag * 2);
+                xy1 = __ldg(last_xy + (size_t)pag * 2 + 1);
+                if (mq == 0) {
+                    sD[prow * 2] = __ldg(last_dxdy + (size_t)pag * 2);
+                    sD[prow * 2 + 1] = __ldg(last_dxdy + (size_t)pag * 2 + 1);
+                }
+            } else if (mq == 0) {
+                sD[prow * 2] = 0.f; sD[prow * 2 + 1] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sBs[prow * LDU + mq + 4 * j] = bs[0][j];
+        }
+        // ---- h0 = A[agent] + Wz z ; c0 = 0
+        float c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int r = rl + 4 * i, ag = sAgent[r];
+            float h0 = 0.f;
+            if (ag >= 0) {
+                h0 = __ldg(A + (size_t)ag * H + u);
+                const float* zp = noise + (size_t)sq.seq_noise[row0 + r] * Z;
+                for (int z = 0; z < Z; ++z) h0 = fmaf(sWz[u * (ZMAX + 1) + z], __ldg(zp + z), h0);
+                if (h0save != nullptr) h0save[(size_t)(row0 + r) * H + u] = h0;
+            }
+            sH[r * LDH + u] = h0;
+            c[i] = 0.f;
+        }
+        const int pcol = pag >= 0 ? sq.seq_out[row0 + prow] : -1;
+        __syncthreads();
+        for (int t = 0; t < T; ++t) {
+            const float* hcur = sH + (t & 1) * ROWS * LDH;
+            float* hnext = sH + ((t + 1) & 1) * ROWS * LDH;
+            float acc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float d0 = sD[(rl + 4 * i) * 2], d1 = sD[(rl + 4 * i) * 2 + 1];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[i][q] = fmaf(wx0[q], d0, fmaf(wx1[q], d1, bb[q]));
+            }
+            tile_rowdot<8, 4, H>(acc, hcur, LDH, rl, 4, sW, LDH, u, H);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int r = rl + 4 * i;
+                float ig = sigmoidf_(acc[i][0]), fg = sigmoidf_(acc[i][1]);
+                float gg = tanhf_(acc[i][2]), og = sigmoidf_(acc[i][3]);
+                c[i] = fmaf(fg, c[i], ig * gg);
+                float tc = tanhf_(c[i]);
+                hnext[r * LDH + u] = og * tc;
+                if (acts != nullptr && sAgent[r] >= 0) {
+                    float* a = acts + ((size_t)t * Rpad + row0 + r) * (6 * H) + u;
+                    a[0] = ig; a[H] = fg; a[2 * H] = gg; a[3 * H] = og; a[4 * H] = c[i]; a[5 * H] = tc;
+                }
+            }
+            __syncthreads();
+            // ---- hidden2pos on h_t
+            {
+                float up[1][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) up[0][j] = sBs[prow * LDU + mq + 4 * j];
+                tile_rowdot<1, 4, H>(up, hnext, LDH, prow, 0, sW1, LDH, mq, 4);
+                float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = lrelu_(up[0][j], 0.01f);
+                    d0 = fmaf(w2a[j], a, d0);
+                    d1 = fmaf(w2b[j], a, d1);
+                }
+                d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+                d0 += __shfl_xor_sync(0xffffffffu, d0, 2); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+                d0 += b2a; d1 += b2b;
+                xy0 += d0; xy1 += d1;
+                if (pcol >= 0) {
+                    if (u1save != nullptr) {
+                        float* us = u1save + ((size_t)t * Rpad + row0 + prow) * M1;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) us[mq + 4 * j] = up[0][j];
+                    }
+                    if (mq == 0) {
+                        size_t o = ((size_t)t * n_cols + pcol) * 2;
+                        *reinterpret_cast<float2*>(out_rel + o) = make_float2(d0, d1);
+                        *reinterpret_cast<float2*>(out_abs + o) = make_float2(xy0, xy1);
+                    }
+                }
+                if (mq == 0) { sD[prow * 2] = d0; sD[prow * 2 + 1] = d1; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Backward.  Inputs: the forward's saved activations, d_abs / d_rel (either may be null).
+__global__ void __launch_bounds__(MGGAN_THREADS)
+decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, const float* __restrict__ last_dxdy,
+                   const float* __restrict__ noise, int Z, DecWeights w, int T, int n_cols,
+                   const float* __restrict__ out_rel, const float* __restrict__ acts,
+                   const float* __restrict__ u1save, const float* __restrict__ h0save,
+                   const float* __restrict__ d_abs, const float* __restrict__ d_rel, DecGrads gr) {
+    extern __shared__ __align__(16) float smem[];
+    float* sW = smem;                       // [4H][LDH]   W_hh
+    float* sW1 = sW + 4 * H * LDH;          // [M1][LDH]   W1h, later W1s
+    float* sG = sW1 + M1 * LDH;             // [ROWS][LDG]
+    float* sHp = sG + ROWS * LDG;           // [ROWS][LDH] h_{t-1}
+    float* sHt = sHp + ROWS * LDH;          // [ROWS][LDH] h_t   (social tile after the loop)
+    float* sDh = sHt + ROWS * LDH;          // [ROWS][LDH] dL/dh from the later step
+    float* sDu = sDh + ROWS * LDH;          // [ROWS][LDU] d(hidden2pos.0 pre-activation)
+    float* sX = sDu + ROWS * LDU;           // [ROWS][2]   step input dxdy_{t-1}
+    float* sWx = sX + ROWS * 2;             // [4H][2]
+    __shared__ int sAgent[ROWS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = (warp & 3) * 8 + (lane & 7);
+    const int rl = (warp >> 2) * 32 + (lane >> 3);
+    const int prow = threadIdx.x >> 2, mq = threadIdx.x & 3;
+    const int d_kq = threadIdx.x & 7, d_r0 = threadIdx.x >> 3;      // dgrad: rows d_r0, d_r0+32
+    const int w_oq = (warp & 3) * 8 + (lane & 7), w_kq = (warp >> 2) * 4 + (lane >> 3);
+    const int e_m = threadIdx.x >> 4, e_kp = threadIdx.x & 15;      // dW1h / dW1s element pair
+    const size_t Rpad = (size_t)n_tiles * ROWS;
+
+    float wacc[4][4];
+    float ax0, ax1, ab, aw2a[4], aw2b[4], ab2a, ab2b, ab1[4], aw1h0, aw1h1, aw1s0, aw1s1, awz[ZMAX];
+    auto zero_acc = [&]() {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) wacc[a][b] = 0.f;
+            aw2a[a] = aw2b[a] = ab1[a] = 0.f;
+        }
+        ax0 = ax1 = ab = ab2a = ab2b = aw1h0 = aw1h1 = aw1s0 = aw1s1 = 0.f;
+#pragma unroll
+        for (int z = 0; z < ZMAX; ++z) awz[z] = 0.f;
+    };
+    auto flush = [&](int g) {
+        atomic_block44(gr.dWhh + (size_t)g * 4 * H * H, H, w_oq * 4, w_kq * 4, wacc);
+        if (threadIdx.x < 4 * H) {
+            atomicAdd(gr.dWx + ((size_t)g * 4 * H + threadIdx.x) * 2, ax0);
+            atomicAdd(gr.dWx + ((size_t)g * 4 * H + threadIdx.x) * 2 + 1, ax1);
+            atomicAdd(gr.db + (size_t)g * 4 * H + threadIdx.x, ab);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(gr.dW2 + (size_t)g * 2 * M1 + mq + 4 * j, aw2a[j]);
+            atomicAdd(gr.dW2 + (size_t)g * 2 * M1 + M1 + mq + 4 * j, aw2b[j]);
+            atomicAdd(gr.db1 + (size_t)g * M1 + mq + 4 * j, ab1[j]);
+        }
+        if (mq == 0) {
+            atomicAdd(gr.db2 + g * 2, ab2a);
+            atomicAdd(gr.db2 + g * 2 + 1, ab2b);
+        }
+        atomicAdd(gr.dW1h + ((size_t)g * M1 + e_m) * H + 2 * e_kp, aw1h0);
+        atomicAdd(gr.dW1h + ((size_t)g * M1 + e_m) * H + 2 * e_kp + 1, aw1h1);
+        atomicAdd(gr.dW1s + ((size_t)g * M1 + e_m) * H + 2 * e_kp, aw1s0);
+        atomicAdd(gr.dW1s + ((size_t)g * M1 + e_m) * H + 2 * e_kp + 1, aw1s1);
+#pragma unroll
+        for (int z = 0; z < ZMAX; ++z)
+            if (z < Z) atomicAdd(gr.dWz + u * Z + z, awz[z]);
+    };
+    zero_acc();
+
+    const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * per, t_end = min(n_tiles, t_begin + per);
+    int cur_g = -1;
+    float w1col[M1], w2a[4], w2b[4];
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const int g = sq.tile_gen[tile];
+        if (g < 0) continue;
+        __syncthreads();
+        if (g != cur_g) {
+            if (cur_g >= 0) { flush(cur_g); zero_acc(); }
+            cur_g = g;
+            stage_matrix(sW, LDH, w.Whh + (size_t)g * 4 * H * H, 4 * H, H);
+            for (int i = threadIdx.x; i < 4 * H * 2; i += MGGAN_THREADS) sWx[i] = __ldg(w.Wx + (size_t)g * 4 * H * 2 + i);
+#pragma unroll
+            for (int m = 0; m < M1; ++m) w1col[m] = __ldg(w.W1h + ((size_t)g * M1 + m) * H + u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                w2a[q] = __ldg(w.W2 + (size_t)g * 2 * M1 + mq + 4 * q);
+                w2b[q] = __ldg(w.W2 + (size_t)g * 2 * M1 + M1 + mq + 4 * q);
+            }
+        }
+        const int row0 = tile * ROWS;
+        if (threadIdx.x < ROWS) sAgent[threadIdx.x] = sq.seq_agent[row0 + threadIdx.x];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sDh[(rl + 4 * i) * LDH + u] = 0.f;
+        __syncthreads();
+        const int pag = sAgent[prow];
+        const int pcol = pag >= 0 ? sq.seq_out[row0 + prow] : -1;
+        float dxy0 = 0.f, dxy1 = 0.f;       // sum_{tau >= t} d_abs[tau]
+        float dn0 = 0.f, dn1 = 0.f;         // gradient reaching dxdy_t through step t+1's input
+        float dbs[4] = {0.f, 0.f, 0.f, 0.f};
+        float dc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dc[i] = 0.f;
+
+        for (int t = T - 1; t >= 0; --t) {
+            // ---- phase 0: hidden2pos backward (thread = row x 4 mid units)
+            {
+                float dr0 = dn0, dr1 = dn1;
+                float du[4] = {0.f, 0.f, 0.f, 0.f};
+                if (pcol >= 0) {
+                    size_t o = ((size_t)t * n_cols + pcol) * 2;
+                    if (d_abs != nullptr) {
+                        float2 v = __ldg(reinterpret_cast<const float2*>(d_abs + o));
+                        dxy0 += v.x; dxy1 += v.y;
+                    }
+                    dr0 += dxy0; dr1 += dxy1;
+                    if (d_rel != nullptr) {
+                        float2 v = __ldg(reinterpret_cast<const float2*>(d_rel + o));
+                        dr0 += v.x; dr1 += v.y;
+                    }
+                    const float* us = u1save + ((size_t)t * Rpad + row0 + prow) * M1;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float up = us[mq + 4 * j];
+                        float a = lrelu_(up, 0.01f);
+                        aw2a[j] = fmaf(dr0, a, aw2a[j]);
+                        aw2b[j] = fmaf(dr1, a, aw2b[j]);
+                        du[j] = (w2a[j] * dr0 + w2b[j] * dr1) * (up > 0.f ? 1.f : 0.01f);
+                        dbs[j] += du[j];
+                    }
+                    if (mq == 0) { ab2a += dr0; ab2b += dr1; }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sDu[prow * LDU + mq + 4 * j] = du[j];
+                // step input dxdy_{t-1}
+                if (mq == 0) {
+                    float2 xv = make_float2(0.f, 0.f);
+                    if (pcol >= 0) {
+                        xv = t > 0 ? __ldg(reinterpret_cast<const float2*>(out_rel + ((size_t)(t - 1) * n_cols + pcol) * 2))
+                                   : __ldg(reinterpret_cast<const float2*>(last_dxdy + (size_t)pag * 2));
+                    }
+                    sX[prow * 2] = xv.x; sX[prow * 2 + 1] = xv.y;
+                }
+            }
+            __syncthreads();
+            // ---- phase 1: dh_t, LSTM cell backward (thread = 8 rows x 1 unit)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int r = rl + 4 * i;
+                float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f, hp = 0.f, ht = 0.f;
+                if (sAgent[r] >= 0) {
+                    const float* a = acts + ((size_t)t * Rpad + row0 + r) * (6 * H) + u;
+                    float ig = a[0], fg = a[H], gg = a[2 * H], og = a[3 * H], tc = a[5 * H];
+                    float cp = 0.f;
+                    if (t > 0) {
+                        const float* ap = a - Rpad * (6 * H);
+                        cp = ap[4 * H];
+                        hp = ap[3 * H] * ap[5 * H];
+                    } else {
+                        hp = h0save[(size_t)(row0 + r) * H + u];
+                    }
+                    ht = og * tc;
+                    float dh = sDh[r * LDH + u];
+#pragma unroll
+                    for (int m = 0; m < M1; m += 4) {
+                        float4 d4 = ld4(sDu + r * LDU + m);
+                        dh = fmaf(w1col[m], d4.x, fmaf(w1col[m + 1], d4.y, fmaf(w1col[m + 2], d4.z, fmaf(w1col[m + 3], d4.w, dh))));
+                    }
+                    float dcc = fmaf(dh * og, 1.f - tc * tc, dc[i]);
+                    dao = dh * tc * og * (1.f - og);
+                    dai = dcc * gg * ig * (1.f - ig);
+                    dag = dcc * ig * (1.f - gg * gg);
+                    daf = dcc * cp * fg * (1.f - fg);
+                    dc[i] = dcc * fg;
+                }
+                sG[r * LDG + u] = dai; sG[r * LDG + H + u] = daf;
+                sG[r * LDG + 2 * H + u] = dag; sG[r * LDG + 3 * H + u] = dao;
+                sHp[r * LDH + u] = hp;
+                sHt[r * LDH + u] = ht;
+            }
+            __syncthreads();
+            // ---- phase 2: dgrad / wgrad tiles
+            {
+                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                tile_dgrad<2, 4 * H>(acc, sG, LDG, d_r0, 32, sW, LDH, d_kq * 4);
+                tile_wgrad<ROWS>(wacc, sG, LDG, w_oq * 4, sHp, LDH, w_kq * 4);
+                // every read of sDh for step t happened before the barrier above
+                st4(sDh + d_r0 * LDH + d_kq * 4, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]));
+                st4(sDh + (d_r0 + 32) * LDH + d_kq * 4, make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]));
+            }
+            if (threadIdx.x < 4 * H) {
+                int o = threadIdx.x;
+#pragma unroll 4
+                for (int r = 0; r < ROWS; ++r) {
+                    float gv = sG[r * LDG + o];
+                    ax0 = fmaf(gv, sX[2 * r], ax0);
+                    ax1 = fmaf(gv, sX[2 * r + 1], ax1);
+                    ab += gv;
+                }
+            }
+            {   // dW1h[e_m][2 e_kp .. +1] += sum_r du[r][e_m] h_t[r][..]
+#pragma unroll 4
+                for (int r = 0; r < ROWS; ++r) {
+                    float d = sDu[r * LDU + e_m];
+                    float2 hv = *reinterpret_cast<const float2*>(sHt + r * LDH + 2 * e_kp);
+                    aw1h0 = fmaf(d, hv.x, aw1h0);
+                    aw1h1 = fmaf(d, hv.y, aw1h1);
+                }
+            }
+            {   // gradient wrt this step's input dxdy_{t-1}: Wx^T dgates (row = prow, o = mq + 4 oo)
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                for (int oo = 0; oo < H; ++oo) {
+                    int o = mq + 4 * oo;
+                    float gv = sG[prow * LDG + o];
+                    s0 = fmaf(gv, sWx[o * 2], s0);
+                    s1 = fmaf(gv, sWx[o * 2 + 1], s1);
+                }
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+                dn0 = s0; dn1 = s1;
+            }
+            __syncthreads();
+        }
+        // ---- epilogue: h0 and the hoisted social / b1 terms
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int r = rl + 4 * i, ag = sAgent[r];
+            if (ag >= 0) {
+                float dh0 = sDh[r * LDH + u];
+                atomicAdd(gr.dA + (size_t)ag * H + u, dh0);
+                const float* zp = noise + (size_t)sq.seq_noise[row0 + r] * Z;
+#pragma unroll
+                for (int z = 0; z < ZMAX; ++z)
+                    if (z < Z) awz[z] = fmaf(dh0, __ldg(zp + z), awz[z]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sDu[prow * LDU + mq + 4 * j] = dbs[j];
+            ab1[j] += dbs[j];
+        }
+        stage_matrix(sW1, LDH, w.W1s + (size_t)g * M1 * H, M1, H);
+        for (int i = threadIdx.x; i < ROWS * H; i += MGGAN_THREADS) {
+            int r = i / H, k = i - r * H, ag = sAgent[r];
+            sHt[r * LDH + k] = ag >= 0 ? __ldg(social + (size_t)ag * H + k) : 0.f;
+        }
+        __syncthreads();
+        if (pag >= 0) {     // dsocial[agent][k] += sum_m W1s[m][k] dBs[row][m],  k = mq*8 .. +7
+            float ds[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ds[k] = 0.f;
+#pragma unroll
+            for (int m = 0; m < M1; ++m) {
+                float d = sDu[prow * LDU + m];
+                float4 wa = ld4(sW1 + m * LDH + mq * 8), wb = ld4(sW1 + m * LDH + mq * 8 + 4);
+                ds[0] = fmaf(d, wa.x, ds[0]); ds[1] = fmaf(d, wa.y, ds[1]); ds[2] = fmaf(d, wa.z, ds[2]); ds[3] = fmaf(d, wa.w, ds[3]);
+                ds[4] = fmaf(d, wb.x, ds[4]); ds[5] = fmaf(d, wb.y, ds[5]); ds[6] = fmaf(d, wb.z, ds[6]); ds[7] = fmaf(d, wb.w, ds[7]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(gr.dsocial + (size_t)pag * H + mq * 8 + k, ds[k]);
+        }
+#pragma unroll 4
+        for (int r = 0; r < ROWS; ++r) {
+            float d = sDu[r * LDU + e_m];
+            float2 sv = *reinterpret_cast<const float2*>(sHt + r * LDH + 2 * e_kp);
+            aw1s0 = fmaf(d, sv.x, aw1s0);
+            aw1s1 = fmaf(d, sv.y, aw1s1);
+        }
+    }
+    if (cur_g >= 0) flush(cur_g);
+}
+
+size_t dec_fwd_smem() {
+    return sizeof(float) * (4 * H * LDH + 2 * M1 * LDH + 2 * ROWS * LDH + ROWS * LDU + ROWS * 2 + H * (ZMAX + 1));
+}
+size_t dec_bwd_smem() {
+    return sizeof(float) * (4 * H * LDH + M1 * LDH + ROWS * LDG + 3 * ROWS * LDH + ROWS * LDU + ROWS * 2 + 4 * H * 2);
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+extern "C" int mggan_decoder_fwd(int n_tiles, const int* tile_gen, const int* seq_agent, const int* seq_noise,
+                                 const int* seq_out, const float* A, const float* social, const float* last_xy,
+                                 const float* last_dxdy, const float* noise, int Z, const float* Wz, const float* Wx,
+                                 const float* b, const float* Whh, const float* W1h, const float* W1s, const float* b1,
+                                 const float* W2, const float* b2, int pred_len, int n_cols, float* out_abs,
+                                 float* out_rel, float* acts, float* u1save, float* h0save, cudaStream_t stream) {
+    MGGAN_REQUIRE(Z >= 1 && Z <= ZMAX, "mggan_decoder_fwd: noise_dim %d not in [1, %d]", Z, ZMAX);
+    MGGAN_REQUIRE(pred_len >= 1 && n_tiles >= 0, "mggan_decoder_fwd: bad pred_len/n_tiles");
+    MGGAN_REQUIRE((acts == nullptr) == (u1save == nullptr) && (acts == nullptr) == (h0save == nullptr),
+                  "mggan_decoder_fwd: save buffers must be all set or all null");
+    if (n_tiles == 0) return MGGAN_OK;
+    DecSeq sq{tile_gen, seq_agent, seq_noise, seq_out};
+    DecWeights w{Wz, Wx, b, Whh, W1h, W1s, b1, W2, b2};
+    size_t sm = dec_fwd_smem();
+    cudaFuncSetAttribute(decoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    int grid = n_tiles < sm_count() * 3 ? n_tiles : sm_count() * 3;
+    decoder_fwd_kernel<<<grid, MGGAN_THREADS, sm, stream>>>(sq, n_tiles, A, social, last_xy, last_dxdy, noise, Z, w,
+                                                            pred_len, n_cols, out_abs, out_rel, acts, u1save, h0save);
+    return mggan_check_launch("decoder_fwd");
+}
+
+extern "C" int mggan_decoder_bwd(int n_tiles, const int* tile_gen, const int* seq_agent, const int* seq_noise,
+                                 const int* seq_out, const float* social, const float* last_dxdy, const float* noise,
+                                 int Z, const float* Wz, const float* Wx, const float* b, const float* Whh,
+                                 const float* W1h, const float* W1s, const float* b1, const float* W2, const float* b2,
+                                 int pred_len, int n_cols, const float* out_rel, const float* acts, const float* u1save,
+                                 const float* h0save, const float* d_abs, const float* d_rel, float* dWz, float* dWx,
+                                 float* db, float* dWhh, float* dW1h, float* dW1s, float* db1, float* dW2, float* db2,
+                                 float* dA, float* dsocial, cudaStream_t stream) {
+    MGGAN_REQUIRE(Z >= 1 && Z <= ZMAX, "mggan_decoder_bwd: noise_dim %d not in [1, %d]", Z, ZMAX);
+    MGGAN_REQUIRE(acts && u1save && h0save, "mggan_decoder_bwd: forward was run without save buffers");
+    if (n_tiles == 0) return MGGAN_OK;
+    DecSeq sq{tile_gen, seq_agent, seq_noise, seq_out};
+    DecWeights w{Wz, Wx, b, Whh, W1h, W1s, b1, W2, b2};
+    DecGrads gr{dWz, dWx, db, dWhh, dW1h, dW1s, db1, dW2, db2, dA, dsocial};
+    size_t sm = dec_bwd_smem();
+    cudaFuncSetAttribute(decoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    int grid = n_tiles < sm_count() * 2 ? n_tiles : sm_count() * 2;
+    decoder_bwd_kernel<<<grid, MGGAN_THREADS, sm, stream>>>(sq, n_tiles, social, last_dxdy, noise, Z, w, pred_len,
+                                                            n_cols, out_rel, acts, u1save, h0save, d_abs, d_rel, gr);
+    return mggan_check_launch("decoder_bwd");
+}

@@ -1,0 +1,191 @@
+// Dense layers of the path (PM-Net, enc_h_to_dec_h, discriminator encoders and heads):
+//   Y = act(X W^T + b),  X (M x K) rows = agents or sampled trajectories, W (O x K) PyTorch layout.
+// References: mggan/utils.py:134-149 (make_mlp), standard.py:91-105, discriminators.py:46-56,76-108.
+//
+// M is large (up to k*N rows), K and O are <= 192, so one strided fp32 tile product covers the
+// forward, the input gradient (dX = dZ W) and the weight gradient (dW = dZ^T X, reduction over
+// the rows split across CTAs and merged with atomics).  64x64 output tile, BK = 16, 4x4
+// register micro-tile, operands transposed into shared memory so the inner loop is two
+// LDS.128 per 16 FMAs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int LDT = BM + 4;
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_SIGMOID_EPS = 3 };
+constexpr float D_EPS = 1e-7f;      // discriminators.py:110, :203-204
+
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(z, 0.f);
+        case ACT_LRELU: return z > 0.f ? z : slope * z;
+        case ACT_SIGMOID_EPS: return (1.f / (1.f + expf(-z))) * (1.f - 2.f * D_EPS) + D_EPS;
+        default: return z;
+    }
+}
+// derivative expressed through the stored output y
+__device__ __forceinline__ float act_bwd(float y, int act, float slope) {
+    switch (act) {
+        case ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case ACT_LRELU: return y > 0.f ? 1.f : slope;
+        case ACT_SIGMOID_EPS: {
+            float s = (y - D_EPS) / (1.f - 2.f * D_EPS);
+            return (1.f - 2.f * D_EPS) * s * (1.f - s);
+        }
+        default: return 1.f;
+    }
+}
+
+struct GemmArgs {
+    const float* A; long long sam, sak;      // A(m, k) = A[m*sam + k*sak]
+    const float* Ay;                         // optional: multiply A(m,k) by act'(Ay(m,k)) (same indexing)
+    const float* B; long long sbn, sbk;      // B(n, k) = B[n*sbn + k*sbk]
+    float* C; long long scm, scn;            // C(m, n)
+    const float* bias;                       // per n (forward)
+    float* colsum;                           // per m: sum_k A(m,k)  (db in the weight-gradient call)
+    int M, N, K;
+    int act; float slope;
+    int splitk;                              // >1: K split over blockIdx.z, atomicAdd epilogue
+};
+
+__global__ void __launch_bounds__(MGGAN_THREADS)
+gemm_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[BK][LDT];
+    __shared__ __align__(16) float Bs[BK][LDT];
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int tm = threadIdx.x >> 4, tn = threadIdx.x & 15;       // 16 x 16 threads, 4 x 4 each
+    int k_begin = 0, k_end = g.K;
+    if (g.splitk > 1) {
+        int per = (g.K + g.splitk - 1) / g.splitk;
+        per = (per + BK - 1) / BK * BK;
+        k_begin = blockIdx.z * per;
+        k_end = min(g.K, k_begin + per);
+        if (k_begin >= k_end) return;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float csum = 0.f;
+    const bool a_kfast = g.sak == 1, b_kfast = g.sbk == 1;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+        for (int it = 0; it < (BM * BK) / MGGAN_THREADS; ++it) {
+            int idx = threadIdx.x + it * MGGAN_THREADS;
+            int mm = a_kfast ? idx / BK : idx % BM, kk = a_kfast ? idx % BK : idx / BM;
+            int m = m0 + mm, k = k0 + kk;
+            float v = 0.f;
+            if (m < g.M && k < k_end) {
+                long long off = m * g.sam + k * g.sak;
+                v = __ldg(g.A + off);
+                if (g.Ay != nullptr) v *= act_bwd(__ldg(g.Ay + off), g.act, g.slope);
+            }
+            As[kk][mm] = v;
+        }
+#pragma unroll
+        for (int it = 0; it < (BN * BK) / MGGAN_THREADS; ++it) {
+            int idx = threadIdx.x + it * MGGAN_THREADS;
+            int nn = b_kfast ? idx / BK : idx % BN, kk = b_kfast ? idx % BK : idx / BN;
+            int n = n0 + nn, k = k0 + kk;
+            float v = 0.f;
+            if (n < g.N && k < k_end) v = __ldg(g.B + n * g.sbn + k * g.sbk);
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 a = ld4(&As[kk][tm * 4]);
+            float4 b = ld4(&Bs[kk][tn * 4]);
+            acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+            acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+            acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+            acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+            acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
+            acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+            acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+            acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+        }
+        if (g.colsum != nullptr && blockIdx.y == 0 && threadIdx.x < BM) {
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) csum += As[kk][threadIdx.x];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + tm * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tn * 4 + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            float* dst = g.C + m * g.scm + n * g.scn;
+            if (g.splitk > 1) {
+                atomicAdd(dst, v);
+            } else {
+                if (g.bias != nullptr) v += __ldg(g.bias + n);
+                *dst = act_fwd(v, g.act, g.slope);
+            }
+        }
+    }
+    if (g.colsum != nullptr && blockIdx.y == 0 && threadIdx.x < BM && m0 + threadIdx.x < g.M)
+        atomicAdd(g.colsum + m0 + threadIdx.x, csum);
+}
+
+int launch(const GemmArgs& g, cudaStream_t s) {
+    dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, g.splitk > 1 ? g.splitk : 1);
+    gemm_kernel<<<grid, MGGAN_THREADS, 0, s>>>(g);
+    return mggan_check_launch("linear");
+}
+
+}  // namespace
+
+extern "C" int mggan_linear_fwd(const float* X, int M, int K, const float* W, const float* bias, int O, int act,
+                                float slope, float* Y, cudaStream_t stream) {
+    MGGAN_REQUIRE(M >= 0 && K >= 1 && O >= 1 && act >= 0 && act <= 3, "mggan_linear_fwd: bad shape/act");
+    if (M == 0) return MGGAN_OK;
+    GemmArgs g{};
+    g.A = X; g.sam = K; g.sak = 1; g.Ay = nullptr;
+    g.B = W; g.sbn = K; g.sbk = 1;
+    g.C = Y; g.scm = O; g.scn = 1;
+    g.bias = bias; g.colsum = nullptr; g.M = M; g.N = O; g.K = K; g.act = act; g.slope = slope; g.splitk = 1;
+    return launch(g, stream);
+}
+
+// dX (may be null) is overwritten; dW and db (may be null) are accumulated into (caller zero-fills).
+extern "C" int mggan_linear_bwd(const float* X, int M, int K, const float* W, int O, int act, float slope,
+                                const float* Y, const float* dY, float* dX, float* dW, float* db,
+                                cudaStream_t stream) {
+    MGGAN_REQUIRE(M >= 0 && K >= 1 && O >= 1 && act >= 0 && act <= 3, "mggan_linear_bwd: bad shape/act");
+    if (M == 0) return MGGAN_OK;
+    const float* Ay = act == ACT_NONE ? nullptr : Y;
+    if (dX != nullptr) {          // dX(m, k) = sum_o dZ(m, o) W(o, k)
+        GemmArgs g{};
+        g.A = dY; g.sam = O; g.sak = 1; g.Ay = Ay;
+        g.B = W; g.sbn = 1; g.sbk = K;
+        g.C = dX; g.scm = K; g.scn = 1;
+        g.M = M; g.N = K; g.K = O; g.act = act; g.slope = slope; g.splitk = 1;
+        int rc = launch(g, stream);
+        g.act = ACT_NONE;
+        if (rc) return rc;
+    }
+    if (dW != nullptr) {          // dW(o, k) = sum_m dZ(m, o) X(m, k) ; db(o) = sum_m dZ(m, o)
+        GemmArgs g{};
+        g.A = dY; g.sam = 1; g.sak = O; g.Ay = Ay;
+        g.B = X; g.sbn = 1; g.sbk = K;
+        g.C = dW; g.scm = K; g.scn = 1;
+        g.colsum = db;
+        g.M = O; g.N = K; g.K = M; g.act = act; g.slope = slope;
+        int tiles = ((O + BM - 1) / BM) * ((K + BN - 1) / BN);
+        int want = (148 * 4 + tiles - 1) / tiles;
+        int maxsplit = (M + 4 * BK - 1) / (4 * BK);
+        g.splitk = want < maxsplit ? want : maxsplit;
+        if (g.splitk < 2) g.splitk = 2;        // epilogue accumulates atomically in this mode
+        return launch(g, stream);
+    }
+    return MGGAN_OK;
+}

@@ -1,0 +1,848 @@
+// Physical (scene) attention: 2 x [conv3x3 pad1 -> BatchNorm2d -> ReLU -> MaxPool2x2] on the
+// per-agent (4,33,33) crop, then a per-position channel-softmax attention -> (N, 64).
+// Reference: mggan/model/modules/cnn.py:101-116 (AttentionGlobal.forward), :119-175
+// (Conv_Blocks), :178-282 (CNN); BatchNorm runs in train mode with batch statistics over
+// (N, H, W), so every conv layer needs a grid-wide reduction before its output can be used.
+//
+// Forward = three streaming passes, one CTA (persistent) per agent:
+//   scene_conv1_fwd   img -> x1 = conv1(img) (stored), per-channel sum / sum-of-squares
+//   scene_bn_finalize stats -> (a, b) = BN as an affine map, running statistics update
+//   scene_block2_fwd  x1 -> BN1 -> ReLU -> pool -> conv2 -> x2 (stored), stats of x2
+//   scene_bn_finalize
+//   scene_attn_fwd    x2 -> BN2 -> ReLU -> pool -> v (64 x C) -> MLP C->32->C -> softmax_c -> sum_c a v
+// Backward walks the same passes in reverse; the gradient w.r.t. a pooled+ReLU'd BatchNorm
+// output is sparse (one position per 2x2 window), so it is stored as (value, 2-bit index).
+// Partial BatchNorm sums are accumulated in fp32 per thread, reduced per CTA and added to the
+// global statistics as doubles (one atomicAdd per channel per CTA).
+#include "common.cuh"
+
+namespace {
+
+constexpr int IMG = 33, IMG2 = IMG * IMG;      // 1089
+constexpr int P1 = 16, P1SQ = 256;             // after first pool
+constexpr int P2 = 8, P2SQ = 64;               // after second pool
+constexpr int CIN = 4;
+constexpr int AH = 32;                         // attention MLP hidden width (cnn.py mlp_dim)
+constexpr int LDI = 36;                        // padded image row (35 used)
+constexpr int IMGPAD = 35 * LDI;               // one padded channel
+constexpr int LDP = 18;                        // padded pooled row
+constexpr int PPAD = LDP * LDP + 1;            // 325: channel stride (odd -> conflict-free across channels)
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Reduce NV per-thread partial sums over the CTA and add them (as doubles) to global memory.
+template <int NV>
+__device__ __forceinline__ void block_reduce_to_global(const float (&v)[NV], double* __restrict__ dst, float* sred) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float s = warp_sum(v[i]);
+        if (lane == 0) sred[warp * NV + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < MGGAN_THREADS / 32; ++w) s += (double)sred[w * NV + threadIdx.x];
+        atomicAdd(dst + threadIdx.x, s);
+    }
+    __syncthreads();
+}
+template <int NV>
+__device__ __forceinline__ void block_reduce_to_global_f(const float (&v)[NV], float* __restrict__ dst, float* sred) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float s = warp_sum(v[i]);
+        if (lane == 0) sred[warp * NV + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        float s = 0.f;
+        for (int w = 0; w < MGGAN_THREADS / 32; ++w) s += sred[w * NV + threadIdx.x];
+        atomicAdd(dst + threadIdx.x, s);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void load_image_padded(float* sImg, const float* __restrict__ img) {
+    for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
+        int ci = i / IMG2, p = i - ci * IMG2, y = p / IMG, x = p - y * IMG;
+        sImg[ci * IMGPAD + (y + 1) * LDI + x + 1] = __ldg(img + i);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pass A: conv1 + statistics
+template <int C>
+__global__ void __launch_bounds__(MGGAN_THREADS)
+scene_conv1_fwd_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N,
+                       const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ x1,
+                       double* __restrict__ stats) {
+    extern __shared__ __align__(16) float smem[];
+    float* sImg = smem;                      // [4][35][36]
+    float* sW = sImg + CIN * IMGPAD;         // [36 taps][C]
+    float* sred = sW + 36 * C;               // [8][2C]
+    for (int i = threadIdx.x; i < 36 * C; i += MGGAN_THREADS) {
+        int c = i / 36, tap = i - c * 36;
+        sW[tap * C + c] = __ldg(W + i);
+    }
+    float bs[C], st[2 * C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { bs[c] = __ldg(bias + c); st[c] = 0.f; st[C + c] = 0.f; }
+
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        const int src = rows ? rows[n] : n;
+        __syncthreads();
+        load_image_padded(sImg, img + (size_t)src * CIN * IMG2);
+        __syncthreads();
+        for (int p0 = threadIdx.x; p0 < IMG2; p0 += 2 * MGGAN_THREADS) {
+            const int p1 = p0 + MGGAN_THREADS;
+            const bool v1 = p1 < IMG2;
+            const int q1 = v1 ? p1 : p0;
+            const int y0 = p0 / IMG, x0 = p0 - y0 * IMG, y1 = q1 / IMG, xx1 = q1 - y1 * IMG;
+            float a0[C], a1[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) { a0[c] = bs[c]; a1[c] = bs[c]; }
+#pragma unroll 1
+            for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float i0 = sImg[ci * IMGPAD + (y0 + ky) * LDI + x0 + kx];
+                        const float i1 = sImg[ci * IMGPAD + (y1 + ky) * LDI + xx1 + kx];
+                        const float* wp = sW + (ci * 9 + ky * 3 + kx) * C;
+#pragma unroll
+                        for (int c = 0; c < C; c += 4) {
+                            float4 w = ld4(wp + c);
+                            a0[c] = fmaf(i0, w.x, a0[c]); a0[c + 1] = fmaf(i0, w.y, a0[c + 1]);
+                            a0[c + 2] = fmaf(i0, w.z, a0[c + 2]); a0[c + 3] = fmaf(i0, w.w, a0[c + 3]);
+                            a1[c] = fmaf(i1, w.x, a1[c]); a1[c + 1] = fmaf(i1, w.y, a1[c + 1]);
+                            a1[c + 2] = fmaf(i1, w.z, a1[c + 2]); a1[c + 3] = fmaf(i1, w.w, a1[c + 3]);
+                        }
+                    }
+            float* o = x1 + (size_t)n * C * IMG2;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                o[c * IMG2 + p0] = a0[c];
+                st[c] += a0[c]; st[C + c] = fmaf(a0[c], a0[c], st[C + c]);
+                if (v1) {
+                    o[c * IMG2 + p1] = a1[c];
+                    st[c] += a1[c]; st[C + c] = fmaf(a1[c], a1[c], st[C + c]);
+                }
+            }
+        }
+    }
+    if (stats != nullptr) block_reduce_to_global<2 * C>(st, stats, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm finalize: statistics -> affine (a, b), mean / invstd for the backward, running stats.
+__global__ void scene_bn_finalize_kernel(const double* __restrict__ stats, double count, int C,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         long long* __restrict__ nbt, float momentum, float eps, int training,
+                                         float* __restrict__ ab, float* __restrict__ mean_istd) {
+    int c = threadIdx.x;
+    if (c < C) {
+        float mean, var;
+        if (training) {
+            double m = stats[c] / count;
+            double v = stats[C + c] / count - m * m;
+            if (v < 0.0) v = 0.0;
+            mean = (float)m; var = (float)v;
+            double unb = count > 1.0 ? v * count / (count - 1.0) : v;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+        } else {
+            mean = running_mean[c]; var = running_var[c];
+        }
+        float istd = rsqrtf(var + eps);
+        istd = istd * (1.5f - 0.5f * (var + eps) * istd * istd);     // one Newton step on rsqrt.approx
+        float a = gamma[c] * istd;
+        ab[c] = a;
+        ab[C + c] = beta[c] - mean * a;
+        mean_istd[c] = mean;
+        mean_istd[C + c] = istd;
+    }
+    if (training && threadIdx.x == 0) nbt[0] += 1;
+}
+
+// BatchNorm backward finalize: sums (sum dy, sum dy*xhat) -> means m1, m2 and dgamma / dbeta.
+__global__ void scene_bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, int C,
+                                             float* __restrict__ m12, float* __restrict__ dgamma,
+                                             float* __restrict__ dbeta) {
+    int c = threadIdx.x;
+    if (c < C) {
+        m12[c] = (float)(sums[c] / count);
+        m12[C + c] = (float)(sums[C + c] / count);
+        atomicAdd(dbeta + c, (float)sums[c]);
+        atomicAdd(dgamma + c, (float)sums[C + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pass B: BN1 -> ReLU -> pool -> conv2 + statistics
+template <int C>
+__device__ __forceinline__ void pool_block1(const float* __restrict__ x1n, const float* __restrict__ ab1, float* sP,
+                                            unsigned char* sIdx, float* sE) {
+    // 2x2 max-pool of relu(a x + b); optional arg index (bit 2 = active) and pre-BN value at the arg
+    for (int i = threadIdx.x; i < C * P1SQ; i += MGGAN_THREADS) {
+        int c = i >> 8, pp = i & 255, py = pp >> 4, px = pp & 15;
+        const float a = ab1[c], b = ab1[C + c];
+        const float* s = x1n + c * IMG2 + (2 * py) * IMG + 2 * px;
+        float r0 = __ldg(s), r1 = __ldg(s + 1), r2 = __ldg(s + IMG), r3 = __ldg(s + IMG + 1);
+        float v0 = fmaf(a, r0, b), v1 = fmaf(a, r1, b), v2 = fmaf(a, r2, b), v3 = fmaf(a, r3, b);
+        float m = v0, e = r0; int arg = 0;
+        if (v1 > m) { m = v1; e = r1; arg = 1; }
+        if (v2 > m) { m = v2; e = r2; arg = 2; }
+        if (v3 > m) { m = v3; e = r3; arg = 3; }
+        sP[c * PPAD + (py + 1) * LDP + px + 1] = fmaxf(m, 0.f);
+        if (sIdx != nullptr) { sIdx[i] = (unsigned char)(arg | (m > 0.f ? 4 : 0)); sE[i] = e; }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(MGGAN_THREADS)
+scene_block2_fwd_kernel(const float* __restrict__ x1, int N, const float* __restrict__ ab1,
+                        const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ x2,
+                        double* __restrict__ stats) {
+    extern __shared__ __align__(16) float smem[];
+    float* sP = smem;                         // [C][PPAD]
+    float* sW = sP + ((C * PPAD + 3) & ~3);   // [C*9 taps][C out]
+    float* sAB = sW + 9 * C * C;              // [2C]
+    float* sred = sAB + 2 * C;                // [8][2C]
+    for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
+        int co = i / (9 * C), r = i - co * 9 * C;           // r = ci*9 + tap
+        sW[r * C + co] = __ldg(W + i);
+    }
+    if (threadIdx.x < 2 * C) sAB[threadIdx.x] = __ldg(ab1 + threadIdx.x);
+    for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) sP[i] = 0.f;    // halo stays zero
+    float bs[C], st[2 * C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { bs[c] = __ldg(bias + c); st[c] = 0.f; st[C + c] = 0.f; }
+    const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
+
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        __syncthreads();
+        pool_block1<C>(x1 + (size_t)n * C * IMG2, sAB, sP, nullptr, nullptr);
+        __syncthreads();
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = bs[c];
+#pragma unroll 2
+        for (int ci = 0; ci < C; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float v = sP[ci * PPAD + (y + ky) * LDP + x + kx];
+                    const float* wp = sW + (ci * 9 + ky * 3 + kx) * C;
+#pragma unroll
+                    for (int c = 0; c < C; c += 4) {
+                        float4 w = ld4(wp + c);
+                        acc[c] = fmaf(v, w.x, acc[c]); acc[c + 1] = fmaf(v, w.y, acc[c + 1]);
+                        acc[c + 2] = fmaf(v, w.z, acc[c + 2]); acc[c + 3] = fmaf(v, w.w, acc[c + 3]);
+                    }
+                }
+        float* o = x2 + (size_t)n * C * P1SQ + threadIdx.x;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            o[c * P1SQ] = acc[c];
+            st[c] += acc[c]; st[C + c] = fmaf(acc[c], acc[c], st[C + c]);
+        }
+    }
+    if (stats != nullptr) block_reduce_to_global<2 * C>(st, stats, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// pass C: BN2 -> ReLU -> pool -> per-position channel attention.  thread = (agent slot, position)
+template <int C>
+struct AttnW {
+    float* sWa1;   // [AH][C]
+    float* sWa2;   // [C][AH]
+    float* sba1;   // [AH]
+    float* sba2;   // [C]
+    float* sAB;    // [2C]
+};
+
+template <int C>
+__device__ __forceinline__ AttnW<C> stage_attn_weights(float* base, const float* Wa1, const float* ba1, const float* Wa2,
+                                                       const float* ba2, const float* ab2) {
+    AttnW<C> w;
+    w.sWa1 = base; w.sWa2 = w.sWa1 + AH * C; w.sba1 = w.sWa2 + C * AH; w.sba2 = w.sba1 + AH; w.sAB = w.sba2 + C;
+    for (int i = threadIdx.x; i < AH * C; i += MGGAN_THREADS) { w.sWa1[i] = __ldg(Wa1 + i); w.sWa2[i] = __ldg(Wa2 + i); }
+    if (threadIdx.x < AH) w.sba1[threadIdx.x] = __ldg(ba1 + threadIdx.x);
+    if (threadIdx.x < C) w.sba2[threadIdx.x] = __ldg(ba2 + threadIdx.x);
+    if (threadIdx.x < 2 * C) w.sAB[threadIdx.x] = __ldg(ab2 + threadIdx.x);
+    return w;
+}
+
+// v[c] = maxpool(relu(BN2(x2))) at one position; optionally the arg index / pre-BN value at the arg.
+template <int C, bool WITH_ARG>
+__device__ __forceinline__ void pool_block2(const float* __restrict__ x2n, const float* sAB, int pos, float (&v)[C],
+                                            int (&arg)[C], float (&e)[C]) {
+    const int py = pos >> 3, px = pos & 7;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float a = sAB[c], b = sAB[C + c];
+        const float2* s = reinterpret_cast<const float2*>(x2n + c * P1SQ + (2 * py) * P1 + 2 * px);
+        float2 t0 = __ldg(s), t1 = __ldg(s + P1 / 2);
+        float v0 = fmaf(a, t0.x, b), v1 = fmaf(a, t0.y, b), v2 = fmaf(a, t1.x, b), v3 = fmaf(a, t1.y, b);
+        float m = v0, ee = t0.x; int ag = 0;
+        if (v1 > m) { m = v1; ee = t0.y; ag = 1; }
+        if (v2 > m) { m = v2; ee = t1.x; ag = 2; }
+        if (v3 > m) { m = v3; ee = t1.y; ag = 3; }
+        v[c] = fmaxf(m, 0.f);
+        if (WITH_ARG) { arg[c] = ag | (m > 0.f ? 4 : 0); e[c] = ee; }
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void attn_mlp(const AttnW<C>& w, const float (&v)[C], float (&hp)[AH], float (&att)[C]) {
+#pragma unroll
+    for (int k = 0; k < AH; ++k) {
+        float s = w.sba1[k];
+#pragma unroll
+        for (int c = 0; c < C; c += 4) {
+            float4 q = ld4(w.sWa1 + k * C + c);
+            s = fmaf(q.x, v[c], fmaf(q.y, v[c + 1], fmaf(q.z, v[c + 2], fmaf(q.w, v[c + 3], s))));
+        }
+        hp[k] = s;                         // pre-activation
+    }
+    float mx = -3.4e38f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float s = w.sba2[c];
+#pragma unroll
+        for (int k = 0; k < AH; k += 4) {
+            float4 q = ld4(w.sWa2 + c * AH + k);
+            s = fmaf(q.x, lrelu_(hp[k], 0.01f), fmaf(q.y, lrelu_(hp[k + 1], 0.01f),
+                fmaf(q.z, lrelu_(hp[k + 2], 0.01f), fmaf(q.w, lrelu_(hp[k + 3], 0.01f), s))));
+        }
+        att[c] = s;
+        mx = fmaxf(mx, s);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { att[c] = __expf(att[c] - mx); sum += att[c]; }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int c = 0; c < C; ++c) att[c] *= inv;
+}
+
+template <int C>
+__global__ void __launch_bounds__(MGGAN_THREADS)
+scene_attn_fwd_kernel(const float* __restrict__ x2, int N, const float* __restrict__ ab2, const float* __restrict__ Wa1,
+                      const float* __restrict__ ba1, const float* __restrict__ Wa2, const float* __restrict__ ba2,
+                      float* __restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    AttnW<C> w = stage_attn_weights<C>(smem, Wa1, ba1, Wa2, ba2, ab2);
+    __syncthreads();
+    const int slot = threadIdx.x >> 6, pos = threadIdx.x & 63;
+    for (int n0 = blockIdx.x * 4; n0 < N; n0 += gridDim.x * 4) {
+        const int n = n0 + slot;
+        if (n >= N) continue;
+        float v[C], hp[AH], att[C], e[C]; int arg[C];
+        pool_block2<C, false>(x2 + (size_t)n * C * P1SQ, w.sAB, pos, v, arg, e);
+        attn_mlp<C>(w, v, hp, att);
+        float o = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) o = fmaf(att[c], v[c], o);
+        out[(size_t)n * P2SQ + pos] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of pass C: d(out) -> attention-MLP weight grads, sparse dy2 (+ arg index), BN2 sums
+template <int C>
+__global__ void __launch_bounds__(MGGAN_THREADS)
+scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restrict__ ab2,
+                      const float* __restrict__ mean_istd2, const float* __restrict__ Wa1,
+                      const float* __restrict__ ba1, const float* __restrict__ Wa2, const float* __restrict__ ba2,
+                      const float* __restrict__ dout, float* __restrict__ dWa1, float* __restrict__ dba1,
+                      float* __restrict__ dWa2, float* __restrict__ dba2, float* __restrict__ dy2,
+                      unsigned char* __restrict__ idx2, double* __restrict__ sums2) {
+    constexpr int LDC = C + 4, LDA = AH + 4;
+    constexpr int NBLK = 4 * C;                   // 2 * (C/4) * (AH/4) weight-gradient blocks
+    constexpr int RG = MGGAN_THREADS / NBLK;      // row groups
+    constexpr int RPG = MGGAN_THREADS / RG;       // rows per group
+    extern __shared__ __align__(16) float smem[];
+    AttnW<C> w = stage_attn_weights<C>(smem, Wa1, ba1, Wa2, ba2, ab2);
+    float* sDS = w.sAB + 2 * C;                   // [256][LDC]
+    float* sV = sDS + MGGAN_THREADS * LDC;        // [256][LDC]
+    float* sHid = sV + MGGAN_THREADS * LDC;       // [256][LDA]
+    float* sDH = sHid + MGGAN_THREADS * LDA;      // [256][LDA]
+    float* sMI = sDH + MGGAN_THREADS * LDA;       // [2C]
+    float* sred = sMI + 2 * C;                    // [8][2C]
+    if (threadIdx.x < 2 * C) sMI[threadIdx.x] = __ldg(mean_istd2 + threadIdx.x);
+    __syncthreads();
+    const int slot = threadIdx.x >> 6, pos = threadIdx.x & 63;
+    const int blk = threadIdx.x % NBLK, rg = threadIdx.x / NBLK;
+    float wacc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wacc[i][j] = 0.f;
+    float bacc = 0.f;            // dba2[c] for t < C ; dba1[k] for C <= t < C + AH
+    float st[2 * C];
+#pragma unroll
+    for (int c = 0; c < 2 * C; ++c) st[c] = 0.f;
+
+    for (int n0 = blockIdx.x * 4; n0 < N; n0 += gridDim.x * 4) {
+        const int n = n0 + slot;
+        float v[C], hp[AH], att[C], e[C], ds[C], dv[C]; int arg[C];
+        float dhid[AH];
+        __syncthreads();
+        if (n < N) {
+            pool_block2<C, true>(x2 + (size_t)n * C * P1SQ, w.sAB, pos, v, arg, e);
+            attn_mlp<C>(w, v, hp, att);
+            const float g = __ldg(dout + (size_t)n * P2SQ + pos);
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) dot = fmaf(att[c], g * v[c], dot);
+#pragma unroll
+            for (int c = 0; c < C; ++c) { ds[c] = att[c] * (g * v[c] - dot); dv[c] = g * att[c]; }
+#pragma unroll
+            for (int k = 0; k < AH; ++k) dhid[k] = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int k = 0; k < AH; k += 4) {
+                    float4 q = ld4(w.sWa2 + c * AH + k);
+                    dhid[k] = fmaf(q.x, ds[c], dhid[k]); dhid[k + 1] = fmaf(q.y, ds[c], dhid[k + 1]);
+                    dhid[k + 2] = fmaf(q.z, ds[c], dhid[k + 2]); dhid[k + 3] = fmaf(q.w, ds[c], dhid[k + 3]);
+                }
+#pragma unroll
+            for (int k = 0; k < AH; ++k) {
+                dhid[k] *= hp[k] > 0.f ? 1.f : 0.01f;
+#pragma unroll
+                for (int c = 0; c < C; c += 4) {
+                    float4 q = ld4(w.sWa1 + k * C + c);
+                    dv[c] = fmaf(q.x, dhid[k], dv[c]); dv[c + 1] = fmaf(q.y, dhid[k], dv[c + 1]);
+                    dv[c + 2] = fmaf(q.z, dhid[k], dv[c + 2]); dv[c + 3] = fmaf(q.w, dhid[k], dv[c + 3]);
+                }
+            }
+            // sparse gradient at the pooled arg position + BatchNorm sums
+            float* dyo = dy2 + (size_t)n * C * P2SQ + pos;
+            unsigned char* ixo = idx2 + (size_t)n * C * P2SQ + pos;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float d = (arg[c] & 4) ? dv[c] : 0.f;
+                dyo[c * P2SQ] = d;
+                ixo[c * P2SQ] = (unsigned char)(arg[c] & 3);
+                float xh = (e[c] - sMI[c]) * sMI[C + c];
+                st[c] += d;
+                st[C + c] = fmaf(d, xh, st[C + c]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) { ds[c] = 0.f; v[c] = 0.f; }
+#pragma unroll
+            for (int k = 0; k < AH; ++k) { dhid[k] = 0.f; hp[k] = 0.f; }
+        }
+#pragma unroll
+        for (int c = 0; c < C; c += 4) {
+            st4(sDS + threadIdx.x * LDC + c, make_float4(ds[c], ds[c + 1], ds[c + 2], ds[c + 3]));
+            st4(sV + threadIdx.x * LDC + c, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+        }
+#pragma unroll
+        for (int k = 0; k < AH; k += 4) {
+            st4(sHid + threadIdx.x * LDA + k, make_float4(lrelu_(hp[k], 0.01f), lrelu_(hp[k + 1], 0.01f),
+                                                          lrelu_(hp[k + 2], 0.01f), lrelu_(hp[k + 3], 0.01f)));
+            st4(sDH + threadIdx.x * LDA + k, make_float4(dhid[k], dhid[k + 1], dhid[k + 2], dhid[k + 3]));
+        }
+        __syncthreads();
+        if (blk < NBLK / 2) {      // dWa2[c][k] += sum_r ds[r][c] hid[r][k]
+            int oq = blk % (C / 4), kq = blk / (C / 4);
+            tile_wgrad<RPG>(wacc, sDS + rg * RPG * LDC, LDC, oq * 4, sHid + rg * RPG * LDA, LDA, kq * 4);
+        } else {                   // dWa1[k][c] += sum_r dhid[r][k] v[r][c]
+            int b2 = blk - NBLK / 2;
+            int oq = b2 % (AH / 4), kq = b2 / (AH / 4);
+            tile_wgrad<RPG>(wacc, sDH + rg * RPG * LDA, LDA, oq * 4, sV + rg * RPG * LDC, LDC, kq * 4);
+        }
+        if (threadIdx.x < C) {
+            for (int r = 0; r < MGGAN_THREADS; ++r) bacc += sDS[r * LDC + threadIdx.x];
+        } else if (threadIdx.x < C + AH) {
+            for (int r = 0; r < MGGAN_THREADS; ++r) bacc += sDH[r * LDA + threadIdx.x - C];
+        }
+    }
+    if (blk < NBLK / 2) {
+        int oq = blk % (C / 4), kq = blk / (C / 4);
+        atomic_block44(dWa2, AH, oq * 4, kq * 4, wacc);
+    } else {
+        int b2 = blk - NBLK / 2;
+        int oq = b2 % (AH / 4), kq = b2 / (AH / 4);
+        atomic_block44(dWa1, C, oq * 4, kq * 4, wacc);
+    }
+    if (threadIdx.x < C) atomicAdd(dba2 + threadIdx.x, bacc);
+    else if (threadIdx.x < C + AH) atomicAdd(dba1 + threadIdx.x - C, bacc);
+    block_reduce_to_global<2 * C>(st, sums2, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of pass B: BN2 backward (dense dx2) -> conv2 weight / input gradients -> sparse dy1, BN1 sums
+template <int C>
+__global__ void __launch_bounds__(MGGAN_THREADS)
+scene_block2_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int N,
+                        const float* __restrict__ ab1, const float* __restrict__ mean_istd1,
+                        const float* __restrict__ ab2, const float* __restrict__ mean_istd2,
+                        const float* __restrict__ m12_2, const float* __restrict__ W,
+                        const float* __restrict__ dy2, const unsigned char* __restrict__ idx2,
+                        float* __restrict__ dW, float* __restrict__ dbias, float* __restrict__ dy1,
+                        unsigned char* __restrict__ idx1, double* __restrict__ sums1) {
+    constexpr int NPAIR = C * C;
+    constexpr int PG = MGGAN_THREADS / NPAIR;          // pixel-row groups for the weight gradient (1 or 4)
+    constexpr int ROWS_PG = P1 / PG;
+    extern __shared__ __align__(16) float smem[];
+    float* sDX = smem;                                   // [C][PPAD]  dx2 with zero halo
+    float* sP = sDX + C * PPAD;                          // [C][PPAD]  p1 with zero halo
+    float* sWT = sP + ((C * PPAD + 3) & ~3);             // [(co*9+tap)][ci]
+    float* sE = sWT + 9 * C * C;                         // [C][256] pre-BN value at the pool arg
+    float* sPar = sE + C * P1SQ;                         // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
+    float* sred = sPar + 10 * C;                         // [8][2C]
+    unsigned char* sIdx = reinterpret_cast<unsigned char*>(sred + 8 * 2 * C);    // [C][256]
+    for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
+        int co = i / (9 * C), r = i - co * 9 * C, ci = r / 9, tap = r - ci * 9;
+        sWT[(co * 9 + tap) * C + ci] = __ldg(W + i);
+    }
+    if (threadIdx.x < 2 * C) {
+        sPar[threadIdx.x] = __ldg(ab1 + threadIdx.x);
+        sPar[2 * C + threadIdx.x] = __ldg(mean_istd1 + threadIdx.x);
+        sPar[4 * C + threadIdx.x] = __ldg(ab2 + threadIdx.x);
+        sPar[6 * C + threadIdx.x] = __ldg(mean_istd2 + threadIdx.x);
+        sPar[8 * C + threadIdx.x] = __ldg(m12_2 + threadIdx.x);
+    }
+    for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) { sDX[i] = 0.f; sP[i] = 0.f; }
+    const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
+    const int pr = threadIdx.x % NPAIR, pg = threadIdx.x / NPAIR;
+    const int w_co = pr / C, w_ci = pr % C;
+    float wacc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wacc[i] = 0.f;
+    float dbs[C], st[2 * C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { dbs[c] = 0.f; st[c] = 0.f; st[C + c] = 0.f; }
+
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        __syncthreads();
+        // dx2 (dense) at this thread's pixel
+        {
+            const int win = (y >> 1) * P2 + (x >> 1), loc = (y & 1) * 2 + (x & 1);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float xv = __ldg(x2 + ((size_t)n * C + c) * P1SQ + threadIdx.x);
+                float xh = (xv - sPar[6 * C + c]) * sPar[7 * C + c];
+                float d = 0.f;
+                if (idx2[((size_t)n * C + c) * P2SQ + win] == loc) d = __ldg(dy2 + ((size_t)n * C + c) * P2SQ + win);
+                float dx = sPar[4 * C + c] * (d - sPar[8 * C + c] - xh * sPar[9 * C + c]);
+                sDX[c * PPAD + (y + 1) * LDP + x + 1] = dx;
+                dbs[c] += dx;
+            }
+        }
+        pool_block1<C>(x1 + (size_t)n * C * IMG2, sPar, sP, sIdx, sE);
+        __syncthreads();
+        // conv2 weight gradient: thread = (co, ci) x pixel-row group, 3x3 taps in registers
+        {
+            const float* dxp = sDX + w_co * PPAD;
+            const float* pp = sP + w_ci * PPAD;
+            for (int yy = pg * ROWS_PG; yy < (pg + 1) * ROWS_PG; ++yy) {
+                float c0[3], c1[3], c2[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { c0[r] = pp[(yy + r) * LDP]; c1[r] = pp[(yy + r) * LDP + 1]; }
+#pragma unroll
+                for (int xx = 0; xx < P1; ++xx) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) c2[r] = pp[(yy + r) * LDP + xx + 2];
+                    const float d = dxp[(yy + 1) * LDP + xx + 1];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        wacc[r * 3] = fmaf(d, c0[r], wacc[r * 3]);
+                        wacc[r * 3 + 1] = fmaf(d, c1[r], wacc[r * 3 + 1]);
+                        wacc[r * 3 + 2] = fmaf(d, c2[r], wacc[r * 3 + 2]);
+                        c0[r] = c1[r]; c1[r] = c2[r];
+                    }
+                }
+            }
+        }
+        // conv2 input gradient at this thread's pixel -> through pool / ReLU / BN1 -> sparse dy1
+        {
+            float acc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll 2
+            for (int co = 0; co < C; ++co)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float d = sDX[co * PPAD + (y + 2 - ky) * LDP + x + 2 - kx];
+                        const float* wp = sWT + (co * 9 + ky * 3 + kx) * C;
+#pragma unroll
+                        for (int c = 0; c < C; c += 4) {
+                            float4 q = ld4(wp + c);
+                            acc[c] = fmaf(d, q.x, acc[c]); acc[c + 1] = fmaf(d, q.y, acc[c + 1]);
+                            acc[c + 2] = fmaf(d, q.z, acc[c + 2]); acc[c + 3] = fmaf(d, q.w, acc[c + 3]);
+                        }
+                    }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int code = sIdx[c * P1SQ + threadIdx.x];
+                const float d = (code & 4) ? acc[c] : 0.f;
+                dy1[((size_t)n * C + c) * P1SQ + threadIdx.x] = d;
+                idx1[((size_t)n * C + c) * P1SQ + threadIdx.x] = (unsigned char)(code & 3);
+                const float xh = (sE[c * P1SQ + threadIdx.x] - sPar[2 * C + c]) * sPar[3 * C + c];
+                st[c] += d;
+                st[C + c] = fmaf(d, xh, st[C + c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(dW + ((size_t)w_co * C + w_ci) * 9 + t, wacc[t]);
+    block_reduce_to_global_f<C>(dbs, dbias, sred);
+    block_reduce_to_global<2 * C>(st, sums1, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of pass A: BN1 backward (dense dx1) -> conv1 weight gradient
+template <int C>
+__global__ void __launch_bounds__(MGGAN_THREADS)
+scene_conv1_bwd_kernel(const float* __restrict__ img, const int* __restrict__ rows, const float* __restrict__ x1,
+                       int N, const float* __restrict__ ab1, const float* __restrict__ mean_istd1,
+                       const float* __restrict__ m12_1, const float* __restrict__ dy1,
+                       const unsigned char* __restrict__ idx1, float* __restrict__ dW, float* __restrict__ dbias) {
+    constexpr int NPAIR = C * CIN;
+    constexpr int PG = MGGAN_THREADS / NPAIR;            // 4 (C=16) or 8 (C=8)
+    constexpr int ROWS_PG = (IMG + PG - 1) / PG;
+    constexpr int LDX = IMG + 1;                         // 34
+    extern __shared__ __align__(16) float smem[];
+    float* sImg = smem;                        // [4][35][36]
+    float* sDX = sImg + CIN * IMGPAD;          // [C][33][34]
+    float* sPar = sDX + C * IMG * LDX;         // ab1[2C] mi1[2C] m12[2C]
+    float* sred = sPar + 6 * C;                // [8][C]
+    if (threadIdx.x < 2 * C) {
+        sPar[threadIdx.x] = __ldg(ab1 + threadIdx.x);
+        sPar[2 * C + threadIdx.x] = __ldg(mean_istd1 + threadIdx.x);
+        sPar[4 * C + threadIdx.x] = __ldg(m12_1 + threadIdx.x);
+    }
+    const int pr = threadIdx.x % NPAIR, pg = threadIdx.x / NPAIR;
+    const int w_c = pr / CIN, w_ci = pr % CIN;
+    float wacc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wacc[i] = 0.f;
+    float dbs[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) dbs[c] = 0.f;
+
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        const int src = rows ? rows[n] : n;
+        __syncthreads();
+        load_image_padded(sImg, img + (size_t)src * CIN * IMG2);
+        for (int p = threadIdx.x; p < IMG2; p += MGGAN_THREADS) {
+            const int y = p / IMG, x = p - y * IMG;
+            const bool inwin = y < 2 * P1 && x < 2 * P1;
+            const int win = (y >> 1) * P1 + (x >> 1), loc = (y & 1) * 2 + (x & 1);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float xv = __ldg(x1 + ((size_t)n * C + c) * IMG2 + p);
+                float xh = (xv - sPar[2 * C + c]) * sPar[3 * C + c];
+                float d = 0.f;
+                if (inwin && idx1[((size_t)n * C + c) * P1SQ + win] == loc) d = __ldg(dy1 + ((size_t)n * C + c) * P1SQ + win);
+                float dx = sPar[c] * (d - sPar[4 * C + c] - xh * sPar[5 * C + c]);
+                sDX[(c * IMG + y) * LDX + x] = dx;
+                dbs[c] += dx;
+            }
+        }
+        __syncthreads();
+        {
+            const float* dxp = sDX + w_c * IMG * LDX;
+            const float* ip = sImg + w_ci * IMGPAD;
+            const int y_end = min(IMG, (pg + 1) * ROWS_PG);
+            for (int yy = pg * ROWS_PG; yy < y_end; ++yy) {
+                float c0[3], c1[3], c2[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { c0[r] = ip[(yy + r) * LDI]; c1[r] = ip[(yy + r) * LDI + 1]; }
+#pragma unroll 3
+                for (int xx = 0; xx < IMG; ++xx) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) c2[r] = ip[(yy + r) * LDI + xx + 2];
+                    const float d = dxp[yy * LDX + xx];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        wacc[r * 3] = fmaf(d, c0[r], wacc[r * 3]);
+                        wacc[r * 3 + 1] = fmaf(d, c1[r], wacc[r * 3 + 1]);
+                        wacc[r * 3 + 2] = fmaf(d, c2[r], wacc[r * 3 + 2]);
+                        c0[r] = c1[r]; c1[r] = c2[r];
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(dW + ((size_t)w_c * CIN + w_ci) * 9 + t, wacc[t]);
+    block_reduce_to_global_f<C>(dbs, dbias, sred);
+}
+
+template <int C>
+size_t conv1_fwd_smem() { return sizeof(float) * (CIN * IMGPAD + 36 * C + 8 * 2 * C); }
+template <int C>
+size_t block2_fwd_smem() { return sizeof(float) * (((C * PPAD + 3) & ~3) + 9 * C * C + 2 * C + 8 * 2 * C); }
+template <int C>
+size_t attn_w_floats() { return 2 * AH * C + AH + C + 2 * C; }
+template <int C>
+size_t attn_fwd_smem() { return sizeof(float) * attn_w_floats<C>(); }
+template <int C>
+size_t attn_bwd_smem() {
+    return sizeof(float) * (attn_w_floats<C>() + 2 * MGGAN_THREADS * (C + 4) + 2 * MGGAN_THREADS * (AH + 4) + 2 * C + 8 * 2 * C);
+}
+template <int C>
+size_t block2_bwd_smem() {
+    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * C + C * P1SQ + 10 * C + 8 * 2 * C) + C * P1SQ;
+}
+template <int C>
+size_t conv1_bwd_smem() { return sizeof(float) * (CIN * IMGPAD + C * IMG * (IMG + 1) + 6 * C + 8 * C); }
+
+int agent_grid(int N, int per_sm) {
+    int g = sm_count() * per_sm;
+    return N < g ? N : g;
+}
+
+#define SCENE_DISPATCH(C_, CALL16, CALL8)                                              \
+    do {                                                                               \
+        if ((C_) == 16) { CALL16; } else if ((C_) == 8) { CALL8; }                     \
+        else return mggan_set_error(MGGAN_ERR_INVALID, "scene kernels built for 8 or 16 channels, got %d", (C_)); \
+    } while (0)
+
+template <int C>
+int conv1_fwd(const float* img, const int* rows, int N, const float* W, const float* b, float* x1, double* stats, cudaStream_t s) {
+    size_t sm = conv1_fwd_smem<C>();
+    cudaFuncSetAttribute(scene_conv1_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    scene_conv1_fwd_kernel<C><<<agent_grid(N, 4), MGGAN_THREADS, sm, s>>>(img, rows, N, W, b, x1, stats);
+    return mggan_check_launch("scene_conv1_fwd");
+}
+template <int C>
+int block2_fwd(const float* x1, int N, const float* ab1, const float* W, const float* b, float* x2, double* stats, cudaStream_t s) {
+    size_t sm = block2_fwd_smem<C>();
+    cudaFuncSetAttribute(scene_block2_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    scene_block2_fwd_kernel<C><<<agent_grid(N, 4), MGGAN_THREADS, sm, s>>>(x1, N, ab1, W, b, x2, stats);
+    return mggan_check_launch("scene_block2_fwd");
+}
+template <int C>
+int attn_fwd(const float* x2, int N, const float* ab2, const float* Wa1, const float* ba1, const float* Wa2, const float* ba2,
+             float* out, cudaStream_t s) {
+    size_t sm = attn_fwd_smem<C>();
+    int g = (N + 3) / 4;
+    int cap = sm_count() * 4;
+    scene_attn_fwd_kernel<C><<<g < cap ? g : cap, MGGAN_THREADS, sm, s>>>(x2, N, ab2, Wa1, ba1, Wa2, ba2, out);
+    return mggan_check_launch("scene_attn_fwd");
+}
+template <int C>
+int attn_bwd(const float* x2, int N, const float* ab2, const float* mi2, const float* Wa1, const float* ba1, const float* Wa2,
+             const float* ba2, const float* dout, float* dWa1, float* dba1, float* dWa2, float* dba2, float* dy2,
+             unsigned char* idx2, double* sums2, cudaStream_t s) {
+    size_t sm = attn_bwd_smem<C>();
+    cudaFuncSetAttribute(scene_attn_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    int g = (N + 3) / 4;
+    int cap = sm_count() * 2;
+    scene_attn_bwd_kernel<C><<<g < cap ? g : cap, MGGAN_THREADS, sm, s>>>(x2, N, ab2, mi2, Wa1, ba1, Wa2, ba2, dout, dWa1,
+                                                                          dba1, dWa2, dba2, dy2, idx2, sums2);
+    return mggan_check_launch("scene_attn_bwd");
+}
+template <int C>
+int block2_bwd(const float* x1, const float* x2, int N, const float* ab1, const float* mi1, const float* ab2, const float* mi2,
+               const float* m12_2, const float* W, const float* dy2, const unsigned char* idx2, float* dW, float* db,
+               float* dy1, unsigned char* idx1, double* sums1, cudaStream_t s) {
+    size_t sm = block2_bwd_smem<C>();
+    cudaFuncSetAttribute(scene_block2_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    scene_block2_bwd_kernel<C><<<agent_grid(N, 2), MGGAN_THREADS, sm, s>>>(x1, x2, N, ab1, mi1, ab2, mi2, m12_2, W, dy2, idx2,
+                                                                           dW, db, dy1, idx1, sums1);
+    return mggan_check_launch("scene_block2_bwd");
+}
+template <int C>
+int conv1_bwd(const float* img, const int* rows, const float* x1, int N, const float* ab1, const float* mi1, const float* m12_1,
+              const float* dy1, const unsigned char* idx1, float* dW, float* db, cudaStream_t s) {
+    size_t sm = conv1_bwd_smem<C>();
+    cudaFuncSetAttribute(scene_conv1_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    scene_conv1_bwd_kernel<C><<<agent_grid(N, 2), MGGAN_THREADS, sm, s>>>(img, rows, x1, N, ab1, mi1, m12_1, dy1, idx1, dW, db);
+    return mggan_check_launch("scene_conv1_bwd");
+}
+
+}  // namespace
+
+extern "C" int mggan_scene_conv1_fwd(const float* img, const int* rows, int N, int C, const float* W, const float* bias,
+                                     float* x1, double* stats, cudaStream_t stream) {
+    if (N <= 0) return MGGAN_OK;
+    SCENE_DISPATCH(C, return conv1_fwd<16>(img, rows, N, W, bias, x1, stats, stream),
+                   return conv1_fwd<8>(img, rows, N, W, bias, x1, stats, stream));
+}
+
+extern "C" int mggan_scene_bn_finalize(const double* stats, double count, int C, const float* gamma, const float* beta,
+                                       float* running_mean, float* running_var, long long* num_batches_tracked,
+                                       float momentum, float eps, int training, float* ab, float* mean_istd,
+                                       cudaStream_t stream) {
+    MGGAN_REQUIRE(C >= 1 && C <= 32, "mggan_scene_bn_finalize: C=%d", C);
+    scene_bn_finalize_kernel<<<1, 32, 0, stream>>>(stats, count, C, gamma, beta, running_mean, running_var,
+                                                   num_batches_tracked, momentum, eps, training, ab, mean_istd);
+    return mggan_check_launch("scene_bn_finalize");
+}
+
+extern "C" int mggan_scene_bn_bwd_finalize(const double* sums, double count, int C, float* m12, float* dgamma,
+                                           float* dbeta, cudaStream_t stream) {
+    MGGAN_REQUIRE(C >= 1 && C <= 32, "mggan_scene_bn_bwd_finalize: C=%d", C);
+    scene_bn_bwd_finalize_kernel<<<1, 32, 0, stream>>>(sums, count, C, m12, dgamma, dbeta);
+    return mggan_check_launch("scene_bn_bwd_finalize");
+}
+
+extern "C" int mggan_scene_block2_fwd(const float* x1, int N, int C, const float* ab1, const float* W, const float* bias,
+                                      float* x2, double* stats, cudaStream_t stream) {
+    if (N <= 0) return MGGAN_OK;
+    SCENE_DISPATCH(C, return block2_fwd<16>(x1, N, ab1, W, bias, x2, stats, stream),
+                   return block2_fwd<8>(x1, N, ab1, W, bias, x2, stats, stream));
+}
+
+extern "C" int mggan_scene_attn_fwd(const float* x2, int N, int C, const float* ab2, const float* Wa1, const float* ba1,
+                                    const float* Wa2, const float* ba2, float* out, cudaStream_t stream) {
+    if (N <= 0) return MGGAN_OK;
+    SCENE_DISPATCH(C, return attn_fwd<16>(x2, N, ab2, Wa1, ba1, Wa2, ba2, out, stream),
+                   return attn_fwd<8>(x2, N, ab2, Wa1, ba1, Wa2, ba2, out, stream));
+}
+
+extern "C" int mggan_scene_attn_bwd(const float* x2, int N, int C, const float* ab2, const float* mean_istd2,
+                                    const float* Wa1, const float* ba1, const float* Wa2, const float* ba2,
+                                    const float* dout, float* dWa1, float* dba1, float* dWa2, float* dba2, float* dy2,
+                                    unsigned char* idx2, double* sums2, cudaStream_t stream) {
+    if (N <= 0) return MGGAN_OK;
+    SCENE_DISPATCH(C, return attn_bwd<16>(x2, N, ab2, mean_istd2, Wa1, ba1, Wa2, ba2, dout, dWa1, dba1, dWa2, dba2, dy2, idx2, sums2, stream),
+                   return attn_bwd<8>(x2, N, ab2, mean_istd2, Wa1, ba1, Wa2, ba2, dout, dWa1, dba1, dWa2, dba2, dy2, idx2, sums2, stream));
+}
+
+extern "C" int mggan_scene_block2_bwd(const float* x1, const float* x2, int N, int C, const float* ab1,
+                                      const float* mean_istd1, const float* ab2, const float* mean_istd2,
+                                      const float* m12_2, const float* W, const float* dy2, const unsigned char* idx2,
+                                      float* dW, float* dbias, float* dy1, unsigned char* idx1, double* sums1,
+                                      cudaStream_t stream) {
+    if (N <= 0) return MGGAN_OK;
+    SCENE_DISPATCH(C, return block2_bwd<16>(x1, x2, N, ab1, mean_istd1, ab2, mean_istd2, m12_2, W, dy2, idx2, dW, dbias, dy1, idx1, sums1, stream),
+                   return block2_bwd<8>(x1, x2, N, ab1, mean_istd1, ab2, mean_istd2, m12_2, W, dy2, idx2, dW, dbias, dy1, idx1, sums1, stream));
+}
+
+extern "C" int mggan_scene_conv1_bwd(const float* img, const int* rows, const float* x1, int N, int C, const float* ab1,
+                                     const float* mean_istd1, const float* m12_1, const float* dy1,
+                                     const unsigned char* idx1, float* dW, float* dbias, cudaStream_t stream) {
+    if (N <= 0) return MGGAN_OK;
+    SCENE_DISPATCH(C, return conv1_bwd<16>(img, rows, x1, N, ab1, mean_istd1, m12_1, dy1, idx1, dW, dbias, stream),
+                   return conv1_bwd<8>(img, rows, x1, N, ab1, mean_istd1, m12_1, dy1, idx1, dW, dbias, stream));
+}

@@ -1,0 +1,133 @@
+"""ctypes binding of `libmggan_b200.so` (the C ABI declared in include/mggan_b200.h).
+
+There is no fallback: if the library is missing, cannot be loaded, or the current device is
+not an sm_100 part, every kernel call raises.  Build it with `python mg-gan_b200/build_ext.py`
+(or `__graft_entry__.build()`); nvcc cross-compiles sm_100a without a GPU.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libmggan_b200.so")
+
+TABLE_MAX = 64
+
+
+class TensorTable(ctypes.Structure):
+    _fields_ = [
+        ("p", ctypes.c_void_p * TABLE_MAX),
+        ("g", ctypes.c_void_p * TABLE_MAX),
+        ("m", ctypes.c_void_p * TABLE_MAX),
+        ("v", ctypes.c_void_p * TABLE_MAX),
+        ("n", ctypes.c_int * TABLE_MAX),
+        ("bc1", ctypes.c_float * TABLE_MAX),
+        ("bc2_sqrt", ctypes.c_float * TABLE_MAX),
+    ]
+
+
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "d": ctypes.c_double,
+       "Q": ctypes.c_ulonglong, "s": ctypes.c_void_p, "t": ctypes.POINTER(TensorTable)}
+
+# name -> argument codes (p pointer, i int, f float, d double, Q uint64, s stream, t table*)
+SIGNATURES = {
+    "mggan_lstm_seq_fwd": "piiippppps",
+    "mggan_lstm_seq_bwd": "piiipppppps",
+    "mggan_linear_fwd": "piippiifps",
+    "mggan_linear_bwd": "piipiifppppps",
+    "mggan_gumbel_sample": "piiiQQps",
+    "mggan_selection_build": "piiiippppppppps",
+    "mggan_selection_all": "iiipppps",
+    "mggan_decoder_fwd": "ipppppppppipppppppppiippppps",
+    "mggan_decoder_bwd": "ipppppppipppppppppiippppppppppppppppps",
+    "mggan_social_attn_fwd": "ppipppipppppps",
+    "mggan_social_attn_bwd": "ppipppippppppppppppps",
+    "mggan_scene_conv1_fwd": "ppiipppps",
+    "mggan_scene_bn_finalize": "pdipppppffipps",
+    "mggan_scene_block2_fwd": "piippppps",
+    "mggan_scene_attn_fwd": "piipppppps",
+    "mggan_scene_attn_bwd": "piipppppppppppppps",
+    "mggan_scene_bn_bwd_finalize": "pdippps",
+    "mggan_scene_block2_bwd": "ppiippppppppppppps",
+    "mggan_scene_conv1_bwd": "pppiippppppps",
+    "mggan_l2_scene_min": "ppiiipifppps",
+    "mggan_bce_scalar_label": "pifppfpps",
+    "mggan_ce_generators": "piippfpps",
+    "mggan_pm_ml_loss": "ppiiiipfffppps",
+    "mggan_grad_sqnorm": "tips",
+    "mggan_clip_adamw": "tipfffffffs",
+    "mggan_multi_copy": "tis",
+}
+# plain (non status-returning) helpers
+_PLAIN = {"mggan_version": ("", ctypes.c_int), "mggan_device_check": ("", ctypes.c_int),
+          "mggan_selection_tiles": ("ii", ctypes.c_int), "mggan_last_error": ("", ctypes.c_char_p)}
+
+EXPORTED = sorted(list(SIGNATURES) + list(_PLAIN))
+
+
+class MgganCudaError(RuntimeError):
+    pass
+
+
+_lib = None
+_device_ok = False
+
+
+def load():
+    """dlopen the library (no device needed) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the MG-GAN B200 path has no CPU/PyTorch fallback. "
+            "Build it with `python mg-gan_b200/build_ext.py`.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, sig in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [_CT[c] for c in sig]
+        fn.restype = ctypes.c_int
+    for name, (sig, res) in _PLAIN.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [_CT[c] for c in sig]
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def _ensure_device():
+    global _device_ok
+    if _device_ok:
+        return
+    if not torch.cuda.is_available():
+        raise MgganCudaError("no CUDA device: the MG-GAN B200 path cannot run (there is no CPU fallback)")
+    lib = load()
+    if lib.mggan_device_check() != 0:
+        raise MgganCudaError(lib.mggan_last_error().decode())
+    _device_ok = True
+
+
+def ptr(t):
+    """Device pointer of a contiguous tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), (t.device, t.shape, t.stride())
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point on the current stream; raise on a non-zero status."""
+    _ensure_device()
+    lib = _lib
+    rc = getattr(lib, name)(*args, stream())
+    if rc != 0:
+        raise MgganCudaError(f"{name} failed ({rc}): {lib.mggan_last_error().decode()}")
+
+
+def selection_tiles(n_seq, num_gens):
+    return load().mggan_selection_tiles(int(n_seq), int(num_gens))
