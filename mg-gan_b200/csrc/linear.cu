@@ -40,7 +40,7 @@ __device__ __forceinline__ float act_bwd(float y, int act, float slope) {
 
 struct GemmArgs {
     const float* A; long long sam, sak;      // A(m, k) = A[m*sam + k*sak]
-    const float* Ay;                         // optional: multiply A(m,k) by act'(Ay(m,k)) (same indexing)
+    const float* Ay; int act_in;             // optional: multiply A(m,k) by act_in'(Ay(m,k)) (same indexing)
     const float* B; long long sbn, sbk;      // B(n, k) = B[n*sbn + k*sbk]
     float* C; long long scm, scn;            // C(m, n)
     const float* bias;                       // per n (forward)
@@ -81,7 +81,7 @@ gemm_kernel(GemmArgs g) {
             if (m < g.M && k < k_end) {
                 long long off = m * g.sam + k * g.sak;
                 v = __ldg(g.A + off);
-                if (g.Ay != nullptr) v *= act_bwd(__ldg(g.Ay + off), g.act, g.slope);
+                if (g.Ay != nullptr) v *= act_bwd(__ldg(g.Ay + off), g.act_in, g.slope);
             }
             As[kk][mm] = v;
         }
@@ -168,9 +168,8 @@ extern "C" int mggan_linear_bwd(const float* X, int M, int K, const float* W, in
         g.A = dY; g.sam = O; g.sak = 1; g.Ay = Ay;
         g.B = W; g.sbn = 1; g.sbk = K;
         g.C = dX; g.scm = K; g.scn = 1;
-        g.M = M; g.N = K; g.K = O; g.act = act; g.slope = slope; g.splitk = 1;
+        g.M = M; g.N = K; g.K = O; g.act = ACT_NONE; g.act_in = act; g.slope = slope; g.splitk = 1;
         int rc = launch(g, stream);
-        g.act = ACT_NONE;
         if (rc) return rc;
     }
     if (dW != nullptr) {          // dW(o, k) = sum_m dZ(m, o) X(m, k) ; db(o) = sum_m dZ(m, o)
@@ -179,7 +178,7 @@ extern "C" int mggan_linear_bwd(const float* X, int M, int K, const float* W, in
         g.B = X; g.sbn = 1; g.sbk = K;
         g.C = dW; g.scm = K; g.scn = 1;
         g.colsum = db;
-        g.M = O; g.N = K; g.K = M; g.act = act; g.slope = slope;
+        g.M = O; g.N = K; g.K = M; g.act = ACT_NONE; g.act_in = act; g.slope = slope;
         int tiles = ((O + BM - 1) / BM) * ((K + BN - 1) / BN);
         int want = (148 * 4 + tiles - 1) / tiles;
         int maxsplit = (M + 4 * BK - 1) / (4 * BK);

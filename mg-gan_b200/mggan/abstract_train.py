@@ -1,0 +1,210 @@
+"""Trainer base (reference: mggan/abstract_train.py:25-322): device, two AdamW optimisers, two
+cosine schedules, the epoch / iteration loop, validation with best-checkpoint tracking and the
+checkpoint layout `{generator, discriminator, gen_opt, disc_opt}` under
+`<log_dir>/<experiment>/<name>/version_<v>/checkpoints/`.
+
+Differences from the reference, all behind the same method names:
+  * the optimisers are `FusedAdamW` (clip + AdamW in two launches, same state_dict layout);
+  * per-iteration loss scalars stay on the device and are averaged once per epoch (the
+    reference calls .item() seven times per iteration);
+  * no global `torch.set_default_tensor_type`: tensors are created on `self.device` explicitly;
+  * only the NS (non-saturating BCE) objective is built — MM / LS / W are "next" rows;
+  * optional data-parallel mode (`mggan.distributed`): scenes are sharded over ranks and the
+    step functions all-reduce gradients, loss normalisers and BatchNorm statistics.
+"""
+import abc
+import math
+from argparse import Namespace
+from collections import defaultdict
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from mggan.data_utils.data_loaders import get_dataloader
+from mggan.logging import Experiment
+from mggan.model.config import get_parser
+from mggan.optim import FusedAdamW
+from mggan.utils import get_argparse_defaults, load_hparams_from_tags_csv
+
+
+def _mean(values):
+    if len(values) == 0:
+        return float("nan")
+    if torch.is_tensor(values[0]):
+        return float(torch.stack([v.detach().float().reshape(()) for v in values]).mean().item())
+    return float(np.mean(values))
+
+
+class MultiGeneratorGAN(abc.ABC):
+    def __init__(self, generator, discriminator, config, writer, dist_ctx=None):
+        self.writer = writer
+        self.config = config
+        self.device = torch.device("cuda" if config.gpus else "cpu")
+        if self.device.type != "cuda":
+            raise RuntimeError("the B200 path has no CPU fallback: run with a CUDA device (--gpus 0)")
+        self.D = discriminator.to(self.device)
+        self.G = generator.to(self.device)
+        self.l2_weight = self.config.l2_loss_weight
+        self.gan_type = self.config.gan_type
+        self.dist = dist_ctx
+        self.log_dir = Path(self.writer.get_data_path(self.writer.name, self.writer.version))
+        self.model_save_dir = self.log_dir / "checkpoints"
+        self.model_save_dir.mkdir(exist_ok=True, parents=True)
+
+        self.optimizerD = FusedAdamW(self.D.parameters(), lr=self.config.d_lr, betas=(config.beta1, 0.999))
+        self.optimizerG = FusedAdamW(self.G.parameters(), lr=self.config.g_lr, betas=(config.beta1, 0.999))
+        self.lr_schedulerD = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizerD, config.epochs, eta_min=0)
+        self.lr_schedulerG = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizerG, config.epochs, eta_min=0)
+        self.epoch = 0
+        if self.config.gan_obj != "NS":
+            raise NotImplementedError("gan_obj='%s': only the default NS objective is on the B200 path" % config.gan_obj)
+        if dist_ctx is not None:
+            dist_ctx.attach(self.G, self.D)
+
+    # ------------------------------------------------------------------ loop
+    def _to_device(self, batch):
+        in_xy = batch["in_xy"].to(self.device, non_blocking=True)
+        in_dxdy = batch["in_dxdy"].to(self.device, non_blocking=True)
+        b = in_xy.size(1)
+        sub_batches = batch["seq_start_end"] if "seq_start_end" in batch else list(zip(range(b), range(1, b + 1)))
+        gt_xy = batch["gt_xy"].to(self.device, non_blocking=True)
+        gt_dxdy = batch["gt_dxdy"].to(self.device, non_blocking=True)
+        img = batch["features"].to(self.device, non_blocking=True) if "features" in batch else None
+        return in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img
+
+    def train_iteration(self, batch, metrics, total_iterations=0):
+        """One D step + G step + PM step on a collated batch (reference loop body :114-168)."""
+        in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img = self._to_device(batch)
+        loss_mask = ~gt_xy.isnan().any(2).any(0)
+        if bool(batch.get("no_nan", False)):
+            loss_mask = None
+        else:
+            gt_dxdy, gt_xy = gt_dxdy[:, loss_mask], gt_xy[:, loss_mask]
+        if (total_iterations % self.config.num_gen_steps == 0) or (self.epoch >= self.config.keep_gen_steps):
+            if self.config.num_unrolling_steps > 0:
+                raise NotImplementedError("num_unrolling_steps > 0 is outside the B200 hot path")
+            self.discriminator_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
+        self.generator_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
+        self.net_chooser_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
+
+    def _loaders(self):
+        kw = dict(dataset=self.config.dataset, batch_size=self.config.batch_size, workers=self.config.workers,
+                  num_scenes=getattr(self.config, "synthetic_scenes", 64),
+                  with_img=getattr(self.config, "scene_dim", 64) > 0, seed=getattr(self.config, "seed", 42))
+        return (get_dataloader(phase="train", augment=self.config.augment, shuffle=True, **kw),
+                get_dataloader(phase="val", augment=False, shuffle=False, **kw))
+
+    def train(self):
+        train_loader, val_loader = self._loaders()
+        total_iterations = 0
+        track_metric = "val/ADE k=20"
+        min_track_metric = math.inf
+        for epoch in range(self.config.epochs):
+            self.epoch += 1
+            self.D.train()
+            self.G.train()
+            metrics = defaultdict(list)
+            for i, batch in enumerate(train_loader):
+                self.train_iteration(batch, metrics, total_iterations)
+                total_iterations += 1
+            if self.epoch % self.config.val_every == 0:
+                self.D.eval()
+                self.G.eval()
+                with torch.no_grad():
+                    m = self.check_accuracy(val_loader, vis=True, prefix="val/", num_k=self.config.top_k_test)
+                    for k, v in m.items():
+                        metrics[f"val/{k}"].append(v)
+                if track_metric in metrics:
+                    cur = _mean(metrics[track_metric])
+                    if cur < min_track_metric:
+                        print(f'Saving best model... "{track_metric}: Before: {min_track_metric}, After: {cur}')
+                        min_track_metric = cur
+                        self.save(checkpoint_name="checkpoint_best.pth")
+            metrics = {k: _mean(v) for k, v in metrics.items()}
+            self.writer.log(metrics, epoch)
+            if self.epoch % self.config.save_every == 0:
+                self.save()
+            self.l2_weight *= self.config.l2_decay_rate        # kept: has no effect in the reference either
+            self.lr_schedulerD.step()
+            self.lr_schedulerG.step()
+            self.writer.save()
+
+    # ------------------------------------------------------------------ abstract steps
+    @abc.abstractmethod
+    def generator_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, train_metrics, loss_mask, img=None):
+        pass
+
+    @abc.abstractmethod
+    def discriminator_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, train_metrics, loss_mask, img=None):
+        pass
+
+    @abc.abstractmethod
+    def net_chooser_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img):
+        pass
+
+    @abc.abstractmethod
+    def check_accuracy(self, loader, vis=False, prefix="", num_k=20):
+        pass
+
+    @abc.abstractmethod
+    def predict(self, in_dxdy, in_xy, sub_batches, img=None, num=20, noise=None):
+        pass
+
+    @staticmethod
+    @abc.abstractmethod
+    def construct_model(config):
+        pass
+
+    # ------------------------------------------------------------------ checkpoints
+    def save(self, checkpoint_name=None):
+        if self.dist is not None and self.dist.rank != 0:
+            return
+        save_obj = {
+            "generator": self.G.state_dict(),
+            "discriminator": self.D.state_dict(),
+            "gen_opt": self.optimizerG.state_dict(),
+            "disc_opt": self.optimizerD.state_dict(),
+        }
+        if not checkpoint_name:
+            checkpoint_name = "checkpoint_{}.pth".format(self.epoch)
+        torch.save(save_obj, self.model_save_dir / checkpoint_name)
+
+    @classmethod
+    def load(cls, log_path: Path, exp_name: str, version: int, checkpoint):
+        version_dir = Path(log_path) / exp_name / "version_{}".format(version)
+        checkpoint_dir = version_dir / "checkpoints"
+        if checkpoint == "latest":
+            epochs = [int(n.stem.split("_")[1]) for n in checkpoint_dir.iterdir() if n.stem.split("_")[1] != "best"]
+            checkpoint = max(epochs)
+        state_dicts = torch.load(checkpoint_dir / "checkpoint_{}.pth".format(checkpoint), map_location="cpu")
+        config = load_hparams_from_tags_csv(version_dir / "meta_tags.csv")
+        defaults = get_argparse_defaults(get_parser())
+        defaults.update(config)
+        config = Namespace(**defaults)
+        g, d = cls.construct_model(config)
+        writer = Experiment(log_path, name=exp_name, version=version)
+        m = cls(g, d, config, writer)
+        m.G.load_state_dict(state_dicts["generator"], strict=False)
+        m.D.load_state_dict(state_dicts["discriminator"], strict=False)
+        try:
+            m.optimizerD.load_state_dict(state_dicts["disc_opt"])
+            m.optimizerG.load_state_dict(state_dicts["gen_opt"])
+        except Exception as e:          # best effort, like the reference
+            print("Could not restore optimizers.", str(e))
+        return m, config
+
+    @classmethod
+    def load_from_path(cls, version_path: Path, checkpoint="best"):
+        version_path = Path(version_path)
+        assert "version" in version_path.stem, "Input path should point to model version directory."
+        exp_folder = version_path.parent.parent
+        model_name = version_path.parent.name
+        version = int(version_path.stem.split("_")[1])
+        return cls.load(exp_folder, model_name, version, checkpoint)
+
+    def test(self, num_k=20, batch_size=8, **kwargs):
+        loader = get_dataloader(dataset=self.config.dataset, phase="test", augment=False, batch_size=batch_size,
+                                workers=self.config.workers, shuffle=False,
+                                with_img=getattr(self.config, "scene_dim", 64) > 0)
+        return self.check_accuracy(loader, vis=False, num_k=num_k, **kwargs)

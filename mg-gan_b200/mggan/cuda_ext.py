@@ -112,7 +112,9 @@ def ptr(t):
     """Device pointer of a contiguous tensor (None -> NULL)."""
     if t is None:
         return None
-    assert t.is_cuda and t.is_contiguous(), (t.device, t.shape, t.stride())
+    if not t.is_cuda:
+        raise MgganCudaError(f"tensor on {t.device}: the MG-GAN B200 path only runs on CUDA (there is no CPU fallback)")
+    assert t.is_contiguous(), (t.shape, t.stride())
     return t.data_ptr()
 
 

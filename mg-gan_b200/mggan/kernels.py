@@ -1,0 +1,509 @@
+"""torch.autograd.Function wrappers over the C ABI (include/mggan_b200.h).
+
+PyTorch allocates the outputs / workspaces and carries the autograd graph; all arithmetic on
+the path happens in the sm_100a kernels of `csrc/`.  Nothing here runs without the library.
+"""
+import math
+
+import torch
+
+from . import cuda_ext as X
+from .cuda_ext import call, ptr
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID_EPS = 0, 1, 2, 3
+TILE = 64
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------- dense layer
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act, slope, grad_on):
+        x, w = _f32(x), _f32(w)
+        b = _f32(b) if b is not None else None
+        M, K = x.shape
+        O = w.shape[0]
+        y = torch.empty(M, O, device=x.device, dtype=torch.float32)
+        call("mggan_linear_fwd", ptr(x), M, K, ptr(w), ptr(b), O, act, float(slope), ptr(y))
+        if grad_on:
+            ctx.save_for_backward(x, w, y)
+        ctx.act, ctx.slope, ctx.has_bias = act, float(slope), b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _f32(dy)
+        M, K = x.shape
+        O = w.shape[0]
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty_like(x) if need_x else None
+        dw = torch.zeros_like(w) if (need_w or need_b) else None
+        db = torch.zeros(O, device=x.device, dtype=torch.float32) if (need_w or need_b) else None
+        call("mggan_linear_bwd", ptr(x), M, K, ptr(w), O, ctx.act, ctx.slope, ptr(y), ptr(dy), ptr(dx), ptr(dw), ptr(db))
+        return dx, (dw if need_w else None), (db if need_b else None), None, None, None
+
+
+def linear(x, w, b=None, act=ACT_NONE, slope=0.0):
+    """act(x @ w.T + b) for 2-D x."""
+    return _Linear.apply(x, w, b, act, slope, torch.is_grad_enabled())
+
+
+# --------------------------------------------------------------------------- encoder LSTM
+class _LstmSeq(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wx, b, whh, grad_on):
+        x, wx, b, whh = _f32(x), _f32(wx), _f32(b), _f32(whh)
+        T, N, _ = x.shape
+        H = whh.shape[1]
+        hT = torch.empty(N, H, device=x.device, dtype=torch.float32)
+        need = grad_on and any(ctx.needs_input_grad[1:4])
+        acts = torch.empty(T, N, 6, H, device=x.device, dtype=torch.float32) if need else None
+        call("mggan_lstm_seq_fwd", ptr(x), T, N, H, ptr(wx), ptr(b), ptr(whh), ptr(hT), ptr(acts))
+        ctx.save_for_backward(x, whh, acts)
+        return hT
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, whh, acts = ctx.saved_tensors
+        T, N, _ = x.shape
+        H = whh.shape[1]
+        dwx = torch.zeros(4 * H, 2, device=x.device, dtype=torch.float32)
+        db = torch.zeros(4 * H, device=x.device, dtype=torch.float32)
+        dwhh = torch.zeros_like(whh)
+        call("mggan_lstm_seq_bwd", ptr(x), T, N, H, ptr(whh), ptr(acts), ptr(_f32(dh)), ptr(dwx), ptr(db), ptr(dwhh))
+        return None, dwx, db, dwhh, None
+
+
+def lstm_encode(x, w_emb, b_emb, w_ih, w_hh, b_ih, b_hh):
+    """TrajectoryEncoder: Linear(2,E) then 1-layer LSTM, returns h_T (N,H).
+
+    The embedding is folded into the input projection (tiny host-side products on the
+    weights, tracked by autograd); the recurrence itself is one kernel."""
+    wx = w_ih @ w_emb                               # (4H, 2)
+    b = w_ih @ b_emb + b_ih + b_hh                  # (4H,)
+    return _LstmSeq.apply(x, wx, b, w_hh, torch.is_grad_enabled())
+
+
+# --------------------------------------------------------------------------- scenes (CSR)
+class SceneIndex:
+    """`seq_start_end` (python list of [start, end)) as device CSR arrays, built once per batch."""
+
+    def __init__(self, sub_batches, device):
+        off = [int(sub_batches[0][0])] if len(sub_batches) else [0]
+        for a, b in sub_batches:
+            assert int(a) == off[-1], "scenes must be contiguous and ordered"
+            off.append(int(b))
+        self.sub_batches = [(int(a), int(b)) for a, b in sub_batches]
+        self.n_scenes = len(sub_batches)
+        self.n_agents = off[-1] - off[0]
+        sizes = [b - a for a, b in self.sub_batches]
+        pair = [0]
+        for s in sizes:
+            pair.append(pair[-1] + s * s)
+        self.n_pairs = pair[-1]
+        self.max_size = max(sizes) if sizes else 0
+        self.scene_off = torch.tensor(off, dtype=torch.int32, device=device)
+        self.pair_off = torch.tensor(pair, dtype=torch.int32, device=device)
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, sub_batches, device):
+        if isinstance(sub_batches, SceneIndex):
+            return sub_batches
+        key = (tuple((int(a), int(b)) for a, b in sub_batches), str(device))
+        hit = cls._cache.get(key)
+        if hit is None:
+            if len(cls._cache) > 16:
+                cls._cache.clear()
+            hit = cls._cache[key] = SceneIndex(sub_batches, device)
+        return hit
+
+
+# --------------------------------------------------------------------------- social attention
+class _SocialAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x4, h, us, w1, b1, w2, b2, scenes, grad_on):
+        x4, h, us, w1, b1, w2, b2 = map(_f32, (x4, h, us, w1, b1, w2, b2))
+        N, HD = h.shape
+        S = torch.empty_like(h)
+        att = torch.empty(max(scenes.n_pairs, 1), device=h.device, dtype=torch.float32)
+        call("mggan_social_attn_fwd", ptr(x4), ptr(h), HD, ptr(us), ptr(scenes.scene_off), ptr(scenes.pair_off),
+             scenes.n_scenes, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(S), ptr(att))
+        if grad_on:
+            ctx.save_for_backward(x4, h, us, w1, b1, w2, b2, att)
+            ctx.scenes = scenes
+        return S
+
+    @staticmethod
+    def backward(ctx, dS):
+        x4, h, us, w1, b1, w2, b2, att = ctx.saved_tensors
+        sc = ctx.scenes
+        N, HD = h.shape
+        dsig = torch.empty_like(att)
+        dh, dus = torch.zeros_like(h), torch.zeros_like(us)
+        dw1, db1, dw2, db2 = torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w2), torch.zeros_like(b2)
+        call("mggan_social_attn_bwd", ptr(x4), ptr(h), HD, ptr(us), ptr(sc.scene_off), ptr(sc.pair_off), sc.n_scenes,
+             ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(att), ptr(_f32(dS)), ptr(dsig), ptr(dh), ptr(dus), ptr(dw1),
+             ptr(db1), ptr(dw2), ptr(db2))
+        return None, dh, dus, dw1, db1, dw2, db2, None, None
+
+
+def social_attention(xy_last, dxdy_last, h, scenes, fc0, fc2, fc4, att_w):
+    """SocialAttention.forward on the rows covered by `scenes`.
+
+    fc0/fc2/fc4: the three Linear layers of EmbedSocialFeatures, att_w: AttentionPooling.W.
+    The last embedding layer and W are folded into per-agent vectors with two dense-layer
+    kernels: q = W h + b (N,F); Us = [fc4.weight^T ; fc4.bias] q (N,65)."""
+    x4 = torch.cat([xy_last, dxdy_last], -1)
+    q = linear(h, att_w.weight, att_w.bias)
+    wc3 = torch.cat([fc4.weight.t(), fc4.bias[None]], 0)        # (65, F)
+    us = linear(q, wc3)
+    return _SocialAttn.apply(x4, h, us, fc0.weight, fc0.bias, fc2.weight, fc2.bias, scenes, torch.is_grad_enabled())
+
+
+# --------------------------------------------------------------------------- scene (physical) attention
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+def _allreduce(t, group):
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(t, group=group)
+
+
+class _SceneAttn(torch.autograd.Function):
+    """AttentionGlobal.forward.  Non-tensor state: the two BatchNorm modules (running buffers are
+    updated in place, like nn.BatchNorm2d in train mode), `rows` (int32 gather or None), training
+    flag and the process group whose ranks share BatchNorm statistics (None = local)."""
+
+    @staticmethod
+    def forward(ctx, img, c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b, bn1, bn2, rows, training, group, grad_on):
+        img = _f32(img)
+        ws = [_f32(t) for t in (c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b)]
+        c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b = ws
+        dev = img.device
+        C = c1w.shape[0]
+        N = int(rows.numel()) if rows is not None else img.shape[0]
+        x1 = torch.empty(N, C, 33, 33, device=dev, dtype=torch.float32)
+        x2 = torch.empty(N, C, 16, 16, device=dev, dtype=torch.float32)
+        out = torch.empty(N, 64, device=dev, dtype=torch.float32)
+        ab1, mi1 = torch.empty(2 * C, device=dev), torch.empty(2 * C, device=dev)
+        ab2, mi2 = torch.empty(2 * C, device=dev), torch.empty(2 * C, device=dev)
+        tr = 1 if training else 0
+        n_glob = torch.tensor([float(N)], device=dev, dtype=torch.float64) if group is not None else None
+        if n_glob is not None:
+            _allreduce(n_glob, group)
+            n_total = float(n_glob.item())
+        else:
+            n_total = float(N)
+        st1 = torch.zeros(2 * C, device=dev, dtype=torch.float64) if training else None
+        call("mggan_scene_conv1_fwd", ptr(img), ptr(rows), N, C, ptr(c1w), ptr(c1b), ptr(x1), ptr(st1))
+        if training:
+            _allreduce(st1, group)
+        call("mggan_scene_bn_finalize", ptr(st1), n_total * 33 * 33, C, ptr(g1), ptr(be1), ptr(bn1.running_mean),
+             ptr(bn1.running_var), ptr(bn1.num_batches_tracked), BN_MOMENTUM, BN_EPS, tr, ptr(ab1), ptr(mi1))
+        st2 = torch.zeros(2 * C, device=dev, dtype=torch.float64) if training else None
+        call("mggan_scene_block2_fwd", ptr(x1), N, C, ptr(ab1), ptr(c2w), ptr(c2b), ptr(x2), ptr(st2))
+        if training:
+            _allreduce(st2, group)
+        call("mggan_scene_bn_finalize", ptr(st2), n_total * 16 * 16, C, ptr(g2), ptr(be2), ptr(bn2.running_mean),
+             ptr(bn2.running_var), ptr(bn2.num_batches_tracked), BN_MOMENTUM, BN_EPS, tr, ptr(ab2), ptr(mi2))
+        call("mggan_scene_attn_fwd", ptr(x2), N, C, ptr(ab2), ptr(a0w), ptr(a0b), ptr(a2w), ptr(a2b), ptr(out))
+        if grad_on and any(ctx.needs_input_grad):
+            assert training, "scene-attention backward needs train-mode BatchNorm (batch statistics)"
+            ctx.save_for_backward(img, c1w, c2w, a0w, a0b, a2w, a2b, x1, x2, ab1, mi1, ab2, mi2)
+            ctx.rows, ctx.group, ctx.n_total, ctx.N, ctx.C = rows, group, n_total, N, C
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, c1w, c2w, a0w, a0b, a2w, a2b, x1, x2, ab1, mi1, ab2, mi2 = ctx.saved_tensors
+        N, C, dev, group = ctx.N, ctx.C, img.device, ctx.group
+        dout = _f32(dout)
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, device=dev, dtype=dt)
+        da0w, da0b, da2w, da2b = z(32, C), z(32), z(C, 32), z(C)
+        dy2 = torch.empty(N, C, 64, device=dev)
+        idx2 = torch.empty(N, C, 64, device=dev, dtype=torch.uint8)
+        sums2 = z(2 * C, dt=torch.float64)
+        call("mggan_scene_attn_bwd", ptr(x2), N, C, ptr(ab2), ptr(mi2), ptr(a0w), ptr(a0b), ptr(a2w), ptr(a2b),
+             ptr(dout), ptr(da0w), ptr(da0b), ptr(da2w), ptr(da2b), ptr(dy2), ptr(idx2), ptr(sums2))
+        # BatchNorm affine gradients are plain sums over the local shard; the means use global sums
+        m12_2, dg2, db2 = torch.empty(2 * C, device=dev), z(C), z(C)
+        loc2 = sums2.clone() if group is not None else sums2
+        _allreduce(sums2, group)
+        call("mggan_scene_bn_bwd_finalize", ptr(sums2), ctx.n_total * 256, C, ptr(m12_2), ptr(dg2), ptr(db2))
+        dc2w, dc2b = z(C, C, 3, 3), z(C)
+        dy1 = torch.empty(N, C, 256, device=dev)
+        idx1 = torch.empty(N, C, 256, device=dev, dtype=torch.uint8)
+        sums1 = z(2 * C, dt=torch.float64)
+        call("mggan_scene_block2_bwd", ptr(x1), ptr(x2), N, C, ptr(ab1), ptr(mi1), ptr(ab2), ptr(mi2), ptr(m12_2),
+             ptr(c2w), ptr(dy2), ptr(idx2), ptr(dc2w), ptr(dc2b), ptr(dy1), ptr(idx1), ptr(sums1))
+        m12_1, dg1, db1 = torch.empty(2 * C, device=dev), z(C), z(C)
+        loc1 = sums1.clone() if group is not None else sums1
+        _allreduce(sums1, group)
+        call("mggan_scene_bn_bwd_finalize", ptr(sums1), ctx.n_total * 1089, C, ptr(m12_1), ptr(dg1), ptr(db1))
+        dc1w, dc1b = z(C, 4, 3, 3), z(C)
+        call("mggan_scene_conv1_bwd", ptr(img), ptr(ctx.rows), ptr(x1), N, C, ptr(ab1), ptr(mi1), ptr(m12_1), ptr(dy1),
+             ptr(idx1), ptr(dc1w), ptr(dc1b))
+        if group is not None:          # keep the shard-local part: the gradient all-reduce sums shards later
+            dg2, db2 = loc2[C:].float(), loc2[:C].float()
+            dg1, db1 = loc1[C:].float(), loc1[:C].float()
+        return (None, dc1w, dc1b, dg1, db1, dc2w, dc2b, dg2, db2, da0w, da0b, da2w, da2b, None, None, None, None, None, None)
+
+
+def scene_attention(img, mod, rows=None, group=None):
+    """mod: an AttentionGlobal parameter container (mggan.model.modules.cnn)."""
+    b1, b2 = mod.CNN.encoder.ConvBlock_1.Block, mod.CNN.encoder.ConvBlock_2.Block
+    a = mod.cnn_attention
+    return _SceneAttn.apply(img, b1.Conv_1.weight, b1.Conv_1.bias, b1.BN_1.weight, b1.BN_1.bias,
+                            b2.Conv_1.weight, b2.Conv_1.bias, b2.BN_1.weight, b2.BN_1.bias,
+                            a[0].weight, a[0].bias, a[2].weight, a[2].bias, b1.BN_1, b2.BN_1, rows,
+                            mod.training, group, torch.is_grad_enabled())
+
+
+# --------------------------------------------------------------------------- generator selection
+class Selection:
+    """Decoder work list (device arrays) for a set of (agent, generator, noise sample, slot) sequences."""
+
+    def __init__(self, n_agents, k, num_gens, n_tiles, tile_gen, seq_agent, seq_noise, seq_out, n_cols, totals=None):
+        self.n_agents, self.k, self.num_gens, self.n_tiles = n_agents, k, num_gens, n_tiles
+        self.tile_gen, self.seq_agent, self.seq_noise, self.seq_out = tile_gen, seq_agent, seq_noise, seq_out
+        self.n_cols, self.totals = n_cols, totals
+
+    @staticmethod
+    def from_indices(idx, num_gens):
+        """idx (n_act, k) int64: sampled generator per agent and sample (get_selection_indices + gather)."""
+        idx = idx.contiguous()
+        n, k = idx.shape
+        dev = idx.device
+        n_tiles = X.selection_tiles(n * k, num_gens)
+        i32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.int32)
+        cnt, base_row, totals = i32(max(n * num_gens, 1)), i32(num_gens + 1), i32(num_gens)
+        rank = torch.empty(max(n * k, 1), device=dev, dtype=torch.uint8)
+        err = torch.zeros(1, device=dev, dtype=torch.int32)
+        tile_gen, seq_agent, seq_noise, seq_out = i32(n_tiles), i32(n_tiles * TILE), i32(n_tiles * TILE), i32(n_tiles * TILE)
+        call("mggan_selection_build", ptr(idx), n, k, num_gens, n_tiles, ptr(cnt), ptr(rank), ptr(base_row), ptr(err),
+             ptr(totals), ptr(tile_gen), ptr(seq_agent), ptr(seq_noise), ptr(seq_out))
+        return Selection(n, k, num_gens, n_tiles, tile_gen, seq_agent, seq_noise, seq_out, k * n, totals)
+
+    @staticmethod
+    def all_generators(n, k, num_gens, device):
+        tiles_per_gen = (n * k + TILE - 1) // TILE
+        n_tiles = num_gens * tiles_per_gen
+        i32 = lambda *s: torch.empty(*s, device=device, dtype=torch.int32)
+        tile_gen = i32(max(n_tiles, 1))
+        seq_agent, seq_noise, seq_out = (i32(max(n_tiles * TILE, 1)) for _ in range(3))
+        call("mggan_selection_all", n, k, num_gens, ptr(tile_gen), ptr(seq_agent), ptr(seq_noise), ptr(seq_out))
+        return Selection(n, k, num_gens, n_tiles, tile_gen, seq_agent, seq_noise, seq_out, k * num_gens * n)
+
+
+def gumbel_sample(logits, k, seed, offset):
+    logits = _f32(logits.detach())
+    n, G = logits.shape
+    idx = torch.empty(n, k, device=logits.device, dtype=torch.int64)
+    call("mggan_gumbel_sample", ptr(logits), n, k, G, int(seed), int(offset), ptr(idx))
+    return idx
+
+
+# --------------------------------------------------------------------------- decoder
+class _Decoder(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, social, last_xy, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2, sel, pred_len, grad_on):
+        ts = [_f32(t) for t in (A, social, last_xy, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2)]
+        A, social, last_xy, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2 = ts
+        dev = A.device
+        Z = wz.shape[1]
+        noise = noise.reshape(-1, Z)
+        out_abs = torch.empty(pred_len, sel.n_cols, 2, device=dev, dtype=torch.float32)
+        out_rel = torch.empty_like(out_abs)
+        need = grad_on and any(ctx.needs_input_grad)
+        R = sel.n_tiles * TILE
+        acts = torch.empty(pred_len, R, 6, 32, device=dev) if need else None
+        u1 = torch.empty(pred_len, R, 16, device=dev) if need else None
+        h0 = torch.empty(R, 32, device=dev) if need else None
+        call("mggan_decoder_fwd", sel.n_tiles, ptr(sel.tile_gen), ptr(sel.seq_agent), ptr(sel.seq_noise),
+             ptr(sel.seq_out), ptr(A), ptr(social), ptr(last_xy), ptr(last_dxdy), ptr(noise), Z, ptr(wz), ptr(wx),
+             ptr(b), ptr(whh), ptr(w1h), ptr(w1s), ptr(b1), ptr(w2), ptr(b2), pred_len, sel.n_cols, ptr(out_abs),
+             ptr(out_rel), ptr(acts), ptr(u1), ptr(h0))
+        if need:
+            ctx.save_for_backward(social, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2, out_rel, acts, u1, h0)
+            ctx.sel, ctx.pred_len, ctx.n_agents = sel, pred_len, A.shape[0]
+        return out_abs, out_rel
+
+    @staticmethod
+    def backward(ctx, d_abs, d_rel):
+        social, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2, out_rel, acts, u1, h0 = ctx.saved_tensors
+        sel = ctx.sel
+        Z = wz.shape[1]
+        zl = torch.zeros_like
+        dwz, dwx, db, dwhh, dw1h, dw1s, db1, dw2, db2 = (zl(t) for t in (wz, wx, b, whh, w1h, w1s, b1, w2, b2))
+        dA = torch.zeros(ctx.n_agents, 32, device=wz.device)
+        dsoc = torch.zeros(ctx.n_agents, 32, device=wz.device)
+        d_abs = _f32(d_abs) if d_abs is not None else None
+        d_rel = _f32(d_rel) if d_rel is not None else None
+        call("mggan_decoder_bwd", sel.n_tiles, ptr(sel.tile_gen), ptr(sel.seq_agent), ptr(sel.seq_noise),
+             ptr(sel.seq_out), ptr(social), ptr(last_dxdy), ptr(noise), Z, ptr(wz), ptr(wx), ptr(b), ptr(whh),
+             ptr(w1h), ptr(w1s), ptr(b1), ptr(w2), ptr(b2), ctx.pred_len, sel.n_cols, ptr(out_rel), ptr(acts), ptr(u1),
+             ptr(h0), ptr(d_abs), ptr(d_rel), ptr(dwz), ptr(dwx), ptr(db), ptr(dwhh), ptr(dw1h), ptr(dw1s), ptr(db1),
+             ptr(dw2), ptr(db2), ptr(dA), ptr(dsoc))
+        return dA, dsoc, None, None, None, dwz, dwx, db, dwhh, dw1h, dw1s, db1, dw2, db2, None, None, None
+
+
+def decode(A, social, last_xy, last_dxdy, noise, wz, gen_weights, sel, pred_len):
+    """gen_weights: dict of stacked per-generator tensors (wx, b, whh, w1h, w1s, b1, w2, b2)."""
+    g = gen_weights
+    return _Decoder.apply(A, social, last_xy, last_dxdy, noise, wz, g["wx"], g["b"], g["whh"], g["w1h"], g["w1s"],
+                          g["b1"], g["w2"], g["b2"], sel, pred_len, torch.is_grad_enabled())
+
+
+# --------------------------------------------------------------------------- losses
+class _L2SceneMin(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, abs_, gt, scenes, inv_norm):
+        abs_, gt = _f32(abs_), _f32(gt)
+        T, k, n, _ = abs_.shape
+        loss = torch.zeros(1, device=abs_.device)
+        best = torch.empty(max(scenes.n_scenes, 1), device=abs_.device, dtype=torch.int32)
+        d_abs = torch.zeros_like(abs_) if ctx.needs_input_grad[0] else None
+        call("mggan_l2_scene_min", ptr(abs_), ptr(gt), T, k, n, ptr(scenes.scene_off), scenes.n_scenes,
+             float(inv_norm), ptr(loss), ptr(best), ptr(d_abs))
+        ctx.save_for_backward(d_abs)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_abs,) = ctx.saved_tensors
+        return d_abs * g, None, None, None
+
+
+def l2_scene_min(abs_, gt, scenes, inv_norm):
+    """(1/N) sum_scenes min_s sum_{i in scene, t} |abs - gt|  (train.py:57-75); inv_norm = 1/N."""
+    return _L2SceneMin.apply(abs_, gt, scenes, inv_norm)
+
+
+class _BceScalar(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, label, gen_idx, counts, inv_denom):
+        p = _f32(p)
+        loss = torch.zeros(1, device=p.device)
+        dp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        gi = gen_idx.contiguous() if gen_idx is not None else None
+        call("mggan_bce_scalar_label", ptr(p), p.numel(), float(label), ptr(gi), ptr(counts), float(inv_denom),
+             ptr(loss), ptr(dp))
+        ctx.save_for_backward(dp)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dp,) = ctx.saved_tensors
+        return dp * g, None, None, None, None
+
+
+def bce_scalar_label(p, label, gen_idx=None, counts=None, inv_denom=None):
+    """inv_denom * sum_i BCE(p_i, label) / counts[gen_idx_i]  (default inv_denom = 1/numel: a mean)."""
+    if inv_denom is None:
+        inv_denom = 1.0 / max(p.numel(), 1)
+    return _BceScalar.apply(p, label, gen_idx, counts, inv_denom)
+
+
+class _CeGen(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, counts, inv_denom):
+        logits = _f32(logits)
+        n, G = logits.shape
+        loss = torch.zeros(1, device=logits.device)
+        dl = torch.empty_like(logits) if ctx.needs_input_grad[0] else None
+        call("mggan_ce_generators", ptr(logits), n, G, ptr(target.contiguous()), ptr(counts), float(inv_denom),
+             ptr(loss), ptr(dl))
+        ctx.save_for_backward(dl)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None, None
+
+
+def ce_generators(logits, target, counts=None, inv_denom=None):
+    """Cross-entropy of (n, G) logits against generator ids, optionally weighted by 1/counts[target]."""
+    if inv_denom is None:
+        inv_denom = 1.0 / max(logits.shape[0], 1)
+    return _CeGen.apply(logits, target.reshape(-1), counts, inv_denom)
+
+
+class _PmMl(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, abs_all, gt, sigma, weight, inv_n):
+        logits, abs_all, gt = _f32(logits), _f32(abs_all), _f32(gt)
+        T, ks, G, n, _ = abs_all.shape
+        loss = torch.zeros(1, device=logits.device)
+        dl = torch.empty_like(logits)
+        target = torch.empty_like(logits)
+        call("mggan_pm_ml_loss", ptr(abs_all), ptr(gt), T, ks, G, n, ptr(logits), float(sigma), float(weight),
+             float(inv_n), ptr(loss), ptr(dl), ptr(target))
+        ctx.save_for_backward(dl)
+        ctx.mark_non_differentiable(target)
+        return loss[0], target
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None, None, None, None
+
+
+def pm_ml_loss(logits, abs_all, gt, sigma, weight=1.0, inv_n=None):
+    """PM-Net "ml" objective (train.py:626-639).  Returns (unweighted loss, target); the gradient
+    carries `weight` (= pi_net_loss_weight), as the reference backpropagates loss * weight."""
+    if inv_n is None:
+        inv_n = 1.0 / max(logits.shape[0], 1)
+    return _PmMl.apply(logits, abs_all, gt, sigma, weight, inv_n)
+
+
+# --------------------------------------------------------------------------- optimiser
+def _tables(entries):
+    """entries: list of (p, g, m, v, n, bc1, bc2_sqrt) -> ctypes tables of <= TABLE_MAX rows."""
+    out = []
+    for s in range(0, len(entries), X.TABLE_MAX):
+        chunk = entries[s:s + X.TABLE_MAX]
+        tb = X.TensorTable()
+        for i, (p, g, m, v, n, bc1, bc2s) in enumerate(chunk):
+            tb.p[i], tb.g[i], tb.m[i], tb.v[i] = p, g, m, v
+            tb.n[i], tb.bc1[i], tb.bc2_sqrt[i] = n, bc1, bc2s
+        out.append((tb, len(chunk)))
+    return out
+
+
+def grad_sqnorm(grads, out=None):
+    """Squared L2 norm of a list of gradient tensors, as a device double (no host sync)."""
+    dev = grads[0].device
+    if out is None:
+        out = torch.zeros(1, device=dev, dtype=torch.float64)
+    ent = [(None, ptr(g), None, None, g.numel(), 1.0, 1.0) for g in grads]
+    for tb, n in _tables(ent):
+        call("mggan_grad_sqnorm", tb, n, ptr(out))
+    return out
+
+
+def clip_adamw(params, grads, exp_avg, exp_avg_sq, steps, sqnorm, max_norm, lr, beta1, beta2, eps, wd,
+               grad_scale=1.0):
+    """One fused clip + AdamW update over parallel lists; `steps` are the per-tensor step counts
+    AFTER this update (bias corrections are computed from them)."""
+    ent = []
+    for p, g, m, v, t in zip(params, grads, exp_avg, exp_avg_sq, steps):
+        ent.append((ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), 1.0 - beta1 ** t, math.sqrt(1.0 - beta2 ** t)))
+    for tb, n in _tables(ent):
+        call("mggan_clip_adamw", tb, n, ptr(sqnorm), float(max_norm), float(grad_scale), float(lr), float(beta1),
+             float(beta2), float(eps), float(wd))
+
+
+def multi_copy(dsts, srcs):
+    ent = [(ptr(d), ptr(s), None, None, d.numel(), 1.0, 1.0) for d, s in zip(dsts, srcs)]
+    for tb, n in _tables(ent):
+        call("mggan_multi_copy", tb, n)

@@ -1,0 +1,105 @@
+"""MultiDiscriminatorTrajectory (reference: mggan/model/modules/discriminators.py:12-263).
+
+Observed-trajectory LSTM (H=64) + prediction MLP -> social attention -> scene attention ->
+sigmoid head (+ generator-id classifier head for gan_type='mgan').  Same constructor,
+parameter names and forward contract; the arithmetic runs in the sm_100a kernels.
+
+Reference behaviour kept on purpose: the reference passes
+`seq_start_end * n_samples` -- the SAME index ranges repeated -- to the social module, so
+attention pooling only ever fills the rows of sample 0 and every other sample gets zeros.  The
+reference still evaluates the pair MLP on all (k N)^2 row pairs and throws the result away;
+here only the n_s^2 in-scene pairs of sample 0 are computed.
+"""
+import torch
+import torch.nn as nn
+
+from mggan import kernels as K
+from mggan.model.modules.cnn import AttentionGlobal
+from mggan.model.modules.common_modules import TrajectoryEncoder
+from mggan.model.modules.social import SocialAttention
+
+
+class MultiDiscriminatorTrajectory(nn.Module):
+    def __init__(self, num_gens, num_discs, unbound_output, h_dim, inp_format, pred_len, gan_type, global_disc,
+                 scene_dim, pool_type="sgan"):
+        super().__init__()
+        assert inp_format in ("rel", "abs", "abs_rel")
+        assert gan_type in ("probgan", "mgan", "infogan", "gan")
+        if (inp_format != "rel" or gan_type not in ("mgan", "gan") or pool_type != "sways" or not global_disc
+                or num_discs != 1 or unbound_output or h_dim != 64):
+            raise NotImplementedError(
+                "B200 path covers the default discriminator: inp_format='rel', gan_type in {'mgan','gan'}, "
+                "pool_type='sways', global_disc=1, one sigmoid-bounded head, h_dim=64")
+        if scene_dim not in (0, 64):
+            raise NotImplementedError("scene_dim must be 0 or 64")
+        self.inp_format, self.unbound_output, self.n_ds = inp_format, unbound_output, num_discs
+        self.gan_type, self.global_disc, self.inp_size = gan_type, global_disc, 2
+        self.in_encoder = TrajectoryEncoder(hidden_size=h_dim, inp_size=2, num_layers=1, embedding_dim=h_dim,
+                                            return_hc=False)
+        self.in_encoder_fc = nn.Sequential(nn.Linear(h_dim, h_dim // 2), nn.LeakyReLU(0.2),
+                                           nn.Linear(h_dim // 2, h_dim // 2))
+        self.pred_encoder = nn.Sequential(nn.Linear(pred_len * 2, h_dim), nn.LeakyReLU(0.2),
+                                          nn.Linear(h_dim, h_dim // 2))
+        self.social = SocialAttention(h_dim, h_dim)
+        h_dim *= 2
+        if scene_dim > 0:
+            self.scene_encoder = AttentionGlobal(noise_attention_dim=0, PhysFeature=True, num_layers=2, channels_cnn=8)
+            h_dim += scene_dim
+        self.discs = nn.ModuleList()
+        for _ in range(num_discs):
+            self.discs.append(nn.Sequential(nn.Linear(h_dim, h_dim // 2), nn.LeakyReLU(0.2), nn.Linear(h_dim // 2, 1),
+                                            nn.Sigmoid()))
+        if gan_type == "mgan":
+            self.gen_id_reconstructor = nn.Sequential(nn.Linear(h_dim, h_dim // 2), nn.LeakyReLU(0.2),
+                                                      nn.Linear(h_dim // 2, num_gens))
+        self.eps = 1e-7
+        self.len_hist = 1.0
+
+    @staticmethod
+    def _mlp2(seq, x, last_act=K.ACT_NONE):
+        h = K.linear(x, seq[0].weight, seq[0].bias, K.ACT_LRELU, 0.2)
+        return K.linear(h, seq[2].weight, seq[2].bias, last_act)
+
+    def encode(self, in_xy, in_dxdy, pred_xy, pred_dxdy, mask=None):
+        """-> (k * N, 64), row = sample * N + agent (reference :113-142)."""
+        in_enc = self._mlp2(self.in_encoder_fc, self.in_encoder(in_dxdy))
+        pred_len, n_samples, b, _ = pred_xy.shape
+        N = in_xy.size(1)
+        pv = pred_dxdy.permute(1, 2, 0, 3).reshape(n_samples * b, -1)
+        pred_enc = self._mlp2(self.pred_encoder, pv)
+        if mask is not None:
+            padded = torch.zeros(N * n_samples, pred_enc.size(1), device=pred_enc.device)
+            padded[mask.repeat(n_samples)] = pred_enc
+            pred_enc = padded
+        return torch.cat([in_enc.repeat(n_samples, 1), pred_enc], dim=1)
+
+    def forward(self, in_xy, in_dxdy, pred_xy, pred_dxdy, seq_start_end, return_all=False, img=None, mask=None):
+        """pred_* (pred_len, k, n_act, 2) (3-D inputs are one sample).  Returns output (n_act, k) in
+        (1e-7, 1 - 1e-7), and for gan_type='mgan' also branch logits (n_act, k, G)."""
+        if pred_xy.dim() == 3:
+            pred_xy, pred_dxdy = pred_xy.unsqueeze(1), pred_dxdy.unsqueeze(1)
+        pred_len, n_samples, b, _ = pred_xy.shape
+        N = in_xy.size(1)
+        enc = self.encode(in_xy, in_dxdy, pred_xy, pred_dxdy, mask)
+        soc0 = self.social(in_xy, in_dxdy, enc[:N], seq_start_end)
+        if n_samples > 1:
+            soc = torch.cat([soc0, enc.new_zeros((n_samples - 1) * N, soc0.shape[1])], 0)
+        else:
+            soc = soc0
+        classifier_inp = torch.cat([soc, enc], dim=1)
+        if mask is not None:
+            classifier_inp = classifier_inp[mask.repeat(n_samples)]
+        if img is not None:
+            rows = None
+            if mask is not None:
+                rows = torch.nonzero(mask).flatten().to(torch.int32)
+            scene = self.scene_encoder(img, rows)
+            classifier_inp = torch.cat([classifier_inp, scene.repeat(n_samples, 1)], 1)
+        output = self._mlp2(self.discs[0], classifier_inp, K.ACT_SIGMOID_EPS)       # sigmoid * (1 - 2 eps) + eps
+        if not return_all:
+            output = output.mean(1)
+        output = output.reshape(n_samples, b).t()
+        if self.gan_type == "gan":
+            return output
+        branch_out = self._mlp2(self.gen_id_reconstructor, classifier_inp)
+        return output, branch_out.reshape(n_samples, b, -1).transpose(0, 1)

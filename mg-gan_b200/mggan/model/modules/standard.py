@@ -1,0 +1,139 @@
+"""MultiGenerator (reference: mggan/model/modules/standard.py:17-302).
+
+Same constructor, attributes, state_dict layout (every decoder registered twice, `gs.{i}.*`
+and `G_{i}.*`, standard.py:86-87) and forward contract.  What changes is the execution: the
+encoder, scene and social attention, the PM-Network MLP, the sampling of generator indices and
+the decoding of exactly the selected (agent, sample, generator) sequences are sm_100a kernels;
+the reference's `forward_all` over G x M x N sequences followed by a gather becomes one decoder
+launch over k x N sequences grouped by generator.
+"""
+import torch
+import torch.nn as nn
+
+from mggan import kernels as K
+from mggan.model.modules.cnn import AttentionGlobal
+from mggan.model.modules.common_modules import GeneratorOutput, RelativeDecoder, TrajectoryEncoder, get_input
+from mggan.model.modules.social import SocialAttention
+from mggan.utils import get_global_noise, make_mlp
+
+
+class MultiGenerator(nn.Module):
+    def __init__(self, z_size, encoder_h_dim, decoder_h_dim, social_feat_size, num_gens, pred_len, embedding_dim,
+                 inp_format, num_social_modules, pool_type, scene_dim, use_pinet, learn_prior=False):
+        super().__init__()
+        assert inp_format in ("rel", "abs", "abs_rel")
+        assert num_social_modules in (0, 1, num_gens)
+        assert pool_type in ("sways", "sgan")
+        if inp_format != "rel" or pool_type != "sways" or social_feat_size <= 0 or num_social_modules != 1:
+            raise NotImplementedError(
+                "B200 path covers the default configuration: inp_format='rel', pool_type='sways', one social module")
+        if encoder_h_dim != 32 or decoder_h_dim != 32 or social_feat_size != 32:
+            raise NotImplementedError("B200 path: h_dim = decoder_h_dim = 32 (config.py defaults)")
+        if scene_dim not in (0, 64):
+            raise NotImplementedError("scene_dim must be 0 (no scene encoder) or 64")
+        self.use_pinet, self.inp_format, self.z_size = use_pinet, inp_format, z_size
+        self.embedding_dim, self.social_feat_size = embedding_dim, social_feat_size
+        self.n_social_modules, self.pool_type = num_social_modules, pool_type
+        self.decoder_h_dim, self.encoder_h_dim, self.scene_dim = decoder_h_dim, encoder_h_dim, scene_dim
+
+        self.encoder = TrajectoryEncoder(inp_size=2, hidden_size=encoder_h_dim, embedding_dim=embedding_dim,
+                                         num_layers=1)
+        if scene_dim > 0:
+            self.scene_encoder = AttentionGlobal(noise_attention_dim=0, PhysFeature=True, num_layers=2,
+                                                 channels_cnn=16)
+        self.social = SocialAttention(social_feat_size, encoder_h_dim)
+        self.gs = nn.ModuleList()
+        for i in range(num_gens):
+            decoder = RelativeDecoder(pred_len=pred_len, embedding_dim=embedding_dim, h_dim=decoder_h_dim,
+                                      num_layers=1, social_feat_size=social_feat_size, z_size=z_size, dropout=0.0,
+                                      inp_format=inp_format)
+            setattr(self, "G_{}".format(i), decoder)
+            self.gs.append(decoder)
+        self.n_gs = len(self.gs)
+        self.pred_len = pred_len
+        self.enc_h_to_dec_h = make_mlp([encoder_h_dim + z_size + scene_dim + social_feat_size, decoder_h_dim],
+                                       batch_norm=False)
+        assert not (use_pinet and learn_prior), "Using conditional distribution already, `learn_prior` has no effect"
+        self.net_chooser = nn.Sequential(
+            nn.Linear(encoder_h_dim + scene_dim + social_feat_size, encoder_h_dim // 2), nn.ReLU(),
+            nn.Linear(encoder_h_dim // 2, encoder_h_dim // 2), nn.ReLU(),
+            nn.Linear(encoder_h_dim // 2, num_gens))
+        self.net_prior = nn.Parameter(torch.zeros(1, self.n_gs), requires_grad=learn_prior)
+        self._sample_calls = 0
+
+    # ------------------------------------------------------------------ pieces
+    def _stacked_decoder_weights(self):
+        per = [g.folded() for g in self.gs]
+        return {k: torch.stack([p[k] for p in per]) for k in per[0]}
+
+    def pm_logits(self, enc_h):
+        if not self.use_pinet:
+            return self.net_prior.expand(enc_h.size(0), -1)
+        nc = self.net_chooser
+        x = K.linear(enc_h, nc[0].weight, nc[0].bias, K.ACT_RELU)
+        x = K.linear(x, nc[2].weight, nc[2].bias, K.ACT_RELU)
+        return K.linear(x, nc[4].weight, nc[4].bias)
+
+    def get_samples(self, enc_h, num_samples=5):
+        """(logits (n, G), generator indices (n, num_samples) int64).  The reference draws with
+        Categorical(logits).sample (standard.py:217-225); here a device Gumbel-max sampler keyed on
+        torch's seed and a call counter draws from the same distribution."""
+        logits = self.pm_logits(enc_h)
+        self._sample_calls += 1
+        idx = K.gumbel_sample(logits, num_samples, torch.initial_seed() & ((1 << 63) - 1), self._sample_calls << 20)
+        return logits, idx
+
+    def _decode(self, in_xy, in_dxdy, enc_h, noise, social_feats, sel):
+        """enc_h (n, C): per-agent encoding; noise (k', n, Z).  Decodes the sequences of `sel`."""
+        w = self.enc_h_to_dec_h[0]
+        C = enc_h.shape[1]
+        A = K.linear(enc_h, w.weight[:, :C], w.bias)               # per-agent half of h0, hoisted
+        wz = w.weight[:, C:]
+        return K.decode(A, social_feats, in_xy[-1], in_dxdy[-1], noise, wz, self._stacked_decoder_weights(), sel,
+                        self.pred_len)
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, in_xy, in_dxdy, sub_batches, noise=None, all_gen_out=True, img=None, num_samples=5, mask=None):
+        """See reference standard.py:111-215.  Returns (GeneratorOutput(rel, abs), logits, idx):
+        rel/abs (pred_len, k, n_act, 2), or (pred_len, k, G, n_act, 2) under no_grad if all_gen_out."""
+        batch_size = in_xy.size(1)
+        enc_h = self.encoder(get_input(in_xy, in_dxdy, self.inp_format))
+        enc_features = [enc_h]
+        if img is not None:
+            enc_features.append(self.scene_encoder(img))
+        social_feats = self.social(in_xy, in_dxdy, enc_h, sub_batches)
+        enc_features.append(social_feats)
+        enc_h = torch.cat(enc_features, -1)
+
+        if noise is not None:
+            assert noise.shape == (num_samples, batch_size, self.z_size)
+        else:
+            noise = get_global_noise(self.z_size, sub_batches, "gaussian", in_xy.device, num_samples)
+        if mask is not None:
+            in_xy, in_dxdy = in_xy[:, mask], in_dxdy[:, mask]
+            enc_h, social_feats, noise = enc_h[mask], social_feats[mask], noise[:, mask]
+            batch_size = enc_h.shape[0]
+        noise = noise.contiguous()
+
+        if all_gen_out:
+            with torch.no_grad():
+                pred_xy, pred_dxdy = self.forward_all(in_xy, in_dxdy, enc_h, noise=noise, social_feats=social_feats)
+            net_chooser_out, sampled_gen_idxs = self.get_samples(enc_h, num_samples)
+        else:
+            with torch.no_grad():
+                net_chooser_out, sampled_gen_idxs = self.get_samples(enc_h, num_samples)
+            sel = K.Selection.from_indices(sampled_gen_idxs, self.n_gs)
+            self.last_selection = sel           # per-generator draw counts for the trainer's reweighting
+            pred_xy, pred_dxdy = self._decode(in_xy, in_dxdy, enc_h, noise, social_feats, sel)
+            pred_xy = pred_xy.view(self.pred_len, num_samples, batch_size, 2)
+            pred_dxdy = pred_dxdy.view(self.pred_len, num_samples, batch_size, 2)
+        return GeneratorOutput(pred_dxdy, pred_xy), net_chooser_out, sampled_gen_idxs
+
+    def forward_all(self, in_xy, in_dxdy, enc_h, noise, social_feats):
+        """Every generator on every (sample, agent): two tensors (pred_len, k, G, n, 2) (abs, rel)
+        (reference standard.py:227-265)."""
+        k, n, _ = noise.shape
+        sel = K.Selection.all_generators(n, k, self.n_gs, enc_h.device)
+        pred_xy, pred_dxdy = self._decode(in_xy, in_dxdy, enc_h, noise.contiguous(), social_feats, sel)
+        shape = (self.pred_len, k, self.n_gs, n, 2)
+        return pred_xy.view(shape), pred_dxdy.view(shape)

@@ -1,0 +1,224 @@
+"""PiNetMultiGeneratorGAN: the three optimisation steps of one MG-GAN training iteration
+(reference: mggan/model/train.py:18-662; D step :137-213, G step :23-135, PM-Network step
+:578-658) plus `predict` / `get_predictions` / `check_accuracy` (:215-289).
+
+The step functions keep the reference's signatures and order of random draws (numpy label
+smoothing: fake then real, once per `get_gan_labels` call; torch noise: one vector per scene,
+sample-major).  What they execute is different: the modules are sm_100a kernels, the losses and
+their gradients are single kernels (`mggan_l2_scene_min`, `mggan_bce_scalar_label`,
+`mggan_ce_generators`, `mggan_pm_ml_loss`), the per-generator reweighting uses the draw counts
+the selection kernel already produced, and no step synchronises with the host.
+
+Only the default configuration is on the path: gan_type in {mgan, gan}, gan_obj NS,
+weighting_target in {ml, none}, l2_loss_type not in {none, mse} (the non-default branches are
+"next" rows in SURVEY.md 8f and raise NotImplementedError).
+"""
+import random
+import time
+from functools import partial
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from mggan import kernels as K
+from mggan.abstract_train import MultiGeneratorGAN
+from mggan.evaluation import evaluate_ade_fde
+from mggan.logging import Experiment
+from mggan.model.config import get_parser
+from mggan.model.model_factory import construct_model
+from mggan.utils import get_gan_labels, get_global_noise, to_numpy
+
+
+def _label_scalars(shape):
+    """(real, fake) scalars of one `get_gan_labels` call (patchable, like the reference's import)."""
+    real, fake = get_gan_labels((1,) if shape is None else (1,))
+    return float(real.flatten()[0]), float(fake.flatten()[0])
+
+
+class _frozen:
+    """Temporarily stop gradient tracking for a module's parameters (the G step needs D's input
+    gradients only; the reference computes D's weight gradients there and discards them)."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+
+    def __enter__(self):
+        for p in self.params:
+            p.requires_grad_(False)
+
+    def __exit__(self, *exc):
+        for p in self.params:
+            p.requires_grad_(True)
+
+
+class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
+    def __init__(self, generator, discriminator, config, writer, dist_ctx=None):
+        super().__init__(generator, discriminator, config, writer, dist_ctx)
+        assert self.gan_type in ("mgan", "gan"), self.gan_type
+        if config.weighting_target not in ("ml", "none"):
+            raise NotImplementedError("weighting_target='%s' is outside the B200 hot path" % config.weighting_target)
+        if config.l2_loss_type == "mse":
+            raise NotImplementedError("l2_loss_type='mse' is outside the B200 hot path")
+
+    # ------------------------------------------------------------------ helpers
+    def _noise(self, sub_batches, num_samples=None):
+        return get_global_noise(self.config.noise_dim, sub_batches, "gaussian", self.device, num_samples)
+
+    def _global(self, value):
+        """Sum of a python number over data-parallel ranks (identity on one GPU)."""
+        return value if self.dist is None else self.dist.sum_scalar(value)
+
+    def _reduce(self):
+        return None if self.dist is None else self.dist.allreduce_grads
+
+    # ------------------------------------------------------------------ G step
+    def generator_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, train_metrics, loss_mask, img=None):
+        cfg = self.config
+        b = in_xy.size(1)
+        k = cfg.num_samples
+        noise = self._noise(sub_batches, k)
+        gen_out, _, gen_idxs = self.G(in_xy, in_dxdy, sub_batches, noise=noise, all_gen_out=False, img=img,
+                                      mask=loss_mask, num_samples=k)
+        n_act = gen_idxs.shape[0]
+        counts = self.G.last_selection.totals
+        if self.dist is not None:
+            counts = self.dist.sum_tensor(counts.clone())
+        denom = self._global(n_act * k)
+        loss = None
+        if cfg.l2_loss_type != "none":
+            scenes = K.SceneIndex.get(sub_batches, self.device)
+            min_l2 = K.l2_scene_min(gen_out.abs, gt_xy, scenes, 1.0 / self._global(b))
+            train_metrics["train/L2_loss"].append(min_l2.detach())
+            loss = cfg.l2_loss_weight * min_l2
+        with _frozen(self.D):
+            disc_out = self.D(in_xy, in_dxdy, gen_out.abs, gen_out.rel, sub_batches, img=img, mask=loss_mask)
+        branch_out = None
+        if isinstance(disc_out, tuple):
+            disc_out, branch_out = disc_out
+        l_real, _ = _label_scalars(disc_out.shape)
+        adv_loss = K.bce_scalar_label(disc_out.contiguous(), l_real, gen_idxs, counts, 1.0 / denom)
+        train_metrics["train/gen_loss"].append(adv_loss.detach())
+        loss = adv_loss if loss is None else loss + adv_loss
+        if self.gan_type == "mgan":
+            clf = K.ce_generators(branch_out.flatten(0, 1), gen_idxs.reshape(-1), counts, 1.0 / denom)
+            train_metrics["train/info_mgan_loss"].append(clf.detach())
+            loss = loss + cfg.clf_loss_weight * clf
+        self.D.zero_grad()
+        self.G.zero_grad()
+        loss.backward()
+        self.optimizerG.step(max_norm=cfg.clipping_threshold_g, reduce_fn=self._reduce())
+
+    # ------------------------------------------------------------------ D step
+    def discriminator_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, train_metrics, loss_mask, img=None):
+        cfg = self.config
+        real_result = self.D(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img=img, mask=loss_mask)
+        if isinstance(real_result, tuple):
+            real_result = real_result[0]
+        n_act = real_result.shape[0]
+        denom = self._global(n_act)
+        l_real, _ = _label_scalars(real_result.shape)
+        real_loss = K.bce_scalar_label(real_result.contiguous(), l_real, inv_denom=1.0 / denom)
+        noise = self._noise(sub_batches)[None]
+        with torch.no_grad():
+            gen_out, _, gen_labels_gt = self.G(in_xy, in_dxdy, sub_batches, noise=noise, all_gen_out=False, img=img,
+                                               num_samples=1, mask=loss_mask)
+        disc_out = self.D(in_xy, in_dxdy, gen_out.abs, gen_out.rel, sub_batches, img=img, mask=loss_mask)
+        train_loss = None
+        if self.gan_type == "mgan":
+            disc_out, branch_out = disc_out
+            ce_loss = K.ce_generators(branch_out.flatten(0, 1), gen_labels_gt.flatten(), None, 1.0 / denom)
+            train_metrics["train/info_mgan_disc_loss"].append(ce_loss.detach())
+            train_loss = ce_loss
+        _, l_fake = _label_scalars(disc_out.shape)
+        fake_loss = K.bce_scalar_label(disc_out.contiguous(), l_fake, inv_denom=1.0 / denom)
+        train_loss = real_loss + fake_loss if train_loss is None else train_loss + real_loss + fake_loss
+        train_metrics["train/discr_loss"].append((fake_loss + real_loss).detach())
+        self.D.zero_grad()
+        train_loss.backward()
+        self.optimizerD.step(max_norm=cfg.clipping_threshold_d, reduce_fn=self._reduce())
+
+    # ------------------------------------------------------------------ PM-Network step
+    def net_chooser_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, mask, img):
+        cfg = self.config
+        if cfg.weighting_target == "none":
+            return
+        gen_out, net_chooser_weights, _ = self.G(in_xy, in_dxdy, sub_batches, noise=None, all_gen_out=True, img=img,
+                                                 num_samples=cfg.num_expectation_samples, mask=mask)
+        with torch.no_grad():
+            probs = torch.softmax(net_chooser_weights, 1).mean(0)
+            for i in range(probs.shape[0]):
+                metrics[f"probs/Gen {i} probability"].append(probs[i])
+        n_act = net_chooser_weights.shape[0]
+        loss, _ = K.pm_ml_loss(net_chooser_weights, gen_out.abs, gt_xy, cfg.sigma, cfg.pi_net_loss_weight,
+                               1.0 / self._global(n_act))
+        metrics["train/net_chooser_loss"].append(loss.detach())
+        self.optimizerG.zero_grad()
+        loss.backward()                 # the gradient already carries pi_net_loss_weight
+        self.optimizerG.step(reduce_fn=self._reduce())
+
+    # ------------------------------------------------------------------ prediction / evaluation
+    def get_predict_func(self, strategy: str):
+        if strategy != "sampling":
+            raise NotImplementedError(
+                f"prediction strategy '{strategy}': only 'sampling' is on the B200 path (SURVEY.md 8f #1)")
+        return self.predict
+
+    def get_predictions(self, loader, num_preds=20, strategy="sampling"):
+        assert isinstance(loader.sampler, torch.utils.data.SequentialSampler)
+        self.D.eval()
+        self.G.eval()
+        pred_func = self.get_predict_func(strategy)
+        all_preds = []
+        for batch in loader:
+            in_xy, in_dxdy, _, _, sub_batches, img = self._to_device(batch)
+            preds, _, _, _ = pred_func(in_dxdy, in_xy, sub_batches, img=img, num=num_preds)
+            all_preds.append(to_numpy(preds))
+        return np.concatenate(all_preds, 2)
+
+    def check_accuracy(self, loader, vis=False, prefix="", num_k=20, predict_strategy="sampling", debug=False,
+                       **kwargs):
+        preds = self.get_predictions(loader, num_preds=num_k, strategy=predict_strategy)
+        return evaluate_ade_fde(loader.dataset, preds, [num_k])
+
+    def predict(self, in_dxdy, in_xy, sub_batches, img=None, num=20, noise=None, mask=None):
+        """-> (abs (pred_len, num, b, 2), rel, probs (b, G) numpy, gen_idxs (b, num) numpy)"""
+        self.G.eval()
+        with torch.no_grad():
+            preds, net_chooser_out, gen_idxs = self.G(in_xy, in_dxdy, sub_batches, noise=noise, all_gen_out=False,
+                                                      img=img, num_samples=num, mask=mask)
+            probs = torch.softmax(net_chooser_out, 1)
+        assert preds.abs.shape[1] == num
+        return preds.abs, preds.rel, to_numpy(probs), to_numpy(gen_idxs)
+
+    @staticmethod
+    def construct_model(config):
+        return construct_model(config)
+
+
+def main(argv=None):
+    args = get_parser().parse_args(argv)
+    torch.manual_seed(getattr(args, "seed", 42))
+    np.random.seed(getattr(args, "seed", 42))
+    if args.checkpoint:
+        output_dir = Path(args.checkpoint)
+        assert output_dir.is_dir()
+        model, config = PiNetMultiGeneratorGAN.load_from_path(output_dir)
+        config.gpus = True
+        config.val_every = 1
+    else:
+        output_dir = Path(args.log_dir) / args.experiment
+        output_dir.mkdir(exist_ok=True, parents=True)
+        print(str(output_dir.resolve()))
+        logger = Experiment(output_dir.resolve(), name=args.name, debug=args.debug,
+                            version=random.randint(10 ** 10, (10 ** 11) - 1))
+        G, D = construct_model(config=args)
+        logger.argparse(args)
+        model = PiNetMultiGeneratorGAN(G, D, args, logger)
+        logger.save()
+    model.train()
+    return model
+
+
+if __name__ == "__main__":
+    main()
