@@ -1,0 +1,368 @@
+"""Benchmark of the MG-GAN training-step hot path (BASELINE.json metric: agent-timesteps/sec, train, G=8).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on the host cores
+
+One step = one training iteration (D step + G step + PM-Network step, forward and backward, with
+the optimiser updates) on one batch of synthetic scenes.  Workload = BASELINE.json configs[3]:
+num_gens=8, univ-shape dense scenes (32 agents), k=20 samples, 8 obs / 12 pred; 512 scenes
+(16,384 agents) PER GPU (weak scaling: scenes are independent, the only exchange is the gradient
+all-reduce + a few scalar normalisers + BatchNorm sums).  agent-timesteps/sec = 20 * agents / s.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "mg-gan_b200"))
+
+T_OBS, T_PRED = 8, 12
+IMG_BYTES = 4 * 33 * 33 * 4
+TRAJ_BYTES = (8 + 7 + 12 + 12) * 2 * 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes", type=int, default=512, help="scenes per GPU")
+    ap.add_argument("--agents", type=int, default=32, help="agents per scene (univ-dense)")
+    ap.add_argument("--num_gens", type=int, default=8)
+    ap.add_argument("--k", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--roofline-kernel", default=None, help="entry point whose launches are timed in the timed region")
+    ap.add_argument("--breakdown", action="store_true", help="print a per-kernel time table to stderr")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return float(p.get("hbm_gbs", 6650.0)), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def param_counts(G, D):
+    pg = sum(p.numel() for p in G.parameters())
+    pd = sum(p.numel() for p in D.parameters())
+    pm = sum(p.numel() for n, p in G.named_parameters()
+             if n.split(".")[0] in ("encoder", "scene_encoder", "social", "net_chooser"))
+    return pg, pd, pm
+
+
+def algorithmic_bytes_per_iter(n_agents, with_img, pg, pd, pm):
+    """B_iter = 3 N (312 + I) + 28 (P_D + P_G + P_PM)."""
+    return 3 * n_agents * (TRAJ_BYTES + (IMG_BYTES if with_img else 0)) + 28 * (pd + pg + pm)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(scenes, agents, seed, pin):
+    import numpy as np
+    import torch
+    from mggan.synthetic import make_batch
+    b = make_batch([agents] * scenes, seed=seed, with_img=True)
+    sse = b.pop("seq_start_end")
+    out = {}
+    for k, v in b.items():
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        out[k] = t.pin_memory() if pin else t
+    out["seq_start_end"] = sse
+    return out
+
+
+# ------------------------------------------------------------------------------------------ ours
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from collections import defaultdict
+    from mggan import cuda_ext
+    from mggan.distributed import DistContext
+    from mggan.logging import Experiment
+    from mggan.model.config import get_parser
+    from mggan.model.model_factory import construct_model
+    from mggan.model.train import PiNetMultiGeneratorGAN
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ctx = DistContext()
+    assert world == a.gpus or world == 1, (world, a.gpus)
+
+    torch.manual_seed(1234)                         # identical initial weights on every rank
+    cfg = get_parser().parse_args(["--num_gens", str(a.num_gens), "--num_samples", str(a.k)])
+    cfg.gpus = True
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        G, D = construct_model(cfg)
+    tr = PiNetMultiGeneratorGAN(G, D, cfg, Experiment(tempfile.mkdtemp(prefix="mggan_bench_"), "bench", version=rank),
+                                dist_ctx=ctx)
+    tr.epoch = 1
+    tr.G.train(); tr.D.train()
+    pg, pd, pm = param_counts(tr.G, tr.D)
+
+    host = make_inputs(a.scenes, a.agents, seed=4000 + rank, pin=True)
+    sse = host["seq_start_end"]
+    n_local = host["in_xy"].shape[1]
+    n_total = n_local * world
+    devb = {k: v.to(dev) for k, v in host.items() if k != "seq_start_end"}
+    metrics = defaultdict(list)
+
+    def step_resident():
+        tr.discriminator_step(devb["in_xy"], devb["in_dxdy"], devb["gt_xy"], devb["gt_dxdy"], sse, metrics, None, devb["features"])
+        tr.generator_step(devb["in_xy"], devb["in_dxdy"], devb["gt_xy"], devb["gt_dxdy"], sse, metrics, None, devb["features"])
+        tr.net_chooser_step(devb["in_xy"], devb["in_dxdy"], devb["gt_xy"], devb["gt_dxdy"], sse, metrics, None, devb["features"])
+        metrics.clear()
+
+    def step_e2e():
+        m = defaultdict(list)
+        tr.train_iteration(host, m)                  # H2D of the batch from pinned memory inside
+        vals = torch.stack([m[k][-1].float().reshape(()) for k in sorted(m) if k.startswith("train/")])
+        return vals.cpu()                            # D2H of the step's loss scalars
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, only=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = cuda_ext.launch_count
+        if only:
+            cuda_ext.profile_start(only=only)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        prof = cuda_ext.profile_stop() if only else {}
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps, (cuda_ext.launch_count - l0) // steps, prof
+
+    # ---- per-kernel breakdown (untimed pass) -> dominant kernel
+    for _ in range(max(1, min(a.warmup, 2))):
+        step_resident()
+    torch.cuda.synchronize()
+    cuda_ext.profile_start()
+    step_resident()
+    prof = cuda_ext.profile_stop()
+    total_prof = sum(t for _, t in prof.values())
+    top = sorted(prof.items(), key=lambda kv: -kv[1][1])
+    dom = a.roofline_kernel or top[0][0]
+    if a.breakdown and rank == 0:
+        for name, (c, t) in top:
+            print(f"  {name:32s} calls {c:4d}  {t:9.3f} ms  {100 * t / total_prof:5.1f}%", file=sys.stderr)
+
+    # ---- device-resident timing (value) with the dominant kernel's launches timed by events
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step, launches, dprof = timed(step_resident, a.steps, max(a.warmup, 3), only=[dom])
+    dom_prof = dprof.get(dom, (0, 0.0))
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end through the public API with host buffers
+    e2e = None
+    if not a.no_e2e:
+        ms_e2e, _, _ = timed(step_e2e, a.steps, max(a.warmup, 3))
+        h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "seq_start_end")
+        e2e = {"value": 20.0 * n_total / (ms_e2e / 1e3), "unit": "agent-timesteps/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 6 * 4}
+
+    hbm_peak, peak_kind = peaks()
+    b_iter = algorithmic_bytes_per_iter(n_local, True, pg, pd, pm)
+    dom_calls, dom_ms = dom_prof
+    dom_avg_ms = dom_ms / max(dom_calls, 1)
+    # algorithmic bytes attributed to one launch of the dominant kernel: the iteration's compulsory traffic
+    #  split over launches in proportion to device time is NOT used; the whole-iteration figure is
+    # reported against the whole step and the kernel's own share is given beside it (DESIGN.md "Roofline").
+    roof = {"bound": "hbm", "kernel": dom, "kernel_avg_ms": dom_avg_ms, "kernel_share_of_step": (dom_ms / a.steps) / ms_step if ms_step else None,
+            "achieved": b_iter / (ms_step / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": b_iter / (ms_step / 1e3) / 1e9 / hbm_peak, "peak_source": peak_kind, "traffic": None,
+            "algorithmic_bytes_per_step": int(b_iter)}
+
+    line = {
+        "metric": "agent-timesteps/sec (train, G=8)", "value": 20.0 * n_total / (ms_step / 1e3),
+        "unit": "agent-timesteps/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"cfg4 univ-dense: num_gens={a.num_gens}, k={a.k}, {a.scenes} scenes x {a.agents} agents per GPU "
+                               f"(N={n_local}/GPU, {n_total} total), 8 obs / 12 pred, scene CNN on; one step = D+G+PM iteration",
+                   "agents_per_gpu": n_local, "parallelism": f"dp{world} (scenes sharded, gradient all-reduce)",
+                   "l2": "inputs (299 MB of crops per step) and saved activations (>3 GB) exceed the 126 MB L2"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        "kernel_breakdown_ms": {n: round(t, 3) for n, (c, t) in top[:8]},
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a, budget_s=20.0)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _oracle_iteration_factory(a, scenes):
+    """One full iteration of the oracle port (oracle/mggan_oracle.py: the reference's algorithm restated on
+    PyTorch CPU ops, in-scene pairs only) on `scenes` univ-dense scenes."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mggan_oracle as O
+    from mggan.model.config import get_parser
+    from mggan.model.model_factory import construct_model
+    from mggan.synthetic import make_batch
+    import contextlib, io
+    torch.manual_seed(1234)
+    cfg = get_parser().parse_args(["--num_gens", str(a.num_gens), "--num_samples", str(a.k)])
+    with contextlib.redirect_stdout(io.StringIO()):
+        G, D = construct_model(cfg)                     # parameter containers only (CPU); no kernels are called
+    sdG = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    sdD = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    b = make_batch([a.agents] * scenes, seed=4000, with_img=True)
+    sse = b.pop("seq_start_end")
+    bt = {k: torch.from_numpy(v) for k, v in b.items()}
+    bt["seq_start_end"] = sse
+    N = bt["in_xy"].shape[1]
+    tr = O.OracleTrainer(sdG, sdD, a.num_gens, num_samples=a.k)
+    gen = torch.Generator().manual_seed(0)
+    rng = np.random.default_rng(0)
+
+    def noise(n):
+        return torch.stack([O.global_noise(8, sse, gen) for _ in range(n)])
+
+    def it():
+        lab = [(float(rng.uniform(0.9, 1.0)), float(rng.uniform(0.0, 0.1))) for _ in range(3)]
+        tr.discriminator_step(bt, noise(1), torch.randint(0, a.num_gens, (N, 1), generator=gen), lab[0], lab[1])
+        tr.generator_step(bt, noise(a.k), torch.randint(0, a.num_gens, (N, a.k), generator=gen), lab[2])
+        tr.net_chooser_step(bt, noise(1))
+
+    return it, N
+
+
+def cpu_baseline(a, budget_s):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    scenes = 8
+    it, N = _oracle_iteration_factory(a, scenes)
+    it()                                               # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while n < 1 or (time.perf_counter() - t0 < budget_s and n < 20):
+        it()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 20.0 * N / dt, "unit": "agent-timesteps/s", "cores": cores, "kind": "port",
+            "sample": f"{n} iterations of {scenes} scenes x {a.agents} agents (N={N}), G={a.num_gens}, k={a.k}; oracle port "
+                      f"(PyTorch CPU, in-scene pairs only: cheaper than the reference's (kN)^2 pair evaluation)",
+            "s_per_iteration": dt}
+
+
+def run_reference(a):
+    """CPU arm: /root/reference does not travel to the GPU box and is pure Python (nothing to pip-install into
+    baseline/_ref that would run there without its own import shims), so this times the oracle port of the
+    reference algorithm on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # size the sample so that (steps + warmup) iterations finish within ~2.5 minutes
+    scenes = 4
+    it, N = _oracle_iteration_factory(a, scenes)
+    it()
+    t0 = time.perf_counter(); it(); t1 = time.perf_counter() - t0
+    total = a.steps + a.warmup
+    budget = 150.0
+    grow = max(1, min(16, int(budget / max(total * t1, 1e-3))))
+    if grow > 1:
+        scenes *= grow
+        it, N = _oracle_iteration_factory(a, scenes)
+    for _ in range(a.warmup):
+        it()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        it()
+    dt = (time.perf_counter() - t0) / max(a.steps, 1)
+    val = 20.0 * N / dt
+    sample = (f"each step = one D+G+PM iteration on {scenes} scenes x {a.agents} agents (N={N}) of the cfg4 workload, "
+              f"G={a.num_gens}, k={a.k}; oracle port of the reference algorithm (PyTorch CPU, {cores} threads)")
+    line = {"impl": "reference", "metric": "agent-timesteps/sec (train, G=8)", "value": val, "unit": "agent-timesteps/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg4 univ-dense: num_gens={a.num_gens}, k={a.k}, bounded sample of {scenes} scenes x {a.agents} agents"},
+            "cpu_baseline": {"value": val, "unit": "agent-timesteps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "agent-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -76,10 +76,11 @@ class MultiGeneratorGAN(abc.ABC):
     def train_iteration(self, batch, metrics, total_iterations=0):
         """One D step + G step + PM step on a collated batch (reference loop body :114-168)."""
         in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img = self._to_device(batch)
-        loss_mask = ~gt_xy.isnan().any(2).any(0)
-        if bool(batch.get("no_nan", False)):
-            loss_mask = None
-        else:
+        # the reference always builds the NaN mask (abstract_train.py:130-132); when no future is masked the
+        # mask is dropped so the step runs without boolean-index gathers (one host sync to decide)
+        loss_mask = None
+        if bool(torch.isnan(gt_xy).any()):
+            loss_mask = ~gt_xy.isnan().any(2).any(0)
             gt_dxdy, gt_xy = gt_dxdy[:, loss_mask], gt_xy[:, loss_mask]
         if (total_iterations % self.config.num_gen_steps == 0) or (self.epoch >= self.config.keep_gen_steps):
             if self.config.num_unrolling_steps > 0:

@@ -122,13 +122,47 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per entry point (for the launch counter; memsets not counted)
+KERNELS_PER_CALL = {"mggan_selection_build": 3, "mggan_linear_bwd": 2}
+launch_count = 0          # kernels launched through this binding since import
+_profile = None           # None | {"only": set or None, "events": [(name, start, end), ...]}
+
+
+def profile_start(only=None):
+    """Record a CUDA-event pair around every call (or only the named entry points) on the launching stream."""
+    global _profile
+    _profile = {"only": set(only) if only else None, "events": []}
+
+
+def profile_stop():
+    """-> {name: (calls, total_ms)}; synchronises the device."""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, s, e in prof["events"]:
+        c, t = out.get(name, (0, 0.0))
+        out[name] = (c + 1, t + s.elapsed_time(e))
+    return out
+
+
 def call(name, *args):
     """Invoke a status-returning entry point on the current stream; raise on a non-zero status."""
+    global launch_count
     _ensure_device()
     lib = _lib
-    rc = getattr(lib, name)(*args, stream())
+    prof = _profile
+    if prof is not None and (prof["only"] is None or name in prof["only"]):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib, name)(*args, stream())
+        e.record()
+        prof["events"].append((name, s, e))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     if rc != 0:
         raise MgganCudaError(f"{name} failed ({rc}): {lib.mggan_last_error().decode()}")
+    launch_count += KERNELS_PER_CALL.get(name, 1)
 
 
 def selection_tiles(n_seq, num_gens):

@@ -45,7 +45,7 @@ class SyntheticScenes(Dataset):
     obs_traj = property(lambda self: self._eval_arrays()[0])
     pred_traj = property(lambda self: self._eval_arrays()[1])
     seq_start_end = property(lambda self: self._eval_arrays()[2])
-    scene_list = property(lambda self: list(range(len(self._eval_arrays()[2]))))
+    scene_list = property(lambda self: [self.dataset_name] * len(self._eval_arrays()[2]))
 
     def __getitem__(self, i):
         b = make_batch([self.sizes[i]], seed=self.seeds[i], with_img=self.with_img, nan_frac=self.nan_frac,

@@ -1,0 +1,89 @@
+"""Data-parallel execution of the training step: scenes are the unit of sharding.
+
+All cross-agent coupling in MG-GAN is inside a scene (social attention, scene-shared noise, the
+scene-level min-L2), so a batch splits into contiguous scene ranges, one per rank, with the
+weights replicated.  What must be exchanged for single-GPU-exact results:
+
+  * gradients: ONE all-reduce(sum) of a flat buffer per optimiser step (D, G, PM) over NCCL
+    (NVLink 5 / NVSwitch inside a box), issued from `FusedAdamW.step(reduce_fn=...)`; the clip
+    norm is then taken on the reduced gradient;
+  * loss normalisers: the global agent / sample counts and the per-generator draw counts
+    (`sum_scalar`, `sum_tensor`);
+  * train-mode BatchNorm statistics of the two scene CNNs: per-channel sums are all-reduced
+    between the statistics pass and the normalisation pass (`AttentionGlobal.stat_group`).
+
+The reference has no multi-GPU path at all (`--gpus` is a truthiness string).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_scenes(sub_batches, world_size, rank, balance="agents"):
+    """Contiguous scene range of `rank` balanced by agents (or by n^2 pairs).  Returns
+    (scene_lo, scene_hi, agent_lo, agent_hi, local seq_start_end re-based to 0)."""
+    sizes = [int(e) - int(s) for s, e in sub_batches]
+    cost = [n * n for n in sizes] if balance == "pairs" else sizes
+    total = sum(cost)
+    bounds, acc, nxt = [0], 0, 1
+    for i, c in enumerate(cost):
+        acc += c
+        while nxt < world_size and acc >= total * nxt / world_size:
+            bounds.append(i + 1)
+            nxt += 1
+    while len(bounds) < world_size:
+        bounds.append(len(sizes))
+    bounds.append(len(sizes))
+    lo, hi = bounds[rank], bounds[rank + 1]
+    a_lo = int(sub_batches[lo][0]) if lo < len(sizes) else int(sub_batches[-1][1])
+    a_hi = int(sub_batches[hi - 1][1]) if hi > lo else a_lo
+    local = [[int(s) - a_lo, int(e) - a_lo] for s, e in sub_batches[lo:hi]]
+    return lo, hi, a_lo, a_hi, local
+
+
+def shard_batch(batch, world_size, rank, balance="agents"):
+    """Slice a collated batch dict (agents along dim 1, images along dim 0) to this rank's scenes."""
+    _, _, a_lo, a_hi, local = shard_scenes(batch["seq_start_end"], world_size, rank, balance)
+    out = {"seq_start_end": local}
+    for k, v in batch.items():
+        if k == "seq_start_end":
+            continue
+        out[k] = v[a_lo:a_hi] if k == "features" else v[:, a_lo:a_hi]
+    return out
+
+
+class DistContext:
+    def __init__(self, group=None):
+        assert dist.is_initialized()
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+
+    def attach(self, G, D):
+        for m in (G, D):
+            enc = getattr(m, "scene_encoder", None)
+            if enc is not None:
+                enc.stat_group = self.group if self.group is not None else dist.group.WORLD
+
+    def sum_scalar(self, value, device=None):
+        t = torch.tensor([float(value)], dtype=torch.float64, device=device or self._device())
+        dist.all_reduce(t, group=self.group)
+        return float(t.item())
+
+    def sum_tensor(self, t):
+        dist.all_reduce(t, group=self.group)
+        return t
+
+    def _device(self):
+        return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else "cpu"
+
+    def allreduce_grads(self, grads):
+        """Sum a list of gradient tensors over ranks with one collective; returns views of the
+        reduced flat buffer in the same order."""
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, group=self.group)
+        out, off = [], 0
+        for g in grads:
+            n = g.numel()
+            out.append(flat[off:off + n].view_as(g))
+            off += n
+        return out

@@ -44,3 +44,40 @@ def evaluate_ade_fde(eval_ds, preds, n_preds_list):
             for key, (value, count) in m.items():
                 accum[f"{key} k={n_preds}"] += value, count
     return defaultdict(float, {key: value / count for key, (value, count) in accum.items()})
+
+
+def get_same_obs_indices(eval_ds):
+    """Groups of scenes that share their observations (multi-future datasets): list of groups, each a
+    list of per-scene agent-index lists (reference :30-40)."""
+    obs_trajs = to_numpy(eval_ds.obs_traj)
+    groups = defaultdict(list)
+    for scene_idx, (start, end) in enumerate(eval_ds.seq_start_end):
+        key = (obs_trajs[start:end].tobytes(), eval_ds.scene_list[scene_idx])
+        groups[key].append(list(range(start, end)))
+    return list(groups.values())
+
+
+def evaluate_precision_recall(eval_ds, all_preds, manifold_radius, n_preds_list, debug=False):
+    """Precision: fraction of predictions inside the tube around the ground-truth futures that share
+    the observation; Recall k=i: fraction of those futures inside the tube around the first i
+    predictions (reference :101-156)."""
+    from mggan.manifold import Manifold
+    gt_trajs = to_numpy(eval_ds.pred_traj)
+    num_preds = max(n_preds_list)
+    pred_mask = np.isnan(gt_trajs).any(-1).any(-1)
+    valid = np.where(~pred_mask)[0]
+    preds = all_preds.transpose(2, 1, 0, 3)                    # (N, k, pred_len, 2)
+    accum = defaultdict(lambda: np.zeros((2,)))
+    for same_scene_indices in get_same_obs_indices(eval_ds):
+        for same_ped_indices in zip(*same_scene_indices):
+            same_ped_indices = np.intersect1d(np.array(same_ped_indices), valid)
+            if len(same_ped_indices) == 0:
+                continue
+            gt_man_samples = gt_trajs[same_ped_indices]
+            gt_man = Manifold(gt_man_samples, manifold_radius)
+            cur_preds = preds[same_ped_indices].reshape(-1, *preds.shape[2:])
+            accum["Precision"] += gt_man.compute_metric(cur_preds[:num_preds]), 1.0
+            for n_samples in n_preds_list:
+                pred_man = Manifold(cur_preds[:n_samples], manifold_radius)
+                accum[f"Recall k={n_samples}"] += pred_man.compute_metric(gt_man_samples), 1.0
+    return defaultdict(float, {key: value / count for key, (value, count) in accum.items()})

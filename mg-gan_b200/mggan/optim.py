@@ -40,7 +40,7 @@ class FusedAdamW(torch.optim.Optimizer):
             return
         grads = [p.grad.contiguous() for _, p in work]
         if reduce_fn is not None:
-            reduce_fn(grads)
+            grads = reduce_fn(grads) or grads
         sq = K.grad_sqnorm(grads) if max_norm and max_norm > 0 else None
         self.last_grad_sqnorm = sq
         start = 0
