@@ -92,18 +92,26 @@ int mggan_social_attn_bwd(const float* x4, const float* h, int HD, const float* 
 
 /* ---- physical attention: AttentionGlobal / CNN / Conv_Blocks, mggan/model/modules/cnn.py:101-116,119-282
  * img (.,4,33,33); rows (N) optional int32 gather of image rows (mask compaction) or NULL; C in {8,16}.
- * x1 (N,C,33,33), x2 (N,C,16,16) pre-BatchNorm conv outputs; stats (2C doubles: sum, sum of squares)
- * accumulated or NULL (eval mode). */
-int mggan_scene_conv1_fwd(const float* img, const int* rows, int N, int C, const float* W, const float* bias,
-                          float* x1, double* stats, cudaStream_t stream);
-/* training != 0: batch statistics (count = elements per channel) + running-stat update (momentum,
- * unbiased variance) + num_batches_tracked += 1; else running statistics.
+ * conv1 is linear in the crop, so train-mode BatchNorm-1 statistics and the dense half of conv1's weight
+ * gradient come from data-only patch statistics R (36x36 doubles, symmetric), P (36 doubles), accumulated. */
+int mggan_scene_patch_stats(const float* img, const int* rows, int N, double* R, double* P, cudaStream_t stream);
+/* count = conv1 outputs per channel (N_total * 33 * 33).  training != 0: batch statistics + running-stat
+ * update (momentum, unbiased variance) + num_batches_tracked += 1; else running statistics.
  * ab (2C) = BN as y = a x + b; mean_istd (2C). */
+int mggan_scene_bn1_from_patches(const double* R, const double* P, double count, int C, const float* W,
+                                 const float* bias, const float* gamma, const float* beta, float* running_mean,
+                                 float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                                 int training, float* ab, float* mean_istd, cudaStream_t stream);
+/* conv1 -> BN1 -> ReLU -> pool -> conv2.  x2 (N,C,16,16) pre-BatchNorm-2 output; stats2 (2C doubles: sum, sum of
+ * squares) accumulated or NULL (eval); e1 (N,C,256) pre-BN value at the pool arg + idx1 (N,C,256 bytes: arg |
+ * active<<2) saved for the backward, or both NULL. */
+int mggan_scene_fused12_fwd(const float* img, const int* rows, int N, int C, const float* W1, const float* b1,
+                            const float* ab1, const float* W2, const float* b2, float* x2, double* stats2, float* e1,
+                            unsigned char* idx1, cudaStream_t stream);
+/* BatchNorm-2 finalize (same contract as above, from per-channel sums). */
 int mggan_scene_bn_finalize(const double* stats, double count, int C, const float* gamma, const float* beta,
                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
                             float eps, int training, float* ab, float* mean_istd, cudaStream_t stream);
-int mggan_scene_block2_fwd(const float* x1, int N, int C, const float* ab1, const float* W, const float* bias,
-                           float* x2, double* stats, cudaStream_t stream);
 /* Wa1 (32,C), ba1 (32), Wa2 (C,32), ba2 (C) = cnn_attention; out (N,64). */
 int mggan_scene_attn_fwd(const float* x2, int N, int C, const float* ab2, const float* Wa1, const float* ba1,
                          const float* Wa2, const float* ba2, float* out, cudaStream_t stream);
@@ -115,13 +123,18 @@ int mggan_scene_attn_bwd(const float* x2, int N, int C, const float* ab2, const 
 /* sums (2C doubles) -> m12 (2C) means for the BatchNorm backward; dgamma, dbeta (C) accumulated. */
 int mggan_scene_bn_bwd_finalize(const double* sums, double count, int C, float* m12, float* dgamma, float* dbeta,
                                 cudaStream_t stream);
-int mggan_scene_block2_bwd(const float* x1, const float* x2, int N, int C, const float* ab1, const float* mean_istd1,
-                           const float* ab2, const float* mean_istd2, const float* m12_2, const float* W,
-                           const float* dy2, const unsigned char* idx2, float* dW, float* dbias, float* dy1,
-                           unsigned char* idx1, double* sums1, cudaStream_t stream);
-int mggan_scene_conv1_bwd(const float* img, const int* rows, const float* x1, int N, int C, const float* ab1,
-                          const float* mean_istd1, const float* m12_1, const float* dy1, const unsigned char* idx1,
-                          float* dW, float* dbias, cudaStream_t stream);
+/* dW2 (C,C,3,3), dbias2 (C), S1 (C,36) = sum dy1 * patch at the pool-arg positions, sums1 (2C doubles): accumulated. */
+int mggan_scene_fused12_bwd(const float* img, const int* rows, int N, int C, const float* x2, const float* e1,
+                            const unsigned char* idx1, const float* ab1, const float* mean_istd1, const float* ab2,
+                            const float* mean_istd2, const float* m12_2, const float* W2, const float* dy2,
+                            const unsigned char* idx2, float* dW2, float* dbias2, float* S1, double* sums1,
+                            cudaStream_t stream);
+/* closed-form BatchNorm-1 backward: dW1 (C,4,3,3) overwritten, dgamma/dbeta (C) overwritten with the local sums.
+ * sums_global: all-reduced sums1 when data-parallel (same pointer as sums_local otherwise); R, P: local shard. */
+int mggan_scene_bn1_bwd_finalize(const double* sums_global, const double* sums_local, double count, int C,
+                                 const float* S1, const double* R, const double* P, const float* W, const float* bias,
+                                 const float* ab1, const float* mean_istd1, float* dW, float* dgamma, float* dbeta,
+                                 cudaStream_t stream);
 
 /* ---- losses: mggan/model/train.py:55-113 (G step), :148-200 (D step), :626-639 (PM step) */
 /* abs (T,k,n,2), gt (T,n,2); loss += sum_scenes min_s sum_{i in scene} sum_t |abs-gt| * inv_norm;

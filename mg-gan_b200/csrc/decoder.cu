@@ -51,7 +51,7 @@ struct DecSeq {
     const int* seq_out;     // output column
 };
 
-__global__ void __launch_bounds__(MGGAN_THREADS)
+__global__ void __launch_bounds__(MGGAN_THREADS, 2)
 decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const float* __restrict__ social,
                    const float* __restrict__ last_xy, const float* __restrict__ last_dxdy,
                    const float* __restrict__ noise, int Z, DecWeights w, int T, int n_cols,
@@ -211,7 +211,7 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
 }
 
 // Backward.  Inputs: the forward's saved activations, d_abs / d_rel (either may be null).
-__global__ void __launch_bounds__(MGGAN_THREADS)
+__global__ void __launch_bounds__(MGGAN_THREADS, 2)
 decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, const float* __restrict__ last_dxdy,
                    const float* __restrict__ noise, int Z, DecWeights w, int T, int n_cols,
                    const float* __restrict__ out_rel, const float* __restrict__ acts,

@@ -4,14 +4,15 @@
 // (Conv_Blocks), :178-282 (CNN); BatchNorm runs in train mode with batch statistics over
 // (N, H, W), so every conv layer needs a grid-wide reduction before its output can be used.
 //
-// Forward = three streaming passes, one CTA (persistent) per agent:
-//   scene_conv1_fwd   img -> x1 = conv1(img) (stored), per-channel sum / sum-of-squares
-//   scene_bn_finalize stats -> (a, b) = BN as an affine map, running statistics update
-//   scene_block2_fwd  x1 -> BN1 -> ReLU -> pool -> conv2 -> x2 (stored), stats of x2
-//   scene_bn_finalize
-//   scene_attn_fwd    x2 -> BN2 -> ReLU -> pool -> v (64 x C) -> MLP C->32->C -> softmax_c -> sum_c a v
-// Backward walks the same passes in reverse; the gradient w.r.t. a pooled+ReLU'd BatchNorm
-// output is sparse (one position per 2x2 window), so it is stored as (value, 2-bit index).
+// conv1 is linear in the crop, so BatchNorm-1's batch statistics (and the dense half of conv1's weight
+// gradient) follow from data-only patch statistics R (36x36), P (36) computed ONCE per batch of crops:
+//   scene_patch_stats        img -> R, P                               (shared by G and D, all three steps)
+//   scene_bn1_from_patches   R, P, W1 -> BN1 as an affine map (a, b), running statistics update
+//   scene_fused12_fwd        img -> conv1 -> BN1 -> ReLU -> pool -> conv2 -> x2 (stored) + sums of x2
+//   scene_bn_finalize        sums -> BN2 affine map
+//   scene_attn_fwd           x2 -> BN2 -> ReLU -> pool -> v (64 x C) -> MLP C->32->C -> softmax_c -> sum_c a v
+// Backward: scene_attn_bwd -> scene_bn_bwd_finalize -> scene_fused12_bwd -> scene_bn1_bwd_finalize.  The
+// gradient w.r.t. a pooled+ReLU'd BatchNorm output is sparse (one position per 2x2 window): (value, 2-bit arg).
 // Partial BatchNorm sums are accumulated in fp32 per thread, reduced per CTA and added to the
 // global statistics as doubles (one atomicAdd per channel per CTA).
 #include "common.cuh"
@@ -85,71 +86,6 @@ __device__ __forceinline__ void load_image_padded(float* sImg, const float* __re
 }
 
 // ------------------------------------------------------------------------------------------
-// pass A: conv1 + statistics
-template <int C>
-__global__ void __launch_bounds__(MGGAN_THREADS)
-scene_conv1_fwd_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N,
-                       const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ x1,
-                       double* __restrict__ stats) {
-    extern __shared__ __align__(16) float smem[];
-    float* sImg = smem;                      // [4][35][36]
-    float* sW = sImg + CIN * IMGPAD;         // [36 taps][C]
-    float* sred = sW + 36 * C;               // [8][2C]
-    for (int i = threadIdx.x; i < 36 * C; i += MGGAN_THREADS) {
-        int c = i / 36, tap = i - c * 36;
-        sW[tap * C + c] = __ldg(W + i);
-    }
-    float bs[C], st[2 * C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) { bs[c] = __ldg(bias + c); st[c] = 0.f; st[C + c] = 0.f; }
-
-    for (int n = blockIdx.x; n < N; n += gridDim.x) {
-        const int src = rows ? rows[n] : n;
-        __syncthreads();
-        load_image_padded(sImg, img + (size_t)src * CIN * IMG2);
-        __syncthreads();
-        for (int p0 = threadIdx.x; p0 < IMG2; p0 += 2 * MGGAN_THREADS) {
-            const int p1 = p0 + MGGAN_THREADS;
-            const bool v1 = p1 < IMG2;
-            const int q1 = v1 ? p1 : p0;
-            const int y0 = p0 / IMG, x0 = p0 - y0 * IMG, y1 = q1 / IMG, xx1 = q1 - y1 * IMG;
-            float a0[C], a1[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) { a0[c] = bs[c]; a1[c] = bs[c]; }
-#pragma unroll 1
-            for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float i0 = sImg[ci * IMGPAD + (y0 + ky) * LDI + x0 + kx];
-                        const float i1 = sImg[ci * IMGPAD + (y1 + ky) * LDI + xx1 + kx];
-                        const float* wp = sW + (ci * 9 + ky * 3 + kx) * C;
-#pragma unroll
-                        for (int c = 0; c < C; c += 4) {
-                            float4 w = ld4(wp + c);
-                            a0[c] = fmaf(i0, w.x, a0[c]); a0[c + 1] = fmaf(i0, w.y, a0[c + 1]);
-                            a0[c + 2] = fmaf(i0, w.z, a0[c + 2]); a0[c + 3] = fmaf(i0, w.w, a0[c + 3]);
-                            a1[c] = fmaf(i1, w.x, a1[c]); a1[c + 1] = fmaf(i1, w.y, a1[c + 1]);
-                            a1[c + 2] = fmaf(i1, w.z, a1[c + 2]); a1[c + 3] = fmaf(i1, w.w, a1[c + 3]);
-                        }
-                    }
-            float* o = x1 + (size_t)n * C * IMG2;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                o[c * IMG2 + p0] = a0[c];
-                st[c] += a0[c]; st[C + c] = fmaf(a0[c], a0[c], st[C + c]);
-                if (v1) {
-                    o[c * IMG2 + p1] = a1[c];
-                    st[c] += a1[c]; st[C + c] = fmaf(a1[c], a1[c], st[C + c]);
-                }
-            }
-        }
-    }
-    if (stats != nullptr) block_reduce_to_global<2 * C>(st, stats, sred);
-}
-
-// ------------------------------------------------------------------------------------------
 // BatchNorm finalize: statistics -> affine (a, b), mean / invstd for the backward, running stats.
 __global__ void scene_bn_finalize_kernel(const double* __restrict__ stats, double count, int C,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -195,77 +131,451 @@ __global__ void scene_bn_bwd_finalize_kernel(const double* __restrict__ sums, do
 }
 
 // ------------------------------------------------------------------------------------------
-// pass B: BN1 -> ReLU -> pool -> conv2 + statistics
-template <int C>
-__device__ __forceinline__ void pool_block1(const float* __restrict__ x1n, const float* __restrict__ ab1, float* sP,
-                                            unsigned char* sIdx, float* sE) {
-    // 2x2 max-pool of relu(a x + b); optional arg index (bit 2 = active) and pre-BN value at the arg
-    for (int i = threadIdx.x; i < C * P1SQ; i += MGGAN_THREADS) {
-        int c = i >> 8, pp = i & 255, py = pp >> 4, px = pp & 15;
-        const float a = ab1[c], b = ab1[C + c];
-        const float* s = x1n + c * IMG2 + (2 * py) * IMG + 2 * px;
-        float r0 = __ldg(s), r1 = __ldg(s + 1), r2 = __ldg(s + IMG), r3 = __ldg(s + IMG + 1);
-        float v0 = fmaf(a, r0, b), v1 = fmaf(a, r1, b), v2 = fmaf(a, r2, b), v3 = fmaf(a, r3, b);
-        float m = v0, e = r0; int arg = 0;
-        if (v1 > m) { m = v1; e = r1; arg = 1; }
-        if (v2 > m) { m = v2; e = r2; arg = 2; }
-        if (v3 > m) { m = v3; e = r3; arg = 3; }
-        sP[c * PPAD + (py + 1) * LDP + px + 1] = fmaxf(m, 0.f);
-        if (sIdx != nullptr) { sIdx[i] = (unsigned char)(arg | (m > 0.f ? 4 : 0)); sE[i] = e; }
+// Patch statistics.  conv1 is linear in the image, so the train-mode BatchNorm-1 statistics and the
+// dense part of the conv1 weight gradient can be written through two data-only quantities:
+//   P[a]    = sum over (agent, pixel) of patch_a            (36 taps a = (ci, ky, kx), zero padded)
+//   R[a][b] = sum over (agent, pixel) of patch_a * patch_b  (36 x 36, symmetric)
+// mean(x1_c) = (W_c . P) / n + b_c,  E[x1_c^2] = (W_c^T R W_c + 2 b_c W_c . P) / n + b_c^2, and
+// sum x1_c * patch_a = (R W_c)_a + b_c P_a.  They depend on the crops only, so one launch serves every
+// scene-CNN forward / backward of a training iteration (G and D, three optimiser steps).
+// warp = 4x4 block of R (45 upper-triangular blocks over 8 warps), lanes = pixels.
+constexpr int NTAP = 36;
+constexpr int NBLK_R = 45;
+
+__global__ void __launch_bounds__(MGGAN_THREADS)
+scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N, double* __restrict__ R,
+                         double* __restrict__ P) {
+    extern __shared__ __align__(16) float smem[];
+    float* sImg = smem;                       // [4][35][36]
+    __shared__ int sOff[NTAP];
+    __shared__ unsigned char sBlk[NBLK_R][2];
+    if (threadIdx.x < NTAP) {
+        int a = threadIdx.x, ci = a / 9, t = a - ci * 9;
+        sOff[a] = ci * IMGPAD + (t / 3) * LDI + (t % 3);
+    }
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int A = 0; A < 9; ++A)
+            for (int B = A; B < 9; ++B) { sBlk[n][0] = (unsigned char)A; sBlk[n][1] = (unsigned char)B; ++n; }
+    }
+    for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int MAXB = (NBLK_R + 7) / 8;    // 6 blocks per warp at most
+    float acc[MAXB][16], ps[MAXB][4];         // fp32 partials over this CTA's agents (~2k terms per lane)
+#pragma unroll
+    for (int j = 0; j < MAXB; ++j) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[j][q] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ps[j][q] = 0.f;
+    }
+    __syncthreads();
+
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        const int src = rows ? rows[n] : n;
+        __syncthreads();
+        const float* ip = img + (size_t)src * CIN * IMG2;
+        for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
+            int ci = i / IMG2, p = i - ci * IMG2, y = p / IMG, x = p - y * IMG;
+            sImg[ci * IMGPAD + (y + 1) * LDI + x + 1] = __ldg(ip + i);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < MAXB; ++j) {
+            const int blk = warp + 8 * j;
+            if (blk >= NBLK_R) continue;
+            const int A = sBlk[blk][0], B = sBlk[blk][1];
+            int oa[4], ob[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { oa[q] = sOff[A * 4 + q]; ob[q] = sOff[B * 4 + q]; }
+            const bool diag = A == B;
+            for (int p = lane; p < IMG2; p += 32) {
+                const int y = p / IMG, x = p - y * IMG, base = y * LDI + x;
+                float va[4], vb[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { va[q] = sImg[base + oa[q]]; vb[q] = sImg[base + ob[q]]; }
+#pragma unroll
+                for (int qa = 0; qa < 4; ++qa)
+#pragma unroll
+                    for (int qb = 0; qb < 4; ++qb) acc[j][qa * 4 + qb] = fmaf(va[qa], vb[qb], acc[j][qa * 4 + qb]);
+                if (diag) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ps[j][q] += va[q];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXB; ++j) {
+        const int blk = warp + 8 * j;
+        if (blk >= NBLK_R) continue;
+        const int A = sBlk[blk][0], B = sBlk[blk][1];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            double v = warp_sum_d((double)acc[j][q]);
+            if (lane == 0) {
+                int a = A * 4 + q / 4, b = B * 4 + (q & 3);
+                atomicAdd(R + a * NTAP + b, v);
+                if (A != B) atomicAdd(R + b * NTAP + a, v);
+            }
+        }
+        if (A == B) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double v = warp_sum_d((double)ps[j][q]);
+                if (lane == 0) atomicAdd(P + A * 4 + q, v);
+            }
+        }
     }
 }
 
+// BatchNorm-1 statistics from the patch statistics (one thread per channel, double precision).
+__global__ void scene_bn1_from_patches_kernel(const double* __restrict__ R, const double* __restrict__ P, double count,
+                                              int C, const float* __restrict__ W, const float* __restrict__ bias,
+                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                                              long long* __restrict__ nbt, float momentum, float eps, int training,
+                                              float* __restrict__ ab, float* __restrict__ mean_istd) {
+    int c = threadIdx.x;
+    if (c < C) {
+        float mean, var;
+        if (training) {
+            const float* w = W + c * NTAP;
+            double wp = 0.0, q = 0.0;
+            for (int a = 0; a < NTAP; ++a) {
+                double rw = 0.0;
+                for (int b = 0; b < NTAP; ++b) rw += R[a * NTAP + b] * (double)w[b];
+                q += (double)w[a] * rw;
+                wp += (double)w[a] * P[a];
+            }
+            double bc = (double)bias[c];
+            double m = wp / count + bc;
+            double ex2 = (q + 2.0 * bc * wp) / count + bc * bc;
+            double v = ex2 - m * m;
+            if (v < 0.0) v = 0.0;
+            mean = (float)m; var = (float)v;
+            double unb = count > 1.0 ? v * count / (count - 1.0) : v;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+        } else {
+            mean = running_mean[c]; var = running_var[c];
+        }
+        float istd = rsqrtf(var + eps);
+        istd = istd * (1.5f - 0.5f * (var + eps) * istd * istd);
+        float a = gamma[c] * istd;
+        ab[c] = a;
+        ab[C + c] = beta[c] - mean * a;
+        mean_istd[c] = mean;
+        mean_istd[C + c] = istd;
+    }
+    if (training && threadIdx.x == 0) nbt[0] += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused forward of both conv blocks: img -> conv1 -> BN1 -> ReLU -> pool -> conv2 -> x2 (+ BN2 sums).
+// thread = pooled pixel: its 2x2 window of conv1 outputs is computed from a 4x4 register patch per input
+// channel (16 loads feed 36*C FMAs), so conv1 never touches global memory.  Optionally saves the pre-BN
+// value at the pool arg (e1) and the arg index | active bit (idx1) for the backward.
 template <int C>
-__global__ void __launch_bounds__(MGGAN_THREADS)
-scene_block2_fwd_kernel(const float* __restrict__ x1, int N, const float* __restrict__ ab1,
-                        const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ x2,
-                        double* __restrict__ stats) {
+__global__ void __launch_bounds__(MGGAN_THREADS, 2)
+scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N,
+                         const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ ab1,
+                         const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ x2,
+                         double* __restrict__ stats2, float* __restrict__ e1, unsigned char* __restrict__ idx1) {
     extern __shared__ __align__(16) float smem[];
-    float* sP = smem;                         // [C][PPAD]
-    float* sW = sP + ((C * PPAD + 3) & ~3);   // [C*9 taps][C out]
-    float* sAB = sW + 9 * C * C;              // [2C]
-    float* sred = sAB + 2 * C;                // [8][2C]
+    float* sImg = smem;                          // [4][35][36]
+    float* sW1 = sImg + CIN * IMGPAD;            // [36 taps][C]
+    float* sP = sW1 + NTAP * C;                  // [C][PPAD]
+    float* sW2 = sP + ((C * PPAD + 3) & ~3);     // [C*9 taps][C out]
+    float* sAB = sW2 + 9 * C * C;                // [2C]
+    float* sred = sAB + 2 * C;                   // [8][2C]
+    for (int i = threadIdx.x; i < NTAP * C; i += MGGAN_THREADS) {
+        int c = i / NTAP, tap = i - c * NTAP;
+        sW1[tap * C + c] = __ldg(W1 + i);
+    }
     for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
-        int co = i / (9 * C), r = i - co * 9 * C;           // r = ci*9 + tap
-        sW[r * C + co] = __ldg(W + i);
+        int co = i / (9 * C), r = i - co * 9 * C;
+        sW2[r * C + co] = __ldg(W2 + i);
     }
     if (threadIdx.x < 2 * C) sAB[threadIdx.x] = __ldg(ab1 + threadIdx.x);
-    for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) sP[i] = 0.f;    // halo stays zero
-    float bs[C], st[2 * C];
+    for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
+    for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) sP[i] = 0.f;
+    float st[2 * C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { bs[c] = __ldg(bias + c); st[c] = 0.f; st[C + c] = 0.f; }
-    const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
+    for (int c = 0; c < 2 * C; ++c) st[c] = 0.f;
+    const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
 
     for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        const int src = rows ? rows[n] : n;
         __syncthreads();
-        pool_block1<C>(x1 + (size_t)n * C * IMG2, sAB, sP, nullptr, nullptr);
+        const float* ip = img + (size_t)src * CIN * IMG2;
+        for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
+            int ci = i / IMG2, p = i - ci * IMG2, y = p / IMG, x = p - y * IMG;
+            sImg[ci * IMGPAD + (y + 1) * LDI + x + 1] = __ldg(ip + i);
+        }
         __syncthreads();
-        float acc[C];
+        {
+            float acc[4][C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = bs[c];
+            for (int c = 0; c < C; ++c) {
+                float bv = __ldg(b1 + c);
+                acc[0][c] = bv; acc[1][c] = bv; acc[2][c] = bv; acc[3][c] = bv;
+            }
+#pragma unroll 1
+            for (int ci = 0; ci < CIN; ++ci) {
+                float pt[4][4];
+                const float* bp = sImg + ci * IMGPAD + (2 * py) * LDI + 2 * px;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float2 u = *reinterpret_cast<const float2*>(bp + r * LDI);
+                    float2 v = *reinterpret_cast<const float2*>(bp + r * LDI + 2);
+                    pt[r][0] = u.x; pt[r][1] = u.y; pt[r][2] = v.x; pt[r][3] = v.y;
+                }
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float* wp = sW1 + (ci * 9 + ky * 3 + kx) * C;
+#pragma unroll
+                        for (int c = 0; c < C; c += 4) {
+                            float4 w = ld4(wp + c);
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) {
+                                const float v = pt[(d >> 1) + ky][(d & 1) + kx];
+                                acc[d][c] = fmaf(v, w.x, acc[d][c]); acc[d][c + 1] = fmaf(v, w.y, acc[d][c + 1]);
+                                acc[d][c + 2] = fmaf(v, w.z, acc[d][c + 2]); acc[d][c + 3] = fmaf(v, w.w, acc[d][c + 3]);
+                            }
+                        }
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float a = sAB[c], b = sAB[C + c];
+                float m = fmaf(a, acc[0][c], b), e = acc[0][c]; int arg = 0;
+#pragma unroll
+                for (int d = 1; d < 4; ++d) {
+                    float v = fmaf(a, acc[d][c], b);
+                    if (v > m) { m = v; e = acc[d][c]; arg = d; }
+                }
+                sP[c * PPAD + (py + 1) * LDP + px + 1] = fmaxf(m, 0.f);
+                if (e1 != nullptr) {
+                    e1[((size_t)n * C + c) * P1SQ + threadIdx.x] = e;
+                    idx1[((size_t)n * C + c) * P1SQ + threadIdx.x] = (unsigned char)(arg | (m > 0.f ? 4 : 0));
+                }
+            }
+        }
+        __syncthreads();
+        float acc2[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc2[c] = __ldg(b2 + c);
 #pragma unroll 2
         for (int ci = 0; ci < C; ++ci)
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    const float v = sP[ci * PPAD + (y + ky) * LDP + x + kx];
-                    const float* wp = sW + (ci * 9 + ky * 3 + kx) * C;
+                    const float v = sP[ci * PPAD + (py + ky) * LDP + px + kx];
+                    const float* wp = sW2 + (ci * 9 + ky * 3 + kx) * C;
 #pragma unroll
                     for (int c = 0; c < C; c += 4) {
                         float4 w = ld4(wp + c);
-                        acc[c] = fmaf(v, w.x, acc[c]); acc[c + 1] = fmaf(v, w.y, acc[c + 1]);
-                        acc[c + 2] = fmaf(v, w.z, acc[c + 2]); acc[c + 3] = fmaf(v, w.w, acc[c + 3]);
+                        acc2[c] = fmaf(v, w.x, acc2[c]); acc2[c + 1] = fmaf(v, w.y, acc2[c + 1]);
+                        acc2[c + 2] = fmaf(v, w.z, acc2[c + 2]); acc2[c + 3] = fmaf(v, w.w, acc2[c + 3]);
                     }
                 }
         float* o = x2 + (size_t)n * C * P1SQ + threadIdx.x;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            o[c * P1SQ] = acc[c];
-            st[c] += acc[c]; st[C + c] = fmaf(acc[c], acc[c], st[C + c]);
+            o[c * P1SQ] = acc2[c];
+            st[c] += acc2[c]; st[C + c] = fmaf(acc2[c], acc2[c], st[C + c]);
         }
     }
-    if (stats != nullptr) block_reduce_to_global<2 * C>(st, stats, sred);
+    if (stats2 != nullptr) block_reduce_to_global<2 * C>(st, stats2, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused backward of both conv blocks.  BN2 backward (dense dx2) -> conv2 weight / input gradients ->
+// pool / ReLU / BN1 -> sparse dy1 (kept in shared memory) -> (a) BN1 sums, (b) the sparse half of the
+// conv1 weight gradient S1[c][tap] = sum dy1 * patch_tap at the pool-arg positions.  The dense half
+// follows from the patch statistics in scene_bn1_bwd_finalize.
+template <int C>
+__global__ void __launch_bounds__(MGGAN_THREADS, 2)
+scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N,
+                         const float* __restrict__ x2, const float* __restrict__ e1,
+                         const unsigned char* __restrict__ idx1, const float* __restrict__ ab1,
+                         const float* __restrict__ mean_istd1, const float* __restrict__ ab2,
+                         const float* __restrict__ mean_istd2, const float* __restrict__ m12_2,
+                         const float* __restrict__ W2, const float* __restrict__ dy2,
+                         const unsigned char* __restrict__ idx2, float* __restrict__ dW2, float* __restrict__ dbias2,
+                         float* __restrict__ S1, double* __restrict__ sums1) {
+    constexpr int NPAIR = C * C;
+    constexpr int PG = MGGAN_THREADS / NPAIR;            // pixel-row groups for the conv2 weight gradient (1 or 4)
+    constexpr int ROWS_PG = P1 / PG;
+    constexpr int QG = MGGAN_THREADS / (C * CIN);        // pooled-pixel groups for the sparse conv1 term (4 or 8)
+    constexpr int Q_PER = P1SQ / QG;
+    extern __shared__ __align__(16) float smem[];
+    float* sDX = smem;                                   // [C][PPAD]  dx2 with zero halo
+    float* sP = sDX + C * PPAD;                          // [C][PPAD]  p1 with zero halo
+    float* sWT = sP + ((C * PPAD + 3) & ~3);             // [(co*9+tap)][ci]
+    float* sDY = sWT + 9 * C * C;                        // [C][256] dy1 (sparse values, dense layout)
+    float* sImg = sDY + C * P1SQ;                        // [4][35][36]
+    float* sPar = sImg + CIN * IMGPAD;                   // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
+    float* sred = sPar + 10 * C;                         // [8][2C]
+    unsigned char* sIdx = reinterpret_cast<unsigned char*>(sred + 8 * 2 * C);    // [C][256]
+    for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
+        int co = i / (9 * C), r = i - co * 9 * C, ci = r / 9, tap = r - ci * 9;
+        sWT[(co * 9 + tap) * C + ci] = __ldg(W2 + i);
+    }
+    if (threadIdx.x < 2 * C) {
+        sPar[threadIdx.x] = __ldg(ab1 + threadIdx.x);
+        sPar[2 * C + threadIdx.x] = __ldg(mean_istd1 + threadIdx.x);
+        sPar[4 * C + threadIdx.x] = __ldg(ab2 + threadIdx.x);
+        sPar[6 * C + threadIdx.x] = __ldg(mean_istd2 + threadIdx.x);
+        sPar[8 * C + threadIdx.x] = __ldg(m12_2 + threadIdx.x);
+    }
+    for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) { sDX[i] = 0.f; sP[i] = 0.f; }
+    for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
+    const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
+    const int pr = threadIdx.x % NPAIR, pg = threadIdx.x / NPAIR;
+    const int w_co = pr / C, w_ci = pr % C;
+    const int s_c = threadIdx.x / (CIN * QG), s_ci = (threadIdx.x / QG) % CIN, s_qg = threadIdx.x % QG;
+    float wacc[9], sacc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { wacc[i] = 0.f; sacc[i] = 0.f; }
+    float dbs[C], st[2 * C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { dbs[c] = 0.f; st[c] = 0.f; st[C + c] = 0.f; }
+
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        const int src = rows ? rows[n] : n;
+        __syncthreads();
+        {
+            const float* ip = img + (size_t)src * CIN * IMG2;
+            for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
+                int ci = i / IMG2, p = i - ci * IMG2, yy = p / IMG, xx = p - yy * IMG;
+                sImg[ci * IMGPAD + (yy + 1) * LDI + xx + 1] = __ldg(ip + i);
+            }
+            const int win = (y >> 1) * P2 + (x >> 1), loc = (y & 1) * 2 + (x & 1);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float xv = __ldg(x2 + ((size_t)n * C + c) * P1SQ + threadIdx.x);
+                float xh = (xv - sPar[6 * C + c]) * sPar[7 * C + c];
+                float d = 0.f;
+                if (idx2[((size_t)n * C + c) * P2SQ + win] == loc) d = __ldg(dy2 + ((size_t)n * C + c) * P2SQ + win);
+                float dx = sPar[4 * C + c] * (d - sPar[8 * C + c] - xh * sPar[9 * C + c]);
+                sDX[c * PPAD + (y + 1) * LDP + x + 1] = dx;
+                dbs[c] += dx;
+            }
+            for (int i = threadIdx.x; i < C * P1SQ; i += MGGAN_THREADS) {
+                int c = i >> 8, pp = i & 255;
+                float e = __ldg(e1 + (size_t)n * C * P1SQ + i);
+                sIdx[i] = idx1[(size_t)n * C * P1SQ + i];
+                sP[c * PPAD + ((pp >> 4) + 1) * LDP + (pp & 15) + 1] = fmaxf(fmaf(sPar[c], e, sPar[C + c]), 0.f);
+            }
+        }
+        __syncthreads();
+        {   // conv2 weight gradient: thread = (co, ci) x pixel-row group, 3x3 taps in registers
+            const float* dxp = sDX + w_co * PPAD;
+            const float* pp = sP + w_ci * PPAD;
+            for (int yy = pg * ROWS_PG; yy < (pg + 1) * ROWS_PG; ++yy) {
+                float c0[3], c1[3], c2[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { c0[r] = pp[(yy + r) * LDP]; c1[r] = pp[(yy + r) * LDP + 1]; }
+#pragma unroll
+                for (int xx = 0; xx < P1; ++xx) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) c2[r] = pp[(yy + r) * LDP + xx + 2];
+                    const float d = dxp[(yy + 1) * LDP + xx + 1];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        wacc[r * 3] = fmaf(d, c0[r], wacc[r * 3]);
+                        wacc[r * 3 + 1] = fmaf(d, c1[r], wacc[r * 3 + 1]);
+                        wacc[r * 3 + 2] = fmaf(d, c2[r], wacc[r * 3 + 2]);
+                        c0[r] = c1[r]; c1[r] = c2[r];
+                    }
+                }
+            }
+        }
+        {   // conv2 input gradient at this thread's pooled pixel -> pool / ReLU / BN1 -> dy1
+            float acc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll 2
+            for (int co = 0; co < C; ++co)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float d = sDX[co * PPAD + (y + 2 - ky) * LDP + x + 2 - kx];
+                        const float* wp = sWT + (co * 9 + ky * 3 + kx) * C;
+#pragma unroll
+                        for (int c = 0; c < C; c += 4) {
+                            float4 q = ld4(wp + c);
+                            acc[c] = fmaf(d, q.x, acc[c]); acc[c + 1] = fmaf(d, q.y, acc[c + 1]);
+                            acc[c + 2] = fmaf(d, q.z, acc[c + 2]); acc[c + 3] = fmaf(d, q.w, acc[c + 3]);
+                        }
+                    }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int code = sIdx[c * P1SQ + threadIdx.x];
+                const float d = (code & 4) ? acc[c] : 0.f;
+                sDY[c * P1SQ + threadIdx.x] = d;
+                const float e = __ldg(e1 + ((size_t)n * C + c) * P1SQ + threadIdx.x);
+                const float xh = (e - sPar[2 * C + c]) * sPar[3 * C + c];
+                st[c] += d;
+                st[C + c] = fmaf(d, xh, st[C + c]);
+            }
+        }
+        __syncthreads();
+        {   // sparse half of the conv1 weight gradient: thread = (c, ci, pooled-pixel group)
+            const float* ipc = sImg + s_ci * IMGPAD;
+            for (int q = s_qg * Q_PER; q < (s_qg + 1) * Q_PER; ++q) {
+                const float d = sDY[s_c * P1SQ + q];
+                if (d == 0.f) continue;
+                const int code = sIdx[s_c * P1SQ + q] & 3;
+                const float* bp = ipc + (2 * (q >> 4) + (code >> 1)) * LDI + 2 * (q & 15) + (code & 1);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) sacc[ky * 3 + kx] = fmaf(d, bp[ky * LDI + kx], sacc[ky * 3 + kx]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        atomicAdd(dW2 + ((size_t)w_co * C + w_ci) * 9 + t, wacc[t]);
+        atomicAdd(S1 + ((size_t)s_c * CIN + s_ci) * 9 + t, sacc[t]);
+    }
+    block_reduce_to_global_f<C>(dbs, dbias2, sred);
+    block_reduce_to_global<2 * C>(st, sums1, sred);
+}
+
+// BatchNorm-1 backward closed form (one thread per (channel, tap), double precision):
+//   dW1[c][a] = a_c ( S1[c][a] - m1_c P_a - m2_c istd_c ( (R W_c)_a + b_c P_a - mu_c P_a ) )
+// m1, m2: means of dy1 and dy1 * xhat1 over ALL `count` conv1 outputs (global sums when data-parallel);
+// S1, R, P are the local shard's (the gradient all-reduce adds the shards).  conv1's bias gradient is
+// identically zero under train-mode BatchNorm.
+__global__ void scene_bn1_bwd_finalize_kernel(const double* __restrict__ sums_global, const double* __restrict__ sums_local,
+                                              double count, int C, const float* __restrict__ S1,
+                                              const double* __restrict__ R, const double* __restrict__ P,
+                                              const float* __restrict__ W, const float* __restrict__ bias,
+                                              const float* __restrict__ ab1, const float* __restrict__ mean_istd1,
+                                              float* __restrict__ dW, float* __restrict__ dgamma,
+                                              float* __restrict__ dbeta) {
+    for (int i = threadIdx.x; i < C * NTAP; i += blockDim.x) {
+        const int c = i / NTAP, a = i - c * NTAP;
+        const double m1 = sums_global[c] / count, m2 = sums_global[C + c] / count;
+        const float* w = W + c * NTAP;
+        double rw = 0.0;
+        for (int b = 0; b < NTAP; ++b) rw += R[a * NTAP + b] * (double)w[b];
+        const double mu = (double)mean_istd1[c], istd = (double)mean_istd1[C + c];
+        const double corr = rw + ((double)bias[c] - mu) * P[a];
+        dW[i] = (float)((double)ab1[c] * ((double)S1[i] - m1 * P[a] - m2 * istd * corr));
+    }
+    if (threadIdx.x < C) {
+        dbeta[threadIdx.x] = (float)sums_local[threadIdx.x];
+        dgamma[threadIdx.x] = (float)sums_local[C + threadIdx.x];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -493,213 +803,13 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
     block_reduce_to_global<2 * C>(st, sums2, sred);
 }
 
-// ------------------------------------------------------------------------------------------
-// backward of pass B: BN2 backward (dense dx2) -> conv2 weight / input gradients -> sparse dy1, BN1 sums
-template <int C>
-__global__ void __launch_bounds__(MGGAN_THREADS)
-scene_block2_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int N,
-                        const float* __restrict__ ab1, const float* __restrict__ mean_istd1,
-                        const float* __restrict__ ab2, const float* __restrict__ mean_istd2,
-                        const float* __restrict__ m12_2, const float* __restrict__ W,
-                        const float* __restrict__ dy2, const unsigned char* __restrict__ idx2,
-                        float* __restrict__ dW, float* __restrict__ dbias, float* __restrict__ dy1,
-                        unsigned char* __restrict__ idx1, double* __restrict__ sums1) {
-    constexpr int NPAIR = C * C;
-    constexpr int PG = MGGAN_THREADS / NPAIR;          // pixel-row groups for the weight gradient (1 or 4)
-    constexpr int ROWS_PG = P1 / PG;
-    extern __shared__ __align__(16) float smem[];
-    float* sDX = smem;                                   // [C][PPAD]  dx2 with zero halo
-    float* sP = sDX + C * PPAD;                          // [C][PPAD]  p1 with zero halo
-    float* sWT = sP + ((C * PPAD + 3) & ~3);             // [(co*9+tap)][ci]
-    float* sE = sWT + 9 * C * C;                         // [C][256] pre-BN value at the pool arg
-    float* sPar = sE + C * P1SQ;                         // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
-    float* sred = sPar + 10 * C;                         // [8][2C]
-    unsigned char* sIdx = reinterpret_cast<unsigned char*>(sred + 8 * 2 * C);    // [C][256]
-    for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
-        int co = i / (9 * C), r = i - co * 9 * C, ci = r / 9, tap = r - ci * 9;
-        sWT[(co * 9 + tap) * C + ci] = __ldg(W + i);
-    }
-    if (threadIdx.x < 2 * C) {
-        sPar[threadIdx.x] = __ldg(ab1 + threadIdx.x);
-        sPar[2 * C + threadIdx.x] = __ldg(mean_istd1 + threadIdx.x);
-        sPar[4 * C + threadIdx.x] = __ldg(ab2 + threadIdx.x);
-        sPar[6 * C + threadIdx.x] = __ldg(mean_istd2 + threadIdx.x);
-        sPar[8 * C + threadIdx.x] = __ldg(m12_2 + threadIdx.x);
-    }
-    for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) { sDX[i] = 0.f; sP[i] = 0.f; }
-    const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
-    const int pr = threadIdx.x % NPAIR, pg = threadIdx.x / NPAIR;
-    const int w_co = pr / C, w_ci = pr % C;
-    float wacc[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) wacc[i] = 0.f;
-    float dbs[C], st[2 * C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) { dbs[c] = 0.f; st[c] = 0.f; st[C + c] = 0.f; }
 
-    for (int n = blockIdx.x; n < N; n += gridDim.x) {
-        __syncthreads();
-        // dx2 (dense) at this thread's pixel
-        {
-            const int win = (y >> 1) * P2 + (x >> 1), loc = (y & 1) * 2 + (x & 1);
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float xv = __ldg(x2 + ((size_t)n * C + c) * P1SQ + threadIdx.x);
-                float xh = (xv - sPar[6 * C + c]) * sPar[7 * C + c];
-                float d = 0.f;
-                if (idx2[((size_t)n * C + c) * P2SQ + win] == loc) d = __ldg(dy2 + ((size_t)n * C + c) * P2SQ + win);
-                float dx = sPar[4 * C + c] * (d - sPar[8 * C + c] - xh * sPar[9 * C + c]);
-                sDX[c * PPAD + (y + 1) * LDP + x + 1] = dx;
-                dbs[c] += dx;
-            }
-        }
-        pool_block1<C>(x1 + (size_t)n * C * IMG2, sPar, sP, sIdx, sE);
-        __syncthreads();
-        // conv2 weight gradient: thread = (co, ci) x pixel-row group, 3x3 taps in registers
-        {
-            const float* dxp = sDX + w_co * PPAD;
-            const float* pp = sP + w_ci * PPAD;
-            for (int yy = pg * ROWS_PG; yy < (pg + 1) * ROWS_PG; ++yy) {
-                float c0[3], c1[3], c2[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { c0[r] = pp[(yy + r) * LDP]; c1[r] = pp[(yy + r) * LDP + 1]; }
-#pragma unroll
-                for (int xx = 0; xx < P1; ++xx) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) c2[r] = pp[(yy + r) * LDP + xx + 2];
-                    const float d = dxp[(yy + 1) * LDP + xx + 1];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        wacc[r * 3] = fmaf(d, c0[r], wacc[r * 3]);
-                        wacc[r * 3 + 1] = fmaf(d, c1[r], wacc[r * 3 + 1]);
-                        wacc[r * 3 + 2] = fmaf(d, c2[r], wacc[r * 3 + 2]);
-                        c0[r] = c1[r]; c1[r] = c2[r];
-                    }
-                }
-            }
-        }
-        // conv2 input gradient at this thread's pixel -> through pool / ReLU / BN1 -> sparse dy1
-        {
-            float acc[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] = 0.f;
-#pragma unroll 2
-            for (int co = 0; co < C; ++co)
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float d = sDX[co * PPAD + (y + 2 - ky) * LDP + x + 2 - kx];
-                        const float* wp = sWT + (co * 9 + ky * 3 + kx) * C;
-#pragma unroll
-                        for (int c = 0; c < C; c += 4) {
-                            float4 q = ld4(wp + c);
-                            acc[c] = fmaf(d, q.x, acc[c]); acc[c + 1] = fmaf(d, q.y, acc[c + 1]);
-                            acc[c + 2] = fmaf(d, q.z, acc[c + 2]); acc[c + 3] = fmaf(d, q.w, acc[c + 3]);
-                        }
-                    }
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const int code = sIdx[c * P1SQ + threadIdx.x];
-                const float d = (code & 4) ? acc[c] : 0.f;
-                dy1[((size_t)n * C + c) * P1SQ + threadIdx.x] = d;
-                idx1[((size_t)n * C + c) * P1SQ + threadIdx.x] = (unsigned char)(code & 3);
-                const float xh = (sE[c * P1SQ + threadIdx.x] - sPar[2 * C + c]) * sPar[3 * C + c];
-                st[c] += d;
-                st[C + c] = fmaf(d, xh, st[C + c]);
-            }
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < 9; ++t) atomicAdd(dW + ((size_t)w_co * C + w_ci) * 9 + t, wacc[t]);
-    block_reduce_to_global_f<C>(dbs, dbias, sred);
-    block_reduce_to_global<2 * C>(st, sums1, sred);
+template <int C>
+size_t fused_fwd_smem() { return sizeof(float) * (CIN * IMGPAD + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * C + 2 * C + 8 * 2 * C); }
+template <int C>
+size_t fused_bwd_smem() {
+    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * C + C * P1SQ + CIN * IMGPAD + 10 * C + 8 * 2 * C) + C * P1SQ;
 }
-
-// ------------------------------------------------------------------------------------------
-// backward of pass A: BN1 backward (dense dx1) -> conv1 weight gradient
-template <int C>
-__global__ void __launch_bounds__(MGGAN_THREADS)
-scene_conv1_bwd_kernel(const float* __restrict__ img, const int* __restrict__ rows, const float* __restrict__ x1,
-                       int N, const float* __restrict__ ab1, const float* __restrict__ mean_istd1,
-                       const float* __restrict__ m12_1, const float* __restrict__ dy1,
-                       const unsigned char* __restrict__ idx1, float* __restrict__ dW, float* __restrict__ dbias) {
-    constexpr int NPAIR = C * CIN;
-    constexpr int PG = MGGAN_THREADS / NPAIR;            // 4 (C=16) or 8 (C=8)
-    constexpr int ROWS_PG = (IMG + PG - 1) / PG;
-    constexpr int LDX = IMG + 1;                         // 34
-    extern __shared__ __align__(16) float smem[];
-    float* sImg = smem;                        // [4][35][36]
-    float* sDX = sImg + CIN * IMGPAD;          // [C][33][34]
-    float* sPar = sDX + C * IMG * LDX;         // ab1[2C] mi1[2C] m12[2C]
-    float* sred = sPar + 6 * C;                // [8][C]
-    if (threadIdx.x < 2 * C) {
-        sPar[threadIdx.x] = __ldg(ab1 + threadIdx.x);
-        sPar[2 * C + threadIdx.x] = __ldg(mean_istd1 + threadIdx.x);
-        sPar[4 * C + threadIdx.x] = __ldg(m12_1 + threadIdx.x);
-    }
-    const int pr = threadIdx.x % NPAIR, pg = threadIdx.x / NPAIR;
-    const int w_c = pr / CIN, w_ci = pr % CIN;
-    float wacc[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) wacc[i] = 0.f;
-    float dbs[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) dbs[c] = 0.f;
-
-    for (int n = blockIdx.x; n < N; n += gridDim.x) {
-        const int src = rows ? rows[n] : n;
-        __syncthreads();
-        load_image_padded(sImg, img + (size_t)src * CIN * IMG2);
-        for (int p = threadIdx.x; p < IMG2; p += MGGAN_THREADS) {
-            const int y = p / IMG, x = p - y * IMG;
-            const bool inwin = y < 2 * P1 && x < 2 * P1;
-            const int win = (y >> 1) * P1 + (x >> 1), loc = (y & 1) * 2 + (x & 1);
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float xv = __ldg(x1 + ((size_t)n * C + c) * IMG2 + p);
-                float xh = (xv - sPar[2 * C + c]) * sPar[3 * C + c];
-                float d = 0.f;
-                if (inwin && idx1[((size_t)n * C + c) * P1SQ + win] == loc) d = __ldg(dy1 + ((size_t)n * C + c) * P1SQ + win);
-                float dx = sPar[c] * (d - sPar[4 * C + c] - xh * sPar[5 * C + c]);
-                sDX[(c * IMG + y) * LDX + x] = dx;
-                dbs[c] += dx;
-            }
-        }
-        __syncthreads();
-        {
-            const float* dxp = sDX + w_c * IMG * LDX;
-            const float* ip = sImg + w_ci * IMGPAD;
-            const int y_end = min(IMG, (pg + 1) * ROWS_PG);
-            for (int yy = pg * ROWS_PG; yy < y_end; ++yy) {
-                float c0[3], c1[3], c2[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { c0[r] = ip[(yy + r) * LDI]; c1[r] = ip[(yy + r) * LDI + 1]; }
-#pragma unroll 3
-                for (int xx = 0; xx < IMG; ++xx) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) c2[r] = ip[(yy + r) * LDI + xx + 2];
-                    const float d = dxp[yy * LDX + xx];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        wacc[r * 3] = fmaf(d, c0[r], wacc[r * 3]);
-                        wacc[r * 3 + 1] = fmaf(d, c1[r], wacc[r * 3 + 1]);
-                        wacc[r * 3 + 2] = fmaf(d, c2[r], wacc[r * 3 + 2]);
-                        c0[r] = c1[r]; c1[r] = c2[r];
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < 9; ++t) atomicAdd(dW + ((size_t)w_c * CIN + w_ci) * 9 + t, wacc[t]);
-    block_reduce_to_global_f<C>(dbs, dbias, sred);
-}
-
-template <int C>
-size_t conv1_fwd_smem() { return sizeof(float) * (CIN * IMGPAD + 36 * C + 8 * 2 * C); }
-template <int C>
-size_t block2_fwd_smem() { return sizeof(float) * (((C * PPAD + 3) & ~3) + 9 * C * C + 2 * C + 8 * 2 * C); }
 template <int C>
 size_t attn_w_floats() { return 2 * AH * C + AH + C + 2 * C; }
 template <int C>
@@ -708,12 +818,6 @@ template <int C>
 size_t attn_bwd_smem() {
     return sizeof(float) * (attn_w_floats<C>() + 2 * MGGAN_THREADS * (C + 4) + 2 * MGGAN_THREADS * (AH + 4) + 2 * C + 8 * 2 * C);
 }
-template <int C>
-size_t block2_bwd_smem() {
-    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * C + C * P1SQ + 10 * C + 8 * 2 * C) + C * P1SQ;
-}
-template <int C>
-size_t conv1_bwd_smem() { return sizeof(float) * (CIN * IMGPAD + C * IMG * (IMG + 1) + 6 * C + 8 * C); }
 
 int agent_grid(int N, int per_sm) {
     int g = sm_count() * per_sm;
@@ -727,18 +831,22 @@ int agent_grid(int N, int per_sm) {
     } while (0)
 
 template <int C>
-int conv1_fwd(const float* img, const int* rows, int N, const float* W, const float* b, float* x1, double* stats, cudaStream_t s) {
-    size_t sm = conv1_fwd_smem<C>();
-    cudaFuncSetAttribute(scene_conv1_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    scene_conv1_fwd_kernel<C><<<agent_grid(N, 4), MGGAN_THREADS, sm, s>>>(img, rows, N, W, b, x1, stats);
-    return mggan_check_launch("scene_conv1_fwd");
+int fused_fwd(const float* img, const int* rows, int N, const float* W1, const float* b1, const float* ab1, const float* W2,
+              const float* b2, float* x2, double* stats2, float* e1, unsigned char* idx1, cudaStream_t s) {
+    size_t sm = fused_fwd_smem<C>();
+    cudaFuncSetAttribute(scene_fused12_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    scene_fused12_fwd_kernel<C><<<agent_grid(N, 2), MGGAN_THREADS, sm, s>>>(img, rows, N, W1, b1, ab1, W2, b2, x2, stats2, e1, idx1);
+    return mggan_check_launch("scene_fused12_fwd");
 }
 template <int C>
-int block2_fwd(const float* x1, int N, const float* ab1, const float* W, const float* b, float* x2, double* stats, cudaStream_t s) {
-    size_t sm = block2_fwd_smem<C>();
-    cudaFuncSetAttribute(scene_block2_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    scene_block2_fwd_kernel<C><<<agent_grid(N, 4), MGGAN_THREADS, sm, s>>>(x1, N, ab1, W, b, x2, stats);
-    return mggan_check_launch("scene_block2_fwd");
+int fused_bwd(const float* img, const int* rows, int N, const float* x2, const float* e1, const unsigned char* idx1,
+              const float* ab1, const float* mi1, const float* ab2, const float* mi2, const float* m12_2, const float* W2,
+              const float* dy2, const unsigned char* idx2, float* dW2, float* db2, float* S1, double* sums1, cudaStream_t s) {
+    size_t sm = fused_bwd_smem<C>();
+    cudaFuncSetAttribute(scene_fused12_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    scene_fused12_bwd_kernel<C><<<agent_grid(N, 2), MGGAN_THREADS, sm, s>>>(img, rows, N, x2, e1, idx1, ab1, mi1, ab2, mi2, m12_2,
+                                                                          W2, dy2, idx2, dW2, db2, S1, sums1);
+    return mggan_check_launch("scene_fused12_bwd");
 }
 template <int C>
 int attn_fwd(const float* x2, int N, const float* ab2, const float* Wa1, const float* ba1, const float* Wa2, const float* ba2,
@@ -761,32 +869,26 @@ int attn_bwd(const float* x2, int N, const float* ab2, const float* mi2, const f
                                                                           dba1, dWa2, dba2, dy2, idx2, sums2);
     return mggan_check_launch("scene_attn_bwd");
 }
-template <int C>
-int block2_bwd(const float* x1, const float* x2, int N, const float* ab1, const float* mi1, const float* ab2, const float* mi2,
-               const float* m12_2, const float* W, const float* dy2, const unsigned char* idx2, float* dW, float* db,
-               float* dy1, unsigned char* idx1, double* sums1, cudaStream_t s) {
-    size_t sm = block2_bwd_smem<C>();
-    cudaFuncSetAttribute(scene_block2_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    scene_block2_bwd_kernel<C><<<agent_grid(N, 2), MGGAN_THREADS, sm, s>>>(x1, x2, N, ab1, mi1, ab2, mi2, m12_2, W, dy2, idx2,
-                                                                           dW, db, dy1, idx1, sums1);
-    return mggan_check_launch("scene_block2_bwd");
-}
-template <int C>
-int conv1_bwd(const float* img, const int* rows, const float* x1, int N, const float* ab1, const float* mi1, const float* m12_1,
-              const float* dy1, const unsigned char* idx1, float* dW, float* db, cudaStream_t s) {
-    size_t sm = conv1_bwd_smem<C>();
-    cudaFuncSetAttribute(scene_conv1_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    scene_conv1_bwd_kernel<C><<<agent_grid(N, 2), MGGAN_THREADS, sm, s>>>(img, rows, x1, N, ab1, mi1, m12_1, dy1, idx1, dW, db);
-    return mggan_check_launch("scene_conv1_bwd");
-}
 
 }  // namespace
 
-extern "C" int mggan_scene_conv1_fwd(const float* img, const int* rows, int N, int C, const float* W, const float* bias,
-                                     float* x1, double* stats, cudaStream_t stream) {
+extern "C" int mggan_scene_patch_stats(const float* img, const int* rows, int N, double* R, double* P,
+                                       cudaStream_t stream) {
     if (N <= 0) return MGGAN_OK;
-    SCENE_DISPATCH(C, return conv1_fwd<16>(img, rows, N, W, bias, x1, stats, stream),
-                   return conv1_fwd<8>(img, rows, N, W, bias, x1, stats, stream));
+    size_t sm = sizeof(float) * CIN * IMGPAD;
+    scene_patch_stats_kernel<<<agent_grid(N, 2), MGGAN_THREADS, sm, stream>>>(img, rows, N, R, P);
+    return mggan_check_launch("scene_patch_stats");
+}
+
+extern "C" int mggan_scene_bn1_from_patches(const double* R, const double* P, double count, int C, const float* W,
+                                            const float* bias, const float* gamma, const float* beta,
+                                            float* running_mean, float* running_var, long long* num_batches_tracked,
+                                            float momentum, float eps, int training, float* ab, float* mean_istd,
+                                            cudaStream_t stream) {
+    MGGAN_REQUIRE(C >= 1 && C <= 32, "mggan_scene_bn1_from_patches: C=%d", C);
+    scene_bn1_from_patches_kernel<<<1, 32, 0, stream>>>(R, P, count, C, W, bias, gamma, beta, running_mean, running_var,
+                                                        num_batches_tracked, momentum, eps, training, ab, mean_istd);
+    return mggan_check_launch("scene_bn1_from_patches");
 }
 
 extern "C" int mggan_scene_bn_finalize(const double* stats, double count, int C, const float* gamma, const float* beta,
@@ -806,11 +908,13 @@ extern "C" int mggan_scene_bn_bwd_finalize(const double* sums, double count, int
     return mggan_check_launch("scene_bn_bwd_finalize");
 }
 
-extern "C" int mggan_scene_block2_fwd(const float* x1, int N, int C, const float* ab1, const float* W, const float* bias,
-                                      float* x2, double* stats, cudaStream_t stream) {
+extern "C" int mggan_scene_fused12_fwd(const float* img, const int* rows, int N, int C, const float* W1, const float* b1,
+                                       const float* ab1, const float* W2, const float* b2, float* x2, double* stats2,
+                                       float* e1, unsigned char* idx1, cudaStream_t stream) {
     if (N <= 0) return MGGAN_OK;
-    SCENE_DISPATCH(C, return block2_fwd<16>(x1, N, ab1, W, bias, x2, stats, stream),
-                   return block2_fwd<8>(x1, N, ab1, W, bias, x2, stats, stream));
+    MGGAN_REQUIRE((e1 == nullptr) == (idx1 == nullptr), "mggan_scene_fused12_fwd: e1 and idx1 must both be set or both NULL");
+    SCENE_DISPATCH(C, return fused_fwd<16>(img, rows, N, W1, b1, ab1, W2, b2, x2, stats2, e1, idx1, stream),
+                   return fused_fwd<8>(img, rows, N, W1, b1, ab1, W2, b2, x2, stats2, e1, idx1, stream));
 }
 
 extern "C" int mggan_scene_attn_fwd(const float* x2, int N, int C, const float* ab2, const float* Wa1, const float* ba1,
@@ -829,20 +933,22 @@ extern "C" int mggan_scene_attn_bwd(const float* x2, int N, int C, const float* 
                    return attn_bwd<8>(x2, N, ab2, mean_istd2, Wa1, ba1, Wa2, ba2, dout, dWa1, dba1, dWa2, dba2, dy2, idx2, sums2, stream));
 }
 
-extern "C" int mggan_scene_block2_bwd(const float* x1, const float* x2, int N, int C, const float* ab1,
-                                      const float* mean_istd1, const float* ab2, const float* mean_istd2,
-                                      const float* m12_2, const float* W, const float* dy2, const unsigned char* idx2,
-                                      float* dW, float* dbias, float* dy1, unsigned char* idx1, double* sums1,
-                                      cudaStream_t stream) {
+extern "C" int mggan_scene_fused12_bwd(const float* img, const int* rows, int N, int C, const float* x2, const float* e1,
+                                       const unsigned char* idx1, const float* ab1, const float* mean_istd1,
+                                       const float* ab2, const float* mean_istd2, const float* m12_2, const float* W2,
+                                       const float* dy2, const unsigned char* idx2, float* dW2, float* dbias2, float* S1,
+                                       double* sums1, cudaStream_t stream) {
     if (N <= 0) return MGGAN_OK;
-    SCENE_DISPATCH(C, return block2_bwd<16>(x1, x2, N, ab1, mean_istd1, ab2, mean_istd2, m12_2, W, dy2, idx2, dW, dbias, dy1, idx1, sums1, stream),
-                   return block2_bwd<8>(x1, x2, N, ab1, mean_istd1, ab2, mean_istd2, m12_2, W, dy2, idx2, dW, dbias, dy1, idx1, sums1, stream));
+    SCENE_DISPATCH(C, return fused_bwd<16>(img, rows, N, x2, e1, idx1, ab1, mean_istd1, ab2, mean_istd2, m12_2, W2, dy2, idx2, dW2, dbias2, S1, sums1, stream),
+                   return fused_bwd<8>(img, rows, N, x2, e1, idx1, ab1, mean_istd1, ab2, mean_istd2, m12_2, W2, dy2, idx2, dW2, dbias2, S1, sums1, stream));
 }
 
-extern "C" int mggan_scene_conv1_bwd(const float* img, const int* rows, const float* x1, int N, int C, const float* ab1,
-                                     const float* mean_istd1, const float* m12_1, const float* dy1,
-                                     const unsigned char* idx1, float* dW, float* dbias, cudaStream_t stream) {
-    if (N <= 0) return MGGAN_OK;
-    SCENE_DISPATCH(C, return conv1_bwd<16>(img, rows, x1, N, ab1, mean_istd1, m12_1, dy1, idx1, dW, dbias, stream),
-                   return conv1_bwd<8>(img, rows, x1, N, ab1, mean_istd1, m12_1, dy1, idx1, dW, dbias, stream));
+extern "C" int mggan_scene_bn1_bwd_finalize(const double* sums_global, const double* sums_local, double count, int C,
+                                            const float* S1, const double* R, const double* P, const float* W,
+                                            const float* bias, const float* ab1, const float* mean_istd1, float* dW,
+                                            float* dgamma, float* dbeta, cudaStream_t stream) {
+    MGGAN_REQUIRE(C >= 1 && C <= 32, "mggan_scene_bn1_bwd_finalize: C=%d", C);
+    scene_bn1_bwd_finalize_kernel<<<1, 256, 0, stream>>>(sums_global, sums_local, count, C, S1, R, P, W, bias, ab1,
+                                                         mean_istd1, dW, dgamma, dbeta);
+    return mggan_check_launch("scene_bn1_bwd_finalize");
 }

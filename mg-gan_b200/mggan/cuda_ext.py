@@ -43,14 +43,15 @@ SIGNATURES = {
     "mggan_decoder_bwd": "ipppppppipppppppppiippppppppppppppppps",
     "mggan_social_attn_fwd": "ppipppipppppps",
     "mggan_social_attn_bwd": "ppipppippppppppppppps",
-    "mggan_scene_conv1_fwd": "ppiipppps",
+    "mggan_scene_patch_stats": "ppipps",
+    "mggan_scene_bn1_from_patches": "ppdipppppppffipps",
+    "mggan_scene_fused12_fwd": "ppiippppppppps",
     "mggan_scene_bn_finalize": "pdipppppffipps",
-    "mggan_scene_block2_fwd": "piippppps",
     "mggan_scene_attn_fwd": "piipppppps",
     "mggan_scene_attn_bwd": "piipppppppppppppps",
     "mggan_scene_bn_bwd_finalize": "pdippps",
-    "mggan_scene_block2_bwd": "ppiippppppppppppps",
-    "mggan_scene_conv1_bwd": "pppiippppppps",
+    "mggan_scene_fused12_bwd": "ppiippppppppppppppps",
+    "mggan_scene_bn1_bwd_finalize": "ppdipppppppppps",
     "mggan_l2_scene_min": "ppiiipifppps",
     "mggan_bce_scalar_label": "pifppfpps",
     "mggan_ce_generators": "piippfpps",

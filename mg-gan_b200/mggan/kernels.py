@@ -178,54 +178,84 @@ def _allreduce(t, group):
         dist.all_reduce(t, group=group)
 
 
+class PatchStats:
+    """Data-only statistics of a batch of crops (R 36x36, P 36; see csrc/scene.cu), computed once and
+    shared by every scene-CNN forward / backward that sees the same `img` tensor (and row selection)."""
+    _cache = []          # [(weakref(img), version, rows_key, PatchStats)]
+
+    def __init__(self, img, rows, group):
+        dev = img.device
+        n = int(rows.numel()) if rows is not None else img.shape[0]
+        buf = torch.zeros(36 * 36 + 36 + 1, device=dev, dtype=torch.float64)
+        self.buf = buf
+        self.R_local, self.P_local = buf[:1296], buf[1296:1332]
+        call("mggan_scene_patch_stats", ptr(img), ptr(rows), n, ptr(self.R_local), ptr(self.P_local))
+        buf[1332] = float(n)
+        if group is not None:
+            g = buf.clone()
+            _allreduce(g, group)
+            self.R, self.P = g[:1296], g[1296:1332]
+            self.n_total = float(g[1332].item())
+        else:
+            self.R, self.P, self.n_total = self.R_local, self.P_local, float(n)
+
+    @classmethod
+    def get(cls, img, rows, rows_key, group):
+        import weakref
+        for ref, ver, rk, ps in cls._cache:
+            if ref() is img and ver == img._version and rk == rows_key:
+                return ps
+        ps = PatchStats(img, rows, group)
+        cls._cache.append((weakref.ref(img), img._version, rows_key, ps))
+        cls._cache[:] = [e for e in cls._cache if e[0]() is not None][-4:]
+        return ps
+
+
 class _SceneAttn(torch.autograd.Function):
     """AttentionGlobal.forward.  Non-tensor state: the two BatchNorm modules (running buffers are
     updated in place, like nn.BatchNorm2d in train mode), `rows` (int32 gather or None), training
     flag and the process group whose ranks share BatchNorm statistics (None = local)."""
 
     @staticmethod
-    def forward(ctx, img, c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b, bn1, bn2, rows, training, group, grad_on):
-        img = _f32(img)
+    def forward(ctx, img, c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b, bn1, bn2, rows, rows_key,
+                training, group, grad_on):
         ws = [_f32(t) for t in (c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b)]
         c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b = ws
+        assert img.dtype == torch.float32 and img.is_contiguous()
         dev = img.device
         C = c1w.shape[0]
         N = int(rows.numel()) if rows is not None else img.shape[0]
-        x1 = torch.empty(N, C, 33, 33, device=dev, dtype=torch.float32)
+        need = grad_on and any(ctx.needs_input_grad)
         x2 = torch.empty(N, C, 16, 16, device=dev, dtype=torch.float32)
         out = torch.empty(N, 64, device=dev, dtype=torch.float32)
         ab1, mi1 = torch.empty(2 * C, device=dev), torch.empty(2 * C, device=dev)
         ab2, mi2 = torch.empty(2 * C, device=dev), torch.empty(2 * C, device=dev)
         tr = 1 if training else 0
-        n_glob = torch.tensor([float(N)], device=dev, dtype=torch.float64) if group is not None else None
-        if n_glob is not None:
-            _allreduce(n_glob, group)
-            n_total = float(n_glob.item())
-        else:
-            n_total = float(N)
-        st1 = torch.zeros(2 * C, device=dev, dtype=torch.float64) if training else None
-        call("mggan_scene_conv1_fwd", ptr(img), ptr(rows), N, C, ptr(c1w), ptr(c1b), ptr(x1), ptr(st1))
-        if training:
-            _allreduce(st1, group)
-        call("mggan_scene_bn_finalize", ptr(st1), n_total * 33 * 33, C, ptr(g1), ptr(be1), ptr(bn1.running_mean),
-             ptr(bn1.running_var), ptr(bn1.num_batches_tracked), BN_MOMENTUM, BN_EPS, tr, ptr(ab1), ptr(mi1))
+        ps = PatchStats.get(img, rows, rows_key, group) if training else None
+        n_total = ps.n_total if ps is not None else float(N)
+        call("mggan_scene_bn1_from_patches", ptr(ps.R) if ps else None, ptr(ps.P) if ps else None, n_total * 1089.0, C,
+             ptr(c1w), ptr(c1b), ptr(g1), ptr(be1), ptr(bn1.running_mean), ptr(bn1.running_var),
+             ptr(bn1.num_batches_tracked), BN_MOMENTUM, BN_EPS, tr, ptr(ab1), ptr(mi1))
         st2 = torch.zeros(2 * C, device=dev, dtype=torch.float64) if training else None
-        call("mggan_scene_block2_fwd", ptr(x1), N, C, ptr(ab1), ptr(c2w), ptr(c2b), ptr(x2), ptr(st2))
+        e1 = torch.empty(N, C, 256, device=dev, dtype=torch.float32) if need else None
+        idx1 = torch.empty(N, C, 256, device=dev, dtype=torch.uint8) if need else None
+        call("mggan_scene_fused12_fwd", ptr(img), ptr(rows), N, C, ptr(c1w), ptr(c1b), ptr(ab1), ptr(c2w), ptr(c2b),
+             ptr(x2), ptr(st2), ptr(e1), ptr(idx1))
         if training:
             _allreduce(st2, group)
-        call("mggan_scene_bn_finalize", ptr(st2), n_total * 16 * 16, C, ptr(g2), ptr(be2), ptr(bn2.running_mean),
+        call("mggan_scene_bn_finalize", ptr(st2), n_total * 256.0, C, ptr(g2), ptr(be2), ptr(bn2.running_mean),
              ptr(bn2.running_var), ptr(bn2.num_batches_tracked), BN_MOMENTUM, BN_EPS, tr, ptr(ab2), ptr(mi2))
         call("mggan_scene_attn_fwd", ptr(x2), N, C, ptr(ab2), ptr(a0w), ptr(a0b), ptr(a2w), ptr(a2b), ptr(out))
-        if grad_on and any(ctx.needs_input_grad):
+        if need:
             assert training, "scene-attention backward needs train-mode BatchNorm (batch statistics)"
-            ctx.save_for_backward(img, c1w, c2w, a0w, a0b, a2w, a2b, x1, x2, ab1, mi1, ab2, mi2)
-            ctx.rows, ctx.group, ctx.n_total, ctx.N, ctx.C = rows, group, n_total, N, C
+            ctx.save_for_backward(img, c1w, c1b, c2w, a0w, a0b, a2w, a2b, x2, e1, idx1, ab1, mi1, ab2, mi2)
+            ctx.rows, ctx.group, ctx.n_total, ctx.N, ctx.C, ctx.ps = rows, group, n_total, N, C, ps
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        img, c1w, c2w, a0w, a0b, a2w, a2b, x1, x2, ab1, mi1, ab2, mi2 = ctx.saved_tensors
-        N, C, dev, group = ctx.N, ctx.C, img.device, ctx.group
+        img, c1w, c1b, c2w, a0w, a0b, a2w, a2b, x2, e1, idx1, ab1, mi1, ab2, mi2 = ctx.saved_tensors
+        N, C, dev, group, ps = ctx.N, ctx.C, img.device, ctx.group, ctx.ps
         dout = _f32(dout)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, device=dev, dtype=dt)
         da0w, da0b, da2w, da2b = z(32, C), z(32), z(C, 32), z(C)
@@ -234,37 +264,38 @@ class _SceneAttn(torch.autograd.Function):
         sums2 = z(2 * C, dt=torch.float64)
         call("mggan_scene_attn_bwd", ptr(x2), N, C, ptr(ab2), ptr(mi2), ptr(a0w), ptr(a0b), ptr(a2w), ptr(a2b),
              ptr(dout), ptr(da0w), ptr(da0b), ptr(da2w), ptr(da2b), ptr(dy2), ptr(idx2), ptr(sums2))
-        # BatchNorm affine gradients are plain sums over the local shard; the means use global sums
+        # BatchNorm affine gradients are sums over the local shard; the means use global sums
         m12_2, dg2, db2 = torch.empty(2 * C, device=dev), z(C), z(C)
         loc2 = sums2.clone() if group is not None else sums2
         _allreduce(sums2, group)
-        call("mggan_scene_bn_bwd_finalize", ptr(sums2), ctx.n_total * 256, C, ptr(m12_2), ptr(dg2), ptr(db2))
-        dc2w, dc2b = z(C, C, 3, 3), z(C)
-        dy1 = torch.empty(N, C, 256, device=dev)
-        idx1 = torch.empty(N, C, 256, device=dev, dtype=torch.uint8)
-        sums1 = z(2 * C, dt=torch.float64)
-        call("mggan_scene_block2_bwd", ptr(x1), ptr(x2), N, C, ptr(ab1), ptr(mi1), ptr(ab2), ptr(mi2), ptr(m12_2),
-             ptr(c2w), ptr(dy2), ptr(idx2), ptr(dc2w), ptr(dc2b), ptr(dy1), ptr(idx1), ptr(sums1))
-        m12_1, dg1, db1 = torch.empty(2 * C, device=dev), z(C), z(C)
-        loc1 = sums1.clone() if group is not None else sums1
-        _allreduce(sums1, group)
-        call("mggan_scene_bn_bwd_finalize", ptr(sums1), ctx.n_total * 1089, C, ptr(m12_1), ptr(dg1), ptr(db1))
-        dc1w, dc1b = z(C, 4, 3, 3), z(C)
-        call("mggan_scene_conv1_bwd", ptr(img), ptr(ctx.rows), ptr(x1), N, C, ptr(ab1), ptr(mi1), ptr(m12_1), ptr(dy1),
-             ptr(idx1), ptr(dc1w), ptr(dc1b))
-        if group is not None:          # keep the shard-local part: the gradient all-reduce sums shards later
+        call("mggan_scene_bn_bwd_finalize", ptr(sums2), ctx.n_total * 256.0, C, ptr(m12_2), ptr(dg2), ptr(db2))
+        if group is not None:
             dg2, db2 = loc2[C:].float(), loc2[:C].float()
-            dg1, db1 = loc1[C:].float(), loc1[:C].float()
-        return (None, dc1w, dc1b, dg1, db1, dc2w, dc2b, dg2, db2, da0w, da0b, da2w, da2b, None, None, None, None, None, None)
+        dc2w, dc2b, S1 = z(C, C, 3, 3), z(C), z(C, 36)
+        sums1 = z(2 * C, dt=torch.float64)
+        call("mggan_scene_fused12_bwd", ptr(img), ptr(ctx.rows), N, C, ptr(x2), ptr(e1), ptr(idx1), ptr(ab1), ptr(mi1),
+             ptr(ab2), ptr(mi2), ptr(m12_2), ptr(c2w), ptr(dy2), ptr(idx2), ptr(dc2w), ptr(dc2b), ptr(S1), ptr(sums1))
+        glob1 = sums1
+        if group is not None:
+            glob1 = sums1.clone()
+            _allreduce(glob1, group)
+        dc1w, dg1, db1 = torch.empty(C, 4, 3, 3, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev)
+        call("mggan_scene_bn1_bwd_finalize", ptr(glob1), ptr(sums1), ctx.n_total * 1089.0, C, ptr(S1), ptr(ps.R_local),
+             ptr(ps.P_local), ptr(c1w), ptr(c1b), ptr(ab1), ptr(mi1), ptr(dc1w), ptr(dg1), ptr(db1))
+        dc1b = z(C)             # identically zero under train-mode BatchNorm
+        return (None, dc1w, dc1b, dg1, db1, dc2w, dc2b, dg2, db2, da0w, da0b, da2w, da2b) + (None,) * 7
 
 
-def scene_attention(img, mod, rows=None, group=None):
-    """mod: an AttentionGlobal parameter container (mggan.model.modules.cnn)."""
+def scene_attention(img, mod, rows=None, group=None, rows_key=None):
+    """mod: an AttentionGlobal parameter container (mggan.model.modules.cnn).  `rows_key`: hashable
+    identity of the row selection (None = all rows), part of the patch-statistics cache key."""
     b1, b2 = mod.CNN.encoder.ConvBlock_1.Block, mod.CNN.encoder.ConvBlock_2.Block
     a = mod.cnn_attention
+    if img.dtype != torch.float32 or not img.is_contiguous():
+        img = img.float().contiguous()
     return _SceneAttn.apply(img, b1.Conv_1.weight, b1.Conv_1.bias, b1.BN_1.weight, b1.BN_1.bias,
                             b2.Conv_1.weight, b2.Conv_1.bias, b2.BN_1.weight, b2.BN_1.bias,
-                            a[0].weight, a[0].bias, a[2].weight, a[2].bias, b1.BN_1, b2.BN_1, rows,
+                            a[0].weight, a[0].bias, a[2].weight, a[2].bias, b1.BN_1, b2.BN_1, rows, rows_key,
                             mod.training, group, torch.is_grad_enabled())
 
 

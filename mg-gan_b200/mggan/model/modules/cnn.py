@@ -49,6 +49,9 @@ class AttentionGlobal(nn.Module):
                                            nn.Linear(mlp_dim, channels_cnn))
         self.stat_group = None          # process group sharing BatchNorm statistics (data-parallel runs)
 
-    def forward(self, features, rows=None):
-        """features (N,4,33,33) -> (N,64).  `rows` (int32) gathers image rows without copying them."""
-        return K.scene_attention(features, self, rows, self.stat_group)
+    def forward(self, features, rows=None, rows_key=None):
+        """features (N,4,33,33) -> (N,64).  `rows` (int32) gathers image rows without copying them;
+        `rows_key` identifies that selection for the per-batch patch-statistics cache."""
+        if rows is not None and rows_key is None:
+            rows_key = ("rows", rows.data_ptr(), rows._version, int(rows.numel()))
+        return K.scene_attention(features, self, rows, self.stat_group, rows_key)

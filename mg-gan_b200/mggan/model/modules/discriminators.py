@@ -90,10 +90,11 @@ class MultiDiscriminatorTrajectory(nn.Module):
         if mask is not None:
             classifier_inp = classifier_inp[mask.repeat(n_samples)]
         if img is not None:
-            rows = None
+            rows, rows_key = None, None
             if mask is not None:
                 rows = torch.nonzero(mask).flatten().to(torch.int32)
-            scene = self.scene_encoder(img, rows)
+                rows_key = ("mask", id(mask), mask._version)
+            scene = self.scene_encoder(img, rows, rows_key)
             classifier_inp = torch.cat([classifier_inp, scene.repeat(n_samples, 1)], 1)
         output = self._mlp2(self.discs[0], classifier_inp, K.ACT_SIGMOID_EPS)       # sigmoid * (1 - 2 eps) + eps
         if not return_all:
