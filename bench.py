@@ -66,6 +66,39 @@ def algorithmic_bytes_per_iter(n_agents, with_img, pg, pd, pm):
     return 3 * n_agents * (TRAJ_BYTES + (IMG_BYTES if with_img else 0)) + 28 * (pd + pg + pm)
 
 
+def algorithmic_flops_per_iter(N, P, k, G):
+    """SURVEY.md 8d MAC counts (x2): D step, G step, PM step of one iteration; P = sum of n_s^2 in-scene pairs."""
+    d_fwd = lambda kk: N * (233344 + 493856 + 4096) + P * (6240 + 128) + kk * N * (3584 + 18528 + 18432 + 96 * G)
+    pm = N * (128 * 16 + 256 + 16 * G)
+    trunk = N * (43232 + 1282624 + 1024) + P * (4192 + 64) + pm
+    dec = lambda seqs: seqs * (136 * 32 + 86784)
+    d_step = 2 * 3 * d_fwd(1) + trunk + dec(N)
+    g_step = 3 * (trunk - pm) + pm + 3 * dec(k * N) + 2 * d_fwd(k)
+    pm_step = 3 * trunk + dec(G * N)
+    return 2.0 * (d_step + g_step + pm_step)
+
+
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4: 148 SMs x 128 FMA lanes x 2 flop x max SM clock
+
+# Algorithmic (compulsory-input) bytes per unit of each kernel that can dominate the step (DESIGN.md section 4):
+# scene kernels read one (4,33,33) fp32 crop per agent; decoder / encoder kernels read the trajectory bytes.
+KERNEL_UNIT_BYTES = {
+    "mggan_scene_fused12_bwd": ("agent crop", IMG_BYTES), "mggan_scene_fused12_fwd": ("agent crop", IMG_BYTES),
+    "mggan_scene_patch_stats": ("agent crop", IMG_BYTES),
+    "mggan_decoder_fwd": ("agent trajectory", TRAJ_BYTES), "mggan_decoder_bwd": ("agent trajectory", TRAJ_BYTES),
+    "mggan_lstm_seq_fwd": ("agent trajectory", TRAJ_BYTES), "mggan_lstm_seq_bwd": ("agent trajectory", TRAJ_BYTES),
+}
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` summary (profiles/ncu_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -173,28 +206,37 @@ def run_ours(a):
         tr.net_chooser_step(devb["in_xy"], devb["in_dxdy"], devb["gt_xy"], devb["gt_dxdy"], sse, metrics, None, devb["features"])
         metrics.clear()
 
-    def step_e2e():
+    loss_ring = torch.empty(max(a.steps, a.warmup, 3), 8, dtype=torch.float32).pin_memory()
+
+    def run_e2e(n):
+        """n iterations through the public loop API with HOST (pinned) batches: the H2D copy of every step's
+        inputs (prefetched on a copy stream while the previous step computes) and an asynchronous D2H of the
+        step's loss scalars are inside the timed region."""
         m = defaultdict(list)
-        tr.train_iteration(host, m)                  # H2D of the batch from pinned memory inside
-        vals = torch.stack([m[k][-1].float().reshape(()) for k in sorted(m) if k.startswith("train/")])
-        return vals.cpu()                            # D2H of the step's loss scalars
+
+        def read_back(i, mm):
+            keys = sorted(kk for kk in mm if kk.startswith("train/"))
+            vals = torch.stack([mm[kk][-1].float().reshape(()) for kk in keys])
+            loss_ring[i, :vals.numel()].copy_(vals, non_blocking=True)
+            mm.clear()
+
+        tr.train_iterations((host for _ in range(n)), m, on_step=read_back)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, only=None):
-        for _ in range(warmup):
-            fn()
+    def timed(run, steps, warmup, only=None):
+        """run(n) enqueues n steps."""
+        run(warmup)
         barrier()
         l0 = cuda_ext.launch_count
         if only:
             cuda_ext.profile_start(only=only)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        run(steps)
         e1.record()
         barrier()
         prof = cuda_ext.profile_stop() if only else {}
@@ -202,6 +244,10 @@ def run_ours(a):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps, (cuda_ext.launch_count - l0) // steps, prof
+
+    def run_resident(n):
+        for _ in range(n):
+            step_resident()
 
     # ---- per-kernel breakdown (untimed pass) -> dominant kernel
     for _ in range(max(1, min(a.warmup, 2))):
@@ -219,29 +265,39 @@ def run_ours(a):
 
     # ---- device-resident timing (value) with the dominant kernel's launches timed by events
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_step, launches, dprof = timed(step_resident, a.steps, max(a.warmup, 3), only=[dom])
+    ms_step, launches, dprof = timed(run_resident, a.steps, max(a.warmup, 3), only=[dom])
     dom_prof = dprof.get(dom, (0, 0.0))
     clocks = sampler.stop() if sampler else None
 
     # ---- end-to-end through the public API with host buffers
     e2e = None
     if not a.no_e2e:
-        ms_e2e, _, _ = timed(step_e2e, a.steps, max(a.warmup, 3))
+        ms_e2e, _, _ = timed(run_e2e, a.steps, max(a.warmup, 3))
         h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "seq_start_end")
         e2e = {"value": 20.0 * n_total / (ms_e2e / 1e3), "unit": "agent-timesteps/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 6 * 4}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 6 * 4,
+               "api": "PiNetMultiGeneratorGAN.train_iterations(host batches): H2D of step i+1 overlaps step i"}
 
     hbm_peak, peak_kind = peaks()
     b_iter = algorithmic_bytes_per_iter(n_local, True, pg, pd, pm)
     dom_calls, dom_ms = dom_prof
     dom_avg_ms = dom_ms / max(dom_calls, 1)
-    # algorithmic bytes attributed to one launch of the dominant kernel: the iteration's compulsory traffic
-    #  split over launches in proportion to device time is NOT used; the whole-iteration figure is
-    # reported against the whole step and the kernel's own share is given beside it (DESIGN.md "Roofline").
-    roof = {"bound": "hbm", "kernel": dom, "kernel_avg_ms": dom_avg_ms, "kernel_share_of_step": (dom_ms / a.steps) / ms_step if ms_step else None,
-            "achieved": b_iter / (ms_step / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": b_iter / (ms_step / 1e3) / 1e9 / hbm_peak, "peak_source": peak_kind, "traffic": None,
-            "algorithmic_bytes_per_step": int(b_iter)}
+    # dominant kernel: algorithmic bytes per launch = per-unit figure x units of one launch (every launch of the
+    # scene / encoder kernels covers all n_local agents), over its average launch duration (CUDA events, timed region)
+    unit_name, unit_bytes = KERNEL_UNIT_BYTES.get(dom, ("agent (crop + trajectory)", IMG_BYTES + TRAJ_BYTES))
+    launch_bytes = unit_bytes * n_local
+    achieved = launch_bytes / (dom_avg_ms / 1e3) / 1e9 if dom_avg_ms > 0 else 0.0
+    flops = algorithmic_flops_per_iter(n_local, sum((e - s) ** 2 for s, e in sse), a.k, a.num_gens)
+    roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": ncu_traffic(dom), "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst)",
+            "algorithmic_bytes_per_launch": int(launch_bytes), "unit_of_work": f"{unit_name}: {unit_bytes} B x {n_local} per launch",
+            "kernel_avg_ms": dom_avg_ms, "kernel_launches_per_step": dom_calls / a.steps,
+            "kernel_share_of_step": (dom_ms / a.steps) / ms_step if ms_step else None,
+            "whole_step": {"algorithmic_bytes": int(b_iter), "achieved_gbs": b_iter / (ms_step / 1e3) / 1e9,
+                           "frac_hbm": b_iter / (ms_step / 1e3) / 1e9 / hbm_peak},
+            "fp32": {"algorithmic_gflop_per_step": flops / 1e9, "achieved_tflops": flops / (ms_step / 1e3) / 1e12,
+                     "peak_tflops": FP32_PEAK_TFLOPS, "frac": flops / (ms_step / 1e3) / 1e12 / FP32_PEAK_TFLOPS,
+                     "note": "the path is FP32-FMA bound (970 FLOP/B), not HBM bound: this is the fraction that measures kernel quality"}}
 
     line = {
         "metric": "agent-timesteps/sec (train, G=8)", "value": 20.0 * n_total / (ms_step / 1e3),

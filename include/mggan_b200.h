@@ -41,6 +41,23 @@ int mggan_linear_fwd(const float* X, int M, int K, const float* W, const float* 
 int mggan_linear_bwd(const float* X, int M, int K, const float* W, int O, int act, float slope, const float* Y,
                      const float* dY, float* dX, float* dW, float* db, cudaStream_t stream);
 
+/* ---- discriminator heads over k samples per agent, per-agent part hoisted: MultiDiscriminatorTrajectory.forward
+ * mggan/model/modules/discriminators.py:178-219 (discs[0] :76-85,198-204; gen_id_reconstructor :103-108,209-217).
+ * The classifier input of row (sample s, agent i) is [soc | in_enc | pred_enc | scene]: only pred_enc depends on s and
+ * soc is non-zero for s == 0 only.  First layers of both heads stacked (NZ = 2 HH rows, HH without
+ * the generator-id head): z[s,i] = base[i] + (s == 0) soc0[i] + W1p pe[s,i];  pe (k*n, 32) row = s*n + i;
+ * base, soc0 (n, NZ) per-agent products computed by the caller (bias in base); W1p (NZ, 32); HH in {64, 96}.
+ * p (k*n) = sigmoid(Wd2 . LReLU_0.2(z[:HH]) + bd2) (1 - 2e-7) + 1e-7;  branch (k*n, G) = Wg2 LReLU_0.2(z[HH:]) + bg2
+ * (G == 0 and branch == NULL for gan_type "gan"). */
+int mggan_disc_heads_fwd(const float* pe, int n, int k, int HH, const float* base, const float* soc0, const float* W1p,
+                         const float* Wd2, const float* bd2, const float* Wg2, const float* bg2, int G, float* p,
+                         float* branch, cudaStream_t stream);
+/* Input gradients only (generator step: the discriminator is frozen).  dp (k*n) = dL/dp or NULL, dbranch (k*n, G) or
+ * NULL.  d_pe (k*n, 32) and d_soc0 (n, NZ) overwritten; d_base (n, NZ) accumulated (caller zero-fills) or NULL. */
+int mggan_disc_heads_bwd(const float* pe, int n, int k, int HH, const float* base, const float* soc0, const float* W1p,
+                         const float* Wd2, const float* Wg2, int G, const float* p, const float* dp,
+                         const float* dbranch, float* d_pe, float* d_soc0, float* d_base, cudaStream_t stream);
+
 /* ---- PM-Net sampling + generator selection: standard.py:217-225, utils.py:234-248, standard.py:190-214 */
 int mggan_gumbel_sample(const float* logits, int n, int k, int G, unsigned long long seed, unsigned long long offset,
                         long long* idx, cudaStream_t stream);

@@ -229,25 +229,39 @@ scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ 
     }
 }
 
-// BatchNorm-1 statistics from the patch statistics (one thread per channel, double precision).
-__global__ void scene_bn1_from_patches_kernel(const double* __restrict__ R, const double* __restrict__ P, double count,
-                                              int C, const float* __restrict__ W, const float* __restrict__ bias,
-                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                              float* __restrict__ running_mean, float* __restrict__ running_var,
-                                              long long* __restrict__ nbt, float momentum, float eps, int training,
-                                              float* __restrict__ ab, float* __restrict__ mean_istd) {
+// BatchNorm-1 statistics from the patch statistics (double precision).  One CTA: R and W staged in shared memory,
+// thread = (channel, tap) partial of W_c^T R W_c and W_c . P, then one thread per channel finishes.
+__global__ void __launch_bounds__(MGGAN_THREADS)
+scene_bn1_from_patches_kernel(const double* __restrict__ R, const double* __restrict__ P, double count,
+                              int C, const float* __restrict__ W, const float* __restrict__ bias,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                              long long* __restrict__ nbt, float momentum, float eps, int training,
+                              float* __restrict__ ab, float* __restrict__ mean_istd) {
+    __shared__ double sR[NTAP * NTAP], sP[NTAP], sQ[32 * NTAP], sWP[32 * NTAP];
+    __shared__ float sW[32 * NTAP];
+    if (training) {
+        for (int i = threadIdx.x; i < NTAP * NTAP; i += blockDim.x) sR[i] = R[i];
+        for (int i = threadIdx.x; i < NTAP; i += blockDim.x) sP[i] = P[i];
+        for (int i = threadIdx.x; i < C * NTAP; i += blockDim.x) sW[i] = __ldg(W + i);
+        __syncthreads();
+        for (int i = threadIdx.x; i < C * NTAP; i += blockDim.x) {
+            const int c = i / NTAP, a = i - c * NTAP;
+            const float* w = sW + c * NTAP;
+            double rw = 0.0;
+#pragma unroll 4
+            for (int b = 0; b < NTAP; ++b) rw += sR[a * NTAP + b] * (double)w[b];
+            sQ[i] = (double)w[a] * rw;
+            sWP[i] = (double)w[a] * sP[a];
+        }
+        __syncthreads();
+    }
     int c = threadIdx.x;
     if (c < C) {
         float mean, var;
         if (training) {
-            const float* w = W + c * NTAP;
             double wp = 0.0, q = 0.0;
-            for (int a = 0; a < NTAP; ++a) {
-                double rw = 0.0;
-                for (int b = 0; b < NTAP; ++b) rw += R[a * NTAP + b] * (double)w[b];
-                q += (double)w[a] * rw;
-                wp += (double)w[a] * P[a];
-            }
+            for (int a = 0; a < NTAP; ++a) { q += sQ[c * NTAP + a]; wp += sWP[c * NTAP + a]; }
             double bc = (double)bias[c];
             double m = wp / count + bc;
             double ex2 = (q + 2.0 * bc * wp) / count + bc * bc;
@@ -886,7 +900,7 @@ extern "C" int mggan_scene_bn1_from_patches(const double* R, const double* P, do
                                             float momentum, float eps, int training, float* ab, float* mean_istd,
                                             cudaStream_t stream) {
     MGGAN_REQUIRE(C >= 1 && C <= 32, "mggan_scene_bn1_from_patches: C=%d", C);
-    scene_bn1_from_patches_kernel<<<1, 32, 0, stream>>>(R, P, count, C, W, bias, gamma, beta, running_mean, running_var,
+    scene_bn1_from_patches_kernel<<<1, MGGAN_THREADS, 0, stream>>>(R, P, count, C, W, bias, gamma, beta, running_mean, running_var,
                                                         num_batches_tracked, momentum, eps, training, ab, mean_istd);
     return mggan_check_launch("scene_bn1_from_patches");
 }

@@ -37,22 +37,23 @@ __global__ void rank_kernel(const long long* __restrict__ idx, int n, int k, int
     }
 #pragma unroll
     for (int g = 0; g < GMAX; ++g)
-        if (g < G) cnt[(size_t)i * G + g] = c[g];
+        if (g < G) cnt[(size_t)g * n + i] = c[g];          // generator-major: coalesced here and in the scan
 }
 
-// single CTA: per-generator exclusive scan over agents, group bases, tile table
+// one CTA per generator: exclusive scan of that generator's per-agent counts (in place), total draws
 __global__ void __launch_bounds__(1024)
-scan_kernel(int* __restrict__ cnt, int n, int G, int n_tiles, int* __restrict__ totals, int* __restrict__ base_row,
-            int* __restrict__ tile_gen) {
+scan_kernel(int* __restrict__ cnt, int n, int* __restrict__ totals) {
     __shared__ int swarp[32];
-    __shared__ int stot[GMAX];
-    const int chunk = (n + blockDim.x - 1) / blockDim.x;
-    const int i0 = threadIdx.x * chunk, i1 = min(n, i0 + chunk);
+    __shared__ int scarry;
+    int* c = cnt + (size_t)blockIdx.x * n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int g = 0; g < G; ++g) {
-        int s = 0;
-        for (int i = i0; i < i1; ++i) s += cnt[(size_t)i * G + g];
-        int incl = s;
+    if (threadIdx.x == 0) scarry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const int v = i < n ? c[i] : 0;
+        const int carry = scarry;          // written before the barrier that closed the previous round
+        int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -68,31 +69,34 @@ scan_kernel(int* __restrict__ cnt, int n, int G, int n_tiles, int* __restrict__ 
                 if (lane >= o) wi += t;
             }
             swarp[lane] = wi - w;
-            if (lane == 31) stot[g] = wi;
+            if (lane == 31) scarry = carry + wi;
         }
         __syncthreads();
-        int run = swarp[warp] + incl - s;
-        for (int i = i0; i < i1; ++i) {
-            int c = cnt[(size_t)i * G + g];
-            cnt[(size_t)i * G + g] = run;          // in place: count -> exclusive offset
-            run += c;
-        }
+        if (i < n) c[i] = carry + swarp[warp] + incl - v;
         __syncthreads();
     }
+    if (threadIdx.x == 0) totals[blockIdx.x] = scarry;
+}
+
+// group bases (each generator's rows padded to a multiple of TILE) and the tile table
+__global__ void bases_kernel(const int* __restrict__ totals, int G, int n_tiles, int* __restrict__ base_row,
+                             int* __restrict__ tile_gen) {
+    __shared__ int sbase[GMAX + 1];
     if (threadIdx.x == 0) {
         int row = 0;
         for (int g = 0; g < G; ++g) {
-            totals[g] = stot[g];
+            sbase[g] = row;
             base_row[g] = row;
-            row += (stot[g] + TILE - 1) / TILE * TILE;
+            row += (totals[g] + TILE - 1) / TILE * TILE;
         }
+        sbase[G] = row;
         base_row[G] = row;
     }
     __syncthreads();
     for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
         int r = t * TILE, gsel = -1;
         for (int g = 0; g < G; ++g)
-            if (r >= base_row[g] && r < base_row[g] + (stot[g] + TILE - 1) / TILE * TILE) gsel = g;
+            if (r >= sbase[g] && r < sbase[g + 1]) gsel = g;
         tile_gen[t] = gsel;
     }
 }
@@ -106,7 +110,7 @@ __global__ void scatter_kernel(const long long* __restrict__ idx, const unsigned
         long long g = idx[(size_t)i * k + j];
         if (g < 0 || g >= G) g = 0;
         int m = rank[(size_t)i * k + j];
-        int row = base_row[g] + off[(size_t)i * G + g] + m;
+        int row = base_row[g] + off[(size_t)g * n + i] + m;
         seq_agent[row] = i;
         seq_noise[row] = m * n + i;
         seq_out[row] = j * n + i;
@@ -168,7 +172,8 @@ extern "C" int mggan_selection_build(const long long* idx, int n, int k, int G, 
     }
     cudaMemsetAsync(seq_agent, 0xFF, sizeof(int) * (size_t)n_tiles * TILE, stream);
     rank_kernel<<<(n + 127) / 128, 128, 0, stream>>>(idx, n, k, G, cnt, rank, err);
-    scan_kernel<<<1, 1024, 0, stream>>>(cnt, n, G, n_tiles, totals, base_row, tile_gen);
+    scan_kernel<<<G, 1024, 0, stream>>>(cnt, n, totals);
+    bases_kernel<<<1, 256, 0, stream>>>(totals, G, n_tiles, base_row, tile_gen);
     scatter_kernel<<<(n + 127) / 128, 128, 0, stream>>>(idx, rank, cnt, base_row, n, k, G, seq_agent, seq_noise, seq_out);
     return mggan_check_launch("selection_build");
 }

@@ -73,21 +73,72 @@ class MultiGeneratorGAN(abc.ABC):
         img = batch["features"].to(self.device, non_blocking=True) if "features" in batch else None
         return in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img
 
-    def train_iteration(self, batch, metrics, total_iterations=0):
-        """One D step + G step + PM step on a collated batch (reference loop body :114-168)."""
+    def _prepare(self, batch):
+        """Collated batch (host or device tensors) -> device tensors + NaN loss mask.  The reference always
+        builds the mask (abstract_train.py:130-132); when no future is masked it is dropped so the step runs
+        without boolean-index gathers.  For host batches the NaN test runs on the host copy (no device sync)."""
+        gt_host = batch["gt_xy"]
+        has_nan = bool(torch.isnan(gt_host).any()) if not gt_host.is_cuda else None
         in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img = self._to_device(batch)
-        # the reference always builds the NaN mask (abstract_train.py:130-132); when no future is masked the
-        # mask is dropped so the step runs without boolean-index gathers (one host sync to decide)
+        if has_nan is None:
+            has_nan = bool(torch.isnan(gt_xy).any())
         loss_mask = None
-        if bool(torch.isnan(gt_xy).any()):
+        if has_nan:
             loss_mask = ~gt_xy.isnan().any(2).any(0)
             gt_dxdy, gt_xy = gt_dxdy[:, loss_mask], gt_xy[:, loss_mask]
+        return in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img, loss_mask
+
+    def _run_prepared(self, prepared, metrics, total_iterations=0):
+        in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img, loss_mask = prepared
         if (total_iterations % self.config.num_gen_steps == 0) or (self.epoch >= self.config.keep_gen_steps):
             if self.config.num_unrolling_steps > 0:
                 raise NotImplementedError("num_unrolling_steps > 0 is outside the B200 hot path")
             self.discriminator_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
         self.generator_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
         self.net_chooser_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
+
+    def train_iteration(self, batch, metrics, total_iterations=0):
+        """One D step + G step + PM step on a collated batch (reference loop body :114-168)."""
+        self._run_prepared(self._prepare(batch), metrics, total_iterations)
+
+    def train_iterations(self, batches, metrics, total_iterations=0, on_step=None):
+        """The reference loop `for batch in loader: <D, G, PM step>` (abstract_train.py:114-168) with the
+        host->device copy of batch i+1 issued on a side stream while batch i computes (pinned host buffers
+        make the copies asynchronous).  `on_step(i, metrics)` runs after each iteration is enqueued.
+        Returns the number of iterations run."""
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+
+        def stage(batch):
+            with torch.cuda.stream(copy_stream):
+                prepared = self._prepare(batch)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            return prepared, ev
+
+        it = iter(batches)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return 0
+        n = 0
+        while nxt is not None:
+            prepared, ev = nxt
+            main.wait_event(ev)
+            for t in prepared:
+                if torch.is_tensor(t):
+                    t.record_stream(main)
+            try:
+                nxt = stage(next(it))
+            except StopIteration:
+                nxt = None
+            self._run_prepared(prepared, metrics, total_iterations + n)
+            if on_step is not None:
+                on_step(n, metrics)
+            n += 1
+        return n
 
     def _loaders(self):
         kw = dict(dataset=self.config.dataset, batch_size=self.config.batch_size, workers=self.config.workers,
@@ -106,9 +157,7 @@ class MultiGeneratorGAN(abc.ABC):
             self.D.train()
             self.G.train()
             metrics = defaultdict(list)
-            for i, batch in enumerate(train_loader):
-                self.train_iteration(batch, metrics, total_iterations)
-                total_iterations += 1
+            total_iterations += self.train_iterations(train_loader, metrics, total_iterations)
             if self.epoch % self.config.val_every == 0:
                 self.D.eval()
                 self.G.eval()

@@ -36,6 +36,8 @@ SIGNATURES = {
     "mggan_lstm_seq_bwd": "piiipppppps",
     "mggan_linear_fwd": "piippiifps",
     "mggan_linear_bwd": "piipiifppppps",
+    "mggan_disc_heads_fwd": "piiipppppppipps",
+    "mggan_disc_heads_bwd": "piiipppppipppppps",
     "mggan_gumbel_sample": "piiiQQps",
     "mggan_selection_build": "piiiippppppppps",
     "mggan_selection_all": "iiipppps",
@@ -124,7 +126,7 @@ def stream():
 
 
 # kernels launched per entry point (for the launch counter; memsets not counted)
-KERNELS_PER_CALL = {"mggan_selection_build": 3, "mggan_linear_bwd": 2}
+KERNELS_PER_CALL = {"mggan_selection_build": 4, "mggan_linear_bwd": 2}
 launch_count = 0          # kernels launched through this binding since import
 _profile = None           # None | {"only": set or None, "events": [(name, start, end), ...]}
 

@@ -54,6 +54,51 @@ def linear(x, w, b=None, act=ACT_NONE, slope=0.0):
     return _Linear.apply(x, w, b, act, slope, torch.is_grad_enabled())
 
 
+# --------------------------------------------------------------------------- discriminator heads (frozen weights)
+class _DiscHeads(torch.autograd.Function):
+    """p, branch = heads(base[i] + (s == 0) soc0[i] + W1p pe[s, i]) -- see include/mggan_b200.h.  Gradients flow to
+    pe, base and soc0 only: the weights must not require grad (generator step / evaluation)."""
+
+    @staticmethod
+    def forward(ctx, pe, base, soc0, w1p, wd2, bd2, wg2, bg2, n, k, grad_on):
+        assert not any(ctx.needs_input_grad[3:8]), "disc_heads: weight gradients are not produced (frozen discriminator only)"
+        pe, base, soc0, w1p, wd2, bd2 = map(_f32, (pe, base, soc0, w1p, wd2, bd2))
+        G = 0 if wg2 is None else wg2.shape[0]
+        HH = wd2.shape[-1]
+        if G:
+            wg2, bg2 = _f32(wg2), _f32(bg2)
+        assert pe.shape == (n * k, 32) and base.shape == soc0.shape == (n, w1p.shape[0])
+        p = torch.empty(n * k, device=pe.device, dtype=torch.float32)
+        branch = torch.empty(n * k, G, device=pe.device, dtype=torch.float32) if G else None
+        call("mggan_disc_heads_fwd", ptr(pe), n, k, HH, ptr(base), ptr(soc0), ptr(w1p), ptr(wd2), ptr(bd2), ptr(wg2),
+             ptr(bg2), G, ptr(p), ptr(branch))
+        if grad_on:
+            ctx.save_for_backward(pe, base, soc0, w1p, wd2, wg2, p)
+            ctx.dims = (n, k, HH, G)
+        if G:
+            return p, branch
+        return p, p.new_zeros(0)
+
+    @staticmethod
+    def backward(ctx, dp, dbranch):
+        pe, base, soc0, w1p, wd2, wg2, p = ctx.saved_tensors
+        n, k, HH, G = ctx.dims
+        d_pe = torch.empty_like(pe)
+        d_soc0 = torch.empty_like(soc0)
+        d_base = torch.zeros_like(base) if ctx.needs_input_grad[1] else None
+        dp = _f32(dp) if dp is not None else None
+        dbranch = _f32(dbranch) if (G and dbranch is not None) else None
+        call("mggan_disc_heads_bwd", ptr(pe), n, k, HH, ptr(base), ptr(soc0), ptr(w1p), ptr(wd2), ptr(wg2), G, ptr(p),
+             ptr(dp), ptr(dbranch), ptr(d_pe), ptr(d_soc0), ptr(d_base))
+        return (d_pe, d_base, d_soc0) + (None,) * 8
+
+
+def disc_heads(pe, base, soc0, w1p, wd2, bd2, wg2, bg2, n, k):
+    """-> (p (k*n,), branch (k*n, G) or None)."""
+    p, br = _DiscHeads.apply(pe, base, soc0, w1p, wd2, bd2, wg2, bg2, n, k, torch.is_grad_enabled())
+    return p, (br if wg2 is not None else None)
+
+
 # --------------------------------------------------------------------------- encoder LSTM
 class _LstmSeq(torch.autograd.Function):
     @staticmethod
@@ -218,7 +263,7 @@ class _SceneAttn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, img, c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b, bn1, bn2, rows, rows_key,
-                training, group, grad_on):
+                training, group, grad_on, holder=None):
         ws = [_f32(t) for t in (c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b)]
         c1w, c1b, g1, be1, c2w, c2b, g2, be2, a0w, a0b, a2w, a2b = ws
         assert img.dtype == torch.float32 and img.is_contiguous()
@@ -246,6 +291,8 @@ class _SceneAttn(torch.autograd.Function):
         call("mggan_scene_bn_finalize", ptr(st2), n_total * 256.0, C, ptr(g2), ptr(be2), ptr(bn2.running_mean),
              ptr(bn2.running_var), ptr(bn2.num_batches_tracked), BN_MOMENTUM, BN_EPS, tr, ptr(ab2), ptr(mi2))
         call("mggan_scene_attn_fwd", ptr(x2), N, C, ptr(ab2), ptr(a0w), ptr(a0b), ptr(a2w), ptr(a2b), ptr(out))
+        if holder is not None and training:
+            holder.update(ps=ps, st2=st2, n_total=n_total, C=C)
         if need:
             assert training, "scene-attention backward needs train-mode BatchNorm (batch statistics)"
             ctx.save_for_backward(img, c1w, c1b, c2w, a0w, a0b, a2w, a2b, x2, e1, idx1, ab1, mi1, ab2, mi2)
@@ -283,20 +330,51 @@ class _SceneAttn(torch.autograd.Function):
         call("mggan_scene_bn1_bwd_finalize", ptr(glob1), ptr(sums1), ctx.n_total * 1089.0, C, ptr(S1), ptr(ps.R_local),
              ptr(ps.P_local), ptr(c1w), ptr(c1b), ptr(ab1), ptr(mi1), ptr(dc1w), ptr(dg1), ptr(db1))
         dc1b = z(C)             # identically zero under train-mode BatchNorm
-        return (None, dc1w, dc1b, dg1, db1, dc2w, dc2b, dg2, db2, da0w, da0b, da2w, da2b) + (None,) * 7
+        return (None, dc1w, dc1b, dg1, db1, dc2w, dc2b, dg2, db2, da0w, da0b, da2w, da2b) + (None,) * 8
+
+
+def _replay_bn_updates(mod, holder):
+    """A second forward of the same crops through the same weights: only its side effect is left to do --
+    the train-mode running-statistics update of both BatchNorm layers (momentum applied once more)."""
+    b1, b2 = mod.CNN.encoder.ConvBlock_1.Block, mod.CNN.encoder.ConvBlock_2.Block
+    C, ps, dev = holder["C"], holder["ps"], holder["st2"].device
+    scratch = torch.empty(4 * C, device=dev)
+    call("mggan_scene_bn1_from_patches", ptr(ps.R), ptr(ps.P), holder["n_total"] * 1089.0, C, ptr(_f32(b1.Conv_1.weight)),
+         ptr(_f32(b1.Conv_1.bias)), ptr(_f32(b1.BN_1.weight)), ptr(_f32(b1.BN_1.bias)), ptr(b1.BN_1.running_mean),
+         ptr(b1.BN_1.running_var), ptr(b1.BN_1.num_batches_tracked), BN_MOMENTUM, BN_EPS, 1, ptr(scratch[:2 * C]),
+         ptr(scratch[2 * C:]))
+    call("mggan_scene_bn_finalize", ptr(holder["st2"]), holder["n_total"] * 256.0, C, ptr(_f32(b2.BN_1.weight)),
+         ptr(_f32(b2.BN_1.bias)), ptr(b2.BN_1.running_mean), ptr(b2.BN_1.running_var), ptr(b2.BN_1.num_batches_tracked),
+         BN_MOMENTUM, BN_EPS, 1, ptr(scratch[:2 * C]), ptr(scratch[2 * C:]))
 
 
 def scene_attention(img, mod, rows=None, group=None, rows_key=None):
     """mod: an AttentionGlobal parameter container (mggan.model.modules.cnn).  `rows_key`: hashable
-    identity of the row selection (None = all rows), part of the patch-statistics cache key."""
+    identity of the row selection (None = all rows), part of the patch-statistics cache key.
+
+    When `mod.memo` is a dict (set by a caller that knows the weights do not change between calls, e.g.
+    the discriminator step's real / fake passes), a repeated call on the same crops returns the SAME output
+    tensor (one autograd node: gradients of both uses add up) and only replays the BatchNorm running-statistics
+    update."""
     b1, b2 = mod.CNN.encoder.ConvBlock_1.Block, mod.CNN.encoder.ConvBlock_2.Block
     a = mod.cnn_attention
     if img.dtype != torch.float32 or not img.is_contiguous():
         img = img.float().contiguous()
-    return _SceneAttn.apply(img, b1.Conv_1.weight, b1.Conv_1.bias, b1.BN_1.weight, b1.BN_1.bias,
-                            b2.Conv_1.weight, b2.Conv_1.bias, b2.BN_1.weight, b2.BN_1.bias,
-                            a[0].weight, a[0].bias, a[2].weight, a[2].bias, b1.BN_1, b2.BN_1, rows, rows_key,
-                            mod.training, group, torch.is_grad_enabled())
+    memo = getattr(mod, "memo", None)
+    key = (id(img), img._version, rows_key, torch.is_grad_enabled(), mod.training)
+    if memo is not None and key in memo:
+        out, holder = memo[key]
+        if mod.training:
+            _replay_bn_updates(mod, holder)
+        return out
+    holder = {} if memo is not None else None
+    out = _SceneAttn.apply(img, b1.Conv_1.weight, b1.Conv_1.bias, b1.BN_1.weight, b1.BN_1.bias,
+                           b2.Conv_1.weight, b2.Conv_1.bias, b2.BN_1.weight, b2.BN_1.bias,
+                           a[0].weight, a[0].bias, a[2].weight, a[2].bias, b1.BN_1, b2.BN_1, rows, rows_key,
+                           mod.training, group, torch.is_grad_enabled(), holder)
+    if memo is not None:
+        memo[key] = (out, holder)
+    return out
 
 
 # --------------------------------------------------------------------------- generator selection

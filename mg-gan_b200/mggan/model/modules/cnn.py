@@ -48,6 +48,7 @@ class AttentionGlobal(nn.Module):
         self.cnn_attention = nn.Sequential(nn.Linear(channels_cnn, mlp_dim), nn.LeakyReLU(),
                                            nn.Linear(mlp_dim, channels_cnn))
         self.stat_group = None          # process group sharing BatchNorm statistics (data-parallel runs)
+        self.memo = None                # dict while a caller guarantees constant weights (kernels.scene_attention)
 
     def forward(self, features, rows=None, rows_key=None):
         """features (N,4,33,33) -> (N,64).  `rows` (int32) gathers image rows without copying them;

@@ -10,6 +10,8 @@ attention pooling only ever fills the rows of sample 0 and every other sample ge
 reference still evaluates the pair MLP on all (k N)^2 row pairs and throws the result away;
 here only the n_s^2 in-scene pairs of sample 0 are computed.
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -54,24 +56,109 @@ class MultiDiscriminatorTrajectory(nn.Module):
                                                       nn.Linear(h_dim // 2, num_gens))
         self.eps = 1e-7
         self.len_hist = 1.0
+        self._obs_memo = None
+
+    @contextlib.contextmanager
+    def share_observed(self):
+        """While active, the features that depend only on the observed inputs and the weights -- the
+        observed-trajectory encoding `in_encoder_fc(in_encoder(in_dxdy))` and the scene features -- are computed
+        once per distinct input tensor and shared by every `forward` (the discriminator step runs D on real and
+        on fake futures of the SAME observations with the SAME weights, train.py:150,171).  The shared tensors
+        are single autograd nodes, so the gradients of all uses add up exactly as in the reference; BatchNorm
+        running statistics are still updated once per forward."""
+        enc = getattr(self, "scene_encoder", None)
+        self._obs_memo = {}
+        if enc is not None:
+            enc.memo = {}
+        try:
+            yield self
+        finally:
+            self._obs_memo = None
+            if enc is not None:
+                enc.memo = None
 
     @staticmethod
     def _mlp2(seq, x, last_act=K.ACT_NONE):
         h = K.linear(x, seq[0].weight, seq[0].bias, K.ACT_LRELU, 0.2)
         return K.linear(h, seq[2].weight, seq[2].bias, last_act)
 
+    def _in_enc(self, in_dxdy):
+        key = (id(in_dxdy), in_dxdy._version, torch.is_grad_enabled())
+        in_enc = self._obs_memo.get(key) if self._obs_memo is not None else None
+        if in_enc is None:
+            in_enc = self._mlp2(self.in_encoder_fc, self.in_encoder(in_dxdy))
+            if self._obs_memo is not None:
+                self._obs_memo[key] = in_enc
+        return in_enc
+
+    def _pred_enc(self, pred_dxdy):
+        pred_len, n_samples, b, _ = pred_dxdy.shape
+        pv = pred_dxdy.permute(1, 2, 0, 3).reshape(n_samples * b, -1)
+        return self._mlp2(self.pred_encoder, pv)
+
     def encode(self, in_xy, in_dxdy, pred_xy, pred_dxdy, mask=None):
         """-> (k * N, 64), row = sample * N + agent (reference :113-142)."""
-        in_enc = self._mlp2(self.in_encoder_fc, self.in_encoder(in_dxdy))
+        in_enc = self._in_enc(in_dxdy)
         pred_len, n_samples, b, _ = pred_xy.shape
         N = in_xy.size(1)
-        pv = pred_dxdy.permute(1, 2, 0, 3).reshape(n_samples * b, -1)
-        pred_enc = self._mlp2(self.pred_encoder, pv)
+        pred_enc = self._pred_enc(pred_dxdy)
         if mask is not None:
             padded = torch.zeros(N * n_samples, pred_enc.size(1), device=pred_enc.device)
             padded[mask.repeat(n_samples)] = pred_enc
             pred_enc = padded
         return torch.cat([in_enc.repeat(n_samples, 1), pred_enc], dim=1)
+
+    def _scene(self, img, mask):
+        rows, rows_key = None, None
+        if mask is not None:
+            rows = torch.nonzero(mask).flatten().to(torch.int32)
+            rows_key = ("mask", id(mask), mask._version)
+        return self.scene_encoder(img, rows, rows_key)
+
+    def _heads_frozen(self):
+        ps = list(self.discs[0].parameters())
+        if self.gan_type == "mgan":
+            ps += list(self.gen_id_reconstructor.parameters())
+        return not torch.is_grad_enabled() or not any(p.requires_grad for p in ps)
+
+    def _forward_hoisted(self, in_xy, in_dxdy, pred_dxdy, seq_start_end, img, mask):
+        """Same function as `forward` for frozen head weights (generator step, evaluation): the first layer of
+        both heads is split by input block, its per-agent part ([in_enc | scene] and, for sample 0, soc) is
+        evaluated once per agent and `mggan_disc_heads_*` adds the per-sample pred_enc part (6x fewer MACs than
+        the k*N x 192 product; no (k*N, 192) classifier input is materialised)."""
+        pred_len, n_samples, b, _ = pred_dxdy.shape
+        N = in_xy.size(1)
+        in_enc = self._in_enc(in_dxdy)                                  # (N, 32)
+        pe = self._pred_enc(pred_dxdy)                                  # (k*b, 32), row = s*b + i
+        pe0 = pe[:b]
+        if mask is not None:
+            pad = torch.zeros(N, pe.size(1), device=pe.device)
+            pad[mask] = pe0
+            pe0 = pad
+        soc = self.social(in_xy, in_dxdy, torch.cat([in_enc, pe0], 1), seq_start_end)       # (N, 64): sample 0
+        d0 = self.discs[0][0]
+        mgan = self.gan_type == "mgan"
+        w1 = torch.cat([d0.weight, self.gen_id_reconstructor[0].weight], 0) if mgan else d0.weight
+        b1 = torch.cat([d0.bias, self.gen_id_reconstructor[0].bias], 0) if mgan else d0.bias
+        hs, he = soc.shape[1], in_enc.shape[1]                           # column blocks: soc | in_enc | pred_enc | scene
+        per_agent = in_enc
+        w_agent = w1[:, hs:hs + he]
+        if mask is not None:
+            soc, per_agent = soc[mask], per_agent[mask]
+        if img is not None:
+            per_agent = torch.cat([per_agent, self._scene(img, mask)], 1)
+            w_agent = torch.cat([w_agent, w1[:, hs + 2 * he:]], 1)
+        base = K.linear(per_agent, w_agent, b1)
+        soc0 = K.linear(soc, w1[:, :hs])
+        w1p = w1[:, hs + he:hs + 2 * he]
+        d2 = self.discs[0][2]
+        g2 = self.gen_id_reconstructor[2] if mgan else None
+        p, branch = K.disc_heads(pe, base, soc0, w1p, d2.weight, d2.bias, g2.weight if mgan else None,
+                                 g2.bias if mgan else None, b, n_samples)
+        output = p.reshape(n_samples, b).t()
+        if not mgan:
+            return output
+        return output, branch.reshape(n_samples, b, -1).transpose(0, 1)
 
     def forward(self, in_xy, in_dxdy, pred_xy, pred_dxdy, seq_start_end, return_all=False, img=None, mask=None):
         """pred_* (pred_len, k, n_act, 2) (3-D inputs are one sample).  Returns output (n_act, k) in
@@ -80,6 +167,8 @@ class MultiDiscriminatorTrajectory(nn.Module):
             pred_xy, pred_dxdy = pred_xy.unsqueeze(1), pred_dxdy.unsqueeze(1)
         pred_len, n_samples, b, _ = pred_xy.shape
         N = in_xy.size(1)
+        if self._heads_frozen():
+            return self._forward_hoisted(in_xy, in_dxdy, pred_dxdy, seq_start_end, img, mask)
         enc = self.encode(in_xy, in_dxdy, pred_xy, pred_dxdy, mask)
         soc0 = self.social(in_xy, in_dxdy, enc[:N], seq_start_end)
         if n_samples > 1:
@@ -90,11 +179,7 @@ class MultiDiscriminatorTrajectory(nn.Module):
         if mask is not None:
             classifier_inp = classifier_inp[mask.repeat(n_samples)]
         if img is not None:
-            rows, rows_key = None, None
-            if mask is not None:
-                rows = torch.nonzero(mask).flatten().to(torch.int32)
-                rows_key = ("mask", id(mask), mask._version)
-            scene = self.scene_encoder(img, rows, rows_key)
+            scene = self._scene(img, mask)
             classifier_inp = torch.cat([classifier_inp, scene.repeat(n_samples, 1)], 1)
         output = self._mlp2(self.discs[0], classifier_inp, K.ACT_SIGMOID_EPS)       # sigmoid * (1 - 2 eps) + eps
         if not return_all:

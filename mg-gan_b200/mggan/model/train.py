@@ -112,6 +112,15 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
     # ------------------------------------------------------------------ D step
     def discriminator_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, train_metrics, loss_mask, img=None):
         cfg = self.config
+        with self.D.share_observed():       # real and fake passes share the observed-input features
+            train_loss = self._discriminator_loss(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, train_metrics,
+                                                  loss_mask, img)
+        self.D.zero_grad()
+        train_loss.backward()
+        self.optimizerD.step(max_norm=cfg.clipping_threshold_d, reduce_fn=self._reduce())
+
+    def _discriminator_loss(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, train_metrics, loss_mask, img=None):
+        cfg = self.config
         real_result = self.D(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img=img, mask=loss_mask)
         if isinstance(real_result, tuple):
             real_result = real_result[0]
@@ -134,9 +143,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
         fake_loss = K.bce_scalar_label(disc_out.contiguous(), l_fake, inv_denom=1.0 / denom)
         train_loss = real_loss + fake_loss if train_loss is None else train_loss + real_loss + fake_loss
         train_metrics["train/discr_loss"].append((fake_loss + real_loss).detach())
-        self.D.zero_grad()
-        train_loss.backward()
-        self.optimizerD.step(max_norm=cfg.clipping_threshold_d, reduce_fn=self._reduce())
+        return train_loss
 
     # ------------------------------------------------------------------ PM-Network step
     def net_chooser_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, mask, img):

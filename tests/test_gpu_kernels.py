@@ -363,3 +363,56 @@ def test_fused_adamw_matches_oracle(K):
         K.clip_adamw(pg, gg, m, v, [step] * len(pg), sq, 50.0, 1e-3, 0.5, 0.999, 1e-8, 0.01)
     for n, p in zip(names, pg):
         check(p, sd[n], 1e-5, "param " + n)
+
+
+# ------------------------------------------------------------------------------------ discriminator, frozen (hoisted heads)
+@pytest.mark.parametrize("G,sizes,with_img,masked,k", [(8, [4, 6, 3], True, True, 20), (4, [1, 3, 2, 5], False, False, 5),
+                                                       (2, [32, 32, 7], True, False, 3), (3, [70], True, True, 1)])
+def test_discriminator_frozen_heads_match_oracle(K, G, sizes, with_img, masked, k):
+    """Generator-step discriminator pass (weights frozen): `mggan_disc_heads_*` with the per-agent part of the
+    first head layer hoisted must give the oracle's outputs and the oracle's gradient w.r.t. the predictions."""
+    from mggan.model.modules.discriminators import MultiDiscriminatorTrajectory
+    from mggan.synthetic import make_batch
+    torch.manual_seed(G + k)
+    D = MultiDiscriminatorTrajectory(num_gens=G, num_discs=1, unbound_output=False, h_dim=64, inp_format="rel", pred_len=12,
+                                     gan_type="mgan", global_disc=1, scene_dim=64 if with_img else 0, pool_type="sways")
+    sd = {kk: v.detach().clone() for kk, v in D.state_dict().items()}
+    b = make_batch(sizes, seed=77 + G, with_img=with_img)
+    sse = b.pop("seq_start_end")
+    bt = {kk: torch.from_numpy(v) for kk, v in b.items()}
+    N = bt["in_xy"].shape[1]
+    g = torch.Generator().manual_seed(5)
+    mask = torch.rand(N, generator=g) > 0.3 if masked else None
+    n_act = int(mask.sum()) if masked else N
+    rel = torch.randn(12, k, n_act, 2, generator=g) * 0.4
+    ab = rel.cumsum(0)
+    d_out = torch.randn(n_act, k, generator=g)
+    d_br = torch.randn(n_act, k, G, generator=g)
+    img = bt.get("features")
+
+    relr = rel.clone().requires_grad_(True)
+    oo, ob = O.discriminator_forward(sd, bt["in_xy"], bt["in_dxdy"], ab, relr, sse, img, mask)
+    ((oo * d_out).sum() + (ob * d_br).sum()).backward()
+
+    D = D.to(DEV).train()
+    for p_ in D.parameters():
+        p_.requires_grad_(False)
+    relg = rel.clone().to(DEV).requires_grad_(True)
+    mg = mask.to(DEV) if masked else None
+    go, gb = D(bt["in_xy"].to(DEV), bt["in_dxdy"].to(DEV), ab.to(DEV), relg, sse, img=img.to(DEV) if with_img else None,
+               mask=mg)
+    check(go, oo, 1e-4, "disc output")
+    check(gb, ob, 1e-4, "branch logits")
+    ((go * d_out.to(DEV)).sum() + (gb * d_br.to(DEV)).sum()).backward()
+    check(relg.grad, relr.grad, 5e-4, "d pred_dxdy")
+
+    # the trainable path (dense-layer kernels on the materialised classifier input) agrees with the hoisted one
+    for p_ in D.parameters():
+        p_.requires_grad_(True)
+    relt = rel.clone().to(DEV).requires_grad_(True)
+    to, tb = D(bt["in_xy"].to(DEV), bt["in_dxdy"].to(DEV), ab.to(DEV), relt, sse, img=img.to(DEV) if with_img else None,
+               mask=mg)
+    check(to, go, 1e-5, "trainable vs hoisted output")
+    check(tb, gb, 1e-5, "trainable vs hoisted branch")
+    ((to * d_out.to(DEV)).sum() + (tb * d_br.to(DEV)).sum()).backward()
+    check(relt.grad, relg.grad, 1e-4, "trainable vs hoisted d pred")
