@@ -20,6 +20,19 @@ def _f32(t):
     return t.contiguous()
 
 
+def _zeros(device, *shapes):
+    """Zero-filled fp32 tensors of the given shapes carved out of ONE allocation (one fill launch instead of one
+    per gradient accumulator); every tensor starts on a 16-byte boundary."""
+    sizes = [int(math.prod(sh)) for sh in shapes]
+    padded = [(n + 3) & ~3 for n in sizes]
+    flat = torch.zeros(sum(padded), device=device, dtype=torch.float32)
+    out, off = [], 0
+    for sh, n, pn in zip(shapes, sizes, padded):
+        out.append(flat[off:off + n].view(sh))
+        off += pn
+    return out
+
+
 # --------------------------------------------------------------------------- dense layer
 class _Linear(torch.autograd.Function):
     @staticmethod
@@ -43,8 +56,7 @@ class _Linear(torch.autograd.Function):
         O = w.shape[0]
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
         dx = torch.empty_like(x) if need_x else None
-        dw = torch.zeros_like(w) if (need_w or need_b) else None
-        db = torch.zeros(O, device=x.device, dtype=torch.float32) if (need_w or need_b) else None
+        dw, db = _zeros(x.device, w.shape, (O,)) if (need_w or need_b) else (None, None)
         call("mggan_linear_bwd", ptr(x), M, K, ptr(w), O, ctx.act, ctx.slope, ptr(y), ptr(dy), ptr(dx), ptr(dw), ptr(db))
         return dx, (dw if need_w else None), (db if need_b else None), None, None, None
 
@@ -118,9 +130,7 @@ class _LstmSeq(torch.autograd.Function):
         x, whh, acts = ctx.saved_tensors
         T, N, _ = x.shape
         H = whh.shape[1]
-        dwx = torch.zeros(4 * H, 2, device=x.device, dtype=torch.float32)
-        db = torch.zeros(4 * H, device=x.device, dtype=torch.float32)
-        dwhh = torch.zeros_like(whh)
+        dwx, db, dwhh = _zeros(x.device, (4 * H, 2), (4 * H,), whh.shape)
         call("mggan_lstm_seq_bwd", ptr(x), T, N, H, ptr(whh), ptr(acts), ptr(_f32(dh)), ptr(dwx), ptr(db), ptr(dwhh))
         return None, dwx, db, dwhh, None
 
@@ -192,8 +202,7 @@ class _SocialAttn(torch.autograd.Function):
         sc = ctx.scenes
         N, HD = h.shape
         dsig = torch.empty_like(att)
-        dh, dus = torch.zeros_like(h), torch.zeros_like(us)
-        dw1, db1, dw2, db2 = torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w2), torch.zeros_like(b2)
+        dh, dus, dw1, db1, dw2, db2 = _zeros(h.device, h.shape, us.shape, w1.shape, b1.shape, w2.shape, b2.shape)
         call("mggan_social_attn_bwd", ptr(x4), ptr(h), HD, ptr(us), ptr(sc.scene_off), ptr(sc.pair_off), sc.n_scenes,
              ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(att), ptr(_f32(dS)), ptr(dsig), ptr(dh), ptr(dus), ptr(dw1),
              ptr(db1), ptr(dw2), ptr(db2))
@@ -305,21 +314,20 @@ class _SceneAttn(torch.autograd.Function):
         N, C, dev, group, ps = ctx.N, ctx.C, img.device, ctx.group, ctx.ps
         dout = _f32(dout)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, device=dev, dtype=dt)
-        da0w, da0b, da2w, da2b = z(32, C), z(32), z(C, 32), z(C)
+        da0w, da0b, da2w, da2b, dg2, db2, dc2w, dc2b, S1, dc1b = _zeros(dev, (32, C), (32,), (C, 32), (C,), (C,), (C,),
+                                                                        (C, C, 3, 3), (C,), (C, 36), (C,))
+        sums2, sums1 = torch.zeros(2, 2 * C, device=dev, dtype=torch.float64).unbind(0)
         dy2 = torch.empty(N, C, 64, device=dev)
         idx2 = torch.empty(N, C, 64, device=dev, dtype=torch.uint8)
-        sums2 = z(2 * C, dt=torch.float64)
         call("mggan_scene_attn_bwd", ptr(x2), N, C, ptr(ab2), ptr(mi2), ptr(a0w), ptr(a0b), ptr(a2w), ptr(a2b),
              ptr(dout), ptr(da0w), ptr(da0b), ptr(da2w), ptr(da2b), ptr(dy2), ptr(idx2), ptr(sums2))
         # BatchNorm affine gradients are sums over the local shard; the means use global sums
-        m12_2, dg2, db2 = torch.empty(2 * C, device=dev), z(C), z(C)
+        m12_2 = torch.empty(2 * C, device=dev)
         loc2 = sums2.clone() if group is not None else sums2
         _allreduce(sums2, group)
         call("mggan_scene_bn_bwd_finalize", ptr(sums2), ctx.n_total * 256.0, C, ptr(m12_2), ptr(dg2), ptr(db2))
         if group is not None:
             dg2, db2 = loc2[C:].float(), loc2[:C].float()
-        dc2w, dc2b, S1 = z(C, C, 3, 3), z(C), z(C, 36)
-        sums1 = z(2 * C, dt=torch.float64)
         call("mggan_scene_fused12_bwd", ptr(img), ptr(ctx.rows), N, C, ptr(x2), ptr(e1), ptr(idx1), ptr(ab1), ptr(mi1),
              ptr(ab2), ptr(mi2), ptr(m12_2), ptr(c2w), ptr(dy2), ptr(idx2), ptr(dc2w), ptr(dc2b), ptr(S1), ptr(sums1))
         glob1 = sums1
@@ -329,7 +337,7 @@ class _SceneAttn(torch.autograd.Function):
         dc1w, dg1, db1 = torch.empty(C, 4, 3, 3, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev)
         call("mggan_scene_bn1_bwd_finalize", ptr(glob1), ptr(sums1), ctx.n_total * 1089.0, C, ptr(S1), ptr(ps.R_local),
              ptr(ps.P_local), ptr(c1w), ptr(c1b), ptr(ab1), ptr(mi1), ptr(dc1w), ptr(dg1), ptr(db1))
-        dc1b = z(C)             # identically zero under train-mode BatchNorm
+        # dc1b stays zero: conv1's bias gradient vanishes identically under train-mode BatchNorm
         return (None, dc1w, dc1b, dg1, db1, dc2w, dc2b, dg2, db2, da0w, da0b, da2w, da2b) + (None,) * 8
 
 
@@ -451,10 +459,9 @@ class _Decoder(torch.autograd.Function):
         social, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2, out_rel, acts, u1, h0 = ctx.saved_tensors
         sel = ctx.sel
         Z = wz.shape[1]
-        zl = torch.zeros_like
-        dwz, dwx, db, dwhh, dw1h, dw1s, db1, dw2, db2 = (zl(t) for t in (wz, wx, b, whh, w1h, w1s, b1, w2, b2))
-        dA = torch.zeros(ctx.n_agents, 32, device=wz.device)
-        dsoc = torch.zeros(ctx.n_agents, 32, device=wz.device)
+        dwz, dwx, db, dwhh, dw1h, dw1s, db1, dw2, db2, dA, dsoc = _zeros(
+            wz.device, wz.shape, wx.shape, b.shape, whh.shape, w1h.shape, w1s.shape, b1.shape, w2.shape, b2.shape,
+            (ctx.n_agents, 32), (ctx.n_agents, 32))
         d_abs = _f32(d_abs) if d_abs is not None else None
         d_rel = _f32(d_rel) if d_rel is not None else None
         call("mggan_decoder_bwd", sel.n_tiles, ptr(sel.tile_gen), ptr(sel.seq_agent), ptr(sel.seq_noise),

@@ -60,6 +60,54 @@ class MultiGenerator(nn.Module):
             nn.Linear(encoder_h_dim // 2, num_gens))
         self.net_prior = nn.Parameter(torch.zeros(1, self.n_gs), requires_grad=learn_prior)
         self._sample_calls = 0
+        self._shared = None             # dict while the trainer guarantees constant weights (see share_trunk)
+
+    # ------------------------------------------------------------------ trunk sharing
+    def share_trunk(self):
+        """Start sharing the observation trunk (trajectory encoder, scene attention, social attention) between
+        forwards on the SAME input tensors.  The discriminator step's no-grad forward (train.py:160) and the
+        generator step's forward (train.py:46) run the same weights on the same observations; between
+        `share_trunk()` and `drop_shared()` the trunk is evaluated once, with its autograd graph, and reused
+        (BatchNorm running statistics are still updated once per forward).  The caller must call
+        `drop_shared()` before the weights change."""
+        self._shared = {}
+        if self.scene_dim > 0:
+            self.scene_encoder.memo = {}
+
+    def drop_shared(self):
+        self._shared = None
+        if self.scene_dim > 0:
+            self.scene_encoder.memo = None
+
+    def _trunk(self, in_xy, in_dxdy, sub_batches, img):
+        """-> (enc_h (N, 32 [+64] + 32), social_feats (N, 32))"""
+        if self._shared is None:
+            return self._trunk_compute(in_xy, in_dxdy, sub_batches, img)
+        scenes = K.SceneIndex.get(sub_batches, in_xy.device)
+        key = (id(in_xy), in_xy._version, id(in_dxdy), in_dxdy._version, id(scenes), self.training)
+        with torch.enable_grad():           # the graph is built even under the D step's no_grad: the G step reuses it
+            hit = self._shared.get(key)
+            if hit is None:
+                enc_h = self.encoder(get_input(in_xy, in_dxdy, self.inp_format))
+                hit = self._shared[key] = (enc_h, self.social(in_xy, in_dxdy, enc_h, scenes))
+            enc_h, social_feats = hit
+            feats = [enc_h]
+            if img is not None:
+                feats.append(self.scene_encoder(img))       # memoised by kernels.scene_attention (replays BN updates)
+            feats.append(social_feats)
+            out = torch.cat(feats, -1)
+        if not torch.is_grad_enabled():
+            out, social_feats = out.detach(), social_feats.detach()
+        return out, social_feats
+
+    def _trunk_compute(self, in_xy, in_dxdy, sub_batches, img):
+        enc_h = self.encoder(get_input(in_xy, in_dxdy, self.inp_format))
+        enc_features = [enc_h]
+        if img is not None:
+            enc_features.append(self.scene_encoder(img))
+        social_feats = self.social(in_xy, in_dxdy, enc_h, sub_batches)
+        enc_features.append(social_feats)
+        return torch.cat(enc_features, -1), social_feats
 
     # ------------------------------------------------------------------ pieces
     def _stacked_decoder_weights(self):
@@ -97,13 +145,7 @@ class MultiGenerator(nn.Module):
         """See reference standard.py:111-215.  Returns (GeneratorOutput(rel, abs), logits, idx):
         rel/abs (pred_len, k, n_act, 2), or (pred_len, k, G, n_act, 2) under no_grad if all_gen_out."""
         batch_size = in_xy.size(1)
-        enc_h = self.encoder(get_input(in_xy, in_dxdy, self.inp_format))
-        enc_features = [enc_h]
-        if img is not None:
-            enc_features.append(self.scene_encoder(img))
-        social_feats = self.social(in_xy, in_dxdy, enc_h, sub_batches)
-        enc_features.append(social_feats)
-        enc_h = torch.cat(enc_features, -1)
+        enc_h, social_feats = self._trunk(in_xy, in_dxdy, sub_batches, img)
 
         if noise is not None:
             assert noise.shape == (num_samples, batch_size, self.z_size)

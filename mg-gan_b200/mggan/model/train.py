@@ -104,6 +104,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
             clf = K.ce_generators(branch_out.flatten(0, 1), gen_idxs.reshape(-1), counts, 1.0 / denom)
             train_metrics["train/info_mgan_loss"].append(clf.detach())
             loss = loss + cfg.clf_loss_weight * clf
+        self.G.drop_shared()                # the trunk graph is now owned by `loss`; the weights are about to change
         self.D.zero_grad()
         self.G.zero_grad()
         loss.backward()
@@ -129,6 +130,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
         l_real, _ = _label_scalars(real_result.shape)
         real_loss = K.bce_scalar_label(real_result.contiguous(), l_real, inv_denom=1.0 / denom)
         noise = self._noise(sub_batches)[None]
+        self.G.share_trunk()                # the generator step that follows runs the same weights on these inputs
         with torch.no_grad():
             gen_out, _, gen_labels_gt = self.G(in_xy, in_dxdy, sub_batches, noise=noise, all_gen_out=False, img=img,
                                                num_samples=1, mask=loss_mask)
@@ -150,6 +152,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
         cfg = self.config
         if cfg.weighting_target == "none":
             return
+        self.G.drop_shared()
         gen_out, net_chooser_weights, _ = self.G(in_xy, in_dxdy, sub_batches, noise=None, all_gen_out=True, img=img,
                                                  num_samples=cfg.num_expectation_samples, mask=mask)
         with torch.no_grad():
