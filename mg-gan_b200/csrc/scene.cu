@@ -138,93 +138,82 @@ __global__ void scene_bn_bwd_finalize_kernel(const double* __restrict__ sums, do
 // mean(x1_c) = (W_c . P) / n + b_c,  E[x1_c^2] = (W_c^T R W_c + 2 b_c W_c . P) / n + b_c^2, and
 // sum x1_c * patch_a = (R W_c)_a + b_c P_a.  They depend on the crops only, so one launch serves every
 // scene-CNN forward / backward of a training iteration (G and D, three optimiser steps).
-// warp = 4x4 block of R (45 upper-triangular blocks over 8 warps), lanes = pixels.
+// A CTA owns ONE pair of input channels (A <= B, 10 pairs) for a strided subset of the agents: it stages the two
+// padded channels, threads own pixels, and each thread keeps the full 9 x 9 tap block of R for that channel pair in
+// registers across all its agents (18 shared-memory loads feed 81 FMAs per pixel), reduced once at the end.
 constexpr int NTAP = 36;
-constexpr int NBLK_R = 45;
+constexpr int NPAIRS_CH = CIN * (CIN + 1) / 2;     // 10
 
-__global__ void __launch_bounds__(MGGAN_THREADS)
-scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N, double* __restrict__ R,
-                         double* __restrict__ P) {
-    extern __shared__ __align__(16) float smem[];
-    float* sImg = smem;                       // [4][35][36]
-    __shared__ int sOff[NTAP];
-    __shared__ unsigned char sBlk[NBLK_R][2];
-    if (threadIdx.x < NTAP) {
-        int a = threadIdx.x, ci = a / 9, t = a - ci * 9;
-        sOff[a] = ci * IMGPAD + (t / 3) * LDI + (t % 3);
-    }
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (int A = 0; A < 9; ++A)
-            for (int B = A; B < 9; ++B) { sBlk[n][0] = (unsigned char)A; sBlk[n][1] = (unsigned char)B; ++n; }
-    }
-    for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int MAXB = (NBLK_R + 7) / 8;    // 6 blocks per warp at most
-    float acc[MAXB][16], ps[MAXB][4];         // fp32 partials over this CTA's agents (~2k terms per lane)
-#pragma unroll
-    for (int j = 0; j < MAXB; ++j) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) acc[j][q] = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ps[j][q] = 0.f;
-    }
-    __syncthreads();
+constexpr int PS_THREADS = 128;                    // ~150 registers per thread (81 accumulators): 3 CTAs per SM
 
-    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+__global__ void __launch_bounds__(PS_THREADS, 3)
+scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N, int slots,
+                         double* __restrict__ R, double* __restrict__ P) {
+    __shared__ __align__(16) float sImg[2 * IMGPAD];          // channels A and B, [35][36] each, zero halo
+    const int bp = blockIdx.x % NPAIRS_CH, slot = blockIdx.x / NPAIRS_CH;
+    int cA = 0, cB = 0;
+    {
+        int q = bp;
+        for (cA = 0; cA < CIN; ++cA) {
+            if (q < CIN - cA) { cB = cA + q; break; }
+            q -= CIN - cA;
+        }
+    }
+    const bool diag = cA == cB;
+    for (int i = threadIdx.x; i < 2 * IMGPAD; i += PS_THREADS) sImg[i] = 0.f;
+    float acc[81], ps[9];
+#pragma unroll
+    for (int q = 0; q < 81; ++q) acc[q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) ps[q] = 0.f;
+    const float* sA = sImg;
+    const float* sB = diag ? sImg : sImg + IMGPAD;
+
+    for (int n = slot; n < N; n += slots) {
         const int src = rows ? rows[n] : n;
         __syncthreads();
-        const float* ip = img + (size_t)src * CIN * IMG2;
-        for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
-            int ci = i / IMG2, p = i - ci * IMG2, y = p / IMG, x = p - y * IMG;
-            sImg[ci * IMGPAD + (y + 1) * LDI + x + 1] = __ldg(ip + i);
+        const float* ipA = img + ((size_t)src * CIN + cA) * IMG2;
+        const float* ipB = img + ((size_t)src * CIN + cB) * IMG2;
+        for (int i = threadIdx.x; i < IMG2; i += PS_THREADS) {
+            int y = i / IMG, x = i - y * IMG;
+            sImg[(y + 1) * LDI + x + 1] = __ldg(ipA + i);
+            if (!diag) sImg[IMGPAD + (y + 1) * LDI + x + 1] = __ldg(ipB + i);
         }
         __syncthreads();
+        for (int p = threadIdx.x; p < IMG2; p += PS_THREADS) {
+            const int y = p / IMG, x = p - y * IMG, base = y * LDI + x;
+            float va[9], vb[9];
 #pragma unroll
-        for (int j = 0; j < MAXB; ++j) {
-            const int blk = warp + 8 * j;
-            if (blk >= NBLK_R) continue;
-            const int A = sBlk[blk][0], B = sBlk[blk][1];
-            int oa[4], ob[4];
+            for (int t = 0; t < 9; ++t) va[t] = sA[base + (t / 3) * LDI + (t % 3)];
+            if (diag) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { oa[q] = sOff[A * 4 + q]; ob[q] = sOff[B * 4 + q]; }
-            const bool diag = A == B;
-            for (int p = lane; p < IMG2; p += 32) {
-                const int y = p / IMG, x = p - y * IMG, base = y * LDI + x;
-                float va[4], vb[4];
+                for (int t = 0; t < 9; ++t) { vb[t] = va[t]; ps[t] += va[t]; }
+            } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { va[q] = sImg[base + oa[q]]; vb[q] = sImg[base + ob[q]]; }
-#pragma unroll
-                for (int qa = 0; qa < 4; ++qa)
-#pragma unroll
-                    for (int qb = 0; qb < 4; ++qb) acc[j][qa * 4 + qb] = fmaf(va[qa], vb[qb], acc[j][qa * 4 + qb]);
-                if (diag) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) ps[j][q] += va[q];
-                }
+                for (int t = 0; t < 9; ++t) vb[t] = sB[base + (t / 3) * LDI + (t % 3)];
             }
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+#pragma unroll
+                for (int j = 0; j < 9; ++j) acc[i * 9 + j] = fmaf(va[i], vb[j], acc[i * 9 + j]);
         }
     }
+    // CTA reduction: warp shuffles in double, then one atomicAdd per entry per warp
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < MAXB; ++j) {
-        const int blk = warp + 8 * j;
-        if (blk >= NBLK_R) continue;
-        const int A = sBlk[blk][0], B = sBlk[blk][1];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            double v = warp_sum_d((double)acc[j][q]);
-            if (lane == 0) {
-                int a = A * 4 + q / 4, b = B * 4 + (q & 3);
-                atomicAdd(R + a * NTAP + b, v);
-                if (A != B) atomicAdd(R + b * NTAP + a, v);
-            }
+    for (int q = 0; q < 81; ++q) {
+        double v = warp_sum_d((double)acc[q]);
+        if (lane == 0) {
+            const int a = cA * 9 + q / 9, b = cB * 9 + q % 9;
+            atomicAdd(R + a * NTAP + b, v);
+            if (!diag) atomicAdd(R + b * NTAP + a, v);
         }
-        if (A == B) {
+    }
+    if (diag) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                double v = warp_sum_d((double)ps[j][q]);
-                if (lane == 0) atomicAdd(P + A * 4 + q, v);
-            }
+        for (int q = 0; q < 9; ++q) {
+            double v = warp_sum_d((double)ps[q]);
+            if (lane == 0) atomicAdd(P + cA * 9 + q, v);
         }
     }
 }
@@ -889,8 +878,9 @@ int attn_bwd(const float* x2, int N, const float* ab2, const float* mi2, const f
 extern "C" int mggan_scene_patch_stats(const float* img, const int* rows, int N, double* R, double* P,
                                        cudaStream_t stream) {
     if (N <= 0) return MGGAN_OK;
-    size_t sm = sizeof(float) * CIN * IMGPAD;
-    scene_patch_stats_kernel<<<agent_grid(N, 2), MGGAN_THREADS, sm, stream>>>(img, rows, N, R, P);
+    int slots = sm_count() * 3 / NPAIRS_CH;          // 44 agent slots x 10 channel pairs = 440 CTAs, 3 per SM
+    if (slots > N) slots = N;
+    scene_patch_stats_kernel<<<slots * NPAIRS_CH, PS_THREADS, 0, stream>>>(img, rows, N, slots, R, P);
     return mggan_check_launch("scene_patch_stats");
 }
 

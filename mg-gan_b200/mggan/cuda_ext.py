@@ -115,13 +115,21 @@ def ptr(t):
     """Device pointer of a contiguous tensor (None -> NULL)."""
     if t is None:
         return None
-    if not t.is_cuda:
-        raise MgganCudaError(f"tensor on {t.device}: the MG-GAN B200 path only runs on CUDA (there is no CPU fallback)")
-    assert t.is_contiguous(), (t.shape, t.stride())
+    if not (t.is_cuda and t.is_contiguous()):
+        if not t.is_cuda:
+            raise MgganCudaError(
+                f"tensor on {t.device}: the MG-GAN B200 path only runs on CUDA (there is no CPU fallback)")
+        raise AssertionError(("non-contiguous tensor", t.shape, t.stride()))
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+    """cudaStream_t of torch's current stream on the current device (raw handle; no Stream object is built)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

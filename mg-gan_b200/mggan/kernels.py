@@ -73,7 +73,8 @@ class _DiscHeads(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pe, base, soc0, w1p, wd2, bd2, wg2, bg2, n, k, grad_on):
-        assert not any(ctx.needs_input_grad[3:8]), "disc_heads: weight gradients are not produced (frozen discriminator only)"
+        assert not (grad_on and any(ctx.needs_input_grad[3:8])), \
+            "disc_heads: weight gradients are not produced (frozen discriminator only)"
         pe, base, soc0, w1p, wd2, bd2 = map(_f32, (pe, base, soc0, w1p, wd2, bd2))
         G = 0 if wg2 is None else wg2.shape[0]
         HH = wd2.shape[-1]
