@@ -27,7 +27,8 @@ constexpr int AH = 32;                         // attention MLP hidden width (cn
 constexpr int LDI = 36;                        // padded image row (35 used)
 constexpr int IMGPAD = 35 * LDI;               // one padded channel
 constexpr int LDP = 18;                        // padded pooled row
-constexpr int PPAD = LDP * LDP + 1;            // 325: channel stride (odd -> conflict-free across channels)
+constexpr int PPAD = LDP * LDP + 2;            // 326: channel stride (even: 8-byte aligned rows for LDS.64; 326 mod 32 = 6 keeps
+                                               // 16 channels on distinct banks)
 
 int sm_count() {
     static int n = 0;
@@ -73,6 +74,23 @@ __device__ __forceinline__ void block_reduce_to_global_f(const float (&v)[NV], f
         for (int w = 0; w < MGGAN_THREADS / 32; ++w) s += sred[w * NV + threadIdx.x];
         atomicAdd(dst + threadIdx.x, s);
     }
+    __syncthreads();
+}
+
+// Per-channel sums kept by threads that own 4 channels (cq*4 .. cq*4+3): shared-memory double atomics, then one
+// global double atomicAdd per channel per CTA.  v[0..3] -> dst[cq*4 + c], v[4..7] -> dst[C + cq*4 + c].
+template <int C>
+__device__ __forceinline__ void quad_reduce_to_global(const float (&v)[8], int cq, double* __restrict__ dst, double* sd) {
+    __syncthreads();
+    if (threadIdx.x < 2 * C) sd[threadIdx.x] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        atomicAdd(sd + cq * 4 + c, (double)v[c]);
+        atomicAdd(sd + C + cq * 4 + c, (double)v[4 + c]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C) atomicAdd(dst + threadIdx.x, sd[threadIdx.x]);
     __syncthreads();
 }
 
@@ -303,10 +321,13 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     if (threadIdx.x < 2 * C) sAB[threadIdx.x] = __ldg(ab1 + threadIdx.x);
     for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
     for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) sP[i] = 0.f;
-    float st[2 * C];
+    constexpr int PX = C / 4;                     // pixels per thread in the conv2 stage (4 x PX outputs per thread)
+    float st[8];                                  // BatchNorm-2 partial sums of this thread's 4 output channels
 #pragma unroll
-    for (int c = 0; c < 2 * C; ++c) st[c] = 0.f;
+    for (int c = 0; c < 8; ++c) st[c] = 0.f;
     const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
+    const int cq = threadIdx.x % (C / 4), gp = threadIdx.x / (C / 4);
+    const int gy = gp / (P1 / PX), gx0 = (gp % (P1 / PX)) * PX;
 
     for (int n = blockIdx.x; n < N; n += gridDim.x) {
         const int src = rows ? rows[n] : n;
@@ -368,32 +389,46 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             }
         }
         __syncthreads();
-        float acc2[C];
+        {   // conv2: thread = PX adjacent pixels of a row x 4 output channels; (PX+2)/2 LDS.64 + 3 LDS.128 per 12 PX FMAs
+            float acc2[PX][4];
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc2[c] = __ldg(b2 + c);
+            for (int c = 0; c < 4; ++c) {
+                const float bv = __ldg(b2 + cq * 4 + c);
+#pragma unroll
+                for (int j = 0; j < PX; ++j) acc2[j][c] = bv;
+            }
 #pragma unroll 2
-        for (int ci = 0; ci < C; ++ci)
+            for (int ci = 0; ci < C; ++ci)
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+                for (int ky = 0; ky < 3; ++ky) {
+                    float pv[PX + 2];
+                    const float* rp = sP + ci * PPAD + (gy + ky) * LDP + gx0;
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float v = sP[ci * PPAD + (py + ky) * LDP + px + kx];
-                    const float* wp = sW2 + (ci * 9 + ky * 3 + kx) * C;
+                    for (int m = 0; m < PX + 2; m += 2) {
+                        float2 t2 = *reinterpret_cast<const float2*>(rp + m);
+                        pv[m] = t2.x; pv[m + 1] = t2.y;
+                    }
 #pragma unroll
-                    for (int c = 0; c < C; c += 4) {
-                        float4 w = ld4(wp + c);
-                        acc2[c] = fmaf(v, w.x, acc2[c]); acc2[c + 1] = fmaf(v, w.y, acc2[c + 1]);
-                        acc2[c + 2] = fmaf(v, w.z, acc2[c + 2]); acc2[c + 3] = fmaf(v, w.w, acc2[c + 3]);
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float4 w = ld4(sW2 + (ci * 9 + ky * 3 + kx) * C + cq * 4);
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) {
+                            acc2[j][0] = fmaf(pv[j + kx], w.x, acc2[j][0]); acc2[j][1] = fmaf(pv[j + kx], w.y, acc2[j][1]);
+                            acc2[j][2] = fmaf(pv[j + kx], w.z, acc2[j][2]); acc2[j][3] = fmaf(pv[j + kx], w.w, acc2[j][3]);
+                        }
                     }
                 }
-        float* o = x2 + (size_t)n * C * P1SQ + threadIdx.x;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            o[c * P1SQ] = acc2[c];
-            st[c] += acc2[c]; st[C + c] = fmaf(acc2[c], acc2[c], st[C + c]);
+            for (int c = 0; c < 4; ++c) {
+                float* o = x2 + ((size_t)n * C + cq * 4 + c) * P1SQ + gy * P1 + gx0;
+                if (PX == 4) st4(o, make_float4(acc2[0][c], acc2[1][c], acc2[2 % PX][c], acc2[3 % PX][c]));
+                else *reinterpret_cast<float2*>(o) = make_float2(acc2[0][c], acc2[1][c]);
+#pragma unroll
+                for (int j = 0; j < PX; ++j) { st[c] += acc2[j][c]; st[4 + c] = fmaf(acc2[j][c], acc2[j][c], st[4 + c]); }
+            }
         }
     }
-    if (stats2 != nullptr) block_reduce_to_global<2 * C>(st, stats2, sred);
+    if (stats2 != nullptr) quad_reduce_to_global<C>(st, cq, stats2, reinterpret_cast<double*>(sred));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -411,9 +446,10 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                          const float* __restrict__ W2, const float* __restrict__ dy2,
                          const unsigned char* __restrict__ idx2, float* __restrict__ dW2, float* __restrict__ dbias2,
                          float* __restrict__ S1, double* __restrict__ sums1) {
-    constexpr int NPAIR = C * C;
-    constexpr int PG = MGGAN_THREADS / NPAIR;            // pixel-row groups for the conv2 weight gradient (1 or 4)
-    constexpr int ROWS_PG = P1 / PG;
+    constexpr int PX = C / 4;                            // pixels per thread in the conv2 input-gradient stage
+    constexpr int NITEM = C * C / 4;                     // (4 output channels, input channel) items of the conv2 weight gradient
+    constexpr int PG = MGGAN_THREADS / NITEM;            // pixel-row groups (4 or 16)
+    constexpr int ROWS_PG = P1 / PG;                     // rows per group (4 or 1)
     constexpr int QG = MGGAN_THREADS / (C * CIN);        // pooled-pixel groups for the sparse conv1 term (4 or 8)
     constexpr int Q_PER = P1SQ / QG;
     extern __shared__ __align__(16) float smem[];
@@ -439,15 +475,25 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) { sDX[i] = 0.f; sP[i] = 0.f; }
     for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
     const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
-    const int pr = threadIdx.x % NPAIR, pg = threadIdx.x / NPAIR;
-    const int w_co = pr / C, w_ci = pr % C;
+    // conv2 weight gradient: thread = (4 output channels, input channel, pixel-row group)
+    const int item = threadIdx.x % NITEM, pg = threadIdx.x / NITEM;
+    const int w_coq = item / C, w_ci = item % C;
+    // conv2 input gradient: thread = (PX adjacent pixels, 4 input channels)
+    const int cq = threadIdx.x % (C / 4), gp = threadIdx.x / (C / 4);
+    const int gy = gp / (P1 / PX), gx0 = (gp % (P1 / PX)) * PX;
     const int s_c = threadIdx.x / (CIN * QG), s_ci = (threadIdx.x / QG) % CIN, s_qg = threadIdx.x % QG;
-    float wacc[9], sacc[9];
+    float wacc[4][9], sacc[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { wacc[i] = 0.f; sacc[i] = 0.f; }
-    float dbs[C], st[2 * C];
+    for (int i = 0; i < 9; ++i) {
+        sacc[i] = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { dbs[c] = 0.f; st[c] = 0.f; st[C + c] = 0.f; }
+        for (int a = 0; a < 4; ++a) wacc[a][i] = 0.f;
+    }
+    float dbs[C], st[8];
+#pragma unroll
+    for (int c = 0; c < C; ++c) dbs[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) st[c] = 0.f;
 
     for (int n = blockIdx.x; n < N; n += gridDim.x) {
         const int src = rows ? rows[n] : n;
@@ -477,56 +523,74 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             }
         }
         __syncthreads();
-        {   // conv2 weight gradient: thread = (co, ci) x pixel-row group, 3x3 taps in registers
-            const float* dxp = sDX + w_co * PPAD;
+        {   // conv2 weight gradient: 3 new p1 values + 4 dx values feed 36 FMAs per pixel
             const float* pp = sP + w_ci * PPAD;
+            const float* dxp = sDX + (w_coq * 4) * PPAD;
+#pragma unroll 1
             for (int yy = pg * ROWS_PG; yy < (pg + 1) * ROWS_PG; ++yy) {
                 float c0[3], c1[3], c2[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) { c0[r] = pp[(yy + r) * LDP]; c1[r] = pp[(yy + r) * LDP + 1]; }
-#pragma unroll
+#pragma unroll 4
                 for (int xx = 0; xx < P1; ++xx) {
 #pragma unroll
                     for (int r = 0; r < 3; ++r) c2[r] = pp[(yy + r) * LDP + xx + 2];
-                    const float d = dxp[(yy + 1) * LDP + xx + 1];
+                    float d[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) d[a] = dxp[a * PPAD + (yy + 1) * LDP + xx + 1];
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        wacc[r * 3] = fmaf(d, c0[r], wacc[r * 3]);
-                        wacc[r * 3 + 1] = fmaf(d, c1[r], wacc[r * 3 + 1]);
-                        wacc[r * 3 + 2] = fmaf(d, c2[r], wacc[r * 3 + 2]);
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            wacc[a][r * 3] = fmaf(d[a], c0[r], wacc[a][r * 3]);
+                            wacc[a][r * 3 + 1] = fmaf(d[a], c1[r], wacc[a][r * 3 + 1]);
+                            wacc[a][r * 3 + 2] = fmaf(d[a], c2[r], wacc[a][r * 3 + 2]);
+                        }
                         c0[r] = c1[r]; c1[r] = c2[r];
                     }
                 }
             }
         }
-        {   // conv2 input gradient at this thread's pooled pixel -> pool / ReLU / BN1 -> dy1
-            float acc[C];
+        {   // conv2 input gradient at PX adjacent pixels x 4 input channels -> pool / ReLU / BN1 -> dy1
+            float acc[PX][4];
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] = 0.f;
+            for (int j = 0; j < PX; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
 #pragma unroll 2
             for (int co = 0; co < C; ++co)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+                for (int ky = 0; ky < 3; ++ky) {
+                    float dv[PX + 2];
+                    const float* rp = sDX + co * PPAD + (gy + 2 - ky) * LDP + gx0;
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float d = sDX[co * PPAD + (y + 2 - ky) * LDP + x + 2 - kx];
-                        const float* wp = sWT + (co * 9 + ky * 3 + kx) * C;
-#pragma unroll
-                        for (int c = 0; c < C; c += 4) {
-                            float4 q = ld4(wp + c);
-                            acc[c] = fmaf(d, q.x, acc[c]); acc[c + 1] = fmaf(d, q.y, acc[c + 1]);
-                            acc[c + 2] = fmaf(d, q.z, acc[c + 2]); acc[c + 3] = fmaf(d, q.w, acc[c + 3]);
-                        }
+                    for (int m = 0; m < PX + 2; m += 2) {
+                        float2 t2 = *reinterpret_cast<const float2*>(rp + m);
+                        dv[m] = t2.x; dv[m + 1] = t2.y;
                     }
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const int code = sIdx[c * P1SQ + threadIdx.x];
-                const float d = (code & 4) ? acc[c] : 0.f;
-                sDY[c * P1SQ + threadIdx.x] = d;
-                const float e = __ldg(e1 + ((size_t)n * C + c) * P1SQ + threadIdx.x);
-                const float xh = (e - sPar[2 * C + c]) * sPar[3 * C + c];
-                st[c] += d;
-                st[C + c] = fmaf(d, xh, st[C + c]);
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float4 q = ld4(sWT + (co * 9 + ky * 3 + kx) * C + cq * 4);
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) {
+                            const float d = dv[j + 2 - kx];
+                            acc[j][0] = fmaf(d, q.x, acc[j][0]); acc[j][1] = fmaf(d, q.y, acc[j][1]);
+                            acc[j][2] = fmaf(d, q.z, acc[j][2]); acc[j][3] = fmaf(d, q.w, acc[j][3]);
+                        }
+                    }
+                }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int ch = cq * 4 + c, pix0 = gy * P1 + gx0;
+                const float mu = sPar[2 * C + ch], is = sPar[3 * C + ch];
+                const float* ep = e1 + ((size_t)n * C + ch) * P1SQ + pix0;
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    const int code = sIdx[ch * P1SQ + pix0 + j];
+                    const float d = (code & 4) ? acc[j][c] : 0.f;
+                    sDY[ch * P1SQ + pix0 + j] = d;
+                    const float xh = (__ldg(ep + j) - mu) * is;
+                    st[c] += d;
+                    st[4 + c] = fmaf(d, xh, st[4 + c]);
+                }
             }
         }
         __syncthreads();
@@ -544,13 +608,20 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             }
         }
     }
+    // conv2 weight gradient: merge the pixel-row groups in shared memory, one global atomic per element per CTA
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) sDY[i] = 0.f;
+    __syncthreads();
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        atomicAdd(dW2 + ((size_t)w_co * C + w_ci) * 9 + t, wacc[t]);
-        atomicAdd(S1 + ((size_t)s_c * CIN + s_ci) * 9 + t, sacc[t]);
-    }
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) atomicAdd(sDY + ((w_coq * 4 + a) * C + w_ci) * 9 + t, wacc[a][t]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) atomicAdd(dW2 + i, sDY[i]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(S1 + ((size_t)s_c * CIN + s_ci) * 9 + t, sacc[t]);
     block_reduce_to_global_f<C>(dbs, dbias2, sred);
-    block_reduce_to_global<2 * C>(st, sums1, sred);
+    quad_reduce_to_global<C>(st, cq, sums1, reinterpret_cast<double*>(sred));
 }
 
 // BatchNorm-1 backward closed form (one thread per (channel, tap), double precision):
