@@ -198,8 +198,13 @@ scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ 
             if (!diag) sImg[IMGPAD + (y + 1) * LDI + x + 1] = __ldg(ipB + i);
         }
         __syncthreads();
-        for (int p = threadIdx.x; p < IMG2; p += PS_THREADS) {
-            const int y = p / IMG, x = p - y * IMG, base = y * LDI + x;
+        // lanes = 32 consecutive pixels of one row (conflict-free shared-memory reads), warps = rows; the 33rd
+        // column is swept afterwards by the first 33 threads
+        for (int it = threadIdx.x >> 5; it < IMG + 2; it += PS_THREADS / 32) {
+            int y, x;
+            if (it < IMG) { y = it; x = threadIdx.x & 31; }
+            else { y = (it - IMG) * 32 + (threadIdx.x & 31); x = IMG - 1; if (y >= IMG) continue; }
+            const int base = y * LDI + x;
             float va[9], vb[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) va[t] = sA[base + (t / 3) * LDI + (t % 3)];
@@ -452,12 +457,13 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     constexpr int ROWS_PG = P1 / PG;                     // rows per group (4 or 1)
     constexpr int QG = MGGAN_THREADS / (C * CIN);        // pooled-pixel groups for the sparse conv1 term (4 or 8)
     constexpr int Q_PER = P1SQ / QG;
+    constexpr int LDY = P1SQ + 4;                        // channel stride of sDY: neighbouring channels on different banks
     extern __shared__ __align__(16) float smem[];
     float* sDX = smem;                                   // [C][PPAD]  dx2 with zero halo
     float* sP = sDX + C * PPAD;                          // [C][PPAD]  p1 with zero halo
     float* sWT = sP + ((C * PPAD + 3) & ~3);             // [(co*9+tap)][ci]
-    float* sDY = sWT + 9 * C * C;                        // [C][256] dy1 (sparse values, dense layout)
-    float* sImg = sDY + C * P1SQ;                        // [4][35][36]
+    float* sDY = sWT + 9 * C * C;                        // [C][LDY] dy1 (sparse values, dense layout)
+    float* sImg = sDY + C * LDY;                         // [4][35][36]
     float* sPar = sImg + CIN * IMGPAD;                   // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
     float* sred = sPar + 10 * C;                         // [8][2C]
     unsigned char* sIdx = reinterpret_cast<unsigned char*>(sred + 8 * 2 * C);    // [C][256]
@@ -582,22 +588,37 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                 const int ch = cq * 4 + c, pix0 = gy * P1 + gx0;
                 const float mu = sPar[2 * C + ch], is = sPar[3 * C + ch];
                 const float* ep = e1 + ((size_t)n * C + ch) * P1SQ + pix0;
+                float ev[PX], dv[PX];
+                unsigned codes;
+                if (PX == 4) {
+                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(ep));
+                    ev[0] = e4.x; ev[1] = e4.y; ev[2 % PX] = e4.z; ev[3 % PX] = e4.w;
+                    codes = *reinterpret_cast<const unsigned*>(sIdx + ch * P1SQ + pix0);
+                } else {
+                    const float2 e2 = __ldg(reinterpret_cast<const float2*>(ep));
+                    ev[0] = e2.x; ev[1] = e2.y;
+                    codes = *reinterpret_cast<const unsigned short*>(sIdx + ch * P1SQ + pix0);
+                }
 #pragma unroll
                 for (int j = 0; j < PX; ++j) {
-                    const int code = sIdx[ch * P1SQ + pix0 + j];
-                    const float d = (code & 4) ? acc[j][c] : 0.f;
-                    sDY[ch * P1SQ + pix0 + j] = d;
-                    const float xh = (__ldg(ep + j) - mu) * is;
+                    const float d = ((codes >> (8 * j)) & 4u) ? acc[j][c] : 0.f;
+                    dv[j] = d;
+                    const float xh = (ev[j] - mu) * is;
                     st[c] += d;
                     st[4 + c] = fmaf(d, xh, st[4 + c]);
                 }
+                if (PX == 4) st4(sDY + ch * LDY + pix0, make_float4(dv[0], dv[1], dv[2 % PX], dv[3 % PX]));
+                else *reinterpret_cast<float2*>(sDY + ch * LDY + pix0) = make_float2(dv[0], dv[1]);
             }
         }
         __syncthreads();
-        {   // sparse half of the conv1 weight gradient: thread = (c, ci, pooled-pixel group)
+        {   // sparse half of the conv1 weight gradient: thread = (c, ci, lane group); lane groups take interleaved
+            // pooled pixels (q = it * QG + group) so that neighbouring lanes read neighbouring banks
             const float* ipc = sImg + s_ci * IMGPAD;
-            for (int q = s_qg * Q_PER; q < (s_qg + 1) * Q_PER; ++q) {
-                const float d = sDY[s_c * P1SQ + q];
+#pragma unroll 2
+            for (int it = 0; it < Q_PER; ++it) {
+                const int q = it * QG + s_qg;
+                const float d = sDY[s_c * LDY + q];
                 if (d == 0.f) continue;
                 const int code = sIdx[s_c * P1SQ + q] & 3;
                 const float* bp = ipc + (2 * (q >> 4) + (code >> 1)) * LDI + 2 * (q & 15) + (code & 1);
@@ -882,7 +903,7 @@ template <int C>
 size_t fused_fwd_smem() { return sizeof(float) * (CIN * IMGPAD + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * C + 2 * C + 8 * 2 * C); }
 template <int C>
 size_t fused_bwd_smem() {
-    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * C + C * P1SQ + CIN * IMGPAD + 10 * C + 8 * 2 * C) + C * P1SQ;
+    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * C + C * (P1SQ + 4) + CIN * IMGPAD + 10 * C + 8 * 2 * C) + C * P1SQ;
 }
 template <int C>
 size_t attn_w_floats() { return 2 * AH * C + AH + C + 2 * C; }

@@ -144,8 +144,15 @@ social_fwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
     }
 }
 
+// Backward.  Phase 1 (per scene): softmax backward -> d sigma (scratch `dsig`) and dh_j = sum_i att_ij dS_i as a
+// small matrix product (no atomics).  Phase 2: the pair MLP backward over tiles of PT pairs in j-major order
+// (pair p -> j = p / n, i = p % n), every dense piece as a register-blocked shared-memory tile product:
+//     S  = A1 W2^T + b2        (PT x 64, K = 32)     recomputed pre-activation of layer 2
+//     D2 = [S > 0] ds u_j ,  dU_j += ds relu(S)      (run-length accumulated per thread, flushed with atomics)
+//     dA1 = D2 W2 [A1 > 0]     (PT x 32, K = 64)
+//     dW2 += D2^T A1, db2 += colsum D2, dW1 += dA1^T F, db1 += colsum dA1   (kept in registers across tiles)
 template <int HD>
-__global__ void __launch_bounds__(MGGAN_THREADS)
+__global__ void __launch_bounds__(MGGAN_THREADS, 2)
 social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, const float* __restrict__ Us,
                   const int* __restrict__ scene_off, const int* __restrict__ pair_off, int n_scenes,
                   const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
@@ -157,19 +164,25 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
     float* sW2 = smem;                       // [F2][LDW2]
     float* sW1 = sW2 + F2 * LDW2;            // [F1][4]
     float* sb2 = sW1 + F1 * 4;               // [F2]
-    float* sDA2 = sb2 + F2;                  // [PT][LDA2]
-    float* sA1 = sDA2 + PT * LDA2;           // [PT][LDA1]
-    float* sDA1 = sA1 + PT * LDA1;           // [PT][LDA1]
-    float* sF = sDA1 + PT * LDA1;            // [PT][4]
-    float* sX = sF + PT * 4;                 // [NMAX][4]
+    float* sX = sb2 + F2;                    // [NMAX][4]
     float* sU = sX + NMAX * 4;               // [NMAX][LDU]
-    float* sHh = sU + NMAX * LDU;            // [NMAX][LDHS]
-    float* sdU = sHh + NMAX * LDHS;          // [NMAX][LDU]
-    float* sdH = sdU + NMAX * LDU;           // [NMAX][LDHS]
-    float* sdS = sdH + NMAX * LDHS;          // [8 warps][HD]
+    float* sA1 = sU + ((NMAX * LDU + 3) & ~3);   // [PT][LDA1]          (phase 1: sHh [NMAX][LDHS])
+    float* sD2 = sA1 + PT * LDA1;            // [PT][LDA2]          (phase 1: sdS [NMAX][LDHS])
+    float* sDA1 = sD2 + PT * LDA2;           // [PT][LDA1]
+    float* sF = sDA1 + PT * LDA1;            // [PT][4]
+    float* sDs = sF + PT * 4;                // [PT] d sigma of the pair
+    int* sJ = reinterpret_cast<int*>(sDs + PT);   // [PT] local neighbour index j of the pair (-1: padding)
+    float* sHh = sA1;
+    float* sdS = sD2;
     stage_pair_weights(sW1, sW2, sb2, W1, b1, W2, b2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wb = threadIdx.x & 127, whalf = threadIdx.x >> 7;    // dW2 block / row half
+    // layer-2 tile product: warp pair -> 32 rows, thread -> rows rl + 4 i (i < 8), columns u + 16 jj (jj < 4)
+    const int u = (warp & 1) * 8 + (lane & 7);
+    const int rl = (warp >> 1) * 32 + (lane >> 3);
+    // input-gradient tile product: rows d_r0 + 32 i (i < 4), columns 4 d_kq .. +3
+    const int d_kq = threadIdx.x & 7, d_r0 = threadIdx.x >> 3;
+    // weight-gradient blocks
+    const int wb = threadIdx.x & 127, whalf = threadIdx.x >> 7;
     const int w_oq = wb & 15, w_kq = wb >> 4;
     float wacc[4][4];
 #pragma unroll
@@ -182,118 +195,150 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
         const int a = scene_off[sc], n = scene_off[sc + 1] - a;
         if (n <= 1) continue;
         const bool staged = n <= NMAX;
+        const size_t poff = (size_t)pair_off[sc];
         __syncthreads();
         if (staged) {
             for (int i = threadIdx.x; i < n * 4; i += MGGAN_THREADS) sX[i] = __ldg(x4 + (size_t)a * 4 + i);
-            for (int i = threadIdx.x; i < n * LDU; i += MGGAN_THREADS) { sU[i] = __ldg(Us + (size_t)a * LDU + i); sdU[i] = 0.f; }
+            for (int i = threadIdx.x; i < n * LDU; i += MGGAN_THREADS) sU[i] = __ldg(Us + (size_t)a * LDU + i);
             for (int i = threadIdx.x; i < n * HD; i += MGGAN_THREADS) {
                 sHh[(i / HD) * LDHS + (i % HD)] = __ldg(h + (size_t)a * HD + i);
-                sdH[(i / HD) * LDHS + (i % HD)] = 0.f;
+                sdS[(i / HD) * LDHS + (i % HD)] = __ldg(dS + (size_t)a * HD + i);
             }
         }
         __syncthreads();
         const float* pX = staged ? sX : x4 + (size_t)a * 4;
         const float* pU = staged ? sU : Us + (size_t)a * LDU;
         const float* pH = staged ? sHh : h + (size_t)a * HD;
-        float* pdU = staged ? sdU : dUs + (size_t)a * LDU;
-        float* pdH = staged ? sdH : dh + (size_t)a * HD;
+        const float* pdS = staged ? sdS : dS + (size_t)a * HD;
         const int ldh = staged ? LDHS : HD;
-        const size_t poff = (size_t)pair_off[sc];
-        // ---- phase 1: softmax backward per agent i, direct path into dh_j
+        // ---- phase 1a: d sigma_ij = att_ij (dS_i . h_j - sum_j' att_ij' dS_i . h_j'), zero on the diagonal
         for (int il = warp; il < n; il += MGGAN_THREADS / 32) {
-            float* myds = sdS + warp * HD;
-            for (int k = lane; k < HD; k += 32) myds[k] = __ldg(dS + (size_t)(a + il) * HD + k);
-            __syncwarp();
             const float* arow = att + poff + (size_t)il * n;
             float* drow = dsig + poff + (size_t)il * n;
+            const float* dsi = pdS + (size_t)il * ldh;
             float r = 0.f;
             for (int jl = lane; jl < n; jl += 32) {
+                const float* hj = pH + (size_t)jl * ldh;
                 float d = 0.f;
-                for (int k = 0; k < HD; ++k) d = fmaf(myds[k], pH[(size_t)jl * ldh + k], d);
+#pragma unroll 8
+                for (int k = 0; k < HD; ++k) d = fmaf(dsi[k], hj[k], d);
                 drow[jl] = d;
                 r = fmaf(arow[jl], d, r);
             }
             r = warp_sum(r);
             for (int jl = lane; jl < n; jl += 32) drow[jl] = jl == il ? 0.f : arow[jl] * (drow[jl] - r);
-            for (int k = lane; k < HD; k += 32) {
-                float dsk = myds[k];
-                for (int jl = 0; jl < n; ++jl) atomicAdd(pdH + (size_t)jl * ldh + k, arow[jl] * dsk);
-            }
-            __syncwarp();
         }
-        __syncthreads();
-        // ---- phase 2/3: pair MLP backward in tiles of PT pairs; thread = (pair, half of the 64 units)
+        // ---- phase 1b: dh_j[k] = sum_i att_ij dS_i[k]   (thread = (j, k))
+        for (int o = threadIdx.x; o < n * HD; o += MGGAN_THREADS) {
+            const int jl = o / HD, k = o - jl * HD;
+            const float* ac = att + poff + jl;
+            float acc = 0.f;
+            for (int il = 0; il < n; ++il) acc = fmaf(__ldg(ac + (size_t)il * n), pdS[(size_t)il * ldh + k], acc);
+            dh[(size_t)(a + jl) * HD + k] = acc;
+        }
+        __syncthreads();                     // dsig complete (written by this CTA only); phase-1 buffers are free
+        // ---- phase 2: pair tiles
         const int npairs = n * n;
         for (int p0 = 0; p0 < npairs; p0 += PT) {
-            const int pl = threadIdx.x >> 1, half = threadIdx.x & 1;
-            const int p = p0 + pl;
-            float a1[F1], da1[F1];
-#pragma unroll
-            for (int k = 0; k < F1; ++k) da1[k] = 0.f;
-            float f1 = 0.f, f2 = 0.f, f3 = 0.f, ds = 0.f;
-            int jl = 0;
-            if (p < npairs) {
-                int il = p / n;
-                jl = p - il * n;
-                ds = dsig[poff + p];
-                pair_features(ld4(pX + 4 * il), ld4(pX + 4 * jl), f1, f2, f3);
-            }
-            pair_layer1(sW1, f1, f2, f3, a1);
-            if (p >= npairs) {
-#pragma unroll
-                for (int k = 0; k < F1; ++k) a1[k] = 0.f;
-            }
-            const float* uj = pU + (size_t)jl * LDU;
-            float* duj = pdU + (size_t)jl * LDU;
-#pragma unroll 1
-            for (int cq = 0; cq < F2 / 2; cq += 4) {
-                float d4[4];
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    int c = half * (F2 / 2) + cq + cc;
-                    float s = pair_layer2_unit(sW2, sb2, c, a1);
-                    float d = 0.f;
-                    if (ds != 0.f) {
-                        atomicAdd(duj + c, ds * fmaxf(s, 0.f));
-                        d = s > 0.f ? ds * uj[c] : 0.f;
-                    }
-                    d4[cc] = d;
-#pragma unroll
-                    for (int k = 0; k < F1; k += 4) {
-                        float4 w = ld4(sW2 + c * LDW2 + k);
-                        da1[k] = fmaf(w.x, d, da1[k]); da1[k + 1] = fmaf(w.y, d, da1[k + 1]);
-                        da1[k + 2] = fmaf(w.z, d, da1[k + 2]); da1[k + 3] = fmaf(w.w, d, da1[k + 3]);
-                    }
+            {   // features + layer 1: thread = (pair, half of the 32 units)
+                const int pl = threadIdx.x >> 1, half = threadIdx.x & 1;
+                const int p = p0 + pl;
+                float f1 = 0.f, f2 = 0.f, f3 = 0.f, ds = 0.f;
+                int jl = -1;
+                if (p < npairs) {
+                    jl = p / n;
+                    const int il = p - jl * n;
+                    ds = dsig[poff + (size_t)il * n + jl];
+                    pair_features(ld4(pX + 4 * il), ld4(pX + 4 * jl), f1, f2, f3);
                 }
-                st4(sDA2 + pl * LDA2 + half * (F2 / 2) + cq, make_float4(d4[0], d4[1], d4[2], d4[3]));
-            }
-            if (half == 0 && ds != 0.f) atomicAdd(duj + F2, ds);
+                float* arow = sA1 + pl * LDA1 + half * (F1 / 2);
 #pragma unroll
-            for (int k = 0; k < F1; ++k) {
-                da1[k] += __shfl_xor_sync(0xffffffffu, da1[k], 1);
-                da1[k] = a1[k] > 0.f ? da1[k] : 0.f;
-            }
-            // each half writes 16 of the 32 columns
+                for (int k = 0; k < F1 / 2; k += 4) {
+                    float v[4];
 #pragma unroll
-            for (int k = 0; k < F1 / 2; k += 4) {
-                int kk = half * (F1 / 2) + k;
-                float4 va, vd;
-                // select with compile-time indices (half is runtime): build both and pick
-                va.x = half ? a1[16 + k] : a1[k];         va.y = half ? a1[17 + k] : a1[k + 1];
-                va.z = half ? a1[18 + k] : a1[k + 2];     va.w = half ? a1[19 + k] : a1[k + 3];
-                vd.x = half ? da1[16 + k] : da1[k];       vd.y = half ? da1[17 + k] : da1[k + 1];
-                vd.z = half ? da1[18 + k] : da1[k + 2];   vd.w = half ? da1[19 + k] : da1[k + 3];
-                st4(sA1 + pl * LDA1 + kk, va);
-                st4(sDA1 + pl * LDA1 + kk, vd);
+                    for (int q = 0; q < 4; ++q) {
+                        float4 w = ld4(sW1 + 4 * (half * (F1 / 2) + k + q));
+                        v[q] = jl >= 0 ? fmaxf(fmaf(w.x, f1, fmaf(w.y, f2, fmaf(w.z, f3, w.w))), 0.f) : 0.f;
+                    }
+                    st4(arow + k, make_float4(v[0], v[1], v[2], v[3]));
+                }
+                if (half == 0) {
+                    st4(sF + pl * 4, make_float4(f1, f2, f3, 0.f));
+                    sDs[pl] = ds;
+                    sJ[pl] = jl;
+                }
             }
-            if (half == 0) st4(sF + pl * 4, make_float4(f1, f2, f3, 0.f));
             __syncthreads();
-            tile_wgrad<PT / 2>(wacc, sDA2 + whalf * (PT / 2) * LDA2, LDA2, w_oq * 4, sA1 + whalf * (PT / 2) * LDA1, LDA1,
+            {   // S = A1 W2^T + b2 -> D2, dU
+                float acc[8][4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float bv = sb2[u + 16 * jj];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i][jj] = bv;
+                }
+                tile_rowdot<8, 4, F1>(acc, sA1, LDA1, rl, 4, sW2, LDW2, u, 16);
+                int curj = -1;
+                float uj[4] = {0.f, 0.f, 0.f, 0.f}, run[4] = {0.f, 0.f, 0.f, 0.f}, run_s = 0.f;
+                const bool sown = u == 0;             // one column owner per row also carries the s_j term
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rl + 4 * i;
+                    const int jl = sJ[r];
+                    const float ds = sDs[r];
+                    if (jl != curj) {
+                        if (curj >= 0) {
+                            float* du = dUs + (size_t)(a + curj) * LDU;
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj)
+                                if (run[jj] != 0.f) atomicAdd(du + u + 16 * jj, run[jj]);
+                            if (sown && run_s != 0.f) atomicAdd(du + F2, run_s);
+                        }
+                        curj = jl;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) { run[jj] = 0.f; uj[jj] = jl >= 0 ? pU[(size_t)jl * LDU + u + 16 * jj] : 0.f; }
+                        run_s = 0.f;
+                    }
+                    float d2[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float sv = acc[i][jj];
+                        run[jj] = fmaf(ds, fmaxf(sv, 0.f), run[jj]);
+                        d2[jj] = sv > 0.f ? ds * uj[jj] : 0.f;
+                        sD2[r * LDA2 + u + 16 * jj] = d2[jj];
+                    }
+                    run_s += ds;
+                }
+                if (curj >= 0) {
+                    float* du = dUs + (size_t)(a + curj) * LDU;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (run[jj] != 0.f) atomicAdd(du + u + 16 * jj, run[jj]);
+                    if (sown && run_s != 0.f) atomicAdd(du + F2, run_s);
+                }
+            }
+            __syncthreads();
+            {   // dA1 = (D2 W2) [A1 > 0]
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+                tile_dgrad<4, F2>(acc, sD2, LDA2, d_r0, 32, sW2, LDW2, d_kq * 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = d_r0 + 32 * i;
+                    const float4 a1 = ld4(sA1 + r * LDA1 + d_kq * 4);
+                    st4(sDA1 + r * LDA1 + d_kq * 4,
+                        make_float4(a1.x > 0.f ? acc[i][0] : 0.f, a1.y > 0.f ? acc[i][1] : 0.f,
+                                    a1.z > 0.f ? acc[i][2] : 0.f, a1.w > 0.f ? acc[i][3] : 0.f));
+                }
+            }
+            __syncthreads();
+            tile_wgrad<PT / 2>(wacc, sD2 + whalf * (PT / 2) * LDA2, LDA2, w_oq * 4, sA1 + whalf * (PT / 2) * LDA1, LDA1,
                                w_kq * 4);
             {
                 const int t = threadIdx.x;
                 if (t < 64) {
-                    for (int r = 0; r < PT; ++r) acc_small += sDA2[r * LDA2 + t];
+                    for (int r = 0; r < PT; ++r) acc_small += sD2[r * LDA2 + t];
                 } else if (t < 160) {
                     int k = (t - 64) / 3, f = (t - 64) % 3;
                     for (int r = 0; r < PT; ++r) acc_small = fmaf(sDA1[r * LDA1 + k], sF[r * 4 + f], acc_small);
@@ -303,10 +348,6 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
                 }
             }
             __syncthreads();
-        }
-        if (staged) {
-            for (int i = threadIdx.x; i < n * LDU; i += MGGAN_THREADS) dUs[(size_t)a * LDU + i] = sdU[i];
-            for (int i = threadIdx.x; i < n * HD; i += MGGAN_THREADS) dh[(size_t)a * HD + i] = sdH[(i / HD) * LDHS + (i % HD)];
         }
     }
     atomic_block44(dW2, F1, w_oq * 4, w_kq * 4, wacc);
@@ -322,8 +363,9 @@ template <int HD>
 size_t soc_fwd_smem() { return sizeof(float) * (F2 * LDW2 + F1 * 4 + F2 + NMAX * 4 + NMAX * LDU + NMAX * (HD + 1)); }
 template <int HD>
 size_t soc_bwd_smem() {
-    return sizeof(float) * (F2 * LDW2 + F1 * 4 + F2 + PT * LDA2 + 2 * PT * LDA1 + PT * 4 + NMAX * 4 +
-                            2 * NMAX * LDU + 2 * NMAX * (HD + 1) + 8 * HD);
+    static_assert(2 * NMAX * (HD + 1) <= PT * LDA1 + PT * LDA2, "phase-1 buffers alias the pair tiles");
+    return sizeof(float) * (F2 * LDW2 + F1 * 4 + F2 + NMAX * 4 + ((NMAX * LDU + 3) & ~3) + 2 * PT * LDA1 + PT * LDA2 +
+                            PT * 4 + 2 * PT);
 }
 
 int sm_count() {
@@ -352,7 +394,7 @@ int launch_bwd(const float* x4, const float* h, const float* Us, const int* so, 
                float* dh, float* dUs, float* dW1, float* db1, float* dW2, float* db2, cudaStream_t st) {
     size_t sm = soc_bwd_smem<HD>();
     cudaFuncSetAttribute(social_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    int grid = ns < sm_count() ? ns : sm_count();
+    int grid = ns < sm_count() * 2 ? ns : sm_count() * 2;
     social_bwd_kernel<HD><<<grid, MGGAN_THREADS, sm, st>>>(x4, h, Us, so, po, ns, W1, b1, W2, b2, att, dS, dsig, dh, dUs,
                                                            dW1, db1, dW2, db2);
     return mggan_check_launch("social_attn_bwd");
