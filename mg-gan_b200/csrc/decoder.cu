@@ -169,8 +169,8 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
                 float tc = tanhf_(c[i]);
                 hnext[r * LDH + u] = og * tc;
                 if (acts != nullptr && sAgent[r] >= 0) {
-                    float* a = acts + ((size_t)t * Rpad + row0 + r) * (6 * H) + u;
-                    a[0] = ig; a[H] = fg; a[2 * H] = gg; a[3 * H] = og; a[4 * H] = c[i]; a[5 * H] = tc;
+                    float2* a = reinterpret_cast<float2*>(acts + (((size_t)t * Rpad + row0 + r) * H + u) * 6);
+                    a[0] = make_float2(ig, fg); a[1] = make_float2(gg, og); a[2] = make_float2(c[i], tc);
                 }
             }
             __syncthreads();
@@ -211,6 +211,14 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
 }
 
 // Backward.  Inputs: the forward's saved activations, d_abs / d_rel (either may be null).
+// Per step and 64-row tile:  phase 0 hidden2pos backward (thread = row x 4 mid units), phase 1 LSTM cell backward
+// (thread = 8 rows x 1 unit; activations read as (i,f | g,o | c,tanh c) float2 triples), phase 2 tile products:
+//   dh_{t-1} = dG W_hh (64 x 32, K = 128)          dW_hh += dG^T h_{t-1} (128 x 32, K = 64 rows)
+//   (dWx | db) += dG^T (x | 1)   via the pad columns 32..34 of the h_{t-1} tile, rows split over the k-quad lanes
+//   dW1h += dU^T h_t (16 x 32)   rows split over the 8 warps
+//   d(dxdy_{t-1}) = dG Wx        thread = (row, quarter of the 128 gates), Wx kept transposed
+// All weight-gradient tiles stay in registers across steps and tiles of one generator and are flushed with one
+// atomicAdd per element per CTA.
 __global__ void __launch_bounds__(MGGAN_THREADS, 2)
 decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, const float* __restrict__ last_dxdy,
                    const float* __restrict__ noise, int Z, DecWeights w, int T, int n_cols,
@@ -219,14 +227,15 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                    const float* __restrict__ d_abs, const float* __restrict__ d_rel, DecGrads gr) {
     extern __shared__ __align__(16) float smem[];
     float* sW = smem;                       // [4H][LDH]   W_hh
-    float* sW1 = sW + 4 * H * LDH;          // [M1][LDH]   W1h, later W1s
-    float* sG = sW1 + M1 * LDH;             // [ROWS][LDG]
-    float* sHp = sG + ROWS * LDG;           // [ROWS][LDH] h_{t-1}
+    float* sW1 = sW + 4 * H * LDH;          // [M1][LDH]   W1s (epilogue)
+    float* sG = sW1 + M1 * LDH;             // [ROWS][LDG] gate pre-activation gradients
+    float* sHp = sG + ROWS * LDG;           // [ROWS][LDH] h_{t-1} | x0 x1 1 0
     float* sHt = sHp + ROWS * LDH;          // [ROWS][LDH] h_t   (social tile after the loop)
     float* sDh = sHt + ROWS * LDH;          // [ROWS][LDH] dL/dh from the later step
     float* sDu = sDh + ROWS * LDH;          // [ROWS][LDU] d(hidden2pos.0 pre-activation)
-    float* sX = sDu + ROWS * LDU;           // [ROWS][2]   step input dxdy_{t-1}
-    float* sWx = sX + ROWS * 2;             // [4H][2]
+    float* sWxT = sDu + ROWS * LDU;         // [2][4H]     Wx transposed
+    float* sZ = sWxT + 2 * 4 * H;           // [ROWS][ZMAX] noise rows of the tile
+    float* sW1sAcc = sZ + ROWS * ZMAX;      // [M1][H]     dW1s of the current generator (per-tile shared-memory adds)
     __shared__ int sAgent[ROWS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -235,29 +244,34 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
     const int prow = threadIdx.x >> 2, mq = threadIdx.x & 3;
     const int d_kq = threadIdx.x & 7, d_r0 = threadIdx.x >> 3;      // dgrad: rows d_r0, d_r0+32
     const int w_oq = (warp & 3) * 8 + (lane & 7), w_kq = (warp >> 2) * 4 + (lane >> 3);
-    const int e_m = threadIdx.x >> 4, e_kp = threadIdx.x & 15;      // dW1h / dW1s element pair
+    const int e_mq = lane & 3, e_kq = lane >> 2;                    // dW1h / dW1s 4x4 block, rows split over warps
+    const int z_u = threadIdx.x & 31, z_g = threadIdx.x >> 5;       // dWz: unit, noise-column group (z_g, z_g + 8)
     const size_t Rpad = (size_t)n_tiles * ROWS;
 
-    float wacc[4][4];
-    float ax0, ax1, ab, aw2a[4], aw2b[4], ab2a, ab2b, ab1[4], aw1h0, aw1h1, aw1s0, aw1s1, awz[ZMAX];
+    float wacc[4][4], xacc[4][3], w1acc[4][4];
+    float aw2a[4], aw2b[4], ab2a, ab2b, ab1[4], awz0, awz1;
     auto zero_acc = [&]() {
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) wacc[a][b] = 0.f;
+            for (int b = 0; b < 4; ++b) { wacc[a][b] = 0.f; w1acc[a][b] = 0.f; }
+            xacc[a][0] = xacc[a][1] = xacc[a][2] = 0.f;
             aw2a[a] = aw2b[a] = ab1[a] = 0.f;
         }
-        ax0 = ax1 = ab = ab2a = ab2b = aw1h0 = aw1h1 = aw1s0 = aw1s1 = 0.f;
-#pragma unroll
-        for (int z = 0; z < ZMAX; ++z) awz[z] = 0.f;
+        ab2a = ab2b = awz0 = awz1 = 0.f;
+        for (int i = threadIdx.x; i < M1 * H; i += MGGAN_THREADS) sW1sAcc[i] = 0.f;     // read again only after a barrier
     };
     auto flush = [&](int g) {
         atomic_block44(gr.dWhh + (size_t)g * 4 * H * H, H, w_oq * 4, w_kq * 4, wacc);
-        if (threadIdx.x < 4 * H) {
-            atomicAdd(gr.dWx + ((size_t)g * 4 * H + threadIdx.x) * 2, ax0);
-            atomicAdd(gr.dWx + ((size_t)g * 4 * H + threadIdx.x) * 2 + 1, ax1);
-            atomicAdd(gr.db + (size_t)g * 4 * H + threadIdx.x, ab);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const size_t o = (size_t)g * 4 * H + w_oq * 4 + a;
+            atomicAdd(gr.dWx + o * 2, xacc[a][0]);
+            atomicAdd(gr.dWx + o * 2 + 1, xacc[a][1]);
+            atomicAdd(gr.db + o, xacc[a][2]);
         }
+        atomic_block44(gr.dW1h + (size_t)g * M1 * H, H, e_mq * 4, e_kq * 4, w1acc);
+        for (int i = threadIdx.x; i < M1 * H; i += MGGAN_THREADS) atomicAdd(gr.dW1s + (size_t)g * M1 * H + i, sW1sAcc[i]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             atomicAdd(gr.dW2 + (size_t)g * 2 * M1 + mq + 4 * j, aw2a[j]);
@@ -268,13 +282,8 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
             atomicAdd(gr.db2 + g * 2, ab2a);
             atomicAdd(gr.db2 + g * 2 + 1, ab2b);
         }
-        atomicAdd(gr.dW1h + ((size_t)g * M1 + e_m) * H + 2 * e_kp, aw1h0);
-        atomicAdd(gr.dW1h + ((size_t)g * M1 + e_m) * H + 2 * e_kp + 1, aw1h1);
-        atomicAdd(gr.dW1s + ((size_t)g * M1 + e_m) * H + 2 * e_kp, aw1s0);
-        atomicAdd(gr.dW1s + ((size_t)g * M1 + e_m) * H + 2 * e_kp + 1, aw1s1);
-#pragma unroll
-        for (int z = 0; z < ZMAX; ++z)
-            if (z < Z) atomicAdd(gr.dWz + u * Z + z, awz[z]);
+        if (z_g < Z) atomicAdd(gr.dWz + z_u * Z + z_g, awz0);
+        if (z_g + 8 < Z) atomicAdd(gr.dWz + z_u * Z + z_g + 8, awz1);
     };
     zero_acc();
 
@@ -287,10 +296,11 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
         if (g < 0) continue;
         __syncthreads();
         if (g != cur_g) {
-            if (cur_g >= 0) { flush(cur_g); zero_acc(); }
+            if (cur_g >= 0) { flush(cur_g); __syncthreads(); zero_acc(); }
             cur_g = g;
             stage_matrix(sW, LDH, w.Whh + (size_t)g * 4 * H * H, 4 * H, H);
-            for (int i = threadIdx.x; i < 4 * H * 2; i += MGGAN_THREADS) sWx[i] = __ldg(w.Wx + (size_t)g * 4 * H * 2 + i);
+            for (int i = threadIdx.x; i < 4 * H * 2; i += MGGAN_THREADS)
+                sWxT[(i & 1) * 4 * H + (i >> 1)] = __ldg(w.Wx + (size_t)g * 4 * H * 2 + i);
 #pragma unroll
             for (int m = 0; m < M1; ++m) w1col[m] = __ldg(w.W1h + ((size_t)g * M1 + m) * H + u);
 #pragma unroll
@@ -306,6 +316,12 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
         __syncthreads();
         const int pag = sAgent[prow];
         const int pcol = pag >= 0 ? sq.seq_out[row0 + prow] : -1;
+        {   // noise rows of the tile (for dWz in the epilogue)
+            const int r = threadIdx.x >> 2;
+            const int ag = sAgent[r];
+            const float* zp = noise + (size_t)(ag >= 0 ? sq.seq_noise[row0 + r] : 0) * Z;
+            for (int z = threadIdx.x & 3; z < ZMAX; z += 4) sZ[r * ZMAX + z] = (ag >= 0 && z < Z) ? __ldg(zp + z) : 0.f;
+        }
         float dxy0 = 0.f, dxy1 = 0.f;       // sum_{tau >= t} d_abs[tau]
         float dn0 = 0.f, dn1 = 0.f;         // gradient reaching dxdy_t through step t+1's input
         float dbs[4] = {0.f, 0.f, 0.f, 0.f};
@@ -343,14 +359,14 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sDu[prow * LDU + mq + 4 * j] = du[j];
-                // step input dxdy_{t-1}
+                // step input dxdy_{t-1} and the constant 1 go to the pad columns of the h_{t-1} tile
                 if (mq == 0) {
                     float2 xv = make_float2(0.f, 0.f);
                     if (pcol >= 0) {
                         xv = t > 0 ? __ldg(reinterpret_cast<const float2*>(out_rel + ((size_t)(t - 1) * n_cols + pcol) * 2))
                                    : __ldg(reinterpret_cast<const float2*>(last_dxdy + (size_t)pag * 2));
                     }
-                    sX[prow * 2] = xv.x; sX[prow * 2 + 1] = xv.y;
+                    st4(sHp + prow * LDH + H, make_float4(xv.x, xv.y, 1.f, 0.f));
                 }
             }
             __syncthreads();
@@ -360,13 +376,15 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 int r = rl + 4 * i;
                 float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f, hp = 0.f, ht = 0.f;
                 if (sAgent[r] >= 0) {
-                    const float* a = acts + ((size_t)t * Rpad + row0 + r) * (6 * H) + u;
-                    float ig = a[0], fg = a[H], gg = a[2 * H], og = a[3 * H], tc = a[5 * H];
+                    const float2* a = reinterpret_cast<const float2*>(acts + (((size_t)t * Rpad + row0 + r) * H + u) * 6);
+                    const float2 q0 = __ldg(a), q1 = __ldg(a + 1), q2 = __ldg(a + 2);
+                    const float ig = q0.x, fg = q0.y, gg = q1.x, og = q1.y, tc = q2.y;
                     float cp = 0.f;
                     if (t > 0) {
-                        const float* ap = a - Rpad * (6 * H);
-                        cp = ap[4 * H];
-                        hp = ap[3 * H] * ap[5 * H];
+                        const float2* ap = a - Rpad * (H * 3);
+                        const float2 p1 = __ldg(ap + 1), p2 = __ldg(ap + 2);
+                        cp = p2.x;
+                        hp = p1.y * p2.y;
                     } else {
                         hp = h0save[(size_t)(row0 + r) * H + u];
                     }
@@ -390,7 +408,7 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 sHt[r * LDH + u] = ht;
             }
             __syncthreads();
-            // ---- phase 2: dgrad / wgrad tiles
+            // ---- phase 2: tile products
             {
                 float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
                 tile_dgrad<2, 4 * H>(acc, sG, LDG, d_r0, 32, sW, LDH, d_kq * 4);
@@ -399,33 +417,29 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 st4(sDh + d_r0 * LDH + d_kq * 4, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]));
                 st4(sDh + (d_r0 + 32) * LDH + d_kq * 4, make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]));
             }
-            if (threadIdx.x < 4 * H) {
-                int o = threadIdx.x;
-#pragma unroll 4
-                for (int r = 0; r < ROWS; ++r) {
-                    float gv = sG[r * LDG + o];
-                    ax0 = fmaf(gv, sX[2 * r], ax0);
-                    ax1 = fmaf(gv, sX[2 * r + 1], ax1);
-                    ab += gv;
+            {   // (dWx | db): rows [8 w_kq, 8 w_kq + 8) of dG^T (x0 x1 1)
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int r = w_kq * 8 + rr;
+                    const float4 gq = ld4(sG + r * LDG + w_oq * 4);
+                    const float4 xq = ld4(sHp + r * LDH + H);
+                    xacc[0][0] = fmaf(gq.x, xq.x, xacc[0][0]); xacc[0][1] = fmaf(gq.x, xq.y, xacc[0][1]); xacc[0][2] = fmaf(gq.x, xq.z, xacc[0][2]);
+                    xacc[1][0] = fmaf(gq.y, xq.x, xacc[1][0]); xacc[1][1] = fmaf(gq.y, xq.y, xacc[1][1]); xacc[1][2] = fmaf(gq.y, xq.z, xacc[1][2]);
+                    xacc[2][0] = fmaf(gq.z, xq.x, xacc[2][0]); xacc[2][1] = fmaf(gq.z, xq.y, xacc[2][1]); xacc[2][2] = fmaf(gq.z, xq.z, xacc[2][2]);
+                    xacc[3][0] = fmaf(gq.w, xq.x, xacc[3][0]); xacc[3][1] = fmaf(gq.w, xq.y, xacc[3][1]); xacc[3][2] = fmaf(gq.w, xq.z, xacc[3][2]);
                 }
             }
-            {   // dW1h[e_m][2 e_kp .. +1] += sum_r du[r][e_m] h_t[r][..]
-#pragma unroll 4
-                for (int r = 0; r < ROWS; ++r) {
-                    float d = sDu[r * LDU + e_m];
-                    float2 hv = *reinterpret_cast<const float2*>(sHt + r * LDH + 2 * e_kp);
-                    aw1h0 = fmaf(d, hv.x, aw1h0);
-                    aw1h1 = fmaf(d, hv.y, aw1h1);
-                }
-            }
-            {   // gradient wrt this step's input dxdy_{t-1}: Wx^T dgates (row = prow, o = mq + 4 oo)
+            // dW1h: rows [8 warp, 8 warp + 8) of dU^T h_t
+            tile_wgrad<8>(w1acc, sDu + warp * 8 * LDU, LDU, e_mq * 4, sHt + warp * 8 * LDH, LDH, e_kq * 4);
+            {   // gradient wrt this step's input dxdy_{t-1}: dG Wx (row = prow, gates 32 mq .. 32 mq + 31)
                 float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-                for (int oo = 0; oo < H; ++oo) {
-                    int o = mq + 4 * oo;
-                    float gv = sG[prow * LDG + o];
-                    s0 = fmaf(gv, sWx[o * 2], s0);
-                    s1 = fmaf(gv, sWx[o * 2 + 1], s1);
+#pragma unroll
+                for (int oo = 0; oo < H; oo += 4) {
+                    const int o = mq * H + oo;
+                    const float4 gq = ld4(sG + prow * LDG + o);
+                    const float4 wa = ld4(sWxT + o), wb = ld4(sWxT + 4 * H + o);
+                    s0 = fmaf(gq.x, wa.x, fmaf(gq.y, wa.y, fmaf(gq.z, wa.z, fmaf(gq.w, wa.w, s0))));
+                    s1 = fmaf(gq.x, wb.x, fmaf(gq.y, wb.y, fmaf(gq.z, wb.z, fmaf(gq.w, wb.w, s1))));
                 }
                 s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
                 s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
@@ -437,13 +451,14 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             int r = rl + 4 * i, ag = sAgent[r];
-            if (ag >= 0) {
-                float dh0 = sDh[r * LDH + u];
-                atomicAdd(gr.dA + (size_t)ag * H + u, dh0);
-                const float* zp = noise + (size_t)sq.seq_noise[row0 + r] * Z;
-#pragma unroll
-                for (int z = 0; z < ZMAX; ++z)
-                    if (z < Z) awz[z] = fmaf(dh0, __ldg(zp + z), awz[z]);
+            if (ag >= 0) atomicAdd(gr.dA + (size_t)ag * H + u, sDh[r * LDH + u]);
+        }
+        {   // dWz[u][z] += sum_r dh0[r][u] z[r][z]   (padding rows have dh0 = 0 and z = 0)
+#pragma unroll 4
+            for (int r = 0; r < ROWS; ++r) {
+                const float d = sDh[r * LDH + z_u];
+                awz0 = fmaf(d, sZ[r * ZMAX + z_g], awz0);
+                awz1 = fmaf(d, sZ[r * ZMAX + z_g + 8], awz1);
             }
         }
 #pragma unroll
@@ -471,14 +486,15 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
 #pragma unroll
             for (int k = 0; k < 8; ++k) atomicAdd(gr.dsocial + (size_t)pag * H + mq * 8 + k, ds[k]);
         }
-#pragma unroll 4
-        for (int r = 0; r < ROWS; ++r) {
-            float d = sDu[r * LDU + e_m];
-            float2 sv = *reinterpret_cast<const float2*>(sHt + r * LDH + 2 * e_kp);
-            aw1s0 = fmaf(d, sv.x, aw1s0);
-            aw1s1 = fmaf(d, sv.y, aw1s1);
+        {   // dW1s: rows [8 warp, 8 warp + 8) of dBs^T social, merged in shared memory
+            float part[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { part[a][0] = 0.f; part[a][1] = 0.f; part[a][2] = 0.f; part[a][3] = 0.f; }
+            tile_wgrad<8>(part, sDu + warp * 8 * LDU, LDU, e_mq * 4, sHt + warp * 8 * LDH, LDH, e_kq * 4);
+            atomic_block44(sW1sAcc, H, e_mq * 4, e_kq * 4, part);
         }
     }
+    __syncthreads();
     if (cur_g >= 0) flush(cur_g);
 }
 
@@ -486,7 +502,7 @@ size_t dec_fwd_smem() {
     return sizeof(float) * (4 * H * LDH + 2 * M1 * LDH + 2 * ROWS * LDH + ROWS * LDU + ROWS * 2 + H * (ZMAX + 1));
 }
 size_t dec_bwd_smem() {
-    return sizeof(float) * (4 * H * LDH + M1 * LDH + ROWS * LDG + 3 * ROWS * LDH + ROWS * LDU + ROWS * 2 + 4 * H * 2);
+    return sizeof(float) * (4 * H * LDH + M1 * LDH + ROWS * LDG + 3 * ROWS * LDH + ROWS * LDU + 2 * 4 * H + ROWS * ZMAX + M1 * H);
 }
 
 int sm_count() {

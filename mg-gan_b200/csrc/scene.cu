@@ -164,10 +164,18 @@ constexpr int NPAIRS_CH = CIN * (CIN + 1) / 2;     // 10
 
 constexpr int PS_THREADS = 128;                    // ~150 registers per thread (81 accumulators): 3 CTAs per SM
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory"); }
+
 __global__ void __launch_bounds__(PS_THREADS, 3)
 scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N, int slots,
                          double* __restrict__ R, double* __restrict__ P) {
-    __shared__ __align__(16) float sImg[2 * IMGPAD];          // channels A and B, [35][36] each, zero halo
+    __shared__ __align__(16) float sImg[2][2 * IMGPAD];       // double buffer x channels A and B, [35][36] each, zero halo
     const int bp = blockIdx.x % NPAIRS_CH, slot = blockIdx.x / NPAIRS_CH;
     int cA = 0, cB = 0;
     {
@@ -178,26 +186,36 @@ scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ 
         }
     }
     const bool diag = cA == cB;
-    for (int i = threadIdx.x; i < 2 * IMGPAD; i += PS_THREADS) sImg[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * IMGPAD; i += PS_THREADS) (&sImg[0][0])[i] = 0.f;
     float acc[81], ps[9];
 #pragma unroll
     for (int q = 0; q < 81; ++q) acc[q] = 0.f;
 #pragma unroll
     for (int q = 0; q < 9; ++q) ps[q] = 0.f;
-    const float* sA = sImg;
-    const float* sB = diag ? sImg : sImg + IMGPAD;
+    __syncthreads();
 
-    for (int n = slot; n < N; n += slots) {
+    // asynchronous staging (cp.async, 4-byte: channel rows are only 4-byte aligned) of the next agent's two channels
+    // while the current one is processed
+    auto stage = [&](int n, int buf) {
         const int src = rows ? rows[n] : n;
-        __syncthreads();
         const float* ipA = img + ((size_t)src * CIN + cA) * IMG2;
         const float* ipB = img + ((size_t)src * CIN + cB) * IMG2;
         for (int i = threadIdx.x; i < IMG2; i += PS_THREADS) {
             int y = i / IMG, x = i - y * IMG;
-            sImg[(y + 1) * LDI + x + 1] = __ldg(ipA + i);
-            if (!diag) sImg[IMGPAD + (y + 1) * LDI + x + 1] = __ldg(ipB + i);
+            cp_async4(&sImg[buf][(y + 1) * LDI + x + 1], ipA + i);
+            if (!diag) cp_async4(&sImg[buf][IMGPAD + (y + 1) * LDI + x + 1], ipB + i);
         }
+        cp_async_commit();
+    };
+    int buf = 0;
+    if (slot < N) stage(slot, 0);
+    for (int n = slot; n < N; n += slots) {
+        const bool more = n + slots < N;
+        if (more) stage(n + slots, buf ^ 1);
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
+        const float* sA = sImg[buf];
+        const float* sB = diag ? sA : sA + IMGPAD;
         // lanes = 32 consecutive pixels of one row (conflict-free shared-memory reads), warps = rows; the 33rd
         // column is swept afterwards by the first 33 threads
         for (int it = threadIdx.x >> 5; it < IMG + 2; it += PS_THREADS / 32) {
@@ -220,6 +238,8 @@ scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ 
 #pragma unroll
                 for (int j = 0; j < 9; ++j) acc[i * 9 + j] = fmaf(va[i], vb[j], acc[i * 9 + j]);
         }
+        __syncthreads();                    // this buffer is overwritten by the staging of the iteration after next
+        buf ^= 1;
     }
     // CTA reduction: warp shuffles in double, then one atomicAdd per entry per warp
     const int lane = threadIdx.x & 31;
