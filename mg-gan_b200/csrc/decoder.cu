@@ -169,8 +169,9 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
                 float tc = tanhf_(c[i]);
                 hnext[r * LDH + u] = og * tc;
                 if (acts != nullptr && sAgent[r] >= 0) {
-                    float2* a = reinterpret_cast<float2*>(acts + (((size_t)t * Rpad + row0 + r) * H + u) * 6);
-                    a[0] = make_float2(ig, fg); a[1] = make_float2(gg, og); a[2] = make_float2(c[i], tc);
+                    // layout (t, row, pair, unit, 2): a warp's float2 stores cover whole 32-byte sectors
+                    float2* a = reinterpret_cast<float2*>(acts) + ((size_t)t * Rpad + row0 + r) * (3 * H) + u;
+                    a[0] = make_float2(ig, fg); a[H] = make_float2(gg, og); a[2 * H] = make_float2(c[i], tc);
                 }
             }
             __syncthreads();
@@ -212,7 +213,7 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
 
 // Backward.  Inputs: the forward's saved activations, d_abs / d_rel (either may be null).
 // Per step and 64-row tile:  phase 0 hidden2pos backward (thread = row x 4 mid units), phase 1 LSTM cell backward
-// (thread = 8 rows x 1 unit; activations read as (i,f | g,o | c,tanh c) float2 triples), phase 2 tile products:
+// (thread = 8 rows x 1 unit; activations read as (i,f | g,o | c,tanh c) float2 triples, layout (t, row, pair, unit, 2)), phase 2 tile products:
 //   dh_{t-1} = dG W_hh (64 x 32, K = 128)          dW_hh += dG^T h_{t-1} (128 x 32, K = 64 rows)
 //   (dWx | db) += dG^T (x | 1)   via the pad columns 32..34 of the h_{t-1} tile, rows split over the k-quad lanes
 //   dW1h += dU^T h_t (16 x 32)   rows split over the 8 warps
@@ -376,13 +377,13 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 int r = rl + 4 * i;
                 float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f, hp = 0.f, ht = 0.f;
                 if (sAgent[r] >= 0) {
-                    const float2* a = reinterpret_cast<const float2*>(acts + (((size_t)t * Rpad + row0 + r) * H + u) * 6);
-                    const float2 q0 = __ldg(a), q1 = __ldg(a + 1), q2 = __ldg(a + 2);
+                    const float2* a = reinterpret_cast<const float2*>(acts) + ((size_t)t * Rpad + row0 + r) * (3 * H) + u;
+                    const float2 q0 = __ldg(a), q1 = __ldg(a + H), q2 = __ldg(a + 2 * H);
                     const float ig = q0.x, fg = q0.y, gg = q1.x, og = q1.y, tc = q2.y;
                     float cp = 0.f;
                     if (t > 0) {
-                        const float2* ap = a - Rpad * (H * 3);
-                        const float2 p1 = __ldg(ap + 1), p2 = __ldg(ap + 2);
+                        const float2* ap = a - Rpad * (3 * H);
+                        const float2 p1 = __ldg(ap + H), p2 = __ldg(ap + 2 * H);
                         cp = p2.x;
                         hp = p1.y * p2.y;
                     } else {
