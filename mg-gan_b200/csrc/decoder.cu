@@ -237,6 +237,8 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
     float* sWxT = sDu + ROWS * LDU;         // [2][4H]     Wx transposed
     float* sZ = sWxT + 2 * 4 * H;           // [ROWS][ZMAX] noise rows of the tile
     float* sW1sAcc = sZ + ROWS * ZMAX;      // [M1][H]     dW1s of the current generator (per-tile shared-memory adds)
+    float* sW1h = sW1sAcc + M1 * H;         // [M1][LDH]   W1h
+    float* sW2 = sW1h + M1 * LDH;           // [2][M1]     hidden2pos.2
     __shared__ int sAgent[ROWS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -291,7 +293,6 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
     const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
     const int t_begin = blockIdx.x * per, t_end = min(n_tiles, t_begin + per);
     int cur_g = -1;
-    float w1col[M1], w2a[4], w2b[4];
     for (int tile = t_begin; tile < t_end; ++tile) {
         const int g = sq.tile_gen[tile];
         if (g < 0) continue;
@@ -302,13 +303,8 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
             stage_matrix(sW, LDH, w.Whh + (size_t)g * 4 * H * H, 4 * H, H);
             for (int i = threadIdx.x; i < 4 * H * 2; i += MGGAN_THREADS)
                 sWxT[(i & 1) * 4 * H + (i >> 1)] = __ldg(w.Wx + (size_t)g * 4 * H * 2 + i);
-#pragma unroll
-            for (int m = 0; m < M1; ++m) w1col[m] = __ldg(w.W1h + ((size_t)g * M1 + m) * H + u);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                w2a[q] = __ldg(w.W2 + (size_t)g * 2 * M1 + mq + 4 * q);
-                w2b[q] = __ldg(w.W2 + (size_t)g * 2 * M1 + M1 + mq + 4 * q);
-            }
+            stage_matrix(sW1h, LDH, w.W1h + (size_t)g * M1 * H, M1, H);
+            if (threadIdx.x < 2 * M1) sW2[threadIdx.x] = __ldg(w.W2 + (size_t)g * 2 * M1 + threadIdx.x);
         }
         const int row0 = tile * ROWS;
         if (threadIdx.x < ROWS) sAgent[threadIdx.x] = sq.seq_agent[row0 + threadIdx.x];
@@ -335,6 +331,9 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
             {
                 float dr0 = dn0, dr1 = dn1;
                 float du[4] = {0.f, 0.f, 0.f, 0.f};
+                float w2a[4], w2b[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { w2a[q] = sW2[mq + 4 * q]; w2b[q] = sW2[M1 + mq + 4 * q]; }
                 if (pcol >= 0) {
                     size_t o = ((size_t)t * n_cols + pcol) * 2;
                     if (d_abs != nullptr) {
@@ -371,42 +370,55 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 }
             }
             __syncthreads();
-            // ---- phase 1: dh_t, LSTM cell backward (thread = 8 rows x 1 unit)
+            // ---- phase 1: dh_t, LSTM cell backward (thread = 8 rows x 1 unit).  The saved activations are read with
+            // unconditional, batched loads (NB rows at a time: one memory latency per batch instead of one per row);
+            // padding rows read their own, never-written slots and are masked afterwards.
+            constexpr int NB = 4;            // rows per load batch (register budget: 5 float2 per row in flight)
+            float w1col[M1];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int r = rl + 4 * i;
-                float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f, hp = 0.f, ht = 0.f;
-                if (sAgent[r] >= 0) {
+            for (int m = 0; m < M1; ++m) w1col[m] = sW1h[m * LDH + u];
+#pragma unroll
+            for (int half = 0; half < 8 / NB; ++half) {
+                float2 q0[NB], q1[NB], q2[NB], p1[NB], p2[NB];
+                float h0v[NB];
+#pragma unroll
+                for (int ii = 0; ii < NB; ++ii) {
+                    const int r = rl + 4 * (half * NB + ii);
                     const float2* a = reinterpret_cast<const float2*>(acts) + ((size_t)t * Rpad + row0 + r) * (3 * H) + u;
-                    const float2 q0 = __ldg(a), q1 = __ldg(a + H), q2 = __ldg(a + 2 * H);
-                    const float ig = q0.x, fg = q0.y, gg = q1.x, og = q1.y, tc = q2.y;
-                    float cp = 0.f;
+                    q0[ii] = __ldg(a); q1[ii] = __ldg(a + H); q2[ii] = __ldg(a + 2 * H);
                     if (t > 0) {
                         const float2* ap = a - Rpad * (3 * H);
-                        const float2 p1 = __ldg(ap + H), p2 = __ldg(ap + 2 * H);
-                        cp = p2.x;
-                        hp = p1.y * p2.y;
+                        p1[ii] = __ldg(ap + H); p2[ii] = __ldg(ap + 2 * H);
                     } else {
-                        hp = h0save[(size_t)(row0 + r) * H + u];
+                        h0v[ii] = __ldg(h0save + (size_t)(row0 + r) * H + u);
                     }
-                    ht = og * tc;
+                }
+#pragma unroll
+                for (int ii = 0; ii < NB; ++ii) {
+                    const int i = half * NB + ii;
+                    const int r = rl + 4 * i;
+                    const bool valid = sAgent[r] >= 0;
+                    const float ig = q0[ii].x, fg = q0[ii].y, gg = q1[ii].x, og = q1[ii].y, tc = q2[ii].y;
+                    const float cp = t > 0 ? p2[ii].x : 0.f;
+                    const float hp = t > 0 ? p1[ii].y * p2[ii].y : h0v[ii];
+                    const float ht = og * tc;
                     float dh = sDh[r * LDH + u];
 #pragma unroll
                     for (int m = 0; m < M1; m += 4) {
                         float4 d4 = ld4(sDu + r * LDU + m);
                         dh = fmaf(w1col[m], d4.x, fmaf(w1col[m + 1], d4.y, fmaf(w1col[m + 2], d4.z, fmaf(w1col[m + 3], d4.w, dh))));
                     }
-                    float dcc = fmaf(dh * og, 1.f - tc * tc, dc[i]);
-                    dao = dh * tc * og * (1.f - og);
-                    dai = dcc * gg * ig * (1.f - ig);
-                    dag = dcc * ig * (1.f - gg * gg);
-                    daf = dcc * cp * fg * (1.f - fg);
-                    dc[i] = dcc * fg;
+                    const float dcc = fmaf(dh * og, 1.f - tc * tc, dc[i]);
+                    const float dao = dh * tc * og * (1.f - og);
+                    const float dai = dcc * gg * ig * (1.f - ig);
+                    const float dag = dcc * ig * (1.f - gg * gg);
+                    const float daf = dcc * cp * fg * (1.f - fg);
+                    dc[i] = valid ? dcc * fg : 0.f;
+                    sG[r * LDG + u] = valid ? dai : 0.f; sG[r * LDG + H + u] = valid ? daf : 0.f;
+                    sG[r * LDG + 2 * H + u] = valid ? dag : 0.f; sG[r * LDG + 3 * H + u] = valid ? dao : 0.f;
+                    sHp[r * LDH + u] = valid ? hp : 0.f;
+                    sHt[r * LDH + u] = valid ? ht : 0.f;
                 }
-                sG[r * LDG + u] = dai; sG[r * LDG + H + u] = daf;
-                sG[r * LDG + 2 * H + u] = dag; sG[r * LDG + 3 * H + u] = dao;
-                sHp[r * LDH + u] = hp;
-                sHt[r * LDH + u] = ht;
             }
             __syncthreads();
             // ---- phase 2: tile products
@@ -503,7 +515,7 @@ size_t dec_fwd_smem() {
     return sizeof(float) * (4 * H * LDH + 2 * M1 * LDH + 2 * ROWS * LDH + ROWS * LDU + ROWS * 2 + H * (ZMAX + 1));
 }
 size_t dec_bwd_smem() {
-    return sizeof(float) * (4 * H * LDH + M1 * LDH + ROWS * LDG + 3 * ROWS * LDH + ROWS * LDU + 2 * 4 * H + ROWS * ZMAX + M1 * H);
+    return sizeof(float) * (4 * H * LDH + M1 * LDH + ROWS * LDG + 3 * ROWS * LDH + ROWS * LDU + 2 * 4 * H + ROWS * ZMAX + M1 * H + M1 * LDH + 2 * M1);
 }
 
 int sm_count() {
