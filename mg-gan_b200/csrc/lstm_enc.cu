@@ -133,31 +133,41 @@ lstm_enc_bwd_kernel(const float* __restrict__ x, int T, int N, const float* __re
         }
         __syncthreads();
         for (int t = T - 1; t >= 0; --t) {
-            // ---- phase 1: cell backward
+            // ---- phase 1: cell backward.  Activation loads are unconditional (row clamped, result masked) and issued
+            // for 4 rows at a time so that their latencies overlap instead of adding up.
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int r = rl + 4 * i, row = row0 + r;
-                float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f, hp = 0.f;
-                if (row < N) {
+            for (int half = 0; half < 2; ++half) {
+                float v[4][5], pv[4][3];
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int row = min(row0 + rl + 4 * (half * 4 + ii), N - 1);
                     const float* a = acts + ((size_t)t * N + row) * (6 * H) + u;
-                    float ig = a[0], fg = a[H], gg = a[2 * H], og = a[3 * H], tc = a[5 * H];
-                    float cp = 0.f;
+                    v[ii][0] = __ldg(a); v[ii][1] = __ldg(a + H); v[ii][2] = __ldg(a + 2 * H); v[ii][3] = __ldg(a + 3 * H);
+                    v[ii][4] = __ldg(a + 5 * H);
                     if (t > 0) {
                         const float* ap = a - (size_t)N * (6 * H);
-                        cp = ap[4 * H];
-                        hp = ap[3 * H] * ap[5 * H];
+                        pv[ii][0] = __ldg(ap + 4 * H); pv[ii][1] = __ldg(ap + 3 * H); pv[ii][2] = __ldg(ap + 5 * H);
                     }
-                    float dh = sDh[r * LDH + u];
-                    float dcc = fmaf(dh * og, 1.f - tc * tc, dc[i]);
-                    dao = dh * tc * og * (1.f - og);
-                    dai = dcc * gg * ig * (1.f - ig);
-                    dag = dcc * ig * (1.f - gg * gg);
-                    daf = dcc * cp * fg * (1.f - fg);
-                    dc[i] = dcc * fg;
                 }
-                sG[r * LDG + u] = dai; sG[r * LDG + H + u] = daf;
-                sG[r * LDG + 2 * H + u] = dag; sG[r * LDG + 3 * H + u] = dao;
-                sHp[r * LDH + u] = hp;
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int i = half * 4 + ii;
+                    const int r = rl + 4 * i;
+                    const bool valid = row0 + r < N;
+                    const float ig = v[ii][0], fg = v[ii][1], gg = v[ii][2], og = v[ii][3], tc = v[ii][4];
+                    const float cp = t > 0 ? pv[ii][0] : 0.f;
+                    const float hp = t > 0 ? pv[ii][1] * pv[ii][2] : 0.f;
+                    const float dh = sDh[r * LDH + u];
+                    const float dcc = fmaf(dh * og, 1.f - tc * tc, dc[i]);
+                    const float dao = dh * tc * og * (1.f - og);
+                    const float dai = dcc * gg * ig * (1.f - ig);
+                    const float dag = dcc * ig * (1.f - gg * gg);
+                    const float daf = dcc * cp * fg * (1.f - fg);
+                    dc[i] = valid ? dcc * fg : 0.f;
+                    sG[r * LDG + u] = valid ? dai : 0.f; sG[r * LDG + H + u] = valid ? daf : 0.f;
+                    sG[r * LDG + 2 * H + u] = valid ? dag : 0.f; sG[r * LDG + 3 * H + u] = valid ? dao : 0.f;
+                    sHp[r * LDH + u] = valid ? hp : 0.f;
+                }
             }
             for (int i = threadIdx.x; i < ROWS; i += MGGAN_THREADS) {
                 int row = row0 + i;
@@ -243,7 +253,8 @@ int launch_bwd(const float* x, int T, int N, const float* Whh, const float* acts
     size_t sm = enc_bwd_smem<H>();
     cudaFuncSetAttribute(lstm_enc_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     int tiles = (N + C::ROWS - 1) / C::ROWS;
-    int grid = tiles < sm_count() ? tiles : sm_count();
+    int per_sm = sm <= 110 * 1024 ? 2 : 1;
+    int grid = tiles < sm_count() * per_sm ? tiles : sm_count() * per_sm;
     lstm_enc_bwd_kernel<H><<<grid, MGGAN_THREADS, sm, s>>>(x, T, N, Whh, acts, dhT, dWx, db, dWhh);
     return mggan_check_launch("lstm_enc_bwd");
 }
