@@ -27,8 +27,10 @@ constexpr int AH = 32;                         // attention MLP hidden width (cn
 constexpr int LDI = 36;                        // padded image row (35 used)
 constexpr int IMGPAD = 35 * LDI;               // one padded channel
 constexpr int LDP = 18;                        // padded pooled row
-constexpr int PPAD = LDP * LDP + 2;            // 326: channel stride (even: 8-byte aligned rows for LDS.64; 326 mod 32 = 6 keeps
-                                               // 16 channels on distinct banks)
+// channel stride of the pooled maps: even (8-byte aligned rows for LDS.64) and chosen so that the channels -- and, for 8
+// channels, two neighbouring rows as well -- fall on distinct banks: 326 = 6 mod 32 for 16 channels, 324 = 4 mod 32 for 8
+template <int C>
+struct PoolPad { static constexpr int value = C == 8 ? LDP * LDP : LDP * LDP + 2; };
 
 int sm_count() {
     static int n = 0;
@@ -328,6 +330,7 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                          const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ ab1,
                          const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ x2,
                          double* __restrict__ stats2, float* __restrict__ e1, unsigned char* __restrict__ idx1) {
+    constexpr int PPAD = PoolPad<C>::value;
     extern __shared__ __align__(16) float smem[];
     float* sImg = smem;                          // [4][35][36]
     float* sW1 = sImg + CIN * IMGPAD;            // [36 taps][C]
@@ -478,6 +481,7 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     constexpr int QG = MGGAN_THREADS / (C * CIN);        // pooled-pixel groups for the sparse conv1 term (4 or 8)
     constexpr int Q_PER = P1SQ / QG;
     constexpr int LDY = P1SQ + 4;                        // channel stride of sDY: neighbouring channels on different banks
+    constexpr int PPAD = PoolPad<C>::value;
     extern __shared__ __align__(16) float smem[];
     float* sDX = smem;                                   // [C][PPAD]  dx2 with zero halo
     float* sP = sDX + C * PPAD;                          // [C][PPAD]  p1 with zero halo
@@ -920,9 +924,10 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
 
 
 template <int C>
-size_t fused_fwd_smem() { return sizeof(float) * (CIN * IMGPAD + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * C + 2 * C + 8 * 2 * C); }
+size_t fused_fwd_smem() { constexpr int PPAD = PoolPad<C>::value; return sizeof(float) * (CIN * IMGPAD + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * C + 2 * C + 8 * 2 * C); }
 template <int C>
 size_t fused_bwd_smem() {
+    constexpr int PPAD = PoolPad<C>::value;
     return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * C + C * (P1SQ + 4) + CIN * IMGPAD + 10 * C + 8 * 2 * C) + C * P1SQ;
 }
 template <int C>
