@@ -68,7 +68,8 @@ int mggan_selection_tiles(int n_seq, int G); /* host helper: tile-table length f
 int mggan_selection_build(const long long* idx, int n, int k, int G, int n_tiles, int* cnt, unsigned char* rank,
                           int* base_row, int* err, int* totals, int* tile_gen, int* seq_agent, int* seq_noise,
                           int* seq_out, cudaStream_t stream);
-/* all generators x k samples (forward_all, standard.py:227-265): G*ceil(n*k/64) tiles. */
+/* all generators x k samples (forward_all, standard.py:227-265): G * 2*ceil(n*k/128) tiles.  Both builders pad every
+ * generator's rows to a multiple of 128 (two 64-row tiles), so tiles 2s and 2s+1 always belong to one generator. */
 int mggan_selection_all(int n, int k, int G, int* tile_gen, int* seq_agent, int* seq_noise, int* seq_out,
                         cudaStream_t stream);
 
@@ -84,6 +85,17 @@ int mggan_decoder_fwd(int n_tiles, const int* tile_gen, const int* seq_agent, co
                       const float* b, const float* Whh, const float* W1h, const float* W1s, const float* b1,
                       const float* W2, const float* b2, int pred_len, int n_cols, float* out_abs, float* out_rel,
                       float* acts, float* u1save, float* h0save, cudaStream_t stream);
+/* Same operator, arguments and outputs as mggan_decoder_fwd, with the per-step gate contraction W_hh h_{t-1}
+ * ((128 rows x 32) . (32 x 128)) on the tcgen05 tensor cores: kind::tf32 with a hi/lo operand split (3 products,
+ * fp32-level accuracy), accumulator in TMEM, one 128-row tile (tiles 2s, 2s+1) per CTA.  n_tiles must be even. */
+int mggan_decoder_fwd_tc(int n_tiles, const int* tile_gen, const int* seq_agent, const int* seq_noise,
+                         const int* seq_out, const float* A, const float* social, const float* last_xy,
+                         const float* last_dxdy, const float* noise, int Z, const float* Wz, const float* Wx,
+                         const float* b, const float* Whh, const float* W1h, const float* W1s, const float* b1,
+                         const float* W2, const float* b2, int pred_len, int n_cols, float* out_abs, float* out_rel,
+                         float* acts, float* u1save, float* h0save, cudaStream_t stream);
+/* Test hook for the tensor-core plumbing: D (128,128) = A (128,32) . B (128,32)^T by the same 3 x TF32 path. */
+int mggan_tc_selftest(const float* A, const float* B, float* D, cudaStream_t stream);
 /* d_abs / d_rel (pred_len, n_cols, 2), either may be NULL.  All gradient outputs accumulated. */
 int mggan_decoder_bwd(int n_tiles, const int* tile_gen, const int* seq_agent, const int* seq_noise,
                       const int* seq_out, const float* social, const float* last_dxdy, const float* noise, int Z,

@@ -7,8 +7,9 @@
 //  * mggan_selection_build: from idx (n_act, k) builds the decoder's work list: every draw
 //    becomes one sequence (agent i, generator g, noise sample m = occurrence rank of g among the
 //    earlier draws of agent i, output slot (j, i)), sequences are grouped by generator in
-//    deterministic (agent-major) order and each group is padded to a multiple of 64 rows so a
-//    decoder CTA tile never mixes generators.  The reference does this with torch.unique in a
+//    deterministic (agent-major) order and each group is padded to a multiple of 128 rows (two
+//    64-row tiles) so that neither a 64-row decoder tile (decoder.cu) nor a 128-row tensor-core
+//    tile (decoder_tc.cu, UMMA M = 128) ever mixes generators.  The reference does this with torch.unique in a
 //    Python loop over agents (one host sync per agent).
 //  * mggan_selection_all: the all-generators work list used by forward_all / the PM step.
 #include "common.cuh"
@@ -18,6 +19,7 @@ namespace {
 
 constexpr int GMAX = 32;
 constexpr int TILE = 64;
+constexpr int GROUP = 128;     // per-generator padding granularity (rows)
 
 __global__ void rank_kernel(const long long* __restrict__ idx, int n, int k, int G, int* __restrict__ cnt,
                             unsigned char* __restrict__ rank, int* __restrict__ err) {
@@ -78,7 +80,7 @@ scan_kernel(int* __restrict__ cnt, int n, int* __restrict__ totals) {
     if (threadIdx.x == 0) totals[blockIdx.x] = scarry;
 }
 
-// group bases (each generator's rows padded to a multiple of TILE) and the tile table
+// group bases (each generator's rows padded to a multiple of GROUP) and the tile table
 __global__ void bases_kernel(const int* __restrict__ totals, int G, int n_tiles, int* __restrict__ base_row,
                              int* __restrict__ tile_gen) {
     __shared__ int sbase[GMAX + 1];
@@ -87,7 +89,7 @@ __global__ void bases_kernel(const int* __restrict__ totals, int G, int n_tiles,
         for (int g = 0; g < G; ++g) {
             sbase[g] = row;
             base_row[g] = row;
-            row += (totals[g] + TILE - 1) / TILE * TILE;
+            row += (totals[g] + GROUP - 1) / GROUP * GROUP;
         }
         sbase[G] = row;
         base_row[G] = row;
@@ -156,7 +158,8 @@ __global__ void gumbel_kernel(const float* __restrict__ logits, int n, int k, in
 
 }  // namespace
 
-extern "C" int mggan_selection_tiles(int n_seq, int G) { return (n_seq + TILE - 1) / TILE + G; }
+// upper bound on 64-row tiles (even): every generator group may add up to GROUP - 1 padding rows
+extern "C" int mggan_selection_tiles(int n_seq, int G) { return ((n_seq + TILE - 1) / TILE + 2 * G + 1) & ~1; }
 
 // scratch: cnt (n*G int32), rank (n*k bytes), base_row (G+1 int32), err (1 int32, caller zero-fills)
 extern "C" int mggan_selection_build(const long long* idx, int n, int k, int G, int n_tiles, int* cnt,
@@ -181,7 +184,7 @@ extern "C" int mggan_selection_build(const long long* idx, int n, int k, int G, 
 extern "C" int mggan_selection_all(int n, int k, int G, int* tile_gen, int* seq_agent, int* seq_noise, int* seq_out,
                                    cudaStream_t stream) {
     MGGAN_REQUIRE(G >= 1 && n >= 0 && k >= 1, "mggan_selection_all: bad arguments");
-    int tiles_per_gen = (n * k + TILE - 1) / TILE;
+    int tiles_per_gen = (n * k + GROUP - 1) / GROUP * (GROUP / TILE);
     int total = G * tiles_per_gen * TILE;
     if (total == 0) return MGGAN_OK;
     int grid = (total + 255) / 256;

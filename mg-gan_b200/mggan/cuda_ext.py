@@ -42,6 +42,8 @@ SIGNATURES = {
     "mggan_selection_build": "piiiippppppppps",
     "mggan_selection_all": "iiipppps",
     "mggan_decoder_fwd": "ipppppppppipppppppppiippppps",
+    "mggan_decoder_fwd_tc": "ipppppppppipppppppppiippppps",
+    "mggan_tc_selftest": "ppps",
     "mggan_decoder_bwd": "ipppppppipppppppppiippppppppppppppppps",
     "mggan_social_attn_fwd": "ppipppipppppps",
     "mggan_social_attn_bwd": "ppipppippppppppppppps",

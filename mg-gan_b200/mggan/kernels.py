@@ -4,6 +4,7 @@ PyTorch allocates the outputs / workspaces and carries the autograd graph; all a
 the path happens in the sm_100a kernels of `csrc/`.  Nothing here runs without the library.
 """
 import math
+import os
 
 import torch
 
@@ -413,7 +414,7 @@ class Selection:
 
     @staticmethod
     def all_generators(n, k, num_gens, device):
-        tiles_per_gen = (n * k + TILE - 1) // TILE
+        tiles_per_gen = 2 * ((n * k + 2 * TILE - 1) // (2 * TILE))      # 128-row groups (mggan_selection_all)
         n_tiles = num_gens * tiles_per_gen
         i32 = lambda *s: torch.empty(*s, device=device, dtype=torch.int32)
         tile_gen = i32(max(n_tiles, 1))
@@ -431,6 +432,11 @@ def gumbel_sample(logits, k, seed, offset):
 
 
 # --------------------------------------------------------------------------- decoder
+# Forward entry point: the tcgen05 (tensor-core, 3 x TF32) kernel by default; MGGAN_DECODER=fp32 selects the FP32-FMA
+# kernel with the same contract (kept for A/B measurements; both are CUDA, neither is a fallback).
+DECODER_FWD = "mggan_decoder_fwd" if os.environ.get("MGGAN_DECODER", "tc") == "fp32" else "mggan_decoder_fwd_tc"
+
+
 class _Decoder(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, social, last_xy, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2, sel, pred_len, grad_on):
@@ -446,7 +452,7 @@ class _Decoder(torch.autograd.Function):
         acts = torch.empty(pred_len, R, 3, 32, 2, device=dev) if need else None
         u1 = torch.empty(pred_len, R, 16, device=dev) if need else None
         h0 = torch.empty(R, 32, device=dev) if need else None
-        call("mggan_decoder_fwd", sel.n_tiles, ptr(sel.tile_gen), ptr(sel.seq_agent), ptr(sel.seq_noise),
+        call(DECODER_FWD, sel.n_tiles, ptr(sel.tile_gen), ptr(sel.seq_agent), ptr(sel.seq_noise),
              ptr(sel.seq_out), ptr(A), ptr(social), ptr(last_xy), ptr(last_dxdy), ptr(noise), Z, ptr(wz), ptr(wx),
              ptr(b), ptr(whh), ptr(w1h), ptr(w1s), ptr(b1), ptr(w2), ptr(b2), pred_len, sel.n_cols, ptr(out_abs),
              ptr(out_rel), ptr(acts), ptr(u1), ptr(h0))

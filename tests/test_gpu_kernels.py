@@ -214,9 +214,24 @@ def _decoder_sd(G, C, Z, seed):
     return rand_sd(shapes, seed, 0.25)
 
 
+def test_tensor_core_gate_product_is_fp32_accurate(K):
+    """tcgen05.mma kind::tf32 with the hi/lo operand split (decoder_tc.cu): D = A B^T against float64."""
+    from mggan.cuda_ext import call, ptr
+    g = torch.Generator().manual_seed(11)
+    for scale in (1.0, 0.05):
+        A = (torch.randn(128, 32, generator=g) * scale).to(DEV)
+        B = (torch.randn(128, 32, generator=g) * 0.3).to(DEV)
+        D = torch.full((128, 128), float("nan"), device=DEV)
+        call("mggan_tc_selftest", ptr(A), ptr(B), ptr(D))
+        ref = A.double() @ B.double().T
+        check(D, ref, 2e-6, "3xTF32 product")
+
+
+@pytest.mark.parametrize("variant", ["mggan_decoder_fwd_tc", "mggan_decoder_fwd"])
 @pytest.mark.parametrize("G,n,k,C", [(1, 4, 3, 128), (4, 17, 20, 64), (8, 70, 20, 128)])
-def test_decoder_selected_and_all(K, G, n, k, C):
+def test_decoder_selected_and_all(K, G, n, k, C, variant, monkeypatch):
     from mggan.model.modules.standard import MultiGenerator
+    monkeypatch.setattr(K, "DECODER_FWD", variant)      # tensor-core (default) and FP32-FMA forward kernels
     Z = 8
     gen = torch.Generator().manual_seed(G * 1000 + n)
     sd = _decoder_sd(G, C, Z, seed=n)
