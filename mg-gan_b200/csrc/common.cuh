@@ -141,3 +141,21 @@ __device__ __forceinline__ void atomic_block44(float* __restrict__ dst, int ld, 
 #pragma unroll
         for (int b = 0; b < 4; ++b) atomicAdd(dst + (o0 + a) * ld + k0 + b, acc[a][b]);
 }
+
+// ---- decoder saved-activation layouts (decoder.cu, decoder_tc.cu) -----------------------------------------------
+// Rows are grouped in 128-row tiles and the row index is the second-fastest dimension, so that the 32 rows a warp of
+// the thread-per-row tensor-core kernel writes for one (pair, unit-pair) are 512 contiguous bytes (4 lines per
+// 16-byte store instead of 32), and the (4 rows x 8 units) float2 accesses of the FP32 kernels stay 64-byte segments.
+//   acts   (T, rows/128, 3 pairs, 16 unit-pairs, 128 rows, 4)   4 floats = pair values of units 2j, 2j+1;
+//                                                               pairs: (i, f) | (g, o) | (c, tanh c)
+//   u1save (T, rows/128, 4, 128 rows, 4)                        hidden2pos.0 pre-activations m = 4 q + (0..3)
+//   h0save (rows/128, 8, 128 rows, 4)                           initial hidden state, units 4 q + (0..3)
+__device__ __forceinline__ size_t dec_acts_off(size_t n_super, int t, size_t row, int pair, int u) {
+    return ((((size_t)t * n_super + (row >> 7)) * 3 + pair) * 16 + (u >> 1)) * 512 + (row & 127) * 4 + (u & 1) * 2;
+}
+__device__ __forceinline__ size_t dec_u1_off(size_t n_super, int t, size_t row, int m) {
+    return (((size_t)t * n_super + (row >> 7)) * 4 + (m >> 2)) * 512 + (row & 127) * 4 + (m & 3);
+}
+__device__ __forceinline__ size_t dec_h0_off(size_t row, int u) {
+    return ((row >> 7) * 8 + (u >> 2)) * 512 + (row & 127) * 4 + (u & 3);
+}

@@ -142,7 +142,7 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
                 h0 = __ldg(A + (size_t)ag * H + u);
                 const float* zp = noise + (size_t)sq.seq_noise[row0 + r] * Z;
                 for (int z = 0; z < Z; ++z) h0 = fmaf(sWz[u * (ZMAX + 1) + z], __ldg(zp + z), h0);
-                if (h0save != nullptr) h0save[(size_t)(row0 + r) * H + u] = h0;
+                if (h0save != nullptr) h0save[dec_h0_off(row0 + r, u)] = h0;
             }
             sH[r * LDH + u] = h0;
             c[i] = 0.f;
@@ -169,9 +169,11 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
                 float tc = tanhf_(c[i]);
                 hnext[r * LDH + u] = og * tc;
                 if (acts != nullptr && sAgent[r] >= 0) {
-                    // layout (t, row, pair, unit, 2): a warp's float2 stores cover whole 32-byte sectors
-                    float2* a = reinterpret_cast<float2*>(acts) + ((size_t)t * Rpad + row0 + r) * (3 * H) + u;
-                    a[0] = make_float2(ig, fg); a[H] = make_float2(gg, og); a[2 * H] = make_float2(c[i], tc);
+                    // layout: dec_acts_off (common.cuh); a warp's float2 stores cover 64-byte segments
+                    float* a = acts + dec_acts_off(Rpad >> 7, t, row0 + r, 0, u);
+                    *reinterpret_cast<float2*>(a) = make_float2(ig, fg);
+                    *reinterpret_cast<float2*>(a + 16 * 512) = make_float2(gg, og);
+                    *reinterpret_cast<float2*>(a + 2 * 16 * 512) = make_float2(c[i], tc);
                 }
             }
             __syncthreads();
@@ -194,9 +196,9 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
                 xy0 += d0; xy1 += d1;
                 if (pcol >= 0) {
                     if (u1save != nullptr) {
-                        float* us = u1save + ((size_t)t * Rpad + row0 + prow) * M1;
+                        float* us = u1save + dec_u1_off(Rpad >> 7, t, row0 + prow, mq);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) us[mq + 4 * j] = up[0][j];
+                        for (int j = 0; j < 4; ++j) us[j * 512] = up[0][j];       // m = mq + 4 j
                     }
                     if (mq == 0) {
                         size_t o = ((size_t)t * n_cols + pcol) * 2;
@@ -213,7 +215,7 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
 
 // Backward.  Inputs: the forward's saved activations, d_abs / d_rel (either may be null).
 // Per step and 64-row tile:  phase 0 hidden2pos backward (thread = row x 4 mid units), phase 1 LSTM cell backward
-// (thread = 8 rows x 1 unit; activations read as (i,f | g,o | c,tanh c) float2 triples, layout (t, row, pair, unit, 2)), phase 2 tile products:
+// (thread = 8 rows x 1 unit; activations read as (i,f | g,o | c,tanh c) float2 triples, layout dec_acts_off in common.cuh), phase 2 tile products:
 //   dh_{t-1} = dG W_hh (64 x 32, K = 128)          dW_hh += dG^T h_{t-1} (128 x 32, K = 64 rows)
 //   (dWx | db) += dG^T (x | 1)   via the pad columns 32..34 of the h_{t-1} tile, rows split over the k-quad lanes
 //   dW1h += dU^T h_t (16 x 32)   rows split over the 8 warps
@@ -345,10 +347,10 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                         float2 v = __ldg(reinterpret_cast<const float2*>(d_rel + o));
                         dr0 += v.x; dr1 += v.y;
                     }
-                    const float* us = u1save + ((size_t)t * Rpad + row0 + prow) * M1;
+                    const float* us = u1save + dec_u1_off(Rpad >> 7, t, row0 + prow, mq);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float up = us[mq + 4 * j];
+                        float up = us[j * 512];                                       // m = mq + 4 j
                         float a = lrelu_(up, 0.01f);
                         aw2a[j] = fmaf(dr0, a, aw2a[j]);
                         aw2b[j] = fmaf(dr1, a, aw2b[j]);
@@ -384,13 +386,16 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
 #pragma unroll
                 for (int ii = 0; ii < NB; ++ii) {
                     const int r = rl + 4 * (half * NB + ii);
-                    const float2* a = reinterpret_cast<const float2*>(acts) + ((size_t)t * Rpad + row0 + r) * (3 * H) + u;
-                    q0[ii] = __ldg(a); q1[ii] = __ldg(a + H); q2[ii] = __ldg(a + 2 * H);
+                    const float* a = acts + dec_acts_off(Rpad >> 7, t, row0 + r, 0, u);
+                    q0[ii] = __ldg(reinterpret_cast<const float2*>(a));
+                    q1[ii] = __ldg(reinterpret_cast<const float2*>(a + 16 * 512));
+                    q2[ii] = __ldg(reinterpret_cast<const float2*>(a + 2 * 16 * 512));
                     if (t > 0) {
-                        const float2* ap = a - Rpad * (3 * H);
-                        p1[ii] = __ldg(ap + H); p2[ii] = __ldg(ap + 2 * H);
+                        const float* ap = a - (Rpad >> 7) * (3 * 16 * 512);
+                        p1[ii] = __ldg(reinterpret_cast<const float2*>(ap + 16 * 512));
+                        p2[ii] = __ldg(reinterpret_cast<const float2*>(ap + 2 * 16 * 512));
                     } else {
-                        h0v[ii] = __ldg(h0save + (size_t)(row0 + r) * H + u);
+                        h0v[ii] = __ldg(h0save + dec_h0_off(row0 + r, u));
                     }
                 }
 #pragma unroll
@@ -538,7 +543,7 @@ extern "C" int mggan_decoder_fwd(int n_tiles, const int* tile_gen, const int* se
                                  const float* W2, const float* b2, int pred_len, int n_cols, float* out_abs,
                                  float* out_rel, float* acts, float* u1save, float* h0save, cudaStream_t stream) {
     MGGAN_REQUIRE(Z >= 1 && Z <= ZMAX, "mggan_decoder_fwd: noise_dim %d not in [1, %d]", Z, ZMAX);
-    MGGAN_REQUIRE(pred_len >= 1 && n_tiles >= 0, "mggan_decoder_fwd: bad pred_len/n_tiles");
+    MGGAN_REQUIRE(pred_len >= 1 && n_tiles >= 0 && (n_tiles & 1) == 0, "mggan_decoder_fwd: bad pred_len / odd n_tiles");
     MGGAN_REQUIRE((acts == nullptr) == (u1save == nullptr) && (acts == nullptr) == (h0save == nullptr),
                   "mggan_decoder_fwd: save buffers must be all set or all null");
     if (n_tiles == 0) return MGGAN_OK;
@@ -562,6 +567,7 @@ extern "C" int mggan_decoder_bwd(int n_tiles, const int* tile_gen, const int* se
                                  float* dA, float* dsocial, cudaStream_t stream) {
     MGGAN_REQUIRE(Z >= 1 && Z <= ZMAX, "mggan_decoder_bwd: noise_dim %d not in [1, %d]", Z, ZMAX);
     MGGAN_REQUIRE(acts && u1save && h0save, "mggan_decoder_bwd: forward was run without save buffers");
+    MGGAN_REQUIRE((n_tiles & 1) == 0, "mggan_decoder_bwd: odd n_tiles (work lists are padded to 128-row groups)");
     if (n_tiles == 0) return MGGAN_OK;
     DecSeq sq{tile_gen, seq_agent, seq_noise, seq_out};
     DecWeights w{Wz, Wx, b, Whh, W1h, W1s, b1, W2, b2};

@@ -153,7 +153,7 @@ decoder_fwd_tc_kernel(DecSeq sq, int n_super, const float* __restrict__ A, const
                       const float* __restrict__ last_xy, const float* __restrict__ last_dxdy,
                       const float* __restrict__ noise, int Z, DecWeights w, int T, int n_cols,
                       float* __restrict__ out_abs, float* __restrict__ out_rel, float* __restrict__ acts,
-                      float* __restrict__ u1save, float* __restrict__ h0save, size_t Rpad) {
+                      float* __restrict__ u1save, float* __restrict__ h0save) {
     extern __shared__ __align__(1024) float smem[];
     float* sAhi = smem + S_AHI;
     float* sAlo = smem + S_ALO;
@@ -272,7 +272,7 @@ decoder_fwd_tc_kernel(DecSeq sq, int n_super, const float* __restrict__ A, const
                         h4.x = fmaf(wz.x, zv[z], h4.x); h4.y = fmaf(wz.y, zv[z], h4.y);
                         h4.z = fmaf(wz.z, zv[z], h4.z); h4.w = fmaf(wz.w, zv[z], h4.w);
                     }
-                    if (h0save != nullptr) *reinterpret_cast<float4*>(h0save + row * H + u4 * 4) = h4;
+                    if (h0save != nullptr) st4(h0save + dec_h0_off(row, u4 * 4), h4);
                 }
                 const float4 hi = make_float4(tf32_hi(h4.x), tf32_hi(h4.y), tf32_hi(h4.z), tf32_hi(h4.w));
                 st4(sAhi + oper_off(tid, u4 * 4), hi);
@@ -294,7 +294,7 @@ decoder_fwd_tc_kernel(DecSeq sq, int n_super, const float* __restrict__ A, const
             float uacc[M1];
 #pragma unroll
             for (int m = 0; m < M1; ++m) uacc[m] = bs[m];
-            float* arow = (acts != nullptr && valid) ? acts + ((size_t)t * Rpad + row) * (6 * H) : nullptr;
+            float* arow = (acts != nullptr && valid) ? acts + dec_acts_off(n_super, t, row, 0, 0) : nullptr;
 #pragma unroll
             for (int u4 = 0; u4 < H / 4; ++u4) {
                 float v[16];
@@ -322,11 +322,11 @@ decoder_fwd_tc_kernel(DecSeq sq, int n_super, const float* __restrict__ A, const
                         uacc[m4 * 4 + 2] = fmaf(w1.z, h, uacc[m4 * 4 + 2]); uacc[m4 * 4 + 3] = fmaf(w1.w, h, uacc[m4 * 4 + 3]);
                     }
                 }
-                if (arow != nullptr) {     // layout (t, row, pair, unit, 2): 8 floats = one 32-byte sector per pair
-                    float* a = arow + u4 * 8;
-                    st4(a, make_float4(pif[0], pif[1], pif[2], pif[3])); st4(a + 4, make_float4(pif[4], pif[5], pif[6], pif[7]));
-                    st4(a + 2 * H, make_float4(pgo[0], pgo[1], pgo[2], pgo[3])); st4(a + 2 * H + 4, make_float4(pgo[4], pgo[5], pgo[6], pgo[7]));
-                    st4(a + 4 * H, make_float4(pct[0], pct[1], pct[2], pct[3])); st4(a + 4 * H + 4, make_float4(pct[4], pct[5], pct[6], pct[7]));
+                if (arow != nullptr) {     // dec_acts_off layout: each st4 of a warp is 512 contiguous bytes (unit pair 2 u4 + {0, 1})
+                    float* a = arow + (u4 * 2) * 512;
+                    st4(a, make_float4(pif[0], pif[1], pif[2], pif[3])); st4(a + 512, make_float4(pif[4], pif[5], pif[6], pif[7]));
+                    st4(a + 16 * 512, make_float4(pgo[0], pgo[1], pgo[2], pgo[3])); st4(a + 17 * 512, make_float4(pgo[4], pgo[5], pgo[6], pgo[7]));
+                    st4(a + 32 * 512, make_float4(pct[0], pct[1], pct[2], pct[3])); st4(a + 33 * 512, make_float4(pct[4], pct[5], pct[6], pct[7]));
                 }
                 if (t + 1 < T) {
                     const float4 hi = make_float4(tf32_hi(hq[0]), tf32_hi(hq[1]), tf32_hi(hq[2]), tf32_hi(hq[3]));
@@ -354,10 +354,10 @@ decoder_fwd_tc_kernel(DecSeq sq, int n_super, const float* __restrict__ A, const
             xy0 += d0; xy1 += d1;
             if (pcol >= 0) {
                 if (u1save != nullptr) {
-                    float* us = u1save + ((size_t)t * Rpad + row) * M1;
+                    float* us = u1save + dec_u1_off(n_super, t, row, 0);
 #pragma unroll
                     for (int m4 = 0; m4 < M1 / 4; ++m4)
-                        st4(us + m4 * 4, make_float4(uacc[m4 * 4], uacc[m4 * 4 + 1], uacc[m4 * 4 + 2], uacc[m4 * 4 + 3]));
+                        st4(us + m4 * 512, make_float4(uacc[m4 * 4], uacc[m4 * 4 + 1], uacc[m4 * 4 + 2], uacc[m4 * 4 + 3]));
                 }
                 const size_t o = ((size_t)t * n_cols + pcol) * 2;
                 *reinterpret_cast<float2*>(out_rel + o) = make_float2(d0, d1);
@@ -447,7 +447,7 @@ extern "C" int mggan_decoder_fwd_tc(int n_tiles, const int* tile_gen, const int*
     const int grid = n_super < sms * 3 ? n_super : sms * 3;
     decoder_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(sq, n_super, A, social, last_xy, last_dxdy, noise, Z,
                                                                       w, pred_len, n_cols, out_abs, out_rel, acts, u1save,
-                                                                      h0save, (size_t)n_tiles * 64);
+                                                                      h0save);
     return mggan_check_launch("decoder_fwd_tc");
 }
 
