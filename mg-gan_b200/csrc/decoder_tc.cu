@@ -113,6 +113,14 @@ constexpr uint64_t DESC_KSTEP = 256 >> 4;
 // K-major, N >> 3 in bits [17,23), M >> 4 in bits [24,29).
 constexpr uint32_t IDESC_M128_N128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+// Gate non-linearities on the MUFU pipe, 4 / 5 instructions each (the cell math of 128 rows x 32 units x 5 activations
+// per step is what bounds this kernel once the contraction is on the tensor core): flush-to-zero ex2 / rcp approximations,
+// |error| ~1e-7, exact saturation at +-inf.
+__device__ __forceinline__ float ex2_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_tc(float x) { return rcp_(1.f + ex2_(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_tc(float x) { return fmaf(-2.f, rcp_(1.f + ex2_(2.8853900817779268f * x)), 1.f); }
+
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // D = Ah.Bh + Al.Bh + Ah.Bl over K = 32 (4 K-steps x 3 products), then commit to the mbarrier.
@@ -304,12 +312,12 @@ decoder_fwd_tc_kernel(DecSeq sq, int n_super, const float* __restrict__ A, const
                 for (int uu = 0; uu < 4; ++uu) {
                     const int u = u4 * 4 + uu;
                     const float4 wi = sWxb[u * 4 + 0], wf = sWxb[u * 4 + 1], wg = sWxb[u * 4 + 2], wo = sWxb[u * 4 + 3];
-                    const float ig = sigmoidf_(v[uu * 4 + 0] + fmaf(wi.x, d0, fmaf(wi.y, d1, wi.z)));
-                    const float fg = sigmoidf_(v[uu * 4 + 1] + fmaf(wf.x, d0, fmaf(wf.y, d1, wf.z)));
-                    const float gg = tanhf_(v[uu * 4 + 2] + fmaf(wg.x, d0, fmaf(wg.y, d1, wg.z)));
-                    const float og = sigmoidf_(v[uu * 4 + 3] + fmaf(wo.x, d0, fmaf(wo.y, d1, wo.z)));
+                    const float ig = sigmoid_tc(v[uu * 4 + 0] + fmaf(wi.x, d0, fmaf(wi.y, d1, wi.z)));
+                    const float fg = sigmoid_tc(v[uu * 4 + 1] + fmaf(wf.x, d0, fmaf(wf.y, d1, wf.z)));
+                    const float gg = tanh_tc(v[uu * 4 + 2] + fmaf(wg.x, d0, fmaf(wg.y, d1, wg.z)));
+                    const float og = sigmoid_tc(v[uu * 4 + 3] + fmaf(wo.x, d0, fmaf(wo.y, d1, wo.z)));
                     c[u] = fmaf(fg, c[u], ig * gg);
-                    const float tc = tanhf_(c[u]);
+                    const float tc = tanh_tc(c[u]);
                     const float h = og * tc;
                     hq[uu] = h;
                     pif[uu * 2] = ig; pif[uu * 2 + 1] = fg;
