@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--roofline-kernel", default=None, help="entry point whose launches are timed in the timed region")
     ap.add_argument("--breakdown", action="store_true", help="print a per-kernel time table to stderr")
+    ap.add_argument("--breakdown-detail", action="store_true", help="per-(entry point, shape) time table to stderr")
     ap.add_argument("--host-profile", type=int, default=0, help="cProfile N resident steps (host-side enqueue cost) to stderr")
     return ap.parse_args()
 
@@ -273,6 +274,11 @@ def run_ours(a):
     for _ in range(max(1, min(a.warmup, 2))):
         step_resident()
     torch.cuda.synchronize()
+    if a.breakdown_detail and rank == 0:
+        cuda_ext.profile_start(detail=True)
+        step_resident()
+        for name, (c, t) in sorted(cuda_ext.profile_stop().items(), key=lambda kv: -kv[1][1])[:60]:
+            print(f"  {name:90s} calls {c:3d}  {t:8.3f} ms", file=sys.stderr)
     cuda_ext.profile_start()
     step_resident()
     prof = cuda_ext.profile_stop()

@@ -141,10 +141,11 @@ launch_count = 0          # kernels launched through this binding since import
 _profile = None           # None | {"only": set or None, "events": [(name, start, end), ...]}
 
 
-def profile_start(only=None):
-    """Record a CUDA-event pair around every call (or only the named entry points) on the launching stream."""
+def profile_start(only=None, detail=False):
+    """Record a CUDA-event pair around every call (or only the named entry points) on the launching stream.
+    detail=True keys the result by entry point AND its integer arguments (shapes)."""
     global _profile
-    _profile = {"only": set(only) if only else None, "events": []}
+    _profile = {"only": set(only) if only else None, "events": [], "detail": detail}
 
 
 def profile_stop():
@@ -170,7 +171,9 @@ def call(name, *args):
         s.record()
         rc = getattr(lib, name)(*args, stream())
         e.record()
-        prof["events"].append((name, s, e))
+        key = name + str(tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and abs(a) < (1 << 31))) \
+            if prof.get("detail") else name
+        prof["events"].append((key, s, e))
     else:
         rc = getattr(lib, name)(*args, stream())
     if rc != 0:
