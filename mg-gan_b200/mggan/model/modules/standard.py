@@ -141,9 +141,13 @@ class MultiGenerator(nn.Module):
                         self.pred_len)
 
     # ------------------------------------------------------------------ reference API
-    def forward(self, in_xy, in_dxdy, sub_batches, noise=None, all_gen_out=True, img=None, num_samples=5, mask=None):
+    def forward(self, in_xy, in_dxdy, sub_batches, noise=None, all_gen_out=True, img=None, num_samples=5, mask=None,
+                gen_idxs=None):
         """See reference standard.py:111-215.  Returns (GeneratorOutput(rel, abs), logits, idx):
-        rel/abs (pred_len, k, n_act, 2), or (pred_len, k, G, n_act, 2) under no_grad if all_gen_out."""
+        rel/abs (pred_len, k, n_act, 2), or (pred_len, k, G, n_act, 2) under no_grad if all_gen_out.
+        `gen_idxs` (additive): generator indices (n_act, k) or a callable logits -> indices used instead of a
+        PM-Network draw when all_gen_out is False -- the prediction strategies of train.py:291-465 decode exactly
+        the sequences they keep instead of all G * k * n and gathering."""
         batch_size = in_xy.size(1)
         enc_h, social_feats = self._trunk(in_xy, in_dxdy, sub_batches, img)
 
@@ -163,7 +167,13 @@ class MultiGenerator(nn.Module):
             net_chooser_out, sampled_gen_idxs = self.get_samples(enc_h, num_samples)
         else:
             with torch.no_grad():
-                net_chooser_out, sampled_gen_idxs = self.get_samples(enc_h, num_samples)
+                if gen_idxs is None:
+                    net_chooser_out, sampled_gen_idxs = self.get_samples(enc_h, num_samples)
+                else:
+                    net_chooser_out = self.pm_logits(enc_h)
+                    sampled_gen_idxs = gen_idxs(net_chooser_out) if callable(gen_idxs) else gen_idxs
+                    sampled_gen_idxs = sampled_gen_idxs.to(device=enc_h.device, dtype=torch.int64)
+                    assert sampled_gen_idxs.shape == (batch_size, num_samples), sampled_gen_idxs.shape
             sel = K.Selection.from_indices(sampled_gen_idxs, self.n_gs)
             self.last_selection = sel           # per-generator draw counts for the trainer's reweighting
             pred_xy, pred_dxdy = self._decode(in_xy, in_dxdy, enc_h, noise, social_feats, sel)

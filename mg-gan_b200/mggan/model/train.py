@@ -11,7 +11,8 @@ the selection kernel already produced, and no step synchronises with the host.
 
 Only the default configuration is on the path: gan_type in {mgan, gan}, gan_obj NS,
 weighting_target in {ml, none}, l2_loss_type not in {none, mse} (the non-default branches are
-"next" rows in SURVEY.md 8f and raise NotImplementedError).
+"next" rows in SURVEY.md 8f and raise NotImplementedError).  All prediction strategies of
+`get_predict_func` (train.py:291-576) are built: they decode only the sequences they keep.
 """
 import random
 import time
@@ -27,7 +28,8 @@ from mggan.evaluation import evaluate_ade_fde
 from mggan.logging import Experiment
 from mggan.model.config import get_parser
 from mggan.model.model_factory import construct_model
-from mggan.utils import get_gan_labels, get_global_noise, to_numpy
+from mggan.utils import (expected_sample_indices, get_gan_labels, get_global_noise, threshold_sample_indices,
+                         to_numpy, uniform_sample_indices)
 
 
 def _label_scalars(shape):
@@ -169,9 +171,21 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
 
     # ------------------------------------------------------------------ prediction / evaluation
     def get_predict_func(self, strategy: str):
-        if strategy != "sampling":
-            raise NotImplementedError(
-                f"prediction strategy '{strategy}': only 'sampling' is on the B200 path (SURVEY.md 8f #1)")
+        """Reference train.py:553-576 (same names, same eps thresholds)."""
+        assert strategy in ("uniform_expected", "sampling", "expected", "rejection", "smart_expected",
+                            "smart_sampling", "uniform_sampling"), strategy
+        if strategy == "expected":
+            return self.predict_expected
+        if strategy == "rejection":
+            return self.predict_rejection
+        if strategy == "uniform_expected":
+            return self.predict_uniform
+        if strategy == "smart_expected":
+            return partial(self.predict_uniform, eps=1.0 / self.G.n_gs)
+        if strategy == "smart_sampling":
+            return partial(self.predict_smart_sampling, eps=1.0 / self.G.n_gs ** 2)
+        if strategy == "uniform_sampling":
+            return partial(self.predict_smart_sampling, eps=0.0)
         return self.predict
 
     def get_predictions(self, loader, num_preds=20, strategy="sampling"):
@@ -200,6 +214,78 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
             probs = torch.softmax(net_chooser_out, 1)
         assert preds.abs.shape[1] == num
         return preds.abs, preds.rel, to_numpy(probs), to_numpy(gen_idxs)
+
+    def _predict_selected(self, index_fn, in_dxdy, in_xy, sub_batches, img, num, noise, mask):
+        """Shared body of the index-selecting strategies.  The reference decodes every generator on num (or
+        num * G) noise samples and gathers prediction j of agent i from (sample = occurrence rank of its generator
+        among the agent's earlier predictions, generator idx[i, j]) (train.py:342-350, 389-403, 453-462); that
+        gather is exactly the selected-sequence decode of the training path, so only num * n sequences are run."""
+        self.G.eval()
+        with torch.no_grad():
+            if noise is not None:
+                noise = noise[:num]            # occurrence ranks are < num: later noise samples are never gathered
+            preds, net_chooser_out, idxs = self.G(
+                in_xy, in_dxdy, sub_batches, noise=noise, all_gen_out=False, img=img, num_samples=num, mask=mask,
+                gen_idxs=lambda logits: index_fn(torch.softmax(logits, 1)))
+            probs = torch.softmax(net_chooser_out, 1)
+        assert preds.abs.shape[1] == num
+        return preds.abs, preds.rel, to_numpy(probs), to_numpy(idxs)
+
+    def predict_expected(self, in_dxdy, in_xy, sub_batches, img=None, num=20, noise=None, mask=None):
+        """Reference train.py:291-351: predictions per generator proportional to the PM-Network probabilities."""
+        return self._predict_selected(partial(expected_sample_indices, num=num), in_dxdy, in_xy, sub_batches, img, num,
+                                      noise, mask)
+
+    def predict_uniform(self, in_dxdy, in_xy, sub_batches, img=None, num=20, noise=None, eps=0.0, mask=None):
+        """Reference train.py:353-412 ('uniform_expected'; 'smart_expected' with eps = 1 / G)."""
+        return self._predict_selected(partial(uniform_sample_indices, num=num, eps=eps), in_dxdy, in_xy, sub_batches,
+                                      img, num, noise, mask)
+
+    def predict_smart_sampling(self, in_dxdy, in_xy, sub_batches, img=None, num=20, noise=None, eps=0.0, mask=None):
+        """Reference train.py:414-465 ('smart_sampling' with eps = 1 / G^2; 'uniform_sampling' with eps = 0)."""
+        return self._predict_selected(partial(threshold_sample_indices, num=num, eps=eps), in_dxdy, in_xy, sub_batches,
+                                      img, num, noise, mask)
+
+    def predict_rejection(self, in_dxdy, in_xy, sub_batches, img=None, num=20, noise=None, sigma=1e-3, N=10,
+                          truncation_ratio=0.7, debug=False, mask=None, eps_noise=None):
+        """Reference train.py:467-551 ("no GAN's land" rejection for single-generator models): draw
+        num + ceil((1 - truncation_ratio) num) samples, estimate each sample's Jacobian Frobenius norm from N
+        perturbed decodes, keep the `num` with the smallest norm.  `eps_noise` (additive): the N perturbations
+        (total, b, noise_dim), drawn here when None."""
+        from math import ceil
+        self.G.eval()
+        assert self.config.num_gens == 1, "Only implemented for single generator"
+        assert 0.0 < truncation_ratio <= 1.0
+        b = in_xy.shape[1]
+        total = num + ceil((1 - truncation_ratio) * num)
+        if noise is None:
+            noise = self._noise(sub_batches, total)
+        with torch.no_grad():
+            preds, net_chooser_out, gen_idxs = self.G(in_xy, in_dxdy, sub_batches, noise=noise, all_gen_out=True,
+                                                      img=img, num_samples=total, mask=mask)
+            nb = preds.abs.shape[3]
+            pred_vec = preds.abs.permute(3, 1, 2, 0, 4).reshape(nb, total, -1)
+            probs = to_numpy(torch.softmax(net_chooser_out, 1))
+            jac = torch.zeros(nb, total, device=pred_vec.device)
+            for i in range(N):
+                eps_i = (torch.randn(total, b, self.config.noise_dim, device=noise.device) * sigma ** 2
+                         if eps_noise is None else eps_noise[i].to(noise.device))
+                preds_eps, _, _ = self.G(in_xy, in_dxdy, sub_batches, noise=noise + eps_i, all_gen_out=True, img=img,
+                                         num_samples=total, mask=mask)
+                pv = preds_eps.abs.permute(3, 1, 2, 0, 4).reshape(nb, total, -1)
+                jac += 1 / (sigma ** 2) * ((pv - pred_vec) ** 2).sum(-1)
+            jac /= N
+        _, indices = torch.sort(jac, dim=1)
+        ar = torch.arange(nb, device=indices.device)
+        if debug:
+            gen_idxs[:] = 1
+            gen_idxs[ar[None], indices[:, :num]] = 0
+            return preds.abs.squeeze(2), preds.rel.squeeze(2), probs, to_numpy(gen_idxs)
+        batch_abs = preds.abs[:, indices[:, :num], 0, ar[:, None]].permute(0, 2, 1, 3)
+        batch_rel = preds.rel[:, indices[:, :num], 0, ar[:, None]].permute(0, 2, 1, 3)
+        gen_idxs = gen_idxs[ar[:, None], indices[:, :num]]
+        assert batch_abs.shape[1] == num
+        return batch_abs, batch_rel, probs, to_numpy(gen_idxs)
 
     @staticmethod
     def construct_model(config):

@@ -113,3 +113,48 @@ def get_selection_indices(sampled_gen_idxs):
     k = idx.shape[1]
     earlier = torch.tril(torch.ones(k, k, dtype=torch.bool, device=idx.device), -1)
     return (same & earlier[None]).sum(-1).to(idx.dtype)
+
+
+# ------------------------------------------------------------------ prediction strategies (index builders)
+def expected_sample_indices(probs, num):
+    """Generator index of each of the `num` predictions of the 'expected' strategy (reference
+    mggan/model/train.py:313-340): round(probs * num) predictions per generator, the rounding surplus / deficit
+    spread one at a time over the generators in descending order of their expected count, then the generators
+    visited round-robin in that order.  probs (b, G) -> (b, num) int64, on probs' device, no per-agent loop."""
+    b, G = probs.shape
+    dev = probs.device
+    expected = torch.round(probs.float() * num).to(torch.int64)
+    sort_idxs = torch.argsort(-expected, dim=1, stable=True)                   # numpy's argsort is stable for G <= 16
+    missing = num - expected.sum(1)
+    rank = torch.arange(G, device=dev)
+    per_rank = torch.clamp((missing.abs()[:, None] - rank[None, :] + G - 1) // G, min=0)
+    expected = expected + torch.zeros_like(expected).scatter_add_(1, sort_idxs, torch.sign(missing)[:, None] * per_rank)
+    assert bool((expected.sum(1) == num).all())
+    counts = expected.gather(1, sort_idxs)                                      # in visiting order
+    rounds = torch.arange(num, device=dev)
+    key = torch.where(rounds[None, None, :] < counts[:, :, None], rounds[None, None, :] * G + rank[None, :, None],
+                      torch.full((1, 1, 1), num * G + G, device=dev, dtype=torch.int64))
+    first = torch.sort(key.reshape(b, G * num), dim=1).values[:, :num]
+    assert bool((first < num * G + G).all()), "fewer than `num` predictions selected"
+    return sort_idxs.gather(1, first % G)
+
+
+def uniform_sample_indices(probs, num, eps=0.0):
+    """'uniform_expected' / 'smart_expected' (reference train.py:353-412): the generators whose PM-Network
+    probability exceeds `eps` (all of them if none does), cycled in descending order of probability.
+    probs (b, G) -> (b, num) int64."""
+    b, G = probs.shape
+    over = probs > eps
+    over = over | (over.sum(1, keepdim=True) < 1)
+    order = torch.argsort(torch.where(over, -probs, torch.full_like(probs, float("inf"))), dim=1, stable=True)
+    n_sel = over.sum(1, keepdim=True)
+    j = torch.arange(num, device=probs.device)[None, :]
+    return order.gather(1, j % n_sel)
+
+
+def threshold_sample_indices(probs, num, eps=0.0):
+    """'smart_sampling' / 'uniform_sampling' (reference train.py:414-465): `num` uniform draws among the generators
+    whose probability exceeds `eps` (all if none does).  probs (b, G) -> (b, num) int64."""
+    over = (probs > eps).float()
+    over[over.sum(1) < 1.0] = 1.0
+    return torch.multinomial(over, num, replacement=True)

@@ -2,8 +2,7 @@
 """Evaluate every `version_*` run under a model folder: ADE / FDE / Mode and Precision / Recall for
 k = 1 .. num_preds-1, written to one CSV (reference: scripts/evaluate.py:19-169, same arguments and
 output columns).  Prediction runs on the B200 kernels (`PiNetMultiGeneratorGAN.get_predictions`),
-metrics on the host.  Only the 'sampling' strategy is on the B200 path; `--pred_strat all` evaluates
-what is available and says so."""
+metrics on the host.  Every prediction strategy of the reference (`get_predict_func`) runs on the B200 kernels."""
 import os
 import sys
 from argparse import ArgumentParser
@@ -33,7 +32,7 @@ parser.add_argument("--pred_strat", default="all", choices=["all", "sampling", "
 parser.add_argument("--no-precision-recall", action="store_true")
 parser.add_argument("--num_scenes", type=int, default=64, help="synthetic datasets: scenes to evaluate")
 
-AVAILABLE = ("sampling",)
+AVAILABLE = ("sampling", "expected", "smart_expected", "rejection")
 
 
 def main(argv=None):
@@ -59,6 +58,12 @@ def main(argv=None):
             except Exception as e:
                 print(e)
                 m, config = PiNetMultiGeneratorGAN.load_from_path(model_dir, "best")
+            if config.num_gens == 1 and pred_strat not in ("sampling", "rejection"):      # reference :119-123
+                continue
+            if config.weighting_target == "none" and "smart" in pred_strat:
+                continue
+            if pred_strat == "rejection" and config.num_gens != 1:
+                continue
             m.G.eval()
             config.augment = False
             if args.eval_set is not None:

@@ -1,0 +1,92 @@
+"""Host logic of the prediction strategies: the vectorised index builders of mggan/utils.py against literal
+transcriptions of the reference's per-agent loops (mggan/model/train.py:313-340, 375-403 of the reference)."""
+import numpy as np
+import torch
+
+from mggan.utils import expected_sample_indices, get_selection_indices, threshold_sample_indices, uniform_sample_indices
+
+
+def ref_expected(probs, num):
+    """Reference train.py:313-340, with np.int -> int."""
+    probs = probs.numpy()
+    expected_num = np.round(probs * num).astype(int)
+    sort_idxs = np.argsort(-expected_num, axis=-1, kind="stable")
+    num_samples_missing = num - np.sum(expected_num, 1)
+    filler = np.zeros_like(expected_num)
+    for b, num_missing in enumerate(num_samples_missing):
+        num_missing_abs = np.abs(num_missing)
+        uniq, counts = np.unique(np.tile(sort_idxs[b], num_missing_abs)[:num_missing_abs], return_counts=True)
+        filler[b, uniq] += np.sign(num_missing) * counts
+    expected_num += filler
+    assert (np.sum(expected_num, 1) == num).all()
+    sample_idxs = []
+    for b_idx in range(expected_num.shape[0]):
+        idxs = []
+        for i in range(num):
+            for idx in sort_idxs[b_idx]:
+                if expected_num[b_idx, idx] > 0:
+                    idxs.append(idx)
+                    expected_num[b_idx, idx] -= 1
+        sample_idxs.append(torch.tensor(idxs[:num]))
+    return torch.stack(sample_idxs, 0)
+
+
+def ref_uniform(probs, num, eps):
+    """Reference train.py:375-403 (index part)."""
+    num_gens = probs.shape[1]
+    over_thresh = probs > eps
+    over_thresh_sum = torch.sum(over_thresh, 1)
+    over_thresh[over_thresh_sum < 1.0] = torch.ones(over_thresh.shape[1]).bool()
+    out = []
+    for b, gen_selector in enumerate(over_thresh):
+        sort_idxs = torch.argsort(-probs[b, gen_selector])
+        out.append(torch.arange(num_gens)[gen_selector][sort_idxs].repeat(num)[:num])
+    return torch.stack(out, 0)
+
+
+def test_expected_indices_match_reference_loops():
+    g = torch.Generator().manual_seed(0)
+    for G, num, b in [(2, 5, 40), (4, 7, 64), (8, 20, 200), (8, 19, 100), (3, 1, 30), (16, 20, 50)]:
+        probs = torch.softmax(torch.randn(b, G, generator=g) * 1.5, 1)
+        got = expected_sample_indices(probs, num)
+        assert got.dtype == torch.int64 and got.shape == (b, num)
+        assert torch.equal(got, ref_expected(probs.clone(), num).to(torch.int64)), (G, num)
+    # degenerate: one generator takes everything; uniform probabilities (all ties)
+    one = torch.zeros(3, 4); one[:, 2] = 1.0
+    assert torch.equal(expected_sample_indices(one, 6), torch.full((3, 6), 2))
+    uni = torch.full((2, 4), 0.25)
+    assert torch.equal(expected_sample_indices(uni, 6), ref_expected(uni.clone(), 6).to(torch.int64))
+
+
+def test_uniform_indices_match_reference_loops():
+    g = torch.Generator().manual_seed(1)
+    for G, num in [(2, 5), (4, 7), (8, 20), (8, 3)]:
+        probs = torch.softmax(torch.randn(50, G, generator=g) * 2.0, 1)
+        for eps in (0.0, 1.0 / G, 0.9999):           # the last one: nobody over the threshold -> everybody
+            got = uniform_sample_indices(probs, num, eps)
+            assert torch.equal(got, ref_uniform(probs.clone(), num, eps)), (G, num, eps)
+
+
+def test_threshold_sampling_only_draws_allowed_generators():
+    torch.manual_seed(2)
+    probs = torch.tensor([[0.7, 0.2, 0.05, 0.05], [0.25, 0.25, 0.25, 0.25], [0.01, 0.01, 0.97, 0.01]])
+    idx = threshold_sample_indices(probs, 400, eps=0.1)
+    assert idx.shape == (3, 400)
+    assert set(idx[0].tolist()) == {0, 1} and set(idx[1].tolist()) == {0, 1, 2, 3} and set(idx[2].tolist()) == {2}
+    assert abs((idx[0] == 0).float().mean().item() - 0.5) < 0.1          # uniform over the allowed ones
+    idx = threshold_sample_indices(probs, 50, eps=0.99)                    # none over the threshold -> all allowed
+    assert len(set(idx.flatten().tolist())) == 4
+
+
+def test_gather_is_the_selected_decode():
+    """out[t, j, i] = all[t, rank(i, j), idx[i, j], i] (train.py:342-350) is what the selection work list encodes:
+    noise sample = occurrence rank, generator = idx."""
+    g = torch.Generator().manual_seed(3)
+    b, G, num = 5, 3, 6
+    idx = torch.randint(0, G, (b, num), generator=g)
+    allp = torch.randn(2, num, G, b, 2, generator=g)
+    offs = get_selection_indices(idx)
+    flat = allp.reshape(2, num * G, b, 2)
+    ref = flat[:, idx + offs * G, torch.arange(b).unsqueeze(1)].transpose(1, 2)
+    mine = torch.stack([torch.stack([allp[:, offs[i, j], idx[i, j], i] for i in range(b)], 1) for j in range(num)], 1)
+    assert torch.equal(ref, mine)
