@@ -172,8 +172,12 @@ int mggan_scene_bn1_bwd_finalize(const double* sums_global, const double* sums_l
  * best (S) argmin sample; d_abs (T,k,n,2) zero-filled by the caller, or NULL. */
 int mggan_l2_scene_min(const float* abs_, const float* gt, int T, int k, int n, const int* scene_off, int n_scenes,
                        float inv_norm, float* loss, int* best, float* d_abs, cudaStream_t stream);
-/* loss += inv_denom * sum_i w_i BCE(p_i, label), w_i = 1/counts[gen_idx[i]] or 1; dp (n) or NULL. */
+/* loss += inv_denom * sum_i w_i BCE(p_i, label), w_i = 1/counts[gen_idx[i]] or 1; dp (n) or NULL.
+ * (gan_obj NS; gan_obj MM's generator term -BCE(d_fake, l_fake) is the same call with a negative inv_denom.) */
 int mggan_bce_scalar_label(const float* p, int n, float label, const long long* gen_idx, const int* counts,
+                           float inv_denom, float* loss, float* dp, cudaStream_t stream);
+/* gan_obj LS (abstract_train.py:72-75): loss += inv_denom * sum_i w_i (p_i - label)^2; dp (n) or NULL. */
+int mggan_mse_scalar_label(const float* p, int n, float label, const long long* gen_idx, const int* counts,
                            float inv_denom, float* loss, float* dp, cudaStream_t stream);
 int mggan_ce_generators(const float* logits, int n, int G, const long long* target, const int* counts,
                         float inv_denom, float* loss, float* dlogits, cudaStream_t stream);

@@ -89,6 +89,21 @@ bce_kernel(const float* __restrict__ p, int n, float label, const long long* __r
     block_add(acc, loss);
 }
 
+// ---- least-squares GAN objective (gan_obj = "LS": nn.MSELoss(reduction="none"), abstract_train.py:72-75) ----
+__global__ void __launch_bounds__(MGGAN_THREADS)
+mse_kernel(const float* __restrict__ p, int n, float label, const long long* __restrict__ gen_idx,
+           const int* __restrict__ counts, float inv_denom, float* __restrict__ loss, float* __restrict__ dp) {
+    float acc = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float w = inv_denom;
+        if (gen_idx != nullptr) w /= (float)counts[gen_idx[i]];
+        const float d = p[i] - label;
+        acc = fmaf(w, d * d, acc);
+        if (dp != nullptr) dp[i] = 2.f * w * d;
+    }
+    block_add(acc, loss);
+}
+
 // ---- cross-entropy over generators, optional 1/count weights (train.py:105-113, :184) --------
 __global__ void __launch_bounds__(MGGAN_THREADS)
 ce_kernel(const float* __restrict__ logits, int n, int G, const long long* __restrict__ target,
@@ -179,6 +194,15 @@ extern "C" int mggan_bce_scalar_label(const float* p, int n, float label, const 
     if (grid > 148 * 4) grid = 148 * 4;
     bce_kernel<<<grid, MGGAN_THREADS, 0, stream>>>(p, n, label, gen_idx, counts, inv_denom, loss, dp);
     return mggan_check_launch("bce_scalar_label");
+}
+
+extern "C" int mggan_mse_scalar_label(const float* p, int n, float label, const long long* gen_idx, const int* counts,
+                                      float inv_denom, float* loss, float* dp, cudaStream_t stream) {
+    if (n <= 0) return MGGAN_OK;
+    int grid = (n + MGGAN_THREADS - 1) / MGGAN_THREADS;
+    if (grid > 148 * 4) grid = 148 * 4;
+    mse_kernel<<<grid, MGGAN_THREADS, 0, stream>>>(p, n, label, gen_idx, counts, inv_denom, loss, dp);
+    return mggan_check_launch("mse_scalar_label");
 }
 
 extern "C" int mggan_ce_generators(const float* logits, int n, int G, const long long* target, const int* counts,

@@ -57,8 +57,17 @@ class MultiGeneratorGAN(abc.ABC):
         self.lr_schedulerD = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizerD, config.epochs, eta_min=0)
         self.lr_schedulerG = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizerG, config.epochs, eta_min=0)
         self.epoch = 0
-        if self.config.gan_obj != "NS":
-            raise NotImplementedError("gan_obj='%s': only the default NS objective is on the B200 path" % config.gan_obj)
+        # GAN objective (reference abstract_train.py:61-85): phi_1 (D on real), phi_2 (D on fake), phi_3 (G on fake), each a
+        # (loss kernel, which label, sign) triple applied to the discriminator output with a scalar smoothed label
+        from mggan import kernels as K
+        if self.config.gan_obj == "NS":
+            self.phi_1, self.phi_2, self.phi_3 = (K.bce_scalar_label, "real", 1.0), (K.bce_scalar_label, "fake", 1.0), (K.bce_scalar_label, "real", 1.0)
+        elif self.config.gan_obj == "MM":
+            self.phi_1, self.phi_2, self.phi_3 = (K.bce_scalar_label, "real", 1.0), (K.bce_scalar_label, "fake", 1.0), (K.bce_scalar_label, "fake", -1.0)
+        elif self.config.gan_obj == "LS":
+            self.phi_1, self.phi_2, self.phi_3 = (K.mse_scalar_label, "real", 1.0), (K.mse_scalar_label, "fake", 1.0), (K.mse_scalar_label, "real", 1.0)
+        else:       # "W" needs calc_gradient_penalty, which cannot run in the reference either
+            raise NotImplementedError("gan_obj='%s' is outside the B200 hot path" % config.gan_obj)
         if dist_ctx is not None:
             dist_ctx.attach(self.G, self.D)
 

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mggan_scene_bn1_bwd_finalize": "ppdipppppppppps",
     "mggan_l2_scene_min": "ppiiipifppps",
     "mggan_bce_scalar_label": "pifppfpps",
+    "mggan_mse_scalar_label": "pifppfpps",
     "mggan_ce_generators": "piippfpps",
     "mggan_pm_ml_loss": "ppiiiipfffppps",
     "mggan_grad_sqnorm": "tips",

@@ -511,22 +511,28 @@ def l2_scene_min(abs_, gt, scenes, inv_norm):
     return _L2SceneMin.apply(abs_, gt, scenes, inv_norm)
 
 
-class _BceScalar(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, p, label, gen_idx, counts, inv_denom):
-        p = _f32(p)
-        loss = torch.zeros(1, device=p.device)
-        dp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
-        gi = gen_idx.contiguous() if gen_idx is not None else None
-        call("mggan_bce_scalar_label", ptr(p), p.numel(), float(label), ptr(gi), ptr(counts), float(inv_denom),
-             ptr(loss), ptr(dp))
-        ctx.save_for_backward(dp)
-        return loss[0]
+def _scalar_label_loss(entry):
+    class _ScalarLabelLoss(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, p, label, gen_idx, counts, inv_denom):
+            p = _f32(p)
+            loss = torch.zeros(1, device=p.device)
+            dp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+            gi = gen_idx.contiguous() if gen_idx is not None else None
+            call(entry, ptr(p), p.numel(), float(label), ptr(gi), ptr(counts), float(inv_denom), ptr(loss), ptr(dp))
+            ctx.save_for_backward(dp)
+            return loss[0]
 
-    @staticmethod
-    def backward(ctx, g):
-        (dp,) = ctx.saved_tensors
-        return dp * g, None, None, None, None
+        @staticmethod
+        def backward(ctx, g):
+            (dp,) = ctx.saved_tensors
+            return dp * g, None, None, None, None
+
+    return _ScalarLabelLoss
+
+
+_BceScalar = _scalar_label_loss("mggan_bce_scalar_label")
+_MseScalar = _scalar_label_loss("mggan_mse_scalar_label")
 
 
 def bce_scalar_label(p, label, gen_idx=None, counts=None, inv_denom=None):
@@ -534,6 +540,13 @@ def bce_scalar_label(p, label, gen_idx=None, counts=None, inv_denom=None):
     if inv_denom is None:
         inv_denom = 1.0 / max(p.numel(), 1)
     return _BceScalar.apply(p, label, gen_idx, counts, inv_denom)
+
+
+def mse_scalar_label(p, label, gen_idx=None, counts=None, inv_denom=None):
+    """inv_denom * sum_i (p_i - label)^2 / counts[gen_idx_i]  (gan_obj LS)."""
+    if inv_denom is None:
+        inv_denom = 1.0 / max(p.numel(), 1)
+    return _MseScalar.apply(p, label, gen_idx, counts, inv_denom)
 
 
 class _CeGen(torch.autograd.Function):

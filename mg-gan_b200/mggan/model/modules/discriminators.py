@@ -28,10 +28,10 @@ class MultiDiscriminatorTrajectory(nn.Module):
         assert inp_format in ("rel", "abs", "abs_rel")
         assert gan_type in ("probgan", "mgan", "infogan", "gan")
         if (inp_format != "rel" or gan_type not in ("mgan", "gan") or pool_type != "sways" or not global_disc
-                or num_discs != 1 or unbound_output or h_dim != 64):
+                or num_discs != 1 or h_dim != 64):
             raise NotImplementedError(
                 "B200 path covers the default discriminator: inp_format='rel', gan_type in {'mgan','gan'}, "
-                "pool_type='sways', global_disc=1, one sigmoid-bounded head, h_dim=64")
+                "pool_type='sways', global_disc=1, one head, h_dim=64")
         if scene_dim not in (0, 64):
             raise NotImplementedError("scene_dim must be 0 or 64")
         self.inp_format, self.unbound_output, self.n_ds = inp_format, unbound_output, num_discs
@@ -167,7 +167,7 @@ class MultiDiscriminatorTrajectory(nn.Module):
             pred_xy, pred_dxdy = pred_xy.unsqueeze(1), pred_dxdy.unsqueeze(1)
         pred_len, n_samples, b, _ = pred_xy.shape
         N = in_xy.size(1)
-        if self._heads_frozen():
+        if self._heads_frozen() and not self.unbound_output:       # the fused heads kernel has the sigmoid built in
             return self._forward_hoisted(in_xy, in_dxdy, pred_dxdy, seq_start_end, img, mask)
         enc = self.encode(in_xy, in_dxdy, pred_xy, pred_dxdy, mask)
         soc0 = self.social(in_xy, in_dxdy, enc[:N], seq_start_end)
@@ -181,7 +181,8 @@ class MultiDiscriminatorTrajectory(nn.Module):
         if img is not None:
             scene = self._scene(img, mask)
             classifier_inp = torch.cat([classifier_inp, scene.repeat(n_samples, 1)], 1)
-        output = self._mlp2(self.discs[0], classifier_inp, K.ACT_SIGMOID_EPS)       # sigmoid * (1 - 2 eps) + eps
+        # sigmoid * (1 - 2 eps) + eps, or the raw score for gan_obj LS / W (reference discriminators.py:83,203)
+        output = self._mlp2(self.discs[0], classifier_inp, K.ACT_NONE if self.unbound_output else K.ACT_SIGMOID_EPS)
         if not return_all:
             output = output.mean(1)
         output = output.reshape(n_samples, b).t()

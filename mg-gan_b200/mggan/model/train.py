@@ -58,8 +58,10 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
     def __init__(self, generator, discriminator, config, writer, dist_ctx=None):
         super().__init__(generator, discriminator, config, writer, dist_ctx)
         assert self.gan_type in ("mgan", "gan"), self.gan_type
-        if config.weighting_target not in ("ml", "none"):
+        if config.weighting_target not in ("ml", "none", "l2", "endpoint", "mgan"):
             raise NotImplementedError("weighting_target='%s' is outside the B200 hot path" % config.weighting_target)
+        if config.weighting_target == "mgan":
+            assert self.gan_type == "mgan"
         if config.l2_loss_type == "mse":
             raise NotImplementedError("l2_loss_type='mse' is outside the B200 hot path")
 
@@ -73,6 +75,13 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
 
     def _reduce(self):
         return None if self.dist is None else self.dist.allreduce_grads
+
+    @staticmethod
+    def _phi(phi, d_out, labels, gen_idx=None, counts=None, inv_denom=None):
+        """Apply one GAN-objective term (abstract_train: phi_1 / phi_2 / phi_3) to discriminator outputs."""
+        fn, which, sign = phi
+        l_real, l_fake = labels
+        return fn(d_out.contiguous(), l_real if which == "real" else l_fake, gen_idx, counts, sign * inv_denom)
 
     # ------------------------------------------------------------------ G step
     def generator_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, train_metrics, loss_mask, img=None):
@@ -98,8 +107,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
         branch_out = None
         if isinstance(disc_out, tuple):
             disc_out, branch_out = disc_out
-        l_real, _ = _label_scalars(disc_out.shape)
-        adv_loss = K.bce_scalar_label(disc_out.contiguous(), l_real, gen_idxs, counts, 1.0 / denom)
+        adv_loss = self._phi(self.phi_3, disc_out, _label_scalars(disc_out.shape), gen_idxs, counts, 1.0 / denom)
         train_metrics["train/gen_loss"].append(adv_loss.detach())
         loss = adv_loss if loss is None else loss + adv_loss
         if self.gan_type == "mgan":
@@ -129,8 +137,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
             real_result = real_result[0]
         n_act = real_result.shape[0]
         denom = self._global(n_act)
-        l_real, _ = _label_scalars(real_result.shape)
-        real_loss = K.bce_scalar_label(real_result.contiguous(), l_real, inv_denom=1.0 / denom)
+        real_loss = self._phi(self.phi_1, real_result, _label_scalars(real_result.shape), inv_denom=1.0 / denom)
         noise = self._noise(sub_batches)[None]
         self.G.share_trunk()                # the generator step that follows runs the same weights on these inputs
         with torch.no_grad():
@@ -143,8 +150,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
             ce_loss = K.ce_generators(branch_out.flatten(0, 1), gen_labels_gt.flatten(), None, 1.0 / denom)
             train_metrics["train/info_mgan_disc_loss"].append(ce_loss.detach())
             train_loss = ce_loss
-        _, l_fake = _label_scalars(disc_out.shape)
-        fake_loss = K.bce_scalar_label(disc_out.contiguous(), l_fake, inv_denom=1.0 / denom)
+        fake_loss = self._phi(self.phi_2, disc_out, _label_scalars(disc_out.shape), inv_denom=1.0 / denom)
         train_loss = real_loss + fake_loss if train_loss is None else train_loss + real_loss + fake_loss
         train_metrics["train/discr_loss"].append((fake_loss + real_loss).detach())
         return train_loss
@@ -162,9 +168,38 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
             for i in range(probs.shape[0]):
                 metrics[f"probs/Gen {i} probability"].append(probs[i])
         n_act = net_chooser_weights.shape[0]
-        loss, _ = K.pm_ml_loss(net_chooser_weights, gen_out.abs, gt_xy, cfg.sigma, cfg.pi_net_loss_weight,
-                               1.0 / self._global(n_act))
-        metrics["train/net_chooser_loss"].append(loss.detach())
+        inv_n = 1.0 / self._global(n_act)
+        if cfg.weighting_target == "ml":
+            loss, _ = K.pm_ml_loss(net_chooser_weights, gen_out.abs, gt_xy, cfg.sigma, cfg.pi_net_loss_weight, inv_n)
+            logged = loss.detach()
+        elif cfg.weighting_target in ("l2", "endpoint"):
+            # reference train.py:618-624 / :641-647: the PM-Network is trained to point at the generator whose best sample
+            # is closest to the ground truth (mean L2 over time, or the end point); target selection is no-grad glue,
+            # the cross-entropy and its gradient are the mggan_ce_generators kernel
+            with torch.no_grad():
+                if cfg.weighting_target == "l2":
+                    dist = torch.norm(gen_out.abs - gt_xy[:, None, None], p=2, dim=-1).mean(0)
+                else:
+                    dist = torch.norm(gen_out.abs[-1] - gt_xy[-1, None, None], p=2, dim=-1)
+                min_idx = torch.argmin(dist.min(0)[0].transpose(0, 1), dim=1)
+            logged = K.ce_generators(net_chooser_weights, min_idx, None, inv_n)
+            loss = logged * cfg.pi_net_loss_weight
+            logged = logged.detach()
+        else:
+            # "mgan", reference train.py:604-614.  As written there, D's branch logits have shape (b, 1, G) and
+            # `torch.softmax(branch_out, 1)` normalises over the singleton sample axis: the "target" is all ones, and its
+            # product with out_probs.log() (b, G) broadcasts to (b, b, G); after .sum(1).mean() the loss is
+            # -(1/G) sum_{j,g} log p[j,g] (a sum over agents, no 1/b), minus the entropy bonus 0.9^epoch * mean_j H(p_j).
+            # Reproduced as executed (the discriminator forward still runs: it advances D's BatchNorm statistics).
+            with torch.no_grad():
+                self.D(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, mask=mask, img=img)
+            logp = torch.log_softmax(net_chooser_weights, 1)
+            loss = -logp.sum() / logp.shape[1]
+            reg = (0.9 ** self.epoch) * -(logp.exp() * logp).sum() * inv_n
+            loss = loss - reg
+            logged = loss.detach()
+            loss = loss * cfg.pi_net_loss_weight
+        metrics["train/net_chooser_loss"].append(logged)
         self.optimizerG.zero_grad()
         loss.backward()                 # the gradient already carries pi_net_loss_weight
         self.optimizerG.step(reduce_fn=self._reduce())

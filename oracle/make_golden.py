@@ -35,6 +35,13 @@ CASES = {
     "cfg1_g1_tiny": dict(num_gens=1, sizes=[4], with_img=True, nan_frac=0.0, k=20, iters=1, seed=11),
     "cfg2_g4_eth_noimg": dict(num_gens=4, sizes=[1, 3, 2, 5, 1, 4], with_img=False, nan_frac=0.0, k=20, iters=1, seed=22),
     "cfg3_g8_sdd_masked": dict(num_gens=8, sizes=[4, 6, 3], with_img=True, nan_frac=0.25, k=20, iters=2, seed=33),
+    # flag-reachable objective variants (abstract_train.py:61-79, train.py:604-647): iteration vectors only
+    "var_ls_l2": dict(num_gens=4, sizes=[2, 3, 1], with_img=False, nan_frac=0.0, k=6, iters=1, seed=44,
+                      flags=["--gan_obj", "LS", "--weighting_target", "l2"], modules=False),
+    "var_mm_endpoint": dict(num_gens=4, sizes=[3, 2], with_img=False, nan_frac=0.0, k=6, iters=1, seed=55,
+                            flags=["--gan_obj", "MM", "--weighting_target", "endpoint"], modules=False),
+    "var_ns_mgan": dict(num_gens=3, sizes=[2, 2], with_img=True, nan_frac=0.0, k=5, iters=1, seed=66,
+                        flags=["--weighting_target", "mgan"], modules=False),
 }
 
 
@@ -56,7 +63,7 @@ def build(ref, case):
     torch.manual_seed(case["seed"])
     np.random.seed(case["seed"])
     args = ref.config.get_parser().parse_args(["--num_gens", str(case["num_gens"]), "--gpus", "",
-                                               "--num_samples", str(case["k"])])
+                                               "--num_samples", str(case["k"])] + case.get("flags", []))
     args.gpus = False
     scene_dim = 64 if case["with_img"] else 0
     args.use_pinet = True
@@ -65,7 +72,7 @@ def build(ref, case):
         pred_len=12, embedding_dim=16, inp_format="rel", num_social_modules=1, pool_type="sways",
         scene_dim=scene_dim, use_pinet=True)
     D = ref.discriminators.MultiDiscriminatorTrajectory(
-        num_gens=case["num_gens"], num_discs=1, unbound_output=False, h_dim=64, inp_format="rel",
+        num_gens=case["num_gens"], num_discs=1, unbound_output=args.gan_obj in ["W", "LS"], h_dim=64, inp_format="rel",
         pred_len=12, gan_type="mgan", global_disc=1, scene_dim=scene_dim, pool_type="sways")
     if case["with_img"]:
         # the CLI path must build the very same thing (model_factory.py:7-86)
@@ -118,7 +125,8 @@ def run_case(ref, name, case):
     n_act = int(mask.sum())
     gt_xy, gt_dxdy = t["gt_xy"][:, mask], t["gt_dxdy"][:, mask]
 
-    out = {"meta/num_gens": np.int64(ng), "meta/k": np.int64(k), "meta/iters": np.int64(case["iters"]),
+    out = {"meta/gan_obj": np.array(args.gan_obj), "meta/weighting_target": np.array(args.weighting_target),
+           "meta/num_gens": np.int64(ng), "meta/k": np.int64(k), "meta/iters": np.int64(case["iters"]),
            "meta/with_img": np.int64(case["with_img"]), "meta/seq_start_end": np.array(sse, dtype=np.int64)}
     for n, v in b.items():
         if n != "seq_start_end":
@@ -143,38 +151,39 @@ def run_case(ref, name, case):
     def scene_noise():
         return torch.cat([torch.randn(1, 8, generator=gen).repeat(e - s, 1) for s, e in sse])
 
-    # ---- module-level vectors on the initial weights (BN buffers restored afterwards)
-    g_state = {k_: v.clone() for k_, v in G.state_dict().items()}
-    d_state = {k_: v.clone() for k_, v in D.state_dict().items()}
-    with torch.no_grad():
-        z3 = torch.stack([scene_noise() for _ in range(3)])
-        inj.idx.append(torch.zeros(n_act, 3, dtype=torch.long))
-        (rel, ab), logits, _ = G(t["in_xy"], t["in_dxdy"], sse, noise=z3, all_gen_out=True, img=img,
-                                 num_samples=3, mask=mask)
-        out["mod/all_noise"], out["mod/all_abs"], out["mod/all_rel"] = z3.numpy(), ab.numpy(), rel.numpy()
-        out["mod/logits"] = logits.numpy()
-        zk = torch.stack([scene_noise() for _ in range(k)])
-        idx = torch.from_numpy(rng.integers(0, ng, size=(n_act, k)))
-        inj.idx.append(idx)
-        (rel, ab), _, _ = G(t["in_xy"], t["in_dxdy"], sse, noise=zk, all_gen_out=False, img=img,
-                            num_samples=k, mask=mask)
-        out["mod/sel_noise"], out["mod/sel_idx"] = zk.numpy(), idx.numpy()
-        out["mod/sel_abs"], out["mod/sel_rel"] = ab.numpy(), rel.numpy()
-        o, br = D(t["in_xy"], t["in_dxdy"], ab, rel, sse, img=img, mask=mask)
-        out["mod/d_fake_out"], out["mod/d_fake_branch"] = o.numpy(), br.numpy()
-        o, br = D(t["in_xy"], t["in_dxdy"], gt_xy, gt_dxdy, sse, img=img, mask=mask)
-        out["mod/d_real_out"], out["mod/d_real_branch"] = o.numpy(), br.numpy()
-        # eval-mode generator (BatchNorm running statistics), as used by predict() train.py:259-289
-        G.eval()
-        inj.idx.append(idx[:, :5])
-        (rel, ab), _, _ = G(t["in_xy"], t["in_dxdy"], sse, noise=zk[:5], all_gen_out=False, img=img,
-                            num_samples=5, mask=mask)
-        out["mod/eval_abs"] = ab.numpy()
-        G.train()
-    sd_np("Gmod", G, out)       # BN buffers after 3 train-mode forwards of G-CNN / 2 of D-CNN
-    sd_np("Dmod", D, out)
-    G.load_state_dict(g_state)
-    D.load_state_dict(d_state)
+    if case.get("modules", True):
+        # ---- module-level vectors on the initial weights (BN buffers restored afterwards)
+        g_state = {k_: v.clone() for k_, v in G.state_dict().items()}
+        d_state = {k_: v.clone() for k_, v in D.state_dict().items()}
+        with torch.no_grad():
+            z3 = torch.stack([scene_noise() for _ in range(3)])
+            inj.idx.append(torch.zeros(n_act, 3, dtype=torch.long))
+            (rel, ab), logits, _ = G(t["in_xy"], t["in_dxdy"], sse, noise=z3, all_gen_out=True, img=img,
+                                     num_samples=3, mask=mask)
+            out["mod/all_noise"], out["mod/all_abs"], out["mod/all_rel"] = z3.numpy(), ab.numpy(), rel.numpy()
+            out["mod/logits"] = logits.numpy()
+            zk = torch.stack([scene_noise() for _ in range(k)])
+            idx = torch.from_numpy(rng.integers(0, ng, size=(n_act, k)))
+            inj.idx.append(idx)
+            (rel, ab), _, _ = G(t["in_xy"], t["in_dxdy"], sse, noise=zk, all_gen_out=False, img=img,
+                                num_samples=k, mask=mask)
+            out["mod/sel_noise"], out["mod/sel_idx"] = zk.numpy(), idx.numpy()
+            out["mod/sel_abs"], out["mod/sel_rel"] = ab.numpy(), rel.numpy()
+            o, br = D(t["in_xy"], t["in_dxdy"], ab, rel, sse, img=img, mask=mask)
+            out["mod/d_fake_out"], out["mod/d_fake_branch"] = o.numpy(), br.numpy()
+            o, br = D(t["in_xy"], t["in_dxdy"], gt_xy, gt_dxdy, sse, img=img, mask=mask)
+            out["mod/d_real_out"], out["mod/d_real_branch"] = o.numpy(), br.numpy()
+            # eval-mode generator (BatchNorm running statistics), as used by predict() train.py:259-289
+            G.eval()
+            inj.idx.append(idx[:, :5])
+            (rel, ab), _, _ = G(t["in_xy"], t["in_dxdy"], sse, noise=zk[:5], all_gen_out=False, img=img,
+                                num_samples=5, mask=mask)
+            out["mod/eval_abs"] = ab.numpy()
+            G.train()
+        sd_np("Gmod", G, out)       # BN buffers after 3 train-mode forwards of G-CNN / 2 of D-CNN
+        sd_np("Dmod", D, out)
+        G.load_state_dict(g_state)
+        D.load_state_dict(d_state)
 
     # ---- full iterations: D step, G step, PM step (abstract_train.py:136-159)
     for it in range(case["iters"]):

@@ -292,10 +292,11 @@ def generator_forward(sd, n_gens, in_xy, in_dxdy, sub_batches, noise, all_gen_ou
 
 # --------------------------------------------------------------------------- discriminator
 def discriminator_forward(sd, in_xy, in_dxdy, pred_xy, pred_dxdy, sub_batches, img=None,
-                          mask=None, training=True, social_mode="scene"):
+                          mask=None, training=True, social_mode="scene", unbound_output=False):
     """MultiDiscriminatorTrajectory.forward, gan_type="mgan" (discriminators.py:113-219).
 
-    Returns (output (N_act, k) in (1e-7, 1-1e-7), branch (N_act, k, G)).
+    Returns (output (N_act, k) in (1e-7, 1-1e-7), branch (N_act, k, G)); with unbound_output
+    (gan_obj LS / W, model_factory.py:14, discriminators.py:83,203) the head has no sigmoid.
     """
     if pred_xy.dim() == 3:
         pred_xy, pred_dxdy = pred_xy[:, None], pred_dxdy[:, None]
@@ -324,8 +325,9 @@ def discriminator_forward(sd, in_xy, in_dxdy, pred_xy, pred_dxdy, sub_batches, i
         if mask is not None:
             img = img[mask]
         c = torch.cat([c, attention_global(sd, "scene_encoder", img, training).repeat(k, 1)], 1)
-    out = torch.sigmoid(_lin(sd, "discs.0.2", lrelu(_lin(sd, "discs.0.0", c), 0.2)))
-    out = out * (1 - 2 * D_EPS) + D_EPS
+    out = _lin(sd, "discs.0.2", lrelu(_lin(sd, "discs.0.0", c), 0.2))
+    if not unbound_output:
+        out = torch.sigmoid(out) * (1 - 2 * D_EPS) + D_EPS
     out = out.mean(1).reshape(k, n_act).t()
     br = _lin(sd, "gen_id_reconstructor.2", lrelu(_lin(sd, "gen_id_reconstructor.0", c), 0.2))
     return out, br.reshape(k, n_act, -1).transpose(0, 1)
@@ -392,7 +394,9 @@ class OracleTrainer:
 
     def __init__(self, sdG, sdD, n_gens, num_samples=20, sigma=1.0, l2_w=1.0, clf_w=1.0,
                  pi_w=1.0, clip_g=500, clip_d=100, lr=1e-3, beta1=0.5, use_pinet=True,
-                 social_mode="scene"):
+                 social_mode="scene", gan_obj="NS", weighting_target="ml", epoch=1):
+        # non-default objectives (abstract_train.py:61-79) and PM-step targets (train.py:604-647)
+        self.gan_obj, self.weighting_target, self.epoch = gan_obj, weighting_target, epoch
         self.G = {k: v.clone() for k, v in sdG.items() if not k.startswith("G_")}
         self.D = {k: v.clone() for k, v in sdD.items()}
         for sd in (self.G, self.D):
@@ -419,7 +423,8 @@ class OracleTrainer:
 
     def _D(self, b, pxy, pdxdy, mask, training=True):
         return discriminator_forward(self.D, b["in_xy"], b["in_dxdy"], pxy, pdxdy, b["seq_start_end"],
-                                     b.get("features"), mask, training, self.social_mode)
+                                     b.get("features"), mask, training, self.social_mode,
+                                     unbound_output=self.gan_obj in ("W", "LS"))
 
     @staticmethod
     def loss_mask(b):
@@ -427,18 +432,29 @@ class OracleTrainer:
         mask = ~torch.isnan(b["gt_xy"]).any(2).any(0)
         return mask, b["gt_xy"][:, mask], b["gt_dxdy"][:, mask]
 
+    def _phi(self, which, d, l_real, l_fake):
+        """phi_1 / phi_2 / phi_3 of abstract_train.py:61-79, reduction="none"."""
+        full = lambda v: torch.full_like(d, v)
+        if self.gan_obj == "LS":
+            return (d - full(l_fake if which == 2 else l_real)) ** 2
+        if which == 1:
+            return _bce(d, full(l_real))
+        if which == 2:
+            return _bce(d, full(l_fake))
+        return _bce(d, full(l_real)) if self.gan_obj == "NS" else -_bce(d, full(l_fake))
+
     # -- steps
     def discriminator_step(self, b, noise, gen_idxs, labels_real, labels_fake):
         """labels_real = (l_real, l_fake) drawn for the real pass, labels_fake for the fake pass
         (utils.py:18-25: fake is drawn first, then real)."""
         mask, gt_xy, gt_dxdy = self.loss_mask(b)
         real, _ = self._D(b, gt_xy, gt_dxdy, mask)
-        real_loss = _bce(real, torch.full_like(real, labels_real[0])).mean()
+        real_loss = self._phi(1, real, *labels_real).mean()
         with torch.no_grad():
             (rel, ab), _, idx = self._G(b, noise, False, 1, mask, gen_idxs)
         fake, branch = self._D(b, ab, rel, mask)
         ce = F.cross_entropy(branch.flatten(0, 1), idx.flatten())
-        fake_loss = _bce(fake, torch.full_like(fake, labels_fake[1])).mean()
+        fake_loss = self._phi(2, fake, *labels_fake).mean()
         loss = ce + real_loss + fake_loss
         grads = self._grads(self.D, loss)
         norm = clip_grad_norm(grads, self.clip_d)
@@ -459,7 +475,7 @@ class OracleTrainer:
         out, branch = self._D(b, ab, rel, mask)
         counts = torch.bincount(idx.flatten(), minlength=self.n_gens).to(out.dtype)
         w = 1.0 / counts[idx]                                            # train.py:92-96
-        adv = (_bce(out, torch.full_like(out, labels[0])) * w).mean()
+        adv = (self._phi(3, out, *labels) * w).mean()
         clf = (F.cross_entropy(branch.flatten(0, 1), idx.reshape(-1), reduction="none").reshape(idx.shape) * w).mean()
         loss = self.l2_w * min_l2 + adv + self.clf_w * clf
         grads = self._grads(self.G, loss)
@@ -473,11 +489,25 @@ class OracleTrainer:
         mask, gt_xy, gt_dxdy = self.loss_mask(b)
         (rel, ab), logits, _ = self._G(b, noise, True, k_exp, mask,
                                         torch.zeros(int(mask.sum()), k_exp, dtype=torch.long))
-        d = ab - gt_xy[:, None, None]
-        logp = (-(d * d) / (2 * self.sigma ** 2) - math.log(self.sigma) - math.log(math.sqrt(2 * math.pi)))
-        logp = logp.sum([0, -1]).mean(0).t()                             # (N_act, G)
-        target = torch.softmax(logp, 1)
-        loss = -(target * torch.softmax(logits, 1).log()).sum(1).mean()
+        if self.weighting_target == "ml":
+            d = ab - gt_xy[:, None, None]
+            logp = (-(d * d) / (2 * self.sigma ** 2) - math.log(self.sigma) - math.log(math.sqrt(2 * math.pi)))
+            logp = logp.sum([0, -1]).mean(0).t()                             # (N_act, G)
+            target = torch.softmax(logp, 1)
+            loss = -(target * torch.softmax(logits, 1).log()).sum(1).mean()
+        elif self.weighting_target in ("l2", "endpoint"):                    # train.py:618-624, :641-647
+            if self.weighting_target == "l2":
+                dist = torch.norm(ab - gt_xy[:, None, None], p=2, dim=-1).mean(0)
+            else:
+                dist = torch.norm(ab[-1] - gt_xy[-1, None, None], p=2, dim=-1)
+            loss = F.cross_entropy(logits, torch.argmin(dist.min(0)[0].transpose(0, 1), dim=1))
+        elif self.weighting_target == "mgan":                                # train.py:604-614
+            _, branch = self._D(b, gt_xy, gt_dxdy, mask)
+            out_probs = torch.softmax(logits, 1)
+            loss = -(torch.softmax(branch, 1) * out_probs.log()).sum(1).mean()
+            loss = loss - (0.9 ** self.epoch) * -(out_probs * out_probs.log()).sum(1).mean()
+        else:
+            raise ValueError(self.weighting_target)
         grads = self._grads(self.G, loss * self.pi_w)
         self.optG.step(self.G, grads)
         return {"loss": loss.detach(), "grads": grads, "logits": logits.detach(), "abs": ab.detach()}

@@ -12,6 +12,8 @@ for p in (os.path.join(ROOT, "mg-gan_b200"), os.path.join(ROOT, "oracle"), ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["cfg1_g1_tiny", "cfg2_g4_eth_noimg", "cfg3_g8_sdd_masked"]
+# objective variants (gan_obj LS / MM, weighting_target l2 / endpoint / mgan): whole-iteration vectors only
+VARIANT_CASES = ["var_ls_l2", "var_mm_endpoint", "var_ns_mgan"]
 
 
 def pytest_configure(config):
@@ -35,4 +37,9 @@ def load_golden(name):
 
 @pytest.fixture(params=GOLDEN_CASES)
 def golden(request):
+    return load_golden(request.param)
+
+
+@pytest.fixture(params=VARIANT_CASES)
+def golden_variant(request):
     return load_golden(request.param)

@@ -37,7 +37,9 @@ def check(a, b, tol, what, atol=0.0):
 def make_config(g):
     from mggan.model.config import get_parser
     args = get_parser().parse_args(["--num_gens", str(g["meta"]["num_gens"]), "--num_samples", str(g["meta"]["k"]),
-                                    "--scene_dim", "64" if g["meta"]["with_img"] else "0"])
+                                    "--scene_dim", "64" if g["meta"]["with_img"] else "0",
+                                    "--gan_obj", g["meta"].get("gan_obj", "NS"),
+                                    "--weighting_target", g["meta"].get("weighting_target", "ml")])
     args.gpus = True
     return args
 
@@ -145,9 +147,17 @@ def test_module_outputs(golden, injected):
 
 
 def test_training_iterations(golden, injected, tmp_path):
+    _run_iterations(golden, injected, tmp_path)
+
+
+def test_training_iterations_objective_variants(golden_variant, injected, tmp_path):
+    """gan_obj LS / MM and weighting_target l2 / endpoint / mgan (abstract_train.py:61-79, train.py:604-647)."""
+    _run_iterations(golden_variant, injected, tmp_path)
+
+
+def _run_iterations(g, inj, tmp_path):
     from mggan.logging import Experiment
     from mggan.model.train import PiNetMultiGeneratorGAN
-    g, inj = golden, injected
     G, D, cfg = build(g)
     tr = PiNetMultiGeneratorGAN(G, D, cfg, Experiment(tmp_path, "golden", version=1))
     tr.epoch = 1

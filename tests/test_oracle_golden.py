@@ -68,10 +68,19 @@ def test_module_outputs(golden):
 
 
 def test_training_iterations(golden):
-    g = golden
+    _run_iterations(golden)
+
+
+def test_training_iterations_objective_variants(golden_variant):
+    """gan_obj LS / MM and weighting_target l2 / endpoint / mgan (abstract_train.py:61-79, train.py:604-647)."""
+    _run_iterations(golden_variant)
+
+
+def _run_iterations(g):
     b = batch_of(g)
     ng, k = g["meta"]["num_gens"], g["meta"]["k"]
-    tr = O.OracleTrainer(g["G0"], g["D0"], ng, num_samples=k)
+    tr = O.OracleTrainer(g["G0"], g["D0"], ng, num_samples=k, gan_obj=g["meta"].get("gan_obj", "NS"),
+                         weighting_target=g["meta"].get("weighting_target", "ml"))
     for it in range(g["meta"]["iters"]):
         r = g[f"it{it}"]
         lab = r["labels"].tolist()
