@@ -59,8 +59,9 @@ int mggan_disc_heads_bwd(const float* pe, int n, int k, int HH, const float* bas
                          const float* dbranch, float* d_pe, float* d_soc0, float* d_base, cudaStream_t stream);
 
 /* ---- PM-Net sampling + generator selection: standard.py:217-225, utils.py:234-248, standard.py:190-214 */
+/* dyn_offset: NULL, or a DEVICE counter added to `offset` (CUDA-graph replay: a new Philox offset per replay). */
 int mggan_gumbel_sample(const float* logits, int n, int k, int G, unsigned long long seed, unsigned long long offset,
-                        long long* idx, cudaStream_t stream);
+                        const unsigned long long* dyn_offset, long long* idx, cudaStream_t stream);
 int mggan_selection_tiles(int n_seq, int G); /* host helper: tile-table length for n_seq sequences */
 /* idx (n,k) int64 -> work list for the decoder.  scratch: cnt (n*G int32), rank (n*k bytes),
  * base_row (G+1 int32), err (1 int32, zero-filled by the caller; set to 1 on an out-of-range index).
@@ -195,6 +196,8 @@ typedef struct MgganTensorTable {
     int n[MGGAN_TABLE_MAX];
     float bc1[MGGAN_TABLE_MAX];      /* 1 - beta1^step */
     float bc2_sqrt[MGGAN_TABLE_MAX]; /* sqrt(1 - beta2^step) */
+    const float* dyn;                /* NULL, or DEVICE array [lr, bc1[64], bc2_sqrt[64]] overriding lr / bc1 / bc2_sqrt
+                                        (CUDA-graph replay: values refreshed by the host between replays) */
 } MgganTensorTable;
 /* table is a HOST pointer (copied into kernel-parameter space). */
 int mggan_grad_sqnorm(const MgganTensorTable* table, int count, double* sqnorm_accum, cudaStream_t stream);

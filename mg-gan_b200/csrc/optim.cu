@@ -7,7 +7,8 @@
 // pass 2 applies  p <- p (1 - lr wd);  m, v updates;  p <- p - lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 // with the clip coefficient min(1, max_norm / (norm + 1e-6)) read from device memory (no host
 // sync).  Per-tensor bias corrections are supplied by the host because AdamW's step count is
-// per tensor (tensors without a gradient are skipped and keep their count).
+// per tensor (tensors without a gradient are skipped and keep their count); when the
+// iteration is replayed as a CUDA graph they (and lr) are read from a device array the host refreshes.
 #include "common.cuh"
 
 #define MGGAN_TABLE_MAX 64
@@ -20,6 +21,8 @@ struct MgganTensorTable {
     int n[MGGAN_TABLE_MAX];
     float bc1[MGGAN_TABLE_MAX];       // 1 - beta1^t
     float bc2_sqrt[MGGAN_TABLE_MAX];  // sqrt(1 - beta2^t)
+    const float* dyn;                 // optional DEVICE array [lr, bc1[64], bc2_sqrt[64]] that overrides lr / bc1 / bc2_sqrt
+                                      // (CUDA-graph replay: the values change every iteration, the launch does not)
 };
 
 namespace {
@@ -59,7 +62,13 @@ adamw_kernel(MgganTensorTable tb, const double* __restrict__ sqnorm, float max_n
     float* m = tb.m[t];
     float* v = tb.v[t];
     const int n = tb.n[t];
-    const float step = lr / tb.bc1[t], bc2s = tb.bc2_sqrt[t], decay = 1.f - lr * wd;
+    float bc1 = tb.bc1[t], bc2s = tb.bc2_sqrt[t];
+    if (tb.dyn != nullptr) {
+        lr = __ldg(tb.dyn);
+        bc1 = __ldg(tb.dyn + 1 + t);
+        bc2s = __ldg(tb.dyn + 1 + MGGAN_TABLE_MAX + t);
+    }
+    const float step = lr / bc1, decay = 1.f - lr * wd;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float gi = g[i] * coef;
         float mi = beta1 * m[i] + (1.f - beta1) * gi;

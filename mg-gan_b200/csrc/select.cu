@@ -138,9 +138,11 @@ __global__ void all_kernel(int n, int k, int G, int tiles_per_gen, int* __restri
 }
 
 __global__ void gumbel_kernel(const float* __restrict__ logits, int n, int k, int G, unsigned long long seed,
-                              unsigned long long offset, long long* __restrict__ idx) {
+                              unsigned long long offset, const unsigned long long* __restrict__ dyn_offset,
+                              long long* __restrict__ idx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (dyn_offset != nullptr) offset += __ldg(dyn_offset);
     curandStatePhilox4_32_10_t st;
     curand_init(seed, (unsigned long long)i, offset, &st);
     for (int j = 0; j < k; ++j) {
@@ -194,9 +196,10 @@ extern "C" int mggan_selection_all(int n, int k, int G, int* tile_gen, int* seq_
 }
 
 extern "C" int mggan_gumbel_sample(const float* logits, int n, int k, int G, unsigned long long seed,
-                                   unsigned long long offset, long long* idx, cudaStream_t stream) {
+                                   unsigned long long offset, const unsigned long long* dyn_offset, long long* idx,
+                                   cudaStream_t stream) {
     MGGAN_REQUIRE(G >= 1 && k >= 1, "mggan_gumbel_sample: bad arguments");
     if (n == 0) return MGGAN_OK;
-    gumbel_kernel<<<(n + 127) / 128, 128, 0, stream>>>(logits, n, k, G, seed, offset, idx);
+    gumbel_kernel<<<(n + 127) / 128, 128, 0, stream>>>(logits, n, k, G, seed, offset, dyn_offset, idx);
     return mggan_check_launch("gumbel_sample");
 }

@@ -57,6 +57,9 @@ class MultiGeneratorGAN(abc.ABC):
         self.lr_schedulerD = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizerD, config.epochs, eta_min=0)
         self.lr_schedulerG = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizerG, config.epochs, eta_min=0)
         self.epoch = 0
+        self._graph = None                 # mggan.graph.GraphedIteration while capturing
+        self._graphs = []                  # captured iterations (one per batch structure, most recent first)
+        self._graph_seen = None            # structure key of the previous eager iteration
         # GAN objective (reference abstract_train.py:61-85): phi_1 (D on real), phi_2 (D on fake), phi_3 (G on fake), each a
         # (loss kernel, which label, sign) triple applied to the discriminator output with a scalar smoothed label
         from mggan import kernels as K
@@ -108,7 +111,34 @@ class MultiGeneratorGAN(abc.ABC):
 
     def train_iteration(self, batch, metrics, total_iterations=0):
         """One D step + G step + PM step on a collated batch (reference loop body :114-168)."""
-        self._run_prepared(self._prepare(batch), metrics, total_iterations)
+        self._run_iteration(self._prepare(batch), metrics, total_iterations)
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def _graph_eligible(self, prepared):
+        cfg = self.config
+        return (getattr(cfg, "cuda_graph", True) and self.dist is None and prepared[6] is None
+                and cfg.gan_obj in ("NS", "MM") and cfg.weighting_target in ("ml", "none")
+                and cfg.num_gen_steps == 1 and cfg.num_unrolling_steps == 0)
+
+    def _run_iteration(self, prepared, metrics, total_iterations=0):
+        """Eager iteration, or the replay of a captured one when this batch has the structure (scene sizes, no masked
+        futures) of the previous one: the iteration is captured the second time a structure repeats (mggan/graph.py)."""
+        if not self._graph_eligible(prepared):
+            return self._run_prepared(prepared, metrics, total_iterations)
+        for g in self._graphs:
+            if g.matches(prepared):
+                for k, v in g.run(prepared).items():
+                    metrics[k].extend(t.clone() for t in v)        # the graph's own tensors are overwritten by the next replay
+                return
+        key = (tuple(prepared[0].shape), prepared[5] is None, tuple(tuple(s) for s in prepared[4]))
+        if self._graph_seen == key:
+            from mggan.graph import GraphedIteration
+            self._run_prepared(prepared, metrics, total_iterations)        # this batch still runs eagerly
+            self._graphs.insert(0, GraphedIteration(self, prepared, total_iterations))
+            del self._graphs[2:]
+            return
+        self._graph_seen = key
+        self._run_prepared(prepared, metrics, total_iterations)
 
     def train_iterations(self, batches, metrics, total_iterations=0, on_step=None):
         """The reference loop `for batch in loader: <D, G, PM step>` (abstract_train.py:114-168) with the
@@ -143,7 +173,7 @@ class MultiGeneratorGAN(abc.ABC):
                 nxt = stage(next(it))
             except StopIteration:
                 nxt = None
-            self._run_prepared(prepared, metrics, total_iterations + n)
+            self._run_iteration(prepared, metrics, total_iterations + n)
             if on_step is not None:
                 on_step(n, metrics)
             n += 1

@@ -24,6 +24,7 @@ class TensorTable(ctypes.Structure):
         ("n", ctypes.c_int * TABLE_MAX),
         ("bc1", ctypes.c_float * TABLE_MAX),
         ("bc2_sqrt", ctypes.c_float * TABLE_MAX),
+        ("dyn", ctypes.c_void_p),
     ]
 
 
@@ -38,7 +39,7 @@ SIGNATURES = {
     "mggan_linear_bwd": "piipiifppppps",
     "mggan_disc_heads_fwd": "piiipppppppipps",
     "mggan_disc_heads_bwd": "piiipppppipppppps",
-    "mggan_gumbel_sample": "piiiQQps",
+    "mggan_gumbel_sample": "piiiQQpps",
     "mggan_selection_build": "piiiippppppppps",
     "mggan_selection_all": "iiipppps",
     "mggan_decoder_fwd": "ipppppppppipppppppppiippppps",

@@ -246,7 +246,7 @@ class PatchStats:
         self.buf = buf
         self.R_local, self.P_local = buf[:1296], buf[1296:1332]
         call("mggan_scene_patch_stats", ptr(img), ptr(rows), n, ptr(self.R_local), ptr(self.P_local))
-        buf[1332] = float(n)
+        buf[1332:1333].fill_(float(n))          # a fill kernel (a python-scalar assignment is a host copy: not capturable)
         if group is not None:
             g = buf.clone()
             _allreduce(g, group)
@@ -423,11 +423,12 @@ class Selection:
         return Selection(n, k, num_gens, n_tiles, tile_gen, seq_agent, seq_noise, seq_out, k * num_gens * n)
 
 
-def gumbel_sample(logits, k, seed, offset):
+def gumbel_sample(logits, k, seed, offset, dyn_offset=None):
+    """dyn_offset: optional device int64 scalar added to `offset` inside the kernel (CUDA-graph replay)."""
     logits = _f32(logits.detach())
     n, G = logits.shape
     idx = torch.empty(n, k, device=logits.device, dtype=torch.int64)
-    call("mggan_gumbel_sample", ptr(logits), n, k, G, int(seed), int(offset), ptr(idx))
+    call("mggan_gumbel_sample", ptr(logits), n, k, G, int(seed), int(offset), ptr(dyn_offset), ptr(idx))
     return idx
 
 
@@ -603,12 +604,14 @@ def pm_ml_loss(logits, abs_all, gt, sigma, weight=1.0, inv_n=None):
 
 
 # --------------------------------------------------------------------------- optimiser
-def _tables(entries):
-    """entries: list of (p, g, m, v, n, bc1, bc2_sqrt) -> ctypes tables of <= TABLE_MAX rows."""
+def _tables(entries, dyn=None):
+    """entries: list of (p, g, m, v, n, bc1, bc2_sqrt) -> ctypes tables of <= TABLE_MAX rows.
+    dyn: optional list of device pointers (one per table) to [lr, bc1[64], bc2_sqrt[64]] overrides."""
     out = []
     for s in range(0, len(entries), X.TABLE_MAX):
         chunk = entries[s:s + X.TABLE_MAX]
         tb = X.TensorTable()
+        tb.dyn = dyn[s // X.TABLE_MAX] if dyn is not None else None
         for i, (p, g, m, v, n, bc1, bc2s) in enumerate(chunk):
             tb.p[i], tb.g[i], tb.m[i], tb.v[i] = p, g, m, v
             tb.n[i], tb.bc1[i], tb.bc2_sqrt[i] = n, bc1, bc2s
@@ -628,13 +631,14 @@ def grad_sqnorm(grads, out=None):
 
 
 def clip_adamw(params, grads, exp_avg, exp_avg_sq, steps, sqnorm, max_norm, lr, beta1, beta2, eps, wd,
-               grad_scale=1.0):
+               grad_scale=1.0, dyn=None):
     """One fused clip + AdamW update over parallel lists; `steps` are the per-tensor step counts
-    AFTER this update (bias corrections are computed from them)."""
+    AFTER this update (bias corrections are computed from them).  dyn: per-table device pointers to
+    [lr, bc1[64], bc2_sqrt[64]] that override the by-value scalars (CUDA-graph replay)."""
     ent = []
     for p, g, m, v, t in zip(params, grads, exp_avg, exp_avg_sq, steps):
         ent.append((ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), 1.0 - beta1 ** t, math.sqrt(1.0 - beta2 ** t)))
-    for tb, n in _tables(ent):
+    for tb, n in _tables(ent, dyn):
         call("mggan_clip_adamw", tb, n, ptr(sqnorm), float(max_norm), float(grad_scale), float(lr), float(beta1),
              float(beta2), float(eps), float(wd))
 

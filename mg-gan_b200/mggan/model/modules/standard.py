@@ -128,7 +128,9 @@ class MultiGenerator(nn.Module):
         torch's seed and a call counter draws from the same distribution."""
         logits = self.pm_logits(enc_h)
         self._sample_calls += 1
-        idx = K.gumbel_sample(logits, num_samples, torch.initial_seed() & ((1 << 63) - 1), self._sample_calls << 20)
+        graph = getattr(self, "_graph", None)          # captured iteration: the Philox offset advances on the device
+        idx = K.gumbel_sample(logits, num_samples, torch.initial_seed() & ((1 << 63) - 1), self._sample_calls << 20,
+                              graph.sampler_offset() if graph is not None else None)
         return logits, idx
 
     def _decode(self, in_xy, in_dxdy, enc_h, noise, social_feats, sel):

@@ -76,12 +76,27 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
     def _reduce(self):
         return None if self.dist is None else self.dist.allreduce_grads
 
+    def _labels(self, shape):
+        """(real, fake) smoothed labels of one get_gan_labels call: python floats, or device scalars while an
+        iteration is captured / replayed as a CUDA graph (mggan/graph.py)."""
+        if self._graph is not None:
+            return self._graph.next_labels()
+        return _label_scalars(shape)
+
     @staticmethod
     def _phi(phi, d_out, labels, gen_idx=None, counts=None, inv_denom=None):
         """Apply one GAN-objective term (abstract_train: phi_1 / phi_2 / phi_3) to discriminator outputs."""
         fn, which, sign = phi
-        l_real, l_fake = labels
-        return fn(d_out.contiguous(), l_real if which == "real" else l_fake, gen_idx, counts, sign * inv_denom)
+        label = labels[0] if which == "real" else labels[1]
+        d_out = d_out.contiguous()
+        if torch.is_tensor(label):
+            # device-resident label (graph replay): BCE is affine in the label, L(l) = L(0) + l (L(1) - L(0)), and so is
+            # its gradient -- two launches of the same kernel with constant labels
+            assert fn is K.bce_scalar_label, "CUDA-graph replay covers the BCE objectives (NS, MM)"
+            l0 = fn(d_out, 0.0, gen_idx, counts, sign * inv_denom)
+            l1 = fn(d_out, 1.0, gen_idx, counts, sign * inv_denom)
+            return l0 + label * (l1 - l0)
+        return fn(d_out, label, gen_idx, counts, sign * inv_denom)
 
     # ------------------------------------------------------------------ G step
     def generator_step(self, in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, train_metrics, loss_mask, img=None):
@@ -107,7 +122,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
         branch_out = None
         if isinstance(disc_out, tuple):
             disc_out, branch_out = disc_out
-        adv_loss = self._phi(self.phi_3, disc_out, _label_scalars(disc_out.shape), gen_idxs, counts, 1.0 / denom)
+        adv_loss = self._phi(self.phi_3, disc_out, self._labels(disc_out.shape), gen_idxs, counts, 1.0 / denom)
         train_metrics["train/gen_loss"].append(adv_loss.detach())
         loss = adv_loss if loss is None else loss + adv_loss
         if self.gan_type == "mgan":
@@ -137,7 +152,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
             real_result = real_result[0]
         n_act = real_result.shape[0]
         denom = self._global(n_act)
-        real_loss = self._phi(self.phi_1, real_result, _label_scalars(real_result.shape), inv_denom=1.0 / denom)
+        real_loss = self._phi(self.phi_1, real_result, self._labels(real_result.shape), inv_denom=1.0 / denom)
         noise = self._noise(sub_batches)[None]
         self.G.share_trunk()                # the generator step that follows runs the same weights on these inputs
         with torch.no_grad():
@@ -150,7 +165,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
             ce_loss = K.ce_generators(branch_out.flatten(0, 1), gen_labels_gt.flatten(), None, 1.0 / denom)
             train_metrics["train/info_mgan_disc_loss"].append(ce_loss.detach())
             train_loss = ce_loss
-        fake_loss = self._phi(self.phi_2, disc_out, _label_scalars(disc_out.shape), inv_denom=1.0 / denom)
+        fake_loss = self._phi(self.phi_2, disc_out, self._labels(disc_out.shape), inv_denom=1.0 / denom)
         train_loss = real_loss + fake_loss if train_loss is None else train_loss + real_loss + fake_loss
         train_metrics["train/discr_loss"].append((fake_loss + real_loss).detach())
         return train_loss

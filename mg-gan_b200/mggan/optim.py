@@ -16,6 +16,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.last_grad_sqnorm = None
+        self.graph = None        # a mggan.graph.GraphedIteration while an iteration is being captured
 
     def _init_state(self, p):
         st = self.state[p]
@@ -52,10 +53,17 @@ class FusedAdamW(torch.optim.Optimizer):
             ps, gs, ms, vs, steps = [], [], [], [], []
             for (_, p), g in zip(work[start:end], grads[start:end]):
                 st = self._init_state(p)
-                st["step"] += 1
+                if self.graph is None:
+                    st["step"] += 1
                 ps.append(p); gs.append(g); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
-                steps.append(int(st["step"].item()))
+                steps.append(max(int(st["step"].item()), 1))
             b1, b2 = group["betas"]
+            dyn = None
+            if self.graph is not None:
+                # captured iteration: lr and the bias corrections come from device memory that the replay loop
+                # refreshes (it also advances the step counters, so nothing is counted during the capture pass)
+                dyn = [K.ptr(self.graph.adam_table(self, group, ps[c:c + K.X.TABLE_MAX]))
+                       for c in range(0, len(ps), K.X.TABLE_MAX)]
             K.clip_adamw(ps, gs, ms, vs, steps, sq, max_norm or 0.0, group["lr"], b1, b2, group["eps"],
-                         group["weight_decay"], grad_scale)
+                         group["weight_decay"], grad_scale, dyn=dyn)
             start = end

@@ -89,9 +89,21 @@ def gan_noise(shape, noise_type, device=None):
     raise ValueError('Unrecognized noise type "%s"' % noise_type)
 
 
+_SCENE_IDS = {}
+
+
 def _scene_ids(sub_batches, device):
-    sizes = torch.tensor([e - s for s, e in sub_batches], device=device)
-    return torch.repeat_interleave(torch.arange(len(sub_batches), device=device), sizes)
+    """Scene index of every agent (device int64), cached per batch structure: building it needs a host->device copy
+    and a size-dependent repeat_interleave, neither of which may run inside a CUDA-graph capture."""
+    key = (tuple((int(s), int(e)) for s, e in sub_batches), str(device))
+    ids = _SCENE_IDS.get(key)
+    if ids is None:
+        if len(_SCENE_IDS) > 16:
+            _SCENE_IDS.clear()
+        sizes = torch.tensor([e - s for s, e in sub_batches], device=device)
+        ids = torch.repeat_interleave(torch.arange(len(sub_batches), device=device), sizes)
+        _SCENE_IDS[key] = ids
+    return ids
 
 
 def get_global_noise(dim, sub_batches, noise_type, device=None, num_samples=None):
