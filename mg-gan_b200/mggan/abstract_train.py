@@ -102,6 +102,8 @@ class MultiGeneratorGAN(abc.ABC):
 
     def _run_prepared(self, prepared, metrics, total_iterations=0):
         in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img, loss_mask = prepared
+        if self.dist is not None and self._graph is None:
+            self.dist.begin_iteration()
         if (total_iterations % self.config.num_gen_steps == 0) or (self.epoch >= self.config.keep_gen_steps):
             if self.config.num_unrolling_steps > 0:
                 raise NotImplementedError("num_unrolling_steps > 0 is outside the B200 hot path")
@@ -116,6 +118,8 @@ class MultiGeneratorGAN(abc.ABC):
     # ------------------------------------------------------------------ CUDA-graph replay
     def _graph_eligible(self, prepared):
         cfg = self.config
+        # single-process only for now: capturing the NCCL collectives of a data-parallel step deadlocked on the first
+        # attempt (2 x B200, torch 2.11 / NCCL 2.28); the capture-safe normalisers (DistContext.freeze) are in place
         return (getattr(cfg, "cuda_graph", True) and self.dist is None and prepared[6] is None
                 and cfg.gan_obj in ("NS", "MM") and cfg.weighting_target in ("ml", "none")
                 and cfg.num_gen_steps == 1 and cfg.num_unrolling_steps == 0)

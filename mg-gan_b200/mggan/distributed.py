@@ -57,6 +57,16 @@ class DistContext:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world_size = dist.get_world_size(group)
+        self._log = []          # (local value, global sum) of every sum_scalar call of the current iteration
+        self._replay = None     # while an iteration is captured as a CUDA graph: the previous iteration's log
+
+    def begin_iteration(self):
+        self._log = []
+
+    def freeze(self, on):
+        """Capture mode: `sum_scalar` has a host read-back, which cannot run inside a CUDA-graph capture; the captured
+        iteration has the structure of the eager one that just ran on every rank, so its normalisers are replayed."""
+        self._replay = list(self._log) if on else None
 
     def attach(self, G, D):
         for m in (G, D):
@@ -65,9 +75,15 @@ class DistContext:
                 enc.stat_group = self.group if self.group is not None else dist.group.WORLD
 
     def sum_scalar(self, value, device=None):
+        if self._replay is not None:
+            local, total = self._replay.pop(0)
+            assert local == float(value), "captured iteration diverged from the eager one it was modelled on"
+            return total
         t = torch.tensor([float(value)], dtype=torch.float64, device=device or self._device())
         dist.all_reduce(t, group=self.group)
-        return float(t.item())
+        total = float(t.item())
+        self._log.append((float(value), total))
+        return total
 
     def sum_tensor(self, t):
         dist.all_reduce(t, group=self.group)

@@ -89,6 +89,8 @@ class GraphedIteration:
             m._graph = self
         for opt in (trainer.optimizerG, trainer.optimizerD):
             opt.graph = self
+        if trainer.dist is not None:
+            trainer.dist.freeze(True)      # host-side normaliser sums: replay the eager iteration that just ran
         try:
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
@@ -96,6 +98,8 @@ class GraphedIteration:
                 s = self.static
                 trainer._run_prepared((s[0], s[1], s[2], s[3], sub_batches, s[4], None), self.metrics, total_iterations)
         finally:
+            if trainer.dist is not None:
+                trainer.dist.freeze(False)
             trainer._graph = None
             for m in (trainer.G, trainer.D):
                 m._graph = None

@@ -238,6 +238,7 @@ class PatchStats:
     """Data-only statistics of a batch of crops (R 36x36, P 36; see csrc/scene.cu), computed once and
     shared by every scene-CNN forward / backward that sees the same `img` tensor (and row selection)."""
     _cache = []          # [(weakref(img), version, rows_key, PatchStats)]
+    _n_total = {}        # (local crops, group) -> global crop count
 
     def __init__(self, img, rows, group):
         dev = img.device
@@ -251,7 +252,11 @@ class PatchStats:
             g = buf.clone()
             _allreduce(g, group)
             self.R, self.P = g[:1296], g[1296:1332]
-            self.n_total = float(g[1332].item())
+            key = (n, id(group))
+            if torch.cuda.is_current_stream_capturing():      # no host read-back inside a CUDA-graph capture: the
+                self.n_total = PatchStats._n_total[key]       # global crop count of this structure was read when it ran eagerly
+            else:
+                self.n_total = PatchStats._n_total[key] = float(g[1332].item())
         else:
             self.R, self.P, self.n_total = self.R_local, self.P_local, float(n)
 
