@@ -21,8 +21,10 @@ namespace {
 constexpr int H = 32;        // decoder hidden size (config.decoder_h_dim default)
 constexpr int M1 = 16;       // hidden2pos mid width = H / 2
 constexpr int ROWS = 64;
-constexpr int LDH = H + 4;   // 36
-constexpr int LDG = 4 * H + 4;
+// Row strides = 8 mod 32: the (4 rows x 8 units) scalar accesses of a warp (rows lane>>3, units lane&7) then fall on
+// 32 distinct banks (with H + 4 the rows were 4 banks apart and every such access was a 2-way conflict).
+constexpr int LDH = H + 8;   // 40
+constexpr int LDG = 4 * H + 8;
 constexpr int LDU = M1 + 4;  // 20
 constexpr int ZMAX = 16;
 
@@ -449,11 +451,13 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
             }
             // dW1h: rows [8 warp, 8 warp + 8) of dU^T h_t
             tile_wgrad<8>(w1acc, sDu + warp * 8 * LDU, LDU, e_mq * 4, sHt + warp * 8 * LDH, LDH, e_kq * 4);
-            {   // gradient wrt this step's input dxdy_{t-1}: dG Wx (row = prow, gates 32 mq .. 32 mq + 31)
+            {   // gradient wrt this step's input dxdy_{t-1}: dG Wx (row = prow; the 4 lanes of a row take interleaved gate
+                // quads, so each load instruction of the quad is 64 contiguous bytes -- a contiguous quarter per lane put
+                // all four on one bank: 4-way conflicts on 24 LDS.128 per step, 16 % of the kernel's shared wavefronts)
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int oo = 0; oo < H; oo += 4) {
-                    const int o = mq * H + oo;
+                    const int o = oo * 4 + mq * 4;
                     const float4 gq = ld4(sG + prow * LDG + o);
                     const float4 wa = ld4(sWxT + o), wb = ld4(sWxT + 4 * H + o);
                     s0 = fmaf(gq.x, wa.x, fmaf(gq.y, wa.y, fmaf(gq.z, wa.z, fmaf(gq.w, wa.w, s0))));

@@ -26,6 +26,11 @@ constexpr int CIN = 4;
 constexpr int AH = 32;                         // attention MLP hidden width (cnn.py mlp_dim)
 constexpr int LDI = 36;                        // padded image row (35 used)
 constexpr int IMGPAD = 35 * LDI;               // one padded channel
+// Channel stride of the crop in the backward kernel: = 8 mod 32.  In the sparse conv1 weight-gradient stage the lanes of a
+// warp that differ only in the input channel read the same (data-dependent) pixel of 4 channels; with the dense stride
+// (1260 = 12 mod 32) channels 0 and 3 sit 4 banks apart and collide with the neighbouring pooled pixels of the other
+// (ncu: 63 M of that stage's 134 M shared wavefronts were conflict replays); 8 banks apart they only meet at the margins.
+constexpr int IMGPAD_BWD = 35 * LDI + 28;
 constexpr int LDP = 18;                        // padded pooled row
 // channel stride of the pooled maps: even (8-byte aligned rows for LDS.64) and chosen so that the channels -- and, for 8
 // channels, two neighbouring rows as well -- fall on distinct banks: 326 = 6 mod 32 for 16 channels, 324 = 4 mod 32 for 8
@@ -488,7 +493,7 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     float* sWT = sP + ((C * PPAD + 3) & ~3);             // [(co*9+tap)][ci]
     float* sDY = sWT + 9 * C * C;                        // [C][LDY] dy1 (sparse values, dense layout)
     float* sImg = sDY + C * LDY;                         // [4][35][36]
-    float* sPar = sImg + CIN * IMGPAD;                   // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
+    float* sPar = sImg + CIN * IMGPAD_BWD;                   // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
     float* sred = sPar + 10 * C;                         // [8][2C]
     unsigned char* sIdx = reinterpret_cast<unsigned char*>(sred + 8 * 2 * C);    // [C][256]
     for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
@@ -503,7 +508,7 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
         sPar[8 * C + threadIdx.x] = __ldg(m12_2 + threadIdx.x);
     }
     for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) { sDX[i] = 0.f; sP[i] = 0.f; }
-    for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
+    for (int i = threadIdx.x; i < CIN * IMGPAD_BWD; i += MGGAN_THREADS) sImg[i] = 0.f;
     const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
     // conv2 weight gradient: thread = (4 output channels, input channel, pixel-row group)
     const int item = threadIdx.x % NITEM, pg = threadIdx.x / NITEM;
@@ -532,7 +537,7 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             const float* ip = img + (size_t)src * CIN * IMG2;
             for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
                 int ci = i / IMG2, p = i - ci * IMG2, yy = p / IMG, xx = p - yy * IMG;
-                sImg[ci * IMGPAD + (yy + 1) * LDI + xx + 1] = __ldg(ip + i);
+                sImg[ci * IMGPAD_BWD + (yy + 1) * LDI + xx + 1] = __ldg(ip + i);
             }
             const int win = (y >> 1) * P2 + (x >> 1), loc = (y & 1) * 2 + (x & 1);
 #pragma unroll
@@ -638,7 +643,7 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
         __syncthreads();
         {   // sparse half of the conv1 weight gradient: thread = (c, ci, lane group); lane groups take interleaved
             // pooled pixels (q = it * QG + group) so that neighbouring lanes read neighbouring banks
-            const float* ipc = sImg + s_ci * IMGPAD;
+            const float* ipc = sImg + s_ci * IMGPAD_BWD;
 #pragma unroll 2
             for (int it = 0; it < Q_PER; ++it) {
                 const int q = it * QG + s_qg;
@@ -928,7 +933,7 @@ size_t fused_fwd_smem() { constexpr int PPAD = PoolPad<C>::value; return sizeof(
 template <int C>
 size_t fused_bwd_smem() {
     constexpr int PPAD = PoolPad<C>::value;
-    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * C + C * (P1SQ + 4) + CIN * IMGPAD + 10 * C + 8 * 2 * C) + C * P1SQ;
+    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * C + C * (P1SQ + 4) + CIN * IMGPAD_BWD + 10 * C + 8 * 2 * C) + C * P1SQ;
 }
 template <int C>
 size_t attn_w_floats() { return 2 * AH * C + AH + C + 2 * C; }
