@@ -176,6 +176,8 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")             # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ctx = None
@@ -208,9 +210,7 @@ def run_ours(a):
 
     def step_resident():
         _K.PatchStats._cache.clear()     # a training loop sees new crops every iteration: never reuse their statistics
-        tr.discriminator_step(devb["in_xy"], devb["in_dxdy"], devb["gt_xy"], devb["gt_dxdy"], sse, metrics, None, devb["features"])
-        tr.generator_step(devb["in_xy"], devb["in_dxdy"], devb["gt_xy"], devb["gt_dxdy"], sse, metrics, None, devb["features"])
-        tr.net_chooser_step(devb["in_xy"], devb["in_dxdy"], devb["gt_xy"], devb["gt_dxdy"], sse, metrics, None, devb["features"])
+        tr._run_prepared(prepared, metrics)      # D step, G step, PM step, launched eagerly
         metrics.clear()
 
     prepared = (devb["in_xy"], devb["in_dxdy"], devb["gt_xy"], devb["gt_dxdy"], sse, devb["features"], None)

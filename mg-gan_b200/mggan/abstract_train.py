@@ -104,6 +104,9 @@ class MultiGeneratorGAN(abc.ABC):
         in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img, loss_mask = prepared
         if self.dist is not None and self._graph is None:
             self.dist.begin_iteration()
+            n_agents = in_xy.size(1)
+            self.dist.prefetch_sums({"agents": n_agents,
+                                     "active": n_agents if loss_mask is None else int(loss_mask.sum())})
         if (total_iterations % self.config.num_gen_steps == 0) or (self.epoch >= self.config.keep_gen_steps):
             if self.config.num_unrolling_steps > 0:
                 raise NotImplementedError("num_unrolling_steps > 0 is outside the B200 hot path")

@@ -51,6 +51,27 @@ def shard_batch(batch, world_size, rank, balance="agents"):
     return out
 
 
+_CPU_GROUPS = {}
+
+
+def host_sum(values, group=None):
+    """All-reduce(sum) of a few HOST numbers.  Under NCCL this goes through a companion gloo group on CPU tensors: the
+    numbers (agent counts, crop counts) are known on the host, and routing them through the GPU costs a stream
+    synchronisation per call (and a host<->device copy that queues behind the batch's H2D transfer on the copy engine).
+    Collective: every rank of `group` must call it at the same point."""
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64)
+    if dist.get_backend(group) == "nccl":
+        key = id(group) if group is not None else None
+        cpu = _CPU_GROUPS.get(key)
+        if cpu is None:
+            ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
+            cpu = _CPU_GROUPS[key] = dist.new_group(ranks=ranks, backend="gloo")
+        dist.all_reduce(t, group=cpu)
+    else:
+        dist.all_reduce(t, group=group)
+    return t.tolist()
+
+
 class DistContext:
     def __init__(self, group=None):
         assert dist.is_initialized()
@@ -79,11 +100,25 @@ class DistContext:
             local, total = self._replay.pop(0)
             assert local == float(value), "captured iteration diverged from the eager one it was modelled on"
             return total
-        t = torch.tensor([float(value)], dtype=torch.float64, device=device or self._device())
-        dist.all_reduce(t, group=self.group)
-        total = float(t.item())
+        total = host_sum([float(value)], self.group)[0]
         self._log.append((float(value), total))
         return total
+
+    def prefetch_sums(self, named):
+        """Sum a few host numbers ({name: local value}) over ranks once per iteration; `fetched(name, value)` answers
+        from them.  The loss normalisers of an iteration (agents, unmasked agents) are known before its first kernel."""
+        if self._replay is not None:
+            return
+        names = sorted(named)
+        vals = [float(named[n]) for n in names]
+        self._pref = {n: (v, g) for n, v, g in zip(names, vals, host_sum(vals, self.group))}
+
+    def fetched(self, name, value):
+        """Global sum of the prefetched number `name`, or None when it was not prefetched with this local value."""
+        pref = getattr(self, "_pref", None)
+        if pref is None or name not in pref or pref[name][0] != float(value):
+            return None
+        return pref[name][1]
 
     def sum_tensor(self, t):
         dist.all_reduce(t, group=self.group)

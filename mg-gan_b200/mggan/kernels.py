@@ -253,10 +253,11 @@ class PatchStats:
             _allreduce(g, group)
             self.R, self.P = g[:1296], g[1296:1332]
             key = (n, id(group))
-            if torch.cuda.is_current_stream_capturing():      # no host read-back inside a CUDA-graph capture: the
-                self.n_total = PatchStats._n_total[key]       # global crop count of this structure was read when it ran eagerly
-            else:
-                self.n_total = PatchStats._n_total[key] = float(g[1332].item())
+            if torch.cuda.is_current_stream_capturing():      # no collective on the host inside a CUDA-graph capture: the
+                self.n_total = PatchStats._n_total[key]       # global crop count of this structure was summed when it ran eagerly
+            else:                                             # the crop count is a host number: summed on the host (gloo)
+                from .distributed import host_sum
+                self.n_total = PatchStats._n_total[key] = host_sum([n], group)[0]
         else:
             self.R, self.P, self.n_total = self.R_local, self.P_local, float(n)
 

@@ -69,9 +69,16 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
     def _noise(self, sub_batches, num_samples=None):
         return get_global_noise(self.config.noise_dim, sub_batches, "gaussian", self.device, num_samples)
 
-    def _global(self, value):
-        """Sum of a python number over data-parallel ranks (identity on one GPU)."""
-        return value if self.dist is None else self.dist.sum_scalar(value)
+    def _global(self, value, name=None):
+        """Sum of a python number over data-parallel ranks (identity on one GPU).  `name`: the quantity ("agents",
+        "active"), answered from the sums the loop body prefetched without stalling the compute stream."""
+        if self.dist is None:
+            return value
+        if name is not None:
+            got = self.dist.fetched(name, value)
+            if got is not None:
+                return got
+        return self.dist.sum_scalar(value)
 
     def _reduce(self):
         return None if self.dist is None else self.dist.allreduce_grads
@@ -110,11 +117,11 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
         counts = self.G.last_selection.totals
         if self.dist is not None:
             counts = self.dist.sum_tensor(counts.clone())
-        denom = self._global(n_act * k)
+        denom = self._global(n_act, "active") * k
         loss = None
         if cfg.l2_loss_type != "none":
             scenes = K.SceneIndex.get(sub_batches, self.device)
-            min_l2 = K.l2_scene_min(gen_out.abs, gt_xy, scenes, 1.0 / self._global(b))
+            min_l2 = K.l2_scene_min(gen_out.abs, gt_xy, scenes, 1.0 / self._global(b, "agents"))
             train_metrics["train/L2_loss"].append(min_l2.detach())
             loss = cfg.l2_loss_weight * min_l2
         with _frozen(self.D):
@@ -151,7 +158,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
         if isinstance(real_result, tuple):
             real_result = real_result[0]
         n_act = real_result.shape[0]
-        denom = self._global(n_act)
+        denom = self._global(n_act, "active")
         real_loss = self._phi(self.phi_1, real_result, self._labels(real_result.shape), inv_denom=1.0 / denom)
         noise = self._noise(sub_batches)[None]
         self.G.share_trunk()                # the generator step that follows runs the same weights on these inputs
@@ -183,7 +190,7 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
             for i in range(probs.shape[0]):
                 metrics[f"probs/Gen {i} probability"].append(probs[i])
         n_act = net_chooser_weights.shape[0]
-        inv_n = 1.0 / self._global(n_act)
+        inv_n = 1.0 / self._global(n_act, "active")
         if cfg.weighting_target == "ml":
             loss, _ = K.pm_ml_loss(net_chooser_weights, gen_out.abs, gt_xy, cfg.sigma, cfg.pi_net_loss_weight, inv_n)
             logged = loss.detach()

@@ -56,6 +56,16 @@ def _worker(rank, world, port, ret):
     ok = ok and ctx.sum_scalar(10 + rank, device="cpu") == 21.0
     t = ctx.sum_tensor(torch.tensor([rank, 1], dtype=torch.int32))
     ok = ok and t.tolist() == [1, 2]
+    # loss normalisers prefetched once per iteration; a value that was not prefetched (or changed) is not answered
+    ctx.prefetch_sums({"agents": 100 + rank, "active": 90 - rank})
+    ok = ok and ctx.fetched("agents", 100 + rank) == 201.0 and ctx.fetched("active", 90 - rank) == 179.0
+    ok = ok and ctx.fetched("agents", 7) is None and ctx.fetched("other", 1) is None
+    # capture mode replays the normalisers of the eager iteration that just ran, in order
+    ctx.begin_iteration()
+    a = ctx.sum_scalar(5 + rank, device="cpu")
+    ctx.freeze(True)
+    ok = ok and ctx.sum_scalar(5 + rank, device="cpu") == a == 11.0
+    ctx.freeze(False)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
