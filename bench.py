@@ -370,7 +370,17 @@ def run_ours(a):
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        # captured graphs hold NCCL kernels of this communicator: drop them first, and never let teardown hang the job
+        import gc
+        import threading
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        tr._graphs.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -471,6 +481,9 @@ def run_reference(a):
 
 
 if __name__ == "__main__":
+    if os.environ.get("MGGAN_FAULT_DUMP"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["MGGAN_FAULT_DUMP"]), exit=True)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

@@ -100,19 +100,25 @@ class MultiGeneratorGAN(abc.ABC):
             gt_dxdy, gt_xy = gt_dxdy[:, loss_mask], gt_xy[:, loss_mask]
         return in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img, loss_mask
 
-    def _run_prepared(self, prepared, metrics, total_iterations=0):
+    def _run_prepared(self, prepared, metrics, total_iterations=0, sums=None):
         in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img, loss_mask = prepared
         if self.dist is not None and self._graph is None:
             self.dist.begin_iteration()
-            n_agents = in_xy.size(1)
-            self.dist.prefetch_sums({"agents": n_agents,
-                                     "active": n_agents if loss_mask is None else int(loss_mask.sum())})
+            if sums is not None:
+                self.dist.set_sums(sums)           # already exchanged by _run_iteration
+            else:
+                self.dist.prefetch_sums(self._local_counts(prepared))
         if (total_iterations % self.config.num_gen_steps == 0) or (self.epoch >= self.config.keep_gen_steps):
             if self.config.num_unrolling_steps > 0:
                 raise NotImplementedError("num_unrolling_steps > 0 is outside the B200 hot path")
             self.discriminator_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
         self.generator_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
         self.net_chooser_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
+
+    @staticmethod
+    def _local_counts(prepared):
+        n_agents = prepared[0].size(1)
+        return {"agents": n_agents, "active": n_agents if prepared[6] is None else int(prepared[6].sum())}
 
     def train_iteration(self, batch, metrics, total_iterations=0):
         """One D step + G step + PM step on a collated batch (reference loop body :114-168)."""
@@ -121,31 +127,46 @@ class MultiGeneratorGAN(abc.ABC):
     # ------------------------------------------------------------------ CUDA-graph replay
     def _graph_eligible(self, prepared):
         cfg = self.config
-        # single-process only for now: capturing the NCCL collectives of a data-parallel step deadlocked on the first
-        # attempt (2 x B200, torch 2.11 / NCCL 2.28); the capture-safe normalisers (DistContext.freeze) are in place
-        return (getattr(cfg, "cuda_graph", True) and self.dist is None and prepared[6] is None
+        # data-parallel runs capture the NCCL collectives too (every rank captures and replays in lockstep; the host-side
+        # normaliser sums are replayed from the eager iteration, DistContext.freeze)
+        return (getattr(cfg, "cuda_graph", True) and prepared[6] is None
                 and cfg.gan_obj in ("NS", "MM") and cfg.weighting_target in ("ml", "none")
                 and cfg.num_gen_steps == 1 and cfg.num_unrolling_steps == 0)
 
     def _run_iteration(self, prepared, metrics, total_iterations=0):
         """Eager iteration, or the replay of a captured one when this batch has the structure (scene sizes, no masked
-        futures) of the previous one: the iteration is captured the second time a structure repeats (mggan/graph.py)."""
-        if not self._graph_eligible(prepared):
-            return self._run_prepared(prepared, metrics, total_iterations)
-        for g in self._graphs:
-            if g.matches(prepared):
-                for k, v in g.run(prepared).items():
-                    metrics[k].extend(t.clone() for t in v)        # the graph's own tensors are overwritten by the next replay
-                return
+        futures) of the previous one: the iteration is captured the second time a structure repeats (mggan/graph.py).
+        Data-parallel: the choice is collective.  One host-side exchange per iteration tells every rank whether ALL
+        ranks hold a matching graph (replay), whether all could capture now (eager + capture), or not (eager); it also
+        carries the global agent counts, and a graph is replayed only under the counts it was captured with (its loss
+        normalisers are baked in)."""
+        eligible = self._graph_eligible(prepared)
+        g = next((x for x in self._graphs if x.matches(prepared)), None) if eligible else None
         key = (tuple(prepared[0].shape), prepared[5] is None, tuple(tuple(s) for s in prepared[4]))
-        if self._graph_seen == key:
-            from mggan.graph import GraphedIteration
-            self._run_prepared(prepared, metrics, total_iterations)        # this batch still runs eagerly
-            self._graphs.insert(0, GraphedIteration(self, prepared, total_iterations))
-            del self._graphs[2:]
+        ready = eligible and (g is not None or self._graph_seen == key)
+        sums = None
+        if self.dist is not None:
+            from mggan.distributed import host_sum
+            local = self._local_counts(prepared)
+            v = host_sum([1.0 if g is not None else 0.0, 1.0 if ready else 0.0, local["agents"], local["active"]],
+                         self.dist.group)
+            sums = {"agents": (float(local["agents"]), v[2]), "active": (float(local["active"]), v[3])}
+            world = self.dist.world_size
+            if g is not None and not (v[0] == world and g.global_counts == (v[2], v[3])):
+                g = None
+            ready = v[1] == world
+        if g is not None:
+            for k, v_ in g.run(prepared).items():
+                metrics[k].extend(t.clone() for t in v_)           # the graph's own tensors are overwritten by the next replay
             return
-        self._graph_seen = key
-        self._run_prepared(prepared, metrics, total_iterations)
+        self._graph_seen = key if eligible else None
+        self._run_prepared(prepared, metrics, total_iterations, sums)       # this batch runs eagerly
+        if ready:
+            from mggan.graph import GraphedIteration
+            new = GraphedIteration(self, prepared, total_iterations)
+            new.global_counts = (sums["agents"][1], sums["active"][1]) if sums is not None else None
+            self._graphs.insert(0, new)
+            del self._graphs[2:]
 
     def train_iterations(self, batches, metrics, total_iterations=0, on_step=None):
         """The reference loop `for batch in loader: <D, G, PM step>` (abstract_train.py:114-168) with the

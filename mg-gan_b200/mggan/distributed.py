@@ -113,6 +113,11 @@ class DistContext:
         vals = [float(named[n]) for n in names]
         self._pref = {n: (v, g) for n, v, g in zip(names, vals, host_sum(vals, self.group))}
 
+    def set_sums(self, table):
+        """{name: (local value, global sum)} exchanged by the caller."""
+        if self._replay is None:
+            self._pref = dict(table)
+
     def fetched(self, name, value):
         """Global sum of the prefetched number `name`, or None when it was not prefetched with this local value."""
         pref = getattr(self, "_pref", None)

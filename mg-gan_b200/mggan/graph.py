@@ -83,6 +83,7 @@ class GraphedIteration:
         self.replays = 0
         self.metrics = defaultdict(list)
         self.total_iterations = total_iterations
+        self.global_counts = None      # data-parallel: (sum of agents, sum of unmasked agents) the normalisers were baked with
 
         trainer._graph = self
         for m in (trainer.G, trainer.D):
