@@ -142,6 +142,33 @@ __device__ __forceinline__ void atomic_block44(float* __restrict__ dst, int ld, 
         for (int b = 0; b < 4; ++b) atomicAdd(dst + (o0 + a) * ld + k0 + b, acc[a][b]);
 }
 
+// ---- warp-level tensor-core tile products with fp32-level accuracy (3 x TF32) -----------------------------------
+// mma.sync m16n8k8 TF32 with both operands split x = hi + lo (hi = x truncated to TF32, lo = x - hi exact):
+// acc += ah.bh + al.bh + ah.bl.  Used where a kernel is bound by the shared-memory wavefronts of FP32 register-tile
+// products (decoder backward): a fragment load feeds 16x8x8 MACs instead of 4, at the price of the legacy tensor path's
+// modest rate (measured 0.46 mma/clk/SM on B200, tools/microbench/mma_rate.cu) -- enough once LDS is the limiter.
+// Fragment layout (PTX ISA, m16n8k8 .tf32), g = lane >> 2, t = lane & 3:
+//   A (16 x 8): a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)      B (8 x 8): b0 (k = t, n = g)  b1 (k = t+4, n = g)
+//   C (16 x 8): c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
+// Rows of A / columns of B / the K index may be permuted freely as long as both operands (and the reader of C) agree.
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], float b0, float b1) {
+    uint32_t b0h, b0l, b1h, b1l;
+    tf32_split(b0, b0h, b0l);
+    tf32_split(b1, b1h, b1l);
+    mma_tf32_16x8x8(c, ah, b0h, b1h);
+    mma_tf32_16x8x8(c, al, b0h, b1h);
+    mma_tf32_16x8x8(c, ah, b0l, b1l);
+}
+
 // ---- decoder saved-activation layouts (decoder.cu, decoder_tc.cu) -----------------------------------------------
 // Rows are grouped in 128-row tiles and the row index is the second-fastest dimension, so that the 32 rows a warp of
 // the thread-per-row tensor-core kernel writes for one (pair, unit-pair) are 512 contiguous bytes (4 lines per

@@ -219,6 +219,8 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
 // Per step and 64-row tile:  phase 0 hidden2pos backward (thread = row x 4 mid units), phase 1 LSTM cell backward
 // (thread = 8 rows x 1 unit; activations read as (i,f | g,o | c,tanh c) float2 triples, layout dec_acts_off in common.cuh), phase 2 tile products:
 //   dh_{t-1} = dG W_hh (64 x 32, K = 128)          dW_hh += dG^T h_{t-1} (128 x 32, K = 64 rows)
+//       -- these two are 80 % of the step's MACs and made the kernel shared-memory-wavefront bound (lsu 86 %) as FP32
+//          register tiles; they run as warp-level 3 x TF32 mma.sync products (common.cuh), 5-6x fewer wavefronts per MAC
 //   (dWx | db) += dG^T (x | 1)   via the pad columns 32..34 of the h_{t-1} tile, rows split over the k-quad lanes
 //   dW1h += dU^T h_t (16 x 32)   rows split over the 8 warps
 //   d(dxdy_{t-1}) = dG Wx        thread = (row, quarter of the 128 gates), Wx kept transposed
@@ -231,8 +233,8 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                    const float* __restrict__ u1save, const float* __restrict__ h0save,
                    const float* __restrict__ d_abs, const float* __restrict__ d_rel, DecGrads gr) {
     extern __shared__ __align__(16) float smem[];
-    float* sW = smem;                       // [4H][LDH]   W_hh
-    float* sW1 = sW + 4 * H * LDH;          // [M1][LDH]   W1s (epilogue)
+    float* sWT = smem;                      // [H][LDG]    W_hh transposed (unit-major): B operand of dh = dG W_hh
+    float* sW1 = sWT + H * LDG;             // [M1][LDH]   W1s (epilogue)
     float* sG = sW1 + M1 * LDH;             // [ROWS][LDG] gate pre-activation gradients
     float* sHp = sG + ROWS * LDG;           // [ROWS][LDH] h_{t-1} | x0 x1 1 0
     float* sHt = sHp + ROWS * LDH;          // [ROWS][LDH] h_t   (social tile after the loop)
@@ -249,7 +251,6 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
     const int u = (warp & 3) * 8 + (lane & 7);
     const int rl = (warp >> 2) * 32 + (lane >> 3);
     const int prow = threadIdx.x >> 2, mq = threadIdx.x & 3;
-    const int d_kq = threadIdx.x & 7, d_r0 = threadIdx.x >> 3;      // dgrad: rows d_r0, d_r0+32
     const int w_oq = (warp & 3) * 8 + (lane & 7), w_kq = (warp >> 2) * 4 + (lane >> 3);
     const int e_mq = lane & 3, e_kq = lane >> 2;                    // dW1h / dW1s 4x4 block, rows split over warps
     const int z_u = threadIdx.x & 31, z_g = threadIdx.x >> 5;       // dWz: unit, noise-column group (z_g, z_g + 8)
@@ -269,7 +270,14 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
         for (int i = threadIdx.x; i < M1 * H; i += MGGAN_THREADS) sW1sAcc[i] = 0.f;     // read again only after a barrier
     };
     auto flush = [&](int g) {
-        atomic_block44(gr.dWhh + (size_t)g * 4 * H * H, H, w_oq * 4, w_kq * 4, wacc);
+        {   // wacc[j] = C fragment of n-tile j: c0, c1 -> gate m0 + 2g, units 8t + j, 8t + 4 + j; c2, c3 -> gate m0 + 2g + 1
+            float* dst = gr.dWhh + (size_t)g * 4 * H * H + (size_t)(warp * 16 + 2 * (lane >> 2)) * H + 8 * (lane & 3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(dst + j, wacc[j][0]); atomicAdd(dst + 4 + j, wacc[j][1]);
+                atomicAdd(dst + H + j, wacc[j][2]); atomicAdd(dst + H + 4 + j, wacc[j][3]);
+            }
+        }
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const size_t o = (size_t)g * 4 * H + w_oq * 4 + a;
@@ -304,7 +312,8 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
         if (g != cur_g) {
             if (cur_g >= 0) { flush(cur_g); __syncthreads(); zero_acc(); }
             cur_g = g;
-            stage_matrix(sW, LDH, w.Whh + (size_t)g * 4 * H * H, 4 * H, H);
+            for (int i = threadIdx.x; i < 4 * H * H; i += MGGAN_THREADS)
+                sWT[(i & (H - 1)) * LDG + (i >> 5)] = __ldg(w.Whh + (size_t)g * 4 * H * H + i);
             for (int i = threadIdx.x; i < 4 * H * 2; i += MGGAN_THREADS)
                 sWxT[(i & 1) * 4 * H + (i >> 1)] = __ldg(w.Wx + (size_t)g * 4 * H * 2 + i);
             stage_matrix(sW1h, LDH, w.W1h + (size_t)g * M1 * H, M1, H);
@@ -430,12 +439,58 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
             __syncthreads();
             // ---- phase 2: tile products
             {
-                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                tile_dgrad<2, 4 * H>(acc, sG, LDG, d_r0, 32, sW, LDH, d_kq * 4);
-                tile_wgrad<ROWS>(wacc, sG, LDG, w_oq * 4, sHp, LDH, w_kq * 4);
-                // every read of sDh for step t happened before the barrier above
-                st4(sDh + d_r0 * LDH + d_kq * 4, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]));
-                st4(sDh + (d_r0 + 32) * LDH + d_kq * 4, make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]));
+                // dh_{t-1} = dG W_hh: warp = 16 rows x 16 units, K = 128 gates.  The K index is permuted (logical k = t,
+                // t+4 <-> gates k0 + 2t, k0 + 2t + 1) so that every fragment is one conflict-free LDS.64.
+                const int g8 = lane >> 2, t4 = lane & 3;
+                {
+                    const int m0 = (warp & 3) * 16, n0 = (warp >> 2) * 16;
+                    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                    const float* pa0 = sG + (m0 + g8) * LDG + 2 * t4;
+                    const float* pa1 = pa0 + 8 * LDG;
+                    const float* pb0 = sWT + (n0 + g8) * LDG + 2 * t4;
+                    const float* pb1 = pb0 + 8 * LDG;
+#pragma unroll 4
+                    for (int k0 = 0; k0 < 4 * H; k0 += 8) {
+                        const float2 x0 = *reinterpret_cast<const float2*>(pa0 + k0);
+                        const float2 x1 = *reinterpret_cast<const float2*>(pa1 + k0);
+                        const float2 y0 = *reinterpret_cast<const float2*>(pb0 + k0);
+                        const float2 y1 = *reinterpret_cast<const float2*>(pb1 + k0);
+                        uint32_t ah[4], al[4];
+                        tf32_split(x0.x, ah[0], al[0]); tf32_split(x1.x, ah[1], al[1]);
+                        tf32_split(x0.y, ah[2], al[2]); tf32_split(x1.y, ah[3], al[3]);
+                        mma_3xtf32(acc[0], ah, al, y0.x, y0.y);
+                        mma_3xtf32(acc[1], ah, al, y1.x, y1.y);
+                    }
+                    // every read of sDh for step t happened before the barrier above
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float* o = sDh + (m0 + g8) * LDH + n0 + 8 * j + 2 * t4;
+                        *reinterpret_cast<float2*>(o) = make_float2(acc[j][0], acc[j][1]);
+                        *reinterpret_cast<float2*>(o + 8 * LDH) = make_float2(acc[j][2], acc[j][3]);
+                    }
+                }
+                // dW_hh += dG^T h_{t-1}: warp = 16 gates x 32 units, K = 64 rows.  Rows of the A fragment are permuted
+                // (logical g, g+8 <-> gates m0 + 2g, m0 + 2g + 1: one LDS.64) and so are the columns of B (n-tile j, logical
+                // column c <-> unit 4c + j: one LDS.128 serves the four n-tiles); wacc[j] is the C fragment of n-tile j.
+                {
+                    const int m0 = warp * 16;
+                    const float* pa = sG + t4 * LDG + m0 + 2 * g8;
+                    const float* pb = sHp + t4 * LDH + 4 * g8;
+#pragma unroll 2
+                    for (int k0 = 0; k0 < ROWS; k0 += 8) {
+                        const float2 x0 = *reinterpret_cast<const float2*>(pa + k0 * LDG);
+                        const float2 x1 = *reinterpret_cast<const float2*>(pa + (k0 + 4) * LDG);
+                        const float4 y0 = ld4(pb + k0 * LDH);
+                        const float4 y1 = ld4(pb + (k0 + 4) * LDH);
+                        uint32_t ah[4], al[4];
+                        tf32_split(x0.x, ah[0], al[0]); tf32_split(x0.y, ah[1], al[1]);
+                        tf32_split(x1.x, ah[2], al[2]); tf32_split(x1.y, ah[3], al[3]);
+                        mma_3xtf32(wacc[0], ah, al, y0.x, y1.x);
+                        mma_3xtf32(wacc[1], ah, al, y0.y, y1.y);
+                        mma_3xtf32(wacc[2], ah, al, y0.z, y1.z);
+                        mma_3xtf32(wacc[3], ah, al, y0.w, y1.w);
+                    }
+                }
             }
             {   // (dWx | db): rows [8 w_kq, 8 w_kq + 8) of dG^T (x0 x1 1)
 #pragma unroll
@@ -524,7 +579,7 @@ size_t dec_fwd_smem() {
     return sizeof(float) * (4 * H * LDH + 2 * M1 * LDH + 2 * ROWS * LDH + ROWS * LDU + ROWS * 2 + H * (ZMAX + 1));
 }
 size_t dec_bwd_smem() {
-    return sizeof(float) * (4 * H * LDH + M1 * LDH + ROWS * LDG + 3 * ROWS * LDH + ROWS * LDU + 2 * 4 * H + ROWS * ZMAX + M1 * H + M1 * LDH + 2 * M1);
+    return sizeof(float) * (H * LDG + M1 * LDH + ROWS * LDG + 3 * ROWS * LDH + ROWS * LDU + 2 * 4 * H + ROWS * ZMAX + M1 * H + M1 * LDH + 2 * M1);
 }
 
 int sm_count() {
