@@ -37,6 +37,13 @@ constexpr int LDP = 18;                        // padded pooled row
 template <int C>
 struct PoolPad { static constexpr int value = C == 8 ? LDP * LDP : LDP * LDP + 2; };
 
+// Forward kernel: strides that make the conv2 tensor-core fragments conflict-free (bank = 8 t + g for lanes (g, t)).
+struct FwdPad {
+    static constexpr int PPAD = LDP * LDP + 4;                               // 328 = 8 mod 32
+};
+template <int C>
+struct FwdLdw2 { static constexpr int value = C == 16 ? 24 : 8; };            // 24 t + g / 8 t + g: 32 distinct banks
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -335,32 +342,32 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                          const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ ab1,
                          const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ x2,
                          double* __restrict__ stats2, float* __restrict__ e1, unsigned char* __restrict__ idx1) {
-    constexpr int PPAD = PoolPad<C>::value;
+    constexpr int PPAD = FwdPad::PPAD;           // channel stride of the pooled map: 8 mod 32 (conflict-free A fragments)
+    constexpr int LDW2 = FwdLdw2<C>::value;        // row stride of the conv2 weights [tap][ci][co]: 8 t + g distinct banks
     extern __shared__ __align__(16) float smem[];
     float* sImg = smem;                          // [4][35][36]
     float* sW1 = sImg + CIN * IMGPAD;            // [36 taps][C]
     float* sP = sW1 + NTAP * C;                  // [C][PPAD]
-    float* sW2 = sP + ((C * PPAD + 3) & ~3);     // [C*9 taps][C out]
-    float* sAB = sW2 + 9 * C * C;                // [2C]
+    float* sW2 = sP + ((C * PPAD + 3) & ~3);     // [9 taps][C in][LDW2]   (C out used)
+    float* sAB = sW2 + 9 * C * LDW2;             // [2C]
     float* sred = sAB + 2 * C;                   // [8][2C]
     for (int i = threadIdx.x; i < NTAP * C; i += MGGAN_THREADS) {
         int c = i / NTAP, tap = i - c * NTAP;
         sW1[tap * C + c] = __ldg(W1 + i);
     }
     for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
-        int co = i / (9 * C), r = i - co * 9 * C;
-        sW2[r * C + co] = __ldg(W2 + i);
+        int co = i / (9 * C), r = i - co * 9 * C, ci = r / 9, tap = r - ci * 9;
+        sW2[(tap * C + ci) * LDW2 + co] = __ldg(W2 + i);
     }
     if (threadIdx.x < 2 * C) sAB[threadIdx.x] = __ldg(ab1 + threadIdx.x);
     for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
     for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) sP[i] = 0.f;
-    constexpr int PX = C / 4;                     // pixels per thread in the conv2 stage (4 x PX outputs per thread)
-    float st[8];                                  // BatchNorm-2 partial sums of this thread's 4 output channels
+    constexpr int NT = C / 8;                     // conv2 n-tiles (8 output channels each) = k-steps per tap (8 input channels)
+    float st[4 * NT];                             // BatchNorm-2 partial sums: channels 8 j + 2 t + {0, 1}: sum [2j + e], squares [2NT + 2j + e]
 #pragma unroll
-    for (int c = 0; c < 8; ++c) st[c] = 0.f;
+    for (int c = 0; c < 4 * NT; ++c) st[c] = 0.f;
     const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
-    const int cq = threadIdx.x % (C / 4), gp = threadIdx.x / (C / 4);
-    const int gy = gp / (P1 / PX), gx0 = (gp % (P1 / PX)) * PX;
+    const int warp = threadIdx.x >> 5, g8 = (threadIdx.x & 31) >> 2, t4 = threadIdx.x & 3;
 
     for (int n = blockIdx.x; n < N; n += gridDim.x) {
         const int src = rows ? rows[n] : n;
@@ -422,46 +429,62 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             }
         }
         __syncthreads();
-        {   // conv2: thread = PX adjacent pixels of a row x 4 output channels; (PX+2)/2 LDS.64 + 3 LDS.128 per 12 PX FMAs
-            float acc2[PX][4];
+        {   // conv2 as warp-level 3 x TF32 tensor-core products (common.cuh): m-tile = one output row (16 pixels), n-tile =
+            // 8 output channels, k-step = 8 input channels of one tap; every fragment element is a conflict-free LDS.32.
+            // The FP32 register-tile form of this stage was half of the kernel's FMA issue and most of its LDS traffic.
+#pragma unroll 1
+            for (int rr = 0; rr < 2; ++rr) {
+                const int y = warp * 2 + rr;
+                float acc[NT][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float bv = __ldg(b2 + cq * 4 + c);
+                for (int j = 0; j < NT; ++j) {
+                    const float ba = __ldg(b2 + 8 * j + 2 * t4), bb = __ldg(b2 + 8 * j + 2 * t4 + 1);
+                    acc[j][0] = ba; acc[j][1] = bb; acc[j][2] = ba; acc[j][3] = bb;
+                }
 #pragma unroll
-                for (int j = 0; j < PX; ++j) acc2[j][c] = bv;
-            }
-#pragma unroll 2
-            for (int ci = 0; ci < C; ++ci)
+                for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    float pv[PX + 2];
-                    const float* rp = sP + ci * PPAD + (gy + ky) * LDP + gx0;
+                    for (int ks = 0; ks < NT; ++ks) {
+                        const float* pa = sP + (ks * 8 + t4) * PPAD + (y + tap / 3) * LDP + g8 + tap % 3;
+                        uint32_t ah[4], al[4];
+                        tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8], ah[1], al[1]);
+                        tf32_split(pa[4 * PPAD], ah[2], al[2]); tf32_split(pa[4 * PPAD + 8], ah[3], al[3]);
+                        const float* pb = sW2 + (tap * C + ks * 8 + t4) * LDW2 + g8;
 #pragma unroll
-                    for (int m = 0; m < PX + 2; m += 2) {
-                        float2 t2 = *reinterpret_cast<const float2*>(rp + m);
-                        pv[m] = t2.x; pv[m + 1] = t2.y;
-                    }
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float4 w = ld4(sW2 + (ci * 9 + ky * 3 + kx) * C + cq * 4);
-#pragma unroll
-                        for (int j = 0; j < PX; ++j) {
-                            acc2[j][0] = fmaf(pv[j + kx], w.x, acc2[j][0]); acc2[j][1] = fmaf(pv[j + kx], w.y, acc2[j][1]);
-                            acc2[j][2] = fmaf(pv[j + kx], w.z, acc2[j][2]); acc2[j][3] = fmaf(pv[j + kx], w.w, acc2[j][3]);
-                        }
+                        for (int j = 0; j < NT; ++j) mma_3xtf32(acc[j], ah, al, pb[8 * j], pb[4 * LDW2 + 8 * j]);
                     }
                 }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float* o = x2 + ((size_t)n * C + cq * 4 + c) * P1SQ + gy * P1 + gx0;
-                if (PX == 4) st4(o, make_float4(acc2[0][c], acc2[1][c], acc2[2 % PX][c], acc2[3 % PX][c]));
-                else *reinterpret_cast<float2*>(o) = make_float2(acc2[0][c], acc2[1][c]);
-#pragma unroll
-                for (int j = 0; j < PX; ++j) { st[c] += acc2[j][c]; st[4 + c] = fmaf(acc2[j][c], acc2[j][c], st[4 + c]); }
+                for (int j = 0; j < NT; ++j) {
+                    float* o = x2 + ((size_t)n * C + 8 * j + 2 * t4) * P1SQ + y * P1 + g8;
+                    o[0] = acc[j][0]; o[8] = acc[j][2]; o[P1SQ] = acc[j][1]; o[P1SQ + 8] = acc[j][3];
+                    st[2 * j] += acc[j][0] + acc[j][2];
+                    st[2 * j + 1] += acc[j][1] + acc[j][3];
+                    st[2 * NT + 2 * j] = fmaf(acc[j][0], acc[j][0], fmaf(acc[j][2], acc[j][2], st[2 * NT + 2 * j]));
+                    st[2 * NT + 2 * j + 1] = fmaf(acc[j][1], acc[j][1], fmaf(acc[j][3], acc[j][3], st[2 * NT + 2 * j + 1]));
+                }
             }
         }
     }
-    if (stats2 != nullptr) quad_reduce_to_global<C>(st, cq, stats2, reinterpret_cast<double*>(sred));
+    if (stats2 != nullptr) {     // lanes that differ in g hold the same channels: shuffle, then shared / global double atomics
+        double* sd = reinterpret_cast<double*>(sred);
+        __syncthreads();
+        if (threadIdx.x < 2 * C) sd[threadIdx.x] = 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4 * NT; ++i) {
+            float v = st[i];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g8 == 0) {
+                const int sq = i >= 2 * NT, jj = (i - (sq ? 2 * NT : 0));
+                atomicAdd(sd + (sq ? C : 0) + 8 * (jj >> 1) + 2 * t4 + (jj & 1), (double)v);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * C) atomicAdd(stats2 + threadIdx.x, sd[threadIdx.x]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -929,7 +952,7 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
 
 
 template <int C>
-size_t fused_fwd_smem() { constexpr int PPAD = PoolPad<C>::value; return sizeof(float) * (CIN * IMGPAD + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * C + 2 * C + 8 * 2 * C); }
+size_t fused_fwd_smem() { constexpr int PPAD = FwdPad::PPAD; return sizeof(float) * (CIN * IMGPAD + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * FwdLdw2<C>::value + 2 * C + 8 * 2 * C); }
 template <int C>
 size_t fused_bwd_smem() {
     constexpr int PPAD = PoolPad<C>::value;
