@@ -41,6 +41,11 @@ struct PoolPad { static constexpr int value = C == 8 ? LDP * LDP : LDP * LDP + 2
 struct FwdPad {
     static constexpr int PPAD = LDP * LDP + 4;                               // 328 = 8 mod 32
 };
+// Backward kernel: dx2 / p1 channel stride 324 (= 4 mod 32) and input-gradient weight rows of 20 floats.
+struct BwdPad {
+    static constexpr int PPAD = LDP * LDP;
+    static constexpr int LDWD = 20;
+};
 template <int C>
 struct FwdLdw2 { static constexpr int value = C == 16 ? 24 : 8; };            // 24 t + g / 8 t + g: 32 distinct banks
 
@@ -432,37 +437,46 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
         {   // conv2 as warp-level 3 x TF32 tensor-core products (common.cuh): m-tile = one output row (16 pixels), n-tile =
             // 8 output channels, k-step = 8 input channels of one tap; every fragment element is a conflict-free LDS.32.
             // The FP32 register-tile form of this stage was half of the kernel's FMA issue and most of its LDS traffic.
-#pragma unroll 1
-            for (int rr = 0; rr < 2; ++rr) {
-                const int y = warp * 2 + rr;
-                float acc[NT][4];
+            {
+                const int y = warp * 2;                   // the warp's two rows are interleaved: 2 NT independent accumulator chains
+                float acc[2][NT][4];
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     const float ba = __ldg(b2 + 8 * j + 2 * t4), bb = __ldg(b2 + 8 * j + 2 * t4 + 1);
-                    acc[j][0] = ba; acc[j][1] = bb; acc[j][2] = ba; acc[j][3] = bb;
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) { acc[rr][j][0] = ba; acc[rr][j][1] = bb; acc[rr][j][2] = ba; acc[rr][j][3] = bb; }
                 }
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
                     for (int ks = 0; ks < NT; ++ks) {
-                        const float* pa = sP + (ks * 8 + t4) * PPAD + (y + tap / 3) * LDP + g8 + tap % 3;
-                        uint32_t ah[4], al[4];
-                        tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8], ah[1], al[1]);
-                        tf32_split(pa[4 * PPAD], ah[2], al[2]); tf32_split(pa[4 * PPAD + 8], ah[3], al[3]);
                         const float* pb = sW2 + (tap * C + ks * 8 + t4) * LDW2 + g8;
+                        float b0[NT], b1[NT];
 #pragma unroll
-                        for (int j = 0; j < NT; ++j) mma_3xtf32(acc[j], ah, al, pb[8 * j], pb[4 * LDW2 + 8 * j]);
+                        for (int j = 0; j < NT; ++j) { b0[j] = pb[8 * j]; b1[j] = pb[4 * LDW2 + 8 * j]; }
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const float* pa = sP + (ks * 8 + t4) * PPAD + (y + rr + tap / 3) * LDP + g8 + tap % 3;
+                            uint32_t ah[4], al[4];
+                            tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8], ah[1], al[1]);
+                            tf32_split(pa[4 * PPAD], ah[2], al[2]); tf32_split(pa[4 * PPAD + 8], ah[3], al[3]);
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) mma_3xtf32(acc[rr][j], ah, al, b0[j], b1[j]);
+                        }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    float* o = x2 + ((size_t)n * C + 8 * j + 2 * t4) * P1SQ + y * P1 + g8;
-                    o[0] = acc[j][0]; o[8] = acc[j][2]; o[P1SQ] = acc[j][1]; o[P1SQ + 8] = acc[j][3];
-                    st[2 * j] += acc[j][0] + acc[j][2];
-                    st[2 * j + 1] += acc[j][1] + acc[j][3];
-                    st[2 * NT + 2 * j] = fmaf(acc[j][0], acc[j][0], fmaf(acc[j][2], acc[j][2], st[2 * NT + 2 * j]));
-                    st[2 * NT + 2 * j + 1] = fmaf(acc[j][1], acc[j][1], fmaf(acc[j][3], acc[j][3], st[2 * NT + 2 * j + 1]));
-                }
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        float* o = x2 + ((size_t)n * C + 8 * j + 2 * t4) * P1SQ + (y + rr) * P1 + g8;
+                        const float* a = acc[rr][j];
+                        o[0] = a[0]; o[8] = a[2]; o[P1SQ] = a[1]; o[P1SQ + 8] = a[3];
+                        st[2 * j] += a[0] + a[2];
+                        st[2 * j + 1] += a[1] + a[3];
+                        st[2 * NT + 2 * j] = fmaf(a[0], a[0], fmaf(a[2], a[2], st[2 * NT + 2 * j]));
+                        st[2 * NT + 2 * j + 1] = fmaf(a[1], a[1], fmaf(a[3], a[3], st[2 * NT + 2 * j + 1]));
+                    }
             }
         }
     }
@@ -502,26 +516,26 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                          const float* __restrict__ W2, const float* __restrict__ dy2,
                          const unsigned char* __restrict__ idx2, float* __restrict__ dW2, float* __restrict__ dbias2,
                          float* __restrict__ S1, double* __restrict__ sums1) {
-    constexpr int PX = C / 4;                            // pixels per thread in the conv2 input-gradient stage
-    constexpr int NITEM = C * C / 4;                     // (4 output channels, input channel) items of the conv2 weight gradient
-    constexpr int PG = MGGAN_THREADS / NITEM;            // pixel-row groups (4 or 16)
-    constexpr int ROWS_PG = P1 / PG;                     // rows per group (4 or 1)
+    constexpr int NT = C / 8;                            // 8-channel tiles (n-tiles; also k-steps per tap of the input gradient)
+    constexpr int UNITS = 9 * NT;                        // (tap, input-channel tile) units of the conv2 weight gradient
+    constexpr int UPW = (UNITS + 7) / 8;                 // units per warp (3 or 2)
     constexpr int QG = MGGAN_THREADS / (C * CIN);        // pooled-pixel groups for the sparse conv1 term (4 or 8)
     constexpr int Q_PER = P1SQ / QG;
     constexpr int LDY = P1SQ + 4;                        // channel stride of sDY: neighbouring channels on different banks
-    constexpr int PPAD = PoolPad<C>::value;
+    constexpr int PPAD = BwdPad::PPAD;                   // 324 = 4 mod 32: bank 4 g + t (weight gradient) / 8 t + g (input gradient)
+    constexpr int LDWD = BwdPad::LDWD;                   // 20: rows co = c0 + 2t of the input-gradient B fragment 8 banks apart
     extern __shared__ __align__(16) float smem[];
     float* sDX = smem;                                   // [C][PPAD]  dx2 with zero halo
     float* sP = sDX + C * PPAD;                          // [C][PPAD]  p1 with zero halo
-    float* sWT = sP + ((C * PPAD + 3) & ~3);             // [(co*9+tap)][ci]
-    float* sDY = sWT + 9 * C * C;                        // [C][LDY] dy1 (sparse values, dense layout)
+    float* sWT = sP + ((C * PPAD + 3) & ~3);             // [tap][co][LDWD]  (ci used)
+    float* sDY = sWT + 9 * C * LDWD;                     // [C][LDY] dy1 (sparse values, dense layout)
     float* sImg = sDY + C * LDY;                         // [4][35][36]
     float* sPar = sImg + CIN * IMGPAD_BWD;                   // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
     float* sred = sPar + 10 * C;                         // [8][2C]
     unsigned char* sIdx = reinterpret_cast<unsigned char*>(sred + 8 * 2 * C);    // [C][256]
     for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
         int co = i / (9 * C), r = i - co * 9 * C, ci = r / 9, tap = r - ci * 9;
-        sWT[(co * 9 + tap) * C + ci] = __ldg(W2 + i);
+        sWT[(tap * C + co) * LDWD + ci] = __ldg(W2 + i);
     }
     if (threadIdx.x < 2 * C) {
         sPar[threadIdx.x] = __ldg(ab1 + threadIdx.x);
@@ -533,25 +547,18 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) { sDX[i] = 0.f; sP[i] = 0.f; }
     for (int i = threadIdx.x; i < CIN * IMGPAD_BWD; i += MGGAN_THREADS) sImg[i] = 0.f;
     const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
-    // conv2 weight gradient: thread = (4 output channels, input channel, pixel-row group)
-    const int item = threadIdx.x % NITEM, pg = threadIdx.x / NITEM;
-    const int w_coq = item / C, w_ci = item % C;
-    // conv2 input gradient: thread = (PX adjacent pixels, 4 input channels)
-    const int cq = threadIdx.x % (C / 4), gp = threadIdx.x / (C / 4);
-    const int gy = gp / (P1 / PX), gx0 = (gp % (P1 / PX)) * PX;
+    const int warp = threadIdx.x >> 5, g8 = (threadIdx.x & 31) >> 2, t4 = threadIdx.x & 3;     // MMA fragment coordinates
     const int s_c = threadIdx.x / (CIN * QG), s_ci = (threadIdx.x / QG) % CIN, s_qg = threadIdx.x % QG;
-    float wacc[4][9], sacc[9];
+    float wacc[UPW][4], sacc[9];                         // wacc[i]: C fragment of unit warp + 8 i (kept across agents)
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        sacc[i] = 0.f;
+    for (int i = 0; i < 9; ++i) sacc[i] = 0.f;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) wacc[a][i] = 0.f;
-    }
-    float dbs[C], st[8];
+    for (int i = 0; i < UPW; ++i) { wacc[i][0] = 0.f; wacc[i][1] = 0.f; wacc[i][2] = 0.f; wacc[i][3] = 0.f; }
+    float dbs[C], st[4 * NT];                            // st: BatchNorm-1 sums of channels 8 j + 2 t + e: [2j + e], [2NT + 2j + e]
 #pragma unroll
     for (int c = 0; c < C; ++c) dbs[c] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) st[c] = 0.f;
+    for (int c = 0; c < 4 * NT; ++c) st[c] = 0.f;
 
     for (int n = blockIdx.x; n < N; n += gridDim.x) {
         const int src = rows ? rows[n] : n;
@@ -581,86 +588,70 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             }
         }
         __syncthreads();
-        {   // conv2 weight gradient: 3 new p1 values + 4 dx values feed 36 FMAs per pixel
-            const float* pp = sP + w_ci * PPAD;
-            const float* dxp = sDX + (w_coq * 4) * PPAD;
+        {   // conv2 weight gradient dW2[co][ci][tap] = sum_pix dx2[co][pix] p1[ci][pix + tap] as warp-level 3 x TF32 products:
+            // M = output channels, N = 8 input channels, K = pixels (8 consecutive x per step); a warp owns the units
+            // (tap, ci tile) warp, warp + 8, warp + 16 and keeps their C fragments across agents.
 #pragma unroll 1
-            for (int yy = pg * ROWS_PG; yy < (pg + 1) * ROWS_PG; ++yy) {
-                float c0[3], c1[3], c2[3];
+            for (int ks = 0; ks < 2 * P1; ++ks) {
+                const int yy = ks >> 1, x0 = (ks & 1) * 8;
+                const float* pa = sDX + g8 * PPAD + (yy + 1) * LDP + x0 + t4 + 1;
+                uint32_t ah[4], al[4];
+                tf32_split(pa[0], ah[0], al[0]);
+                tf32_split(pa[4], ah[2], al[2]);
+                if (C == 16) {
+                    tf32_split(pa[8 * PPAD], ah[1], al[1]);
+                    tf32_split(pa[8 * PPAD + 4], ah[3], al[3]);
+                } else {
+                    ah[1] = al[1] = ah[3] = al[3] = 0u;
+                }
 #pragma unroll
-                for (int r = 0; r < 3; ++r) { c0[r] = pp[(yy + r) * LDP]; c1[r] = pp[(yy + r) * LDP + 1]; }
-#pragma unroll 4
-                for (int xx = 0; xx < P1; ++xx) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) c2[r] = pp[(yy + r) * LDP + xx + 2];
-                    float d[4];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) d[a] = dxp[a * PPAD + (yy + 1) * LDP + xx + 1];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            wacc[a][r * 3] = fmaf(d[a], c0[r], wacc[a][r * 3]);
-                            wacc[a][r * 3 + 1] = fmaf(d[a], c1[r], wacc[a][r * 3 + 1]);
-                            wacc[a][r * 3 + 2] = fmaf(d[a], c2[r], wacc[a][r * 3 + 2]);
-                        }
-                        c0[r] = c1[r]; c1[r] = c2[r];
+                for (int i = 0; i < UPW; ++i) {
+                    const int unit = warp + 8 * i;
+                    if (unit < UNITS) {
+                        const int tap = unit / NT, j = unit - tap * NT;
+                        const float* pb = sP + (8 * j + g8) * PPAD + (yy + tap / 3) * LDP + x0 + t4 + tap % 3;
+                        mma_3xtf32(wacc[i], ah, al, pb[0], pb[4]);
                     }
                 }
             }
         }
-        {   // conv2 input gradient at PX adjacent pixels x 4 input channels -> pool / ReLU / BN1 -> dy1
-            float acc[PX][4];
+        {   // conv2 input gradient as warp-level 3 x TF32 products: m-tile = one row of 16 pixels, N = 8 input channels,
+            // K = output channels of one tap (logical k = t, t + 4 <-> co = c0 + 2t, c0 + 2t + 1), then pool / ReLU / BN1 -> dy1
+#pragma unroll 1
+            for (int rr = 0; rr < 2; ++rr) {
+                const int yy = warp * 2 + rr;
+                float acc[NT][4];
 #pragma unroll
-            for (int j = 0; j < PX; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
-#pragma unroll 2
-            for (int co = 0; co < C; ++co)
+                for (int j = 0; j < NT; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    float dv[PX + 2];
-                    const float* rp = sDX + co * PPAD + (gy + 2 - ky) * LDP + gx0;
+                for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                    for (int m = 0; m < PX + 2; m += 2) {
-                        float2 t2 = *reinterpret_cast<const float2*>(rp + m);
-                        dv[m] = t2.x; dv[m + 1] = t2.y;
+                    for (int ks = 0; ks < NT; ++ks) {
+                        const float* pa = sDX + (ks * 8 + 2 * t4) * PPAD + (yy + 2 - tap / 3) * LDP + g8 + 2 - tap % 3;
+                        uint32_t ah[4], al[4];
+                        tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8], ah[1], al[1]);
+                        tf32_split(pa[PPAD], ah[2], al[2]); tf32_split(pa[PPAD + 8], ah[3], al[3]);
+                        const float* pb = sWT + (tap * C + ks * 8 + 2 * t4) * LDWD + g8;
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) mma_3xtf32(acc[j], ah, al, pb[8 * j], pb[LDWD + 8 * j]);
                     }
+                }
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float4 q = ld4(sWT + (co * 9 + ky * 3 + kx) * C + cq * 4);
+                for (int j = 0; j < NT; ++j)
 #pragma unroll
-                        for (int j = 0; j < PX; ++j) {
-                            const float d = dv[j + 2 - kx];
-                            acc[j][0] = fmaf(d, q.x, acc[j][0]); acc[j][1] = fmaf(d, q.y, acc[j][1]);
-                            acc[j][2] = fmaf(d, q.z, acc[j][2]); acc[j][3] = fmaf(d, q.w, acc[j][3]);
+                    for (int e = 0; e < 2; ++e) {
+                        const int ch = 8 * j + 2 * t4 + e;
+                        const float mu = sPar[2 * C + ch], is = sPar[3 * C + ch];
+#pragma unroll
+                        for (int hx = 0; hx < 2; ++hx) {
+                            const int pix = yy * P1 + g8 + 8 * hx;
+                            const float ev = __ldg(e1 + ((size_t)n * C + ch) * P1SQ + pix);
+                            const float d = (sIdx[ch * P1SQ + pix] & 4) ? acc[j][2 * hx + e] : 0.f;
+                            st[2 * j + e] += d;
+                            st[2 * NT + 2 * j + e] = fmaf(d, (ev - mu) * is, st[2 * NT + 2 * j + e]);
+                            sDY[ch * LDY + pix] = d;
                         }
                     }
-                }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int ch = cq * 4 + c, pix0 = gy * P1 + gx0;
-                const float mu = sPar[2 * C + ch], is = sPar[3 * C + ch];
-                const float* ep = e1 + ((size_t)n * C + ch) * P1SQ + pix0;
-                float ev[PX], dv[PX];
-                unsigned codes;
-                if (PX == 4) {
-                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(ep));
-                    ev[0] = e4.x; ev[1] = e4.y; ev[2 % PX] = e4.z; ev[3 % PX] = e4.w;
-                    codes = *reinterpret_cast<const unsigned*>(sIdx + ch * P1SQ + pix0);
-                } else {
-                    const float2 e2 = __ldg(reinterpret_cast<const float2*>(ep));
-                    ev[0] = e2.x; ev[1] = e2.y;
-                    codes = *reinterpret_cast<const unsigned short*>(sIdx + ch * P1SQ + pix0);
-                }
-#pragma unroll
-                for (int j = 0; j < PX; ++j) {
-                    const float d = ((codes >> (8 * j)) & 4u) ? acc[j][c] : 0.f;
-                    dv[j] = d;
-                    const float xh = (ev[j] - mu) * is;
-                    st[c] += d;
-                    st[4 + c] = fmaf(d, xh, st[4 + c]);
-                }
-                if (PX == 4) st4(sDY + ch * LDY + pix0, make_float4(dv[0], dv[1], dv[2 % PX], dv[3 % PX]));
-                else *reinterpret_cast<float2*>(sDY + ch * LDY + pix0) = make_float2(dv[0], dv[1]);
             }
         }
         __syncthreads();
@@ -681,20 +672,43 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             }
         }
     }
-    // conv2 weight gradient: merge the pixel-row groups in shared memory, one global atomic per element per CTA
-    __syncthreads();
-    for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) sDY[i] = 0.f;
-    __syncthreads();
+    // conv2 weight gradient: C fragments -> global (c0, c1: co = g, ci = 8 j + 2t + {0, 1}; c2, c3: co = g + 8)
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int t = 0; t < 9; ++t) atomicAdd(sDY + ((w_coq * 4 + a) * C + w_ci) * 9 + t, wacc[a][t]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) atomicAdd(dW2 + i, sDY[i]);
+    for (int i = 0; i < UPW; ++i) {
+        const int unit = warp + 8 * i;
+        if (unit < UNITS) {
+            const int tap = unit / NT, j = unit - tap * NT;
+            float* dst = dW2 + ((size_t)g8 * C + 8 * j + 2 * t4) * 9 + tap;
+            atomicAdd(dst, wacc[i][0]);
+            atomicAdd(dst + 9, wacc[i][1]);
+            if (C == 16) {
+                atomicAdd(dst + 8 * C * 9, wacc[i][2]);
+                atomicAdd(dst + 8 * C * 9 + 9, wacc[i][3]);
+            }
+        }
+    }
 #pragma unroll
     for (int t = 0; t < 9; ++t) atomicAdd(S1 + ((size_t)s_c * CIN + s_ci) * 9 + t, sacc[t]);
     block_reduce_to_global_f<C>(dbs, dbias2, sred);
-    quad_reduce_to_global<C>(st, cq, sums1, reinterpret_cast<double*>(sred));
+    {   // BatchNorm-1 sums: lanes that differ in g hold the same channels
+        double* sd = reinterpret_cast<double*>(sred);
+        __syncthreads();
+        if (threadIdx.x < 2 * C) sd[threadIdx.x] = 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4 * NT; ++i) {
+            float v = st[i];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g8 == 0) {
+                const int sq = i >= 2 * NT, jj = i - (sq ? 2 * NT : 0);
+                atomicAdd(sd + (sq ? C : 0) + 8 * (jj >> 1) + 2 * t4 + (jj & 1), (double)v);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * C) atomicAdd(sums1 + threadIdx.x, sd[threadIdx.x]);
+    }
 }
 
 // BatchNorm-1 backward closed form (one thread per (channel, tap), double precision):
@@ -955,8 +969,8 @@ template <int C>
 size_t fused_fwd_smem() { constexpr int PPAD = FwdPad::PPAD; return sizeof(float) * (CIN * IMGPAD + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * FwdLdw2<C>::value + 2 * C + 8 * 2 * C); }
 template <int C>
 size_t fused_bwd_smem() {
-    constexpr int PPAD = PoolPad<C>::value;
-    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * C + C * (P1SQ + 4) + CIN * IMGPAD_BWD + 10 * C + 8 * 2 * C) + C * P1SQ;
+    constexpr int PPAD = BwdPad::PPAD;
+    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * BwdPad::LDWD + C * (P1SQ + 4) + CIN * IMGPAD_BWD + 10 * C + 8 * 2 * C) + C * P1SQ;
 }
 template <int C>
 size_t attn_w_floats() { return 2 * AH * C + AH + C + 2 * C; }
