@@ -32,10 +32,6 @@ constexpr int IMGPAD = 35 * LDI;               // one padded channel
 // (ncu: 63 M of that stage's 134 M shared wavefronts were conflict replays); 8 banks apart they only meet at the margins.
 constexpr int IMGPAD_BWD = 35 * LDI + 28;
 constexpr int LDP = 18;                        // padded pooled row
-// channel stride of the pooled maps: even (8-byte aligned rows for LDS.64) and chosen so that the channels -- and, for 8
-// channels, two neighbouring rows as well -- fall on distinct banks: 326 = 6 mod 32 for 16 channels, 324 = 4 mod 32 for 8
-template <int C>
-struct PoolPad { static constexpr int value = C == 8 ? LDP * LDP : LDP * LDP + 2; };
 
 // Forward kernel: strides that make the conv2 tensor-core fragments conflict-free (bank = 8 t + g for lanes (g, t)).
 struct FwdPad {
@@ -94,32 +90,6 @@ __device__ __forceinline__ void block_reduce_to_global_f(const float (&v)[NV], f
         atomicAdd(dst + threadIdx.x, s);
     }
     __syncthreads();
-}
-
-// Per-channel sums kept by threads that own 4 channels (cq*4 .. cq*4+3): shared-memory double atomics, then one
-// global double atomicAdd per channel per CTA.  v[0..3] -> dst[cq*4 + c], v[4..7] -> dst[C + cq*4 + c].
-template <int C>
-__device__ __forceinline__ void quad_reduce_to_global(const float (&v)[8], int cq, double* __restrict__ dst, double* sd) {
-    __syncthreads();
-    if (threadIdx.x < 2 * C) sd[threadIdx.x] = 0.0;
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        atomicAdd(sd + cq * 4 + c, (double)v[c]);
-        atomicAdd(sd + C + cq * 4 + c, (double)v[4 + c]);
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * C) atomicAdd(dst + threadIdx.x, sd[threadIdx.x]);
-    __syncthreads();
-}
-
-__device__ __forceinline__ void load_image_padded(float* sImg, const float* __restrict__ img) {
-    for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
-    __syncthreads();
-    for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
-        int ci = i / IMG2, p = i - ci * IMG2, y = p / IMG, x = p - y * IMG;
-        sImg[ci * IMGPAD + (y + 1) * LDI + x + 1] = __ldg(img + i);
-    }
 }
 
 // ------------------------------------------------------------------------------------------
