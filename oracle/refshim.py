@@ -132,3 +132,47 @@ def load_reference():
                 sys.modules[k] = v
     _LOADED = ns
     return ns
+
+
+def load_reference_module(name):
+    """Import one more module of the reference (e.g. "mggan.data_utils.BaseTrajectories", "mggan.evaluation") into a
+    private namespace with the same sys.modules / sys.path swap and import-time stubs as `load_reference`."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    sys.dont_write_bytecode = True
+    saved = {k: v for k, v in sys.modules.items() if k == "mggan" or k.startswith("mggan.")}
+    for k in saved:
+        del sys.modules[k]
+    saved_path = list(sys.path)
+    sys.path.insert(0, REFERENCE_ROOT)
+    stubs = ["test_tube", "matplotlib", "matplotlib.pyplot", "matplotlib.patheffects",
+             "matplotlib.patches", "shapely", "shapely.geometry", "shapely.ops", "seaborn"]
+    saved_stubs = {k: sys.modules.get(k) for k in stubs}
+    _stub("test_tube", HyperOptArgumentParser=_HyperOptArgumentParser, Experiment=_Experiment)
+    mpl = _stub("matplotlib")
+    mpl.pyplot = _stub("matplotlib.pyplot")
+    mpl.patheffects = _stub("matplotlib.patheffects")
+    mpl.patches = _stub("matplotlib.patches", Circle=object)
+    _stub("shapely")
+    _stub("shapely.geometry", Polygon=object, MultiPolygon=object, Point=object)
+    _stub("shapely.ops", unary_union=None, cascaded_union=None)
+    _stub("seaborn")
+    try:
+        import torch
+        import numpy as np
+        rng_t = torch.random.get_rng_state()
+        rng_n = np.random.get_state()
+        mod = importlib.import_module(name)
+        torch.random.set_rng_state(rng_t)
+        np.random.set_state(rng_n)
+    finally:
+        for k in [k for k in sys.modules if k == "mggan" or k.startswith("mggan.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        sys.path[:] = saved_path
+        for k, v in saved_stubs.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
