@@ -186,6 +186,33 @@ int mggan_pm_ml_loss(const float* abs_all, const float* gt, int T, int ks, int G
                      float sigma, float weight, float inv_n, float* loss, float* dlogits, float* target_out,
                      cudaStream_t stream);
 
+/* ---- crop features cut on the device from scene images resident in HBM: BaseDataset.ImageFeatures_small,
+ * mggan/data_utils/BaseTrajectories.py:254-288 (called per agent from trajectories_scene.py:343-351).
+ * atlas: the u8 RGB pixels (H, W, 3) of every scene's `small_image`, back to back; img_off (n_images) int64 byte offsets;
+ * img_wh (n_images, 2) int32 (width, height); img_scale (n_images) = float32(1 / scaling_small) (1 for format "pixel");
+ * agent_img (N) int32 image of each agent (out of range: no image, RGB channels = -1); last_xy (N, 2) = in_xy[-1].
+ * features (N, 4, 33, 33): channels 0-2 = -1 + u8 * 2 / 256 of the box [c - 16, c + 17) around the centre pixel
+ * c = int(last_xy * scale) (zeros outside the image, like PIL's crop), channel 3 one-hot at [16, 16].  Bit-exact. */
+int mggan_scene_crop(const unsigned char* atlas, const long long* img_off, const int* img_wh, const float* img_scale,
+                     int n_images, const int* agent_img, const float* last_xy, int N, float* features,
+                     cudaStream_t stream);
+
+/* ---- evaluation metrics (scripts/evaluate.py sweep): mggan/manifold.py:9-18,70-77 via evaluation.py:101-156, and
+ * mggan/metrics.py:6-20,99-141 via evaluation.py:43-78. */
+/* traj (P, T, 2) pool of trajectories; radius (T) DOUBLES = linspace(r / T, r, T); desc (n_tests, 3) int32 =
+ * (test trajectory, first entry of its manifold in man_list, number of entries); man_list: int32 trajectory indices.
+ * inside (n_tests) bytes: 1 when at every step the test is closer than radius[t] to some manifold sample (float32
+ * distances exactly as numpy computes them; an empty manifold gives 0). */
+int mggan_tube_inside(const float* traj, int T, const double* radius, const int* desc, int n_tests,
+                      const int* man_list, unsigned char* inside, cudaStream_t stream);
+/* preds (T, K, n, 2), gt (T, n, 2) without masked agents, scene_off (S+1) int32, scene_scale (S) or NULL (pixel datasets
+ * scale coordinates by 1 / ratio).  Row sc of ade / fde (S, K) doubles: entry kk-1 = min over the first kk samples of the
+ * scene's summed displacement error (all steps / final step); mode (S, K) int32: agents whose best final displacement
+ * among the first kk samples is < mode_thresh.  K <= 64. */
+int mggan_min_ade_fde(const float* preds, const float* gt, int T, int K, int n, const int* scene_off, int n_scenes,
+                      const float* scene_scale, float mode_thresh, double* ade, double* fde, int* mode,
+                      cudaStream_t stream);
+
 /* ---- optimiser: clip_grad_norm_ + AdamW, train.py:131-135,209-213,656-658; abstract_train.py:45-57 */
 #define MGGAN_TABLE_MAX 64
 typedef struct MgganTensorTable {

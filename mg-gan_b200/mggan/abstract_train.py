@@ -60,6 +60,7 @@ class MultiGeneratorGAN(abc.ABC):
         self._graph = None                 # mggan.graph.GraphedIteration while capturing
         self._graphs = []                  # captured iterations (one per batch structure, most recent first)
         self._graph_seen = None            # structure key of the previous eager iteration
+        self.scene_images = None           # SceneImageStore: crops are cut on the device for batches carrying `image_ids`
         # GAN objective (reference abstract_train.py:61-85): phi_1 (D on real), phi_2 (D on fake), phi_3 (G on fake), each a
         # (loss kernel, which label, sign) triple applied to the discriminator output with a scalar smoothed label
         from mggan import kernels as K
@@ -83,7 +84,18 @@ class MultiGeneratorGAN(abc.ABC):
         gt_xy = batch["gt_xy"].to(self.device, non_blocking=True)
         gt_dxdy = batch["gt_dxdy"].to(self.device, non_blocking=True)
         img = batch["features"].to(self.device, non_blocking=True) if "features" in batch else None
+        if img is None and "image_ids" in batch:
+            # crops cut on the device from the resident scene images (mggan_scene_crop) instead of a host-built
+            # `features` tensor: 4 bytes per agent cross PCIe instead of 17,424
+            if self.scene_images is None:
+                raise RuntimeError("the batch carries image_ids but no SceneImageStore is attached "
+                                   "(trainer.attach_scene_images(dataset.scene_image_store()))")
+            img = self.scene_images.crop(batch["image_ids"], in_xy[-1])
         return in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img
+
+    def attach_scene_images(self, store):
+        """Keep a dataset's scene images resident in HBM (mggan/data_utils/scene_images.py)."""
+        self.scene_images = store
 
     def _prepare(self, batch):
         """Collated batch (host or device tensors) -> device tensors + NaN loss mask.  The reference always
@@ -210,12 +222,20 @@ class MultiGeneratorGAN(abc.ABC):
     def _loaders(self):
         kw = dict(dataset=self.config.dataset, batch_size=self.config.batch_size, workers=self.config.workers,
                   num_scenes=getattr(self.config, "synthetic_scenes", 64),
-                  with_img=getattr(self.config, "scene_dim", 64) > 0, seed=getattr(self.config, "seed", 42))
+                  with_img=getattr(self.config, "scene_dim", 64) > 0, seed=getattr(self.config, "seed", 42),
+                  images="resident" if getattr(self.config, "resident_images", False) else "agent")
         return (get_dataloader(phase="train", augment=self.config.augment, shuffle=True, **kw),
                 get_dataloader(phase="val", augment=False, shuffle=False, **kw))
 
     def train(self):
         train_loader, val_loader = self._loaders()
+        if getattr(self.config, "resident_images", False) and getattr(self.config, "scene_dim", 64) > 0:
+            # one store for both phases: validation image ids follow the training ones
+            from mggan.data_utils.scene_images import SceneImageStore
+            tr_ds, va_ds = train_loader.dataset, val_loader.dataset
+            va_ds.image_id_offset = len(tr_ds)
+            self.attach_scene_images(SceneImageStore(tr_ds.scene_image_list() + va_ds.scene_image_list(),
+                                                     tr_ds.scaling_small, self.device))
         total_iterations = 0
         track_metric = "val/ADE k=20"
         min_track_metric = math.inf

@@ -62,6 +62,9 @@ SIGNATURES = {
     "mggan_mse_scalar_label": "pifppfpps",
     "mggan_ce_generators": "piippfpps",
     "mggan_pm_ml_loss": "ppiiiipfffppps",
+    "mggan_scene_crop": "ppppippips",
+    "mggan_tube_inside": "pippipps",
+    "mggan_min_ade_fde": "ppiiipipfppps",
     "mggan_grad_sqnorm": "tips",
     "mggan_clip_adamw": "tipfffffffs",
     "mggan_multi_copy": "tis",

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader, Dataset
 
-from mggan.synthetic import SCENE_SHAPES, make_batch, scene_sizes
+from mggan.synthetic import SCALING_SMALL, SCENE_SHAPES, make_batch, make_image_batch, make_scene_image, scene_sizes
 
 _PHASE_SEED = {"train": 0, "val": 1, "test": 2}
 
@@ -19,9 +19,13 @@ _PHASE_SEED = {"train": 0, "val": 1, "test": 2}
 class SyntheticScenes(Dataset):
     """One item = one scene in the `seq_collate_scene` field layout."""
 
-    def __init__(self, shape, num_scenes, phase="train", with_img=True, seed=42):
+    def __init__(self, shape, num_scenes, phase="train", with_img=True, seed=42, images="agent"):
+        """images: "agent" = an independent texture per agent (default); "host_crop" = `features` cut on the host from one
+        image per scene (the reference's pipeline); "resident" = items carry `image_ids` and the crops are cut on the
+        device from `scene_image_store()` (mggan/data_utils/scene_images.py)."""
+        assert images in ("agent", "host_crop", "resident"), images
         rng = np.random.default_rng(seed * 31 + _PHASE_SEED.get(phase, 3))
-        self.shape, self.with_img = shape, with_img
+        self.shape, self.with_img, self.images = shape, with_img, images
         self.sizes = scene_sizes(shape, num_scenes, rng)
         self.seeds = rng.integers(0, 2 ** 31 - 1, size=num_scenes).tolist()
         self.multi_future = 4 if shape == "gofp" else 1
@@ -48,9 +52,27 @@ class SyntheticScenes(Dataset):
     scene_list = property(lambda self: [self.dataset_name] * len(self._eval_arrays()[2]))
 
     def __getitem__(self, i):
-        b = make_batch([self.sizes[i]], seed=self.seeds[i], with_img=self.with_img, nan_frac=self.nan_frac,
-                       multi_future=self.multi_future)
-        return b
+        if self.with_img and self.images != "agent":
+            # multi-future scenes are replicas of one scene: they share its image
+            b, _ = make_image_batch([self.sizes[i]], seed=self.seeds[i], resident=self.images == "resident",
+                                    nan_frac=self.nan_frac, multi_future=self.multi_future)
+            if "image_ids" in b:
+                b["image_ids"][:] = self.image_id_offset + i
+            return b
+        return make_batch([self.sizes[i]], seed=self.seeds[i], with_img=self.with_img, nan_frac=self.nan_frac,
+                          multi_future=self.multi_future)
+
+    image_id_offset = 0          # added to the item index when several datasets share one SceneImageStore
+    scaling_small = SCALING_SMALL
+
+    def scene_image_list(self):
+        return [make_scene_image(self.seeds[i] * 1000) for i in range(len(self))]
+
+    def scene_image_store(self, device="cuda"):
+        """The dataset's scene images uploaded once (image id = image_id_offset + item index)."""
+        from mggan.data_utils.scene_images import SceneImageStore
+        assert self.image_id_offset == 0
+        return SceneImageStore(self.scene_image_list(), SCALING_SMALL, device)
 
 
 def seq_collate_scene(items):
@@ -63,16 +85,18 @@ def seq_collate_scene(items):
         out[key] = torch.from_numpy(np.concatenate([it[key] for it in items], 1))
     if "features" in items[0]:
         out["features"] = torch.from_numpy(np.concatenate([it["features"] for it in items], 0))
+    if "image_ids" in items[0]:
+        out["image_ids"] = torch.from_numpy(np.concatenate([it["image_ids"] for it in items], 0))
     out["seq_start_end"] = sse
     return out
 
 
 def get_dataloader(dataset, phase="train", augment=False, batch_size=8, workers=0, shuffle=False, split=None,
-                   num_scenes=64, with_img=True, seed=42):
+                   num_scenes=64, with_img=True, seed=42, images="agent"):
     if not dataset.startswith("synthetic_"):
         raise NotImplementedError(
             f"dataset '{dataset}': the reference datasets (data.zip) are not shipped; use synthetic_"
             f"{{{','.join(SCENE_SHAPES)}}}")
     shape = dataset[len("synthetic_"):]
-    ds = SyntheticScenes(shape, num_scenes, phase, with_img, seed)
+    ds = SyntheticScenes(shape, num_scenes, phase, with_img, seed, images)
     return DataLoader(ds, batch_size=batch_size, shuffle=shuffle, num_workers=workers, collate_fn=seq_collate_scene)

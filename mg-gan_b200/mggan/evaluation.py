@@ -81,3 +81,77 @@ def evaluate_precision_recall(eval_ds, all_preds, manifold_radius, n_preds_list,
                 pred_man = Manifold(cur_preds[:n_samples], manifold_radius)
                 accum[f"Recall k={n_samples}"] += pred_man.compute_metric(gt_man_samples), 1.0
     return defaultdict(float, {key: value / count for key, (value, count) in accum.items()})
+
+
+# ------------------------------------------------------------------------------------------------ device metrics
+# Same results as the two host functions above, with the arithmetic in sm_100a kernels (csrc/data_eval.cu); the
+# bookkeeping (masks, groups, descriptors) stays on the host like the reference's.  SURVEY.md 8f #3.
+def _scene_scales(eval_ds, n_scenes):
+    if eval_ds.dataset_name in ("stanford", "gofp"):        # pixel datasets (reference evaluation.py:60-61)
+        return np.array([1.0 / eval_ds.images[eval_ds.scene_list[i]]["ratio"] for i in range(n_scenes)], np.float32)
+    return None
+
+
+def evaluate_ade_fde_cuda(eval_ds, preds, n_preds_list, device="cuda"):
+    """`evaluate_ade_fde` on the device: preds (pred_len, k, N_total, 2) numpy or tensor.  One launch gives every
+    k = 1 .. K at once (prefix minima over the samples)."""
+    from mggan import kernels as K
+    gt_trajs = to_numpy(eval_ds.pred_traj)
+    pred_mask = np.isnan(gt_trajs).any(-1).any(-1)
+    start_end = adjust_seq_start_end_for_mask(eval_ds.seq_start_end, pred_mask)
+    keep = torch.from_numpy(np.where(~pred_mask)[0]).to(device)
+    p = torch.as_tensor(preds).to(device=device, dtype=torch.float32)
+    assert max(n_preds_list) <= p.shape[1], (max(n_preds_list), p.shape)
+    p = p.index_select(2, keep).contiguous()
+    gt = torch.from_numpy(gt_trajs[~pred_mask]).transpose(0, 1).contiguous().to(device)
+    off = torch.tensor([start_end[0][0]] + [e for _, e in start_end], dtype=torch.int32, device=device)
+    scales = _scene_scales(eval_ds, len(start_end))
+    ade, fde, mode = K.min_ade_fde(p, gt, off, None if scales is None else torch.from_numpy(scales).to(device))
+    ade, fde, mode = ade.sum(0).cpu().numpy(), fde.sum(0).cpu().numpy(), mode.sum(0).cpu().numpy()
+    n, pred_len = gt.shape[1], gt.shape[0]
+    out = defaultdict(float)
+    for k in n_preds_list:
+        out[f"FDE k={k}"] = fde[k - 1] / n
+        out[f"ADE k={k}"] = ade[k - 1] / (pred_len * n)
+        out[f"Mode k={k}"] = mode[k - 1] / n
+    return out
+
+
+def evaluate_precision_recall_cuda(eval_ds, all_preds, manifold_radius, n_preds_list, device="cuda"):
+    """`evaluate_precision_recall` with every tube test of the sweep in ONE launch of `mggan_tube_inside`: trajectories go
+    into one pool (ground-truth futures, then predictions agent-major), each test is a descriptor (test trajectory,
+    manifold = a run of trajectory indices)."""
+    from mggan import kernels as K
+    gt_trajs = to_numpy(eval_ds.pred_traj).astype(np.float32)
+    N, pred_len = gt_trajs.shape[:2]
+    num_preds = max(n_preds_list)
+    valid = np.where(~np.isnan(gt_trajs).any(-1).any(-1))[0]
+    p = torch.as_tensor(all_preds).to(device=device, dtype=torch.float32)          # (pred_len, k, N, 2)
+    k = p.shape[1]
+    pool = torch.cat([torch.from_numpy(gt_trajs).to(device), p.permute(2, 1, 0, 3).reshape(N * k, pred_len, 2)])
+    desc, man_list, segments = [], [], []                  # segments: (metric key, first descriptor, descriptors)
+    for same_scene_indices in get_same_obs_indices(eval_ds):
+        for same_ped_indices in zip(*same_scene_indices):
+            peds = np.intersect1d(np.array(same_ped_indices), valid)
+            if len(peds) == 0:
+                continue
+            rows = (N + peds[:, None] * k + np.arange(k)[None, :]).reshape(-1)     # cur_preds, agent-major
+            gt_first = len(man_list)
+            man_list.extend(peds.tolist())
+            pr_first = len(man_list)
+            man_list.extend(rows[:num_preds].tolist())
+            tests = rows[:num_preds]
+            segments.append(("Precision", len(desc), len(tests)))
+            desc.extend((int(t), gt_first, len(peds)) for t in tests)
+            for n_samples in n_preds_list:
+                segments.append((f"Recall k={n_samples}", len(desc), len(peds)))
+                desc.extend((int(t), pr_first, min(n_samples, len(rows))) for t in peds)
+    if not desc:
+        return defaultdict(float)
+    radius = torch.from_numpy(np.linspace(manifold_radius / pred_len, manifold_radius, pred_len, endpoint=True)).to(device)
+    inside = K.tube_inside(pool, radius, torch.tensor(desc, dtype=torch.int32, device=device),
+                           torch.tensor(man_list, dtype=torch.int32, device=device)).cpu().numpy()
+    accum = defaultdict(lambda: np.zeros((2,)))
+    for key, first, count in segments:
+        accum[key] += np.sum(inside[first:first + count]) / count, 1.0
+    return defaultdict(float, {key: value / count for key, (value, count) in accum.items()})

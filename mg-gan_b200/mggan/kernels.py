@@ -653,3 +653,44 @@ def multi_copy(dsts, srcs):
     ent = [(ptr(d), ptr(s), None, None, d.numel(), 1.0, 1.0) for d, s in zip(dsts, srcs)]
     for tb, n in _tables(ent):
         call("mggan_multi_copy", tb, n)
+
+
+# --------------------------------------------------------------------------- data side / evaluation (no autograd)
+def scene_crop(atlas, img_off, img_wh, img_scale, agent_img, last_xy):
+    """(N, 4, 33, 33) crop features cut from the resident u8 scene-image atlas (mggan_scene_crop)."""
+    n = int(agent_img.numel())
+    last_xy = _f32(last_xy)
+    assert last_xy.shape == (n, 2) and agent_img.dtype == torch.int32 and atlas.dtype == torch.uint8
+    out = torch.empty(n, 4, 33, 33, device=last_xy.device, dtype=torch.float32)
+    call("mggan_scene_crop", ptr(atlas), ptr(img_off), ptr(img_wh), ptr(img_scale), int(img_scale.numel()),
+         ptr(agent_img.contiguous()), ptr(last_xy), n, ptr(out))
+    return out
+
+
+def tube_inside(traj, radius, desc, man_list):
+    """traj (P, T, 2) fp32, radius (T) float64, desc (n, 3) int32, man_list int32 -> (n,) bool (mggan_tube_inside)."""
+    traj = _f32(traj)
+    assert traj.dim() == 3 and traj.shape[2] == 2 and radius.dtype == torch.float64 and radius.numel() == traj.shape[1]
+    assert desc.dtype == torch.int32 and man_list.dtype == torch.int32 and desc.dim() == 2 and desc.shape[1] == 3
+    n = desc.shape[0]
+    inside = torch.empty(n, device=traj.device, dtype=torch.uint8)
+    if man_list.numel() == 0:           # keep a valid pointer for descriptors with empty manifolds
+        man_list = torch.zeros(1, device=traj.device, dtype=torch.int32)
+    call("mggan_tube_inside", ptr(traj), traj.shape[1], ptr(radius.contiguous()), ptr(desc.contiguous()), n,
+         ptr(man_list.contiguous()), ptr(inside))
+    return inside.bool()
+
+
+def min_ade_fde(preds, gt, scene_off, scene_scale=None, mode_thresh=3.0):
+    """preds (T, K, n, 2), gt (T, n, 2), scene_off (S+1) int32 -> ade, fde (S, K) float64 prefix minima over the samples,
+    mode (S, K) int32 (mggan_min_ade_fde)."""
+    preds, gt = _f32(preds), _f32(gt)
+    T, K, n, _ = preds.shape
+    assert gt.shape == (T, n, 2) and scene_off.dtype == torch.int32
+    S = scene_off.numel() - 1
+    ade = torch.empty(S, K, device=preds.device, dtype=torch.float64)
+    fde = torch.empty_like(ade)
+    mode = torch.empty(S, K, device=preds.device, dtype=torch.int32)
+    call("mggan_min_ade_fde", ptr(preds), ptr(gt), T, K, n, ptr(scene_off.contiguous()), S,
+         ptr(_f32(scene_scale)) if scene_scale is not None else None, float(mode_thresh), ptr(ade), ptr(fde), ptr(mode))
+    return ade, fde, mode

@@ -85,6 +85,9 @@ _EXTRA_FLAGS = [
                          help="0 builds G and D without the scene CNN (img=None); the reference hard-codes 64")),
     ("--synthetic_scenes", dict(type=int, default=64, help="scenes per epoch for the synthetic_* datasets")),
     ("--seed", dict(type=int, default=42)),
+    ("--resident_images", dict(type=int, default=0, choices=[0, 1],
+                               help="synthetic_* datasets: keep one image per scene resident in HBM and cut the agents' "
+                                    "33x33 crops on the device (mggan_scene_crop) instead of shipping host-built features")),
     ("--cuda_graph", dict(type=int, default=1, choices=[0, 1],
                           help="replay the training iteration as a CUDA graph when consecutive batches have the same structure")),
 ]

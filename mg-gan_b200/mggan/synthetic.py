@@ -115,3 +115,61 @@ def make_config_batch(shape, num_scenes, seed=0, with_img=True):
     if shape == "gofp":
         return make_batch(sizes, seed=seed, with_img=with_img, nan_frac=0.25, multi_future=4)
     return make_batch(sizes, seed=seed, with_img=with_img)
+
+
+# ---- scene images + crops: the reference cuts every agent's 33 x 33 crop from its scene's
+# `small_image` on the host (BaseTrajectories.py:254-288); the B200 path can keep the images in HBM and cut the crops in
+# `mggan_scene_crop` instead (mggan/data_utils/scene_images.py).  Both need scene images, which the per-agent textures
+# of `make_batch` are not: these helpers make one seeded image per scene.
+SCALING_SMALL = 0.5          # metres per small-image pixel (BaseTrajectories.py:40)
+IMAGE_HW = (64, 64)
+
+
+def make_scene_image(seed, hw=IMAGE_HW):
+    """Seeded smooth u8 RGB texture (H, W, 3)."""
+    rng = np.random.default_rng(seed)
+    h, w = hw
+    coarse = rng.integers(0, 256, size=(3, 9, 9)).astype(np.float32)
+    py, px = np.linspace(0.0, 8.0, h, dtype=np.float32), np.linspace(0.0, 8.0, w, dtype=np.float32)
+    y0, x0 = np.minimum(np.floor(py).astype(np.int64), 7), np.minimum(np.floor(px).astype(np.int64), 7)
+    fy, fx = py - y0, px - x0
+    rows = coarse[:, y0, :] * (1 - fy)[None, :, None] + coarse[:, y0 + 1, :] * fy[None, :, None]
+    img = rows[:, :, x0] * (1 - fx)[None, None, :] + rows[:, :, x0 + 1] * fx[None, None, :]
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8).transpose(1, 2, 0))
+
+
+def host_crop_features(image_u8, last_xy, scaling_small=SCALING_SMALL):
+    """The reference's HOST pipeline for a scene's agents: (n, 2) last observed positions -> (n, 4, 33, 33) features
+    (`ImageFeatures_small`, BaseTrajectories.py:254-288: centre = int(xy / scaling_small) in float32, box [c-16, c+17)
+    zero-padded like PIL's crop, -1 + u8 * 2 / 256, one-hot position channel).  Dataset-side code, like the reference's."""
+    h, w, _ = image_u8.shape
+    n = len(last_xy)
+    c = (np.asarray(last_xy, np.float32) * np.float32(1.0 / scaling_small)).astype(np.int64)
+    ys = c[:, 1, None] - CROP // 2 + np.arange(CROP)[None]                    # (n, 33)
+    xs = c[:, 0, None] - CROP // 2 + np.arange(CROP)[None]
+    ok = ((ys >= 0) & (ys < h))[:, :, None] & ((xs >= 0) & (xs < w))[:, None, :]
+    patch = image_u8[np.clip(ys, 0, h - 1)[:, :, None], np.clip(xs, 0, w - 1)[:, None, :]]      # (n, 33, 33, 3)
+    patch = np.where(ok[..., None], patch, 0).astype(np.float32)
+    feat = np.zeros((n, 4, CROP, CROP), np.float32)
+    feat[:, :3] = (-1.0 + patch * (2.0 / 256.0)).transpose(0, 3, 1, 2)
+    feat[:, 3, CROP // 2, CROP // 2] = 1.0
+    return feat
+
+
+def make_image_batch(sizes, seed=0, resident=False, first_image_id=0, **kw):
+    """`make_batch` with one scene image per entry of `sizes` (the replicas of a multi-future scene share theirs).
+    resident=False: `features` are cut on the host from the scene images (the reference's pipeline); resident=True: the
+    batch carries `image_ids` (N,) int32 instead and the crops are cut on the device from a `SceneImageStore`.
+    Returns (batch, [scene images])."""
+    batch = make_batch(sizes, seed=seed, with_img=False, **kw)
+    sse = batch["seq_start_end"]
+    rep = len(sse) // len(sizes)                     # multi_future replicas per scene
+    images = [make_scene_image(seed * 1000 + i) for i in range(len(sizes))]
+    if resident:
+        batch["image_ids"] = np.concatenate([np.full(e - s, first_image_id + j // rep, np.int32)
+                                             for j, (s, e) in enumerate(sse)])
+    else:
+        last = batch["in_xy"][-1]
+        batch["features"] = np.concatenate([host_crop_features(images[j // rep], last[s:e])
+                                            for j, (s, e) in enumerate(sse)])
+    return batch, images

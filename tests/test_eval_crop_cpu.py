@@ -75,3 +75,70 @@ def test_crop_oracle_matches_reference(crops):
     rgb = feats[:, :3]
     assert (rgb.reshape(len(feats), -1) == -1.0).all(1).any()
     assert ((rgb == -1.0).reshape(len(feats), -1).mean(1) > 0.2).sum() >= 4
+
+
+def test_device_metric_host_logic_matches_reference(ev, monkeypatch):
+    """The descriptor / offset construction and the reductions of `evaluate_*_cuda` (host logic), with the two kernels
+    replaced by straightforward torch / numpy stand-ins; the kernels themselves are checked on the GPU
+    (tests/test_gpu_zdata_eval.py)."""
+    from mggan import evaluation as E
+    from mggan import kernels as K
+
+    def fake_tube(traj, radius, desc, man_list):
+        traj, r, out = traj.numpy(), radius.numpy(), []
+        for t, f, c in desc.tolist():
+            out.append(bool(DO.tube_inside(traj[man_list[f:f + c].numpy()], traj[t][None], float(r[-1]))[0]))
+        return torch.tensor(out)
+
+    def fake_min(preds, gt, off, scale=None, mode_thresh=3.0):
+        T, Kk, n, _ = preds.shape
+        S = off.numel() - 1
+        err = (preds - gt[:, None]).pow(2).sum(-1).sqrt().double()
+        ade, fde = torch.zeros(S, Kk, dtype=torch.float64), torch.zeros(S, Kk, dtype=torch.float64)
+        mode = torch.zeros(S, Kk, dtype=torch.int32)
+        for s in range(S):
+            a, b = int(off[s]), int(off[s + 1])
+            ade[s] = torch.cummin(err[:, :, a:b].sum(0).sum(1), 0).values
+            fde[s] = torch.cummin(err[-1, :, a:b].sum(1), 0).values
+            mode[s] = (torch.cummin(err[-1, :, a:b], 0).values < mode_thresh).sum(1).int()
+        return ade, fde, mode
+
+    monkeypatch.setattr(K, "tube_inside", fake_tube)
+    monkeypatch.setattr(K, "min_ade_fde", fake_min)
+    ds, Kk = eval_ds(ev), int(ev["meta/K"])
+    nl = list(range(1, Kk + 1))
+    for name in ("pred", "near"):
+        got = E.evaluate_precision_recall_cuda(ds, ev[name + "/abs"], float(ev["meta/radius"]), nl, device="cpu")
+        assert len(got) == Kk + 1
+        for k in got:
+            assert got[k] == pytest.approx(float(ev[f"pr_{name}/{k}"]), abs=1e-12), (name, k)
+    got = E.evaluate_ade_fde_cuda(ds, ev["pred/abs"], nl, device="cpu")
+    assert len(got) == 3 * Kk
+    for k in got:
+        assert got[k] == pytest.approx(float(ev["ade_fde/" + k]), rel=1e-5), k
+
+
+def test_synthetic_scene_image_modes():
+    """Dataset side of the resident-image path: host-cut features equal the crop oracle, the resident mode carries
+    image ids that index the dataset's image list, multi-future replicas share their scene's image."""
+    from mggan.data_utils.data_loaders import get_dataloader
+    from mggan.synthetic import SCALING_SMALL, make_image_batch
+    host, images = make_image_batch([3, 5, 1], seed=4)
+    res, _ = make_image_batch([3, 5, 1], seed=4, resident=True)
+    assert "features" not in res and res["image_ids"].dtype == np.int32
+    assert res["image_ids"].tolist() == [0] * 3 + [1] * 5 + [2]
+    last = host["in_xy"][-1]
+    for a in range(9):
+        want = DO.image_features_small(images[res["image_ids"][a]], last[a], SCALING_SMALL)
+        assert np.array_equal(want, host["features"][a])
+    dl_h = get_dataloader("synthetic_gofp", batch_size=3, num_scenes=5, images="host_crop")
+    dl_r = get_dataloader("synthetic_gofp", batch_size=3, num_scenes=5, images="resident")
+    imgs = dl_r.dataset.scene_image_list()
+    assert len(imgs) == 5
+    for bh, br in zip(dl_h, dl_r):
+        assert torch.equal(bh["in_xy"], br["in_xy"]) and bh["seq_start_end"] == br["seq_start_end"]
+        ids = br["image_ids"].numpy()
+        assert ids.min() >= 0 and ids.max() < 5 and "features" not in br
+        for a in range(0, len(ids), 5):
+            want = DO.image_features_small(imgs[ids[a]], bh["in_xy"][-1, a].numpy(), SCALING_SMALL)
+            assert np.array_equal(want, bh["features"][a].numpy())
