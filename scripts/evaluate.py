@@ -15,7 +15,8 @@ import pandas as pd  # noqa: E402
 import torch  # noqa: E402
 
 from mggan.data_utils.data_loaders import get_dataloader  # noqa: E402
-from mggan.evaluation import evaluate_ade_fde, evaluate_precision_recall  # noqa: E402
+from mggan.evaluation import (evaluate_ade_fde, evaluate_ade_fde_cuda, evaluate_precision_recall,  # noqa: E402
+                              evaluate_precision_recall_cuda)
 from mggan.model.train import PiNetMultiGeneratorGAN  # noqa: E402
 
 parser = ArgumentParser()
@@ -31,6 +32,8 @@ parser.add_argument("--num_preds", default=20, type=int)
 parser.add_argument("--pred_strat", default="all", choices=["all", "sampling", "expected", "smart_expected", "rejection"])
 parser.add_argument("--no-precision-recall", action="store_true")
 parser.add_argument("--num_scenes", type=int, default=64, help="synthetic datasets: scenes to evaluate")
+parser.add_argument("--metrics_device", choices=["host", "cuda"], default="host",
+                    help="host: numpy metrics like the reference; cuda: mggan_min_ade_fde / mggan_tube_inside (same results)")
 
 AVAILABLE = ("sampling", "expected", "smart_expected", "rejection")
 
@@ -82,9 +85,11 @@ def main(argv=None):
                              ("Sigma", config.sigma)):
                 all_results[col].append(val)
             preds = m.get_predictions(loader, max(num_preds_list), strategy=pred_strat)
-            metric_dict = dict(evaluate_ade_fde(loader.dataset, preds, num_preds_list))
+            ade_fde, prec_rec = ((evaluate_ade_fde_cuda, evaluate_precision_recall_cuda) if args.metrics_device == "cuda"
+                                 else (evaluate_ade_fde, evaluate_precision_recall))
+            metric_dict = dict(ade_fde(loader.dataset, preds, num_preds_list))
             if not args.no_precision_recall:
-                metric_dict.update(evaluate_precision_recall(loader.dataset, preds, args.radius, num_preds_list))
+                metric_dict.update(prec_rec(loader.dataset, preds, args.radius, num_preds_list))
             for k, v in metric_dict.items():
                 all_results[k].append(v)
             pd.DataFrame(all_results).to_csv(output_csv)
