@@ -329,6 +329,8 @@ def discriminator_forward(sd, in_xy, in_dxdy, pred_xy, pred_dxdy, sub_batches, i
     if not unbound_output:
         out = torch.sigmoid(out) * (1 - 2 * D_EPS) + D_EPS
     out = out.mean(1).reshape(k, n_act).t()
+    if "gen_id_reconstructor.0.weight" not in sd:            # gan_type "gan": no generator-id head (:210-211)
+        return out, None
     br = _lin(sd, "gen_id_reconstructor.2", lrelu(_lin(sd, "gen_id_reconstructor.0", c), 0.2))
     return out, br.reshape(k, n_act, -1).transpose(0, 1)
 
@@ -453,7 +455,8 @@ class OracleTrainer:
         with torch.no_grad():
             (rel, ab), _, idx = self._G(b, noise, False, 1, mask, gen_idxs)
         fake, branch = self._D(b, ab, rel, mask)
-        ce = F.cross_entropy(branch.flatten(0, 1), idx.flatten())
+        # gan_type "gan" has no classifier term (train.py:181-186)
+        ce = F.cross_entropy(branch.flatten(0, 1), idx.flatten()) if branch is not None else fake.new_zeros(())
         fake_loss = self._phi(2, fake, *labels_fake).mean()
         loss = ce + real_loss + fake_loss
         grads = self._grads(self.D, loss)
@@ -476,14 +479,15 @@ class OracleTrainer:
         counts = torch.bincount(idx.flatten(), minlength=self.n_gens).to(out.dtype)
         w = 1.0 / counts[idx]                                            # train.py:92-96
         adv = (self._phi(3, out, *labels) * w).mean()
-        clf = (F.cross_entropy(branch.flatten(0, 1), idx.reshape(-1), reduction="none").reshape(idx.shape) * w).mean()
+        clf = ((F.cross_entropy(branch.flatten(0, 1), idx.reshape(-1), reduction="none").reshape(idx.shape) * w).mean()
+               if branch is not None else out.new_zeros(()))                # train.py:101-113
         loss = self.l2_w * min_l2 + adv + self.clf_w * clf
         grads = self._grads(self.G, loss)
         norm = clip_grad_norm(grads, self.clip_g)
         self.optG.step(self.G, grads)
         return {"loss": loss.detach(), "l2": min_l2.detach(), "adv": adv.detach(), "clf": clf.detach(),
                 "grads": grads, "grad_norm": norm, "abs": ab.detach(), "rel": rel.detach(),
-                "d_out": out.detach(), "branch": branch.detach()}
+                "d_out": out.detach(), "branch": branch.detach() if branch is not None else None}
 
     def net_chooser_step(self, b, noise, k_exp=1):
         mask, gt_xy, gt_dxdy = self.loss_mask(b)

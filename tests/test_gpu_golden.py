@@ -39,7 +39,8 @@ def make_config(g):
     args = get_parser().parse_args(["--num_gens", str(g["meta"]["num_gens"]), "--num_samples", str(g["meta"]["k"]),
                                     "--scene_dim", "64" if g["meta"]["with_img"] else "0",
                                     "--gan_obj", g["meta"].get("gan_obj", "NS"),
-                                    "--weighting_target", g["meta"].get("weighting_target", "ml")])
+                                    "--weighting_target", g["meta"].get("weighting_target", "ml"),
+                                    "--gan_type", g["meta"].get("gan_type", "mgan")])
     args.gpus = True
     return args
 
@@ -189,7 +190,11 @@ def _run_iterations(g, inj, tmp_path):
                 check(gd[key[7:]], v, 2e-3, key, atol=1e-6)
                 n += 1
         assert n >= 25
-        check(metrics["train/info_mgan_disc_loss"][0], r["metric/train/info_mgan_disc_loss"], 1e-3, "ce")
+        plain = g["meta"].get("gan_type", "mgan") == "gan"           # no generator-id head, no classifier terms
+        if plain:
+            assert "train/info_mgan_disc_loss" not in metrics
+        else:
+            check(metrics["train/info_mgan_disc_loss"][0], r["metric/train/info_mgan_disc_loss"], 1e-3, "ce")
         check(metrics["train/discr_loss"][0], r["metric/train/discr_loss"], 1e-3, "discr_loss")
 
         inj.noise, inj.idx, inj.labels = [r["g_noise"]], [r["g_idx"]], [lab[2]]
@@ -206,7 +211,10 @@ def _run_iterations(g, inj, tmp_path):
         assert "net_chooser.0.weight" not in gg
         check(metrics["train/L2_loss"][0], r["metric/train/L2_loss"], 1e-3, "l2")
         check(metrics["train/gen_loss"][0], r["metric/train/gen_loss"], 1e-3, "adv")
-        check(metrics["train/info_mgan_loss"][0], r["metric/train/info_mgan_loss"], 1e-3, "clf")
+        if plain:
+            assert "train/info_mgan_loss" not in metrics
+        else:
+            check(metrics["train/info_mgan_loss"][0], r["metric/train/info_mgan_loss"], 1e-3, "clf")
 
         inj.noise, inj.idx, inj.labels = [r["pm_noise"]], [torch.zeros(n_act, 1, dtype=torch.long)], []
         tr.net_chooser_step(b["in_xy"], b["in_dxdy"], gt_xy, gt_dxdy, sse, metrics, mask, img)

@@ -76,6 +76,12 @@ def test_training_iterations_objective_variants(golden_variant):
     _run_iterations(golden_variant)
 
 
+def test_training_iterations_gan_type_plain(golden_late_variant):
+    """gan_type "gan": no generator-id head, no classifier terms (discriminators.py:210-211, train.py:101,181)."""
+    assert golden_late_variant["meta"]["gan_type"] == "gan"
+    _run_iterations(golden_late_variant)
+
+
 def _run_iterations(g):
     b = batch_of(g)
     ng, k = g["meta"]["num_gens"], g["meta"]["k"]
@@ -85,7 +91,11 @@ def _run_iterations(g):
         r = g[f"it{it}"]
         lab = r["labels"].tolist()
         d = tr.discriminator_step(b, r["d_noise"][None], r["d_idx"], lab[0], lab[1])
-        close(d["ce"], r["metric/train/info_mgan_disc_loss"], what="ce")
+        plain = g["meta"].get("gan_type", "mgan") == "gan"
+        if plain:
+            assert "metric/train/info_mgan_disc_loss" not in r and "metric/train/info_mgan_loss" not in r
+        else:
+            close(d["ce"], r["metric/train/info_mgan_disc_loss"], what="ce")
         close(d["real"] + d["fake"], r["metric/train/discr_loss"], what="discr_loss")
         for n, v in r.items():
             if n.startswith("D_grad/"):
@@ -93,7 +103,8 @@ def _run_iterations(g):
         gs = tr.generator_step(b, r["g_noise"], r["g_idx"], lab[2])
         close(gs["l2"], r["metric/train/L2_loss"], what="l2")
         close(gs["adv"], r["metric/train/gen_loss"], what="adv")
-        close(gs["clf"], r["metric/train/info_mgan_loss"], what="clf")
+        if not plain:
+            close(gs["clf"], r["metric/train/info_mgan_loss"], what="clf")
         n_checked = 0
         for n, v in r.items():
             if n.startswith("G_grad/"):
