@@ -8,7 +8,7 @@ Differences from the reference, all behind the same method names:
   * per-iteration loss scalars stay on the device and are averaged once per epoch (the
     reference calls .item() seven times per iteration);
   * no global `torch.set_default_tensor_type`: tensors are created on `self.device` explicitly;
-  * only the NS (non-saturating BCE) objective is built — MM / LS / W are "next" rows;
+  * gan_obj NS / MM / LS are built; W raises NotImplementedError (it cannot run in the reference either);
   * optional data-parallel mode (`mggan.distributed`): scenes are sharded over ranks and the
     step functions all-reduce gradients, loss normalisers and BatchNorm statistics.
 """
