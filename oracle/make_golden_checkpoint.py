@@ -60,6 +60,8 @@ def main():
         for k, v in sorted(vars(args).items()):
             if v is None or callable(v) or isinstance(v, (list, dict)):
                 continue
+            if k == "gpus":
+                v = True          # what the reference's main() records for a CUDA run (train.py:671-672); this run was on CPU
             f.write(f"{k},{v}\n")
 
     # eval-mode outputs of the saved generator on the same batch (noise and PM-Network draws injected)
