@@ -167,6 +167,22 @@ class SceneIndex:
         self.max_size = max(sizes) if sizes else 0
         self.scene_off = torch.tensor(off, dtype=torch.int32, device=device)
         self.pair_off = torch.tensor(pair, dtype=torch.int32, device=device)
+        self._pairs = None
+
+    def pair_index(self):
+        """(ia, ib) int64 device tensors over the sum n_s^2 ordered in-scene pairs, scene-major then a-major (pair
+        a * n_s + b of a scene), built on first use (the pooling variant `--pool_type sgan` gathers with them)."""
+        if self._pairs is None:
+            import numpy as np
+            ia, ib = [], []
+            for a, b in self.sub_batches:
+                r = np.arange(a, b, dtype=np.int64)
+                ia.append(np.repeat(r, b - a))
+                ib.append(np.tile(r, b - a))
+            cat = (lambda v: np.concatenate(v) if v else np.zeros(0, np.int64))
+            dev = self.scene_off.device
+            self._pairs = (torch.from_numpy(cat(ia)).to(dev), torch.from_numpy(cat(ib)).to(dev))
+        return self._pairs
 
     _cache = {}
 

@@ -19,6 +19,7 @@ from mggan import kernels as K
 from mggan.model.modules.cnn import AttentionGlobal
 from mggan.model.modules.common_modules import TrajectoryEncoder
 from mggan.model.modules.social import SocialAttention
+from mggan.model.modules.social_gan import PoolHiddenNet
 
 
 class MultiDiscriminatorTrajectory(nn.Module):
@@ -27,11 +28,12 @@ class MultiDiscriminatorTrajectory(nn.Module):
         super().__init__()
         assert inp_format in ("rel", "abs", "abs_rel")
         assert gan_type in ("probgan", "mgan", "infogan", "gan")
-        if (inp_format != "rel" or gan_type not in ("mgan", "gan") or pool_type != "sways" or not global_disc
-                or num_discs != 1 or h_dim != 64):
+        assert pool_type in ("sways", "sgan")
+        if (inp_format != "rel" or gan_type not in ("mgan", "gan") or not global_disc or num_discs != 1 or h_dim != 64):
             raise NotImplementedError(
                 "B200 path covers the default discriminator: inp_format='rel', gan_type in {'mgan','gan'}, "
-                "pool_type='sways', global_disc=1, one head, h_dim=64")
+                "global_disc=1, one head, h_dim=64")
+        self.pool_type = pool_type
         if scene_dim not in (0, 64):
             raise NotImplementedError("scene_dim must be 0 or 64")
         self.inp_format, self.unbound_output, self.n_ds = inp_format, unbound_output, num_discs
@@ -42,7 +44,10 @@ class MultiDiscriminatorTrajectory(nn.Module):
                                            nn.Linear(h_dim // 2, h_dim // 2))
         self.pred_encoder = nn.Sequential(nn.Linear(pred_len * 2, h_dim), nn.LeakyReLU(0.2),
                                           nn.Linear(h_dim, h_dim // 2))
-        self.social = SocialAttention(h_dim, h_dim)
+        if pool_type == "sways":
+            self.social = SocialAttention(h_dim, h_dim)
+        else:                                        # reference discriminators.py:62-67
+            self.social = PoolHiddenNet(embedding_dim=16, h_dim=h_dim, mlp_dim=h_dim, bottleneck_dim=h_dim)
         h_dim *= 2
         if scene_dim > 0:
             self.scene_encoder = AttentionGlobal(noise_attention_dim=0, PhysFeature=True, num_layers=2, channels_cnn=8)
@@ -148,8 +153,16 @@ class MultiDiscriminatorTrajectory(nn.Module):
         if img is not None:
             per_agent = torch.cat([per_agent, self._scene(img, mask)], 1)
             w_agent = torch.cat([w_agent, w1[:, hs + 2 * he:]], 1)
-        base = K.linear(per_agent, w_agent, b1)
-        soc0 = K.linear(soc, w1[:, :hs])
+        if self.pool_type == "sgan":
+            # `seq_start_end * n_samples` makes PoolHiddenNet emit the sample-0 pooling once per sample (it concatenates one
+            # block per listed range, social_gan.py:227-228): the social term is per agent, not sample-0 only
+            per_agent = torch.cat([soc, per_agent], 1)
+            w_agent = torch.cat([w1[:, :hs], w_agent], 1)
+            base = K.linear(per_agent, w_agent, b1)
+            soc0 = torch.zeros_like(base)
+        else:
+            base = K.linear(per_agent, w_agent, b1)
+            soc0 = K.linear(soc, w1[:, :hs])
         w1p = w1[:, hs + he:hs + 2 * he]
         d2 = self.discs[0][2]
         g2 = self.gen_id_reconstructor[2] if mgan else None
@@ -171,7 +184,9 @@ class MultiDiscriminatorTrajectory(nn.Module):
             return self._forward_hoisted(in_xy, in_dxdy, pred_dxdy, seq_start_end, img, mask)
         enc = self.encode(in_xy, in_dxdy, pred_xy, pred_dxdy, mask)
         soc0 = self.social(in_xy, in_dxdy, enc[:N], seq_start_end)
-        if n_samples > 1:
+        if n_samples > 1 and self.pool_type == "sgan":
+            soc = soc0.repeat(n_samples, 1)          # one pooled block per repeated range (social_gan.py:227-228)
+        elif n_samples > 1:
             soc = torch.cat([soc0, enc.new_zeros((n_samples - 1) * N, soc0.shape[1])], 0)
         else:
             soc = soc0

@@ -14,6 +14,7 @@ from mggan import kernels as K
 from mggan.model.modules.cnn import AttentionGlobal
 from mggan.model.modules.common_modules import GeneratorOutput, RelativeDecoder, TrajectoryEncoder, get_input
 from mggan.model.modules.social import SocialAttention
+from mggan.model.modules.social_gan import PoolHiddenNet
 from mggan.utils import get_global_noise, make_mlp
 
 
@@ -24,9 +25,8 @@ class MultiGenerator(nn.Module):
         assert inp_format in ("rel", "abs", "abs_rel")
         assert num_social_modules in (0, 1, num_gens)
         assert pool_type in ("sways", "sgan")
-        if inp_format != "rel" or pool_type != "sways" or social_feat_size <= 0 or num_social_modules != 1:
-            raise NotImplementedError(
-                "B200 path covers the default configuration: inp_format='rel', pool_type='sways', one social module")
+        if inp_format != "rel" or social_feat_size <= 0 or num_social_modules != 1:
+            raise NotImplementedError("B200 path covers the default configuration: inp_format='rel', one social module")
         if encoder_h_dim != 32 or decoder_h_dim != 32 or social_feat_size != 32:
             raise NotImplementedError("B200 path: h_dim = decoder_h_dim = 32 (config.py defaults)")
         if scene_dim not in (0, 64):
@@ -41,7 +41,11 @@ class MultiGenerator(nn.Module):
         if scene_dim > 0:
             self.scene_encoder = AttentionGlobal(noise_attention_dim=0, PhysFeature=True, num_layers=2,
                                                  channels_cnn=16)
-        self.social = SocialAttention(social_feat_size, encoder_h_dim)
+        if pool_type == "sways":
+            self.social = SocialAttention(social_feat_size, encoder_h_dim)
+        else:                                        # reference standard.py:66-71
+            self.social = PoolHiddenNet(embedding_dim=embedding_dim, h_dim=encoder_h_dim, mlp_dim=social_feat_size,
+                                        bottleneck_dim=encoder_h_dim)
         self.gs = nn.ModuleList()
         for i in range(num_gens):
             decoder = RelativeDecoder(pred_len=pred_len, embedding_dim=embedding_dim, h_dim=decoder_h_dim,

@@ -42,6 +42,9 @@ CASES = {
                             flags=["--gan_obj", "MM", "--weighting_target", "endpoint"], modules=False),
     "var_ns_mgan": dict(num_gens=3, sizes=[2, 2], with_img=True, nan_frac=0.0, k=5, iters=1, seed=66,
                         flags=["--weighting_target", "mgan"], modules=False),
+    # --pool_type sgan: PoolHiddenNet instead of the Social-Ways attention in G and D (social_gan.py:157-229)
+    "var_sgan_pool": dict(num_gens=3, sizes=[3, 1, 4, 2], with_img=False, nan_frac=0.0, k=5, iters=1, seed=88,
+                          flags=["--pool_type", "sgan"], modules=False),
     # gan_type "gan": plain discriminator, no generator-id head (discriminators.py:210-211, train.py:101,181)
     "var_gan_plain": dict(num_gens=3, sizes=[3, 1, 2], with_img=True, nan_frac=0.0, k=5, iters=1, seed=77,
                           flags=["--gan_type", "gan"], modules=False),
@@ -72,11 +75,11 @@ def build(ref, case):
     args.use_pinet = True
     G = ref.standard.MultiGenerator(
         z_size=8, encoder_h_dim=32, decoder_h_dim=32, social_feat_size=32, num_gens=case["num_gens"],
-        pred_len=12, embedding_dim=16, inp_format="rel", num_social_modules=1, pool_type="sways",
+        pred_len=12, embedding_dim=16, inp_format="rel", num_social_modules=1, pool_type=args.pool_type,
         scene_dim=scene_dim, use_pinet=True)
     D = ref.discriminators.MultiDiscriminatorTrajectory(
         num_gens=case["num_gens"], num_discs=1, unbound_output=args.gan_obj in ["W", "LS"], h_dim=64, inp_format="rel",
-        pred_len=12, gan_type=args.gan_type, global_disc=1, scene_dim=scene_dim, pool_type="sways")
+        pred_len=12, gan_type=args.gan_type, global_disc=1, scene_dim=scene_dim, pool_type=args.pool_type)
     if case["with_img"]:
         # the CLI path must build the very same thing (model_factory.py:7-86)
         G2, D2 = ref.model_factory.construct_model(args)
@@ -129,7 +132,7 @@ def run_case(ref, name, case):
     gt_xy, gt_dxdy = t["gt_xy"][:, mask], t["gt_dxdy"][:, mask]
 
     out = {"meta/gan_obj": np.array(args.gan_obj), "meta/weighting_target": np.array(args.weighting_target),
-           "meta/gan_type": np.array(args.gan_type),
+           "meta/gan_type": np.array(args.gan_type), "meta/pool_type": np.array(args.pool_type),
            "meta/num_gens": np.int64(ng), "meta/k": np.int64(k), "meta/iters": np.int64(case["iters"]),
            "meta/with_img": np.int64(case["with_img"]), "meta/seq_start_end": np.array(sse, dtype=np.int64)}
     for n, v in b.items():

@@ -156,6 +156,24 @@ def social_attention(sd, pre, xy_last, dxdy_last, h, sub_batches, mode="scene"):
     return S
 
 
+def pool_hidden_net(sd, pre, xy_last, h, sub_batches):
+    """PoolHiddenNet.forward (social_gan.py:203-229), `--pool_type sgan`: per scene, for every ordered pair (a, b)
+    MLP([Linear_2->E(pos_b - pos_a), h_b]) with mlp_pre_pool = Linear, ReLU, Linear (make_mlp of 3 dims, utils.py:134-149),
+    then max over b (b = a included).  Output rows follow the order of `sub_batches` (concatenation, :227-228): the
+    discriminator's `seq_start_end * n_samples` therefore yields n_samples copies of the sample-0 pooling."""
+    out = []
+    for a, b in sub_batches:
+        n = b - a
+        hid = h[a:b].repeat(n, 1)                                      # H1, H2, ..., H1, H2, ...   (row a' * n + b')
+        p1 = xy_last[a:b].repeat(n, 1)                                 # pos of b'
+        p2 = xy_last[a:b].unsqueeze(1).repeat(1, n, 1).view(-1, 2)     # pos of a'
+        emb = _lin(sd, pre + ".spatial_embedding", p1 - p2)
+        x = torch.cat([emb, hid], 1)
+        y = _lin(sd, pre + ".mlp_pre_pool.2", torch.relu(_lin(sd, pre + ".mlp_pre_pool.0", x)))
+        out.append(y.view(n, n, -1).max(1)[0])
+    return torch.cat(out, 0)
+
+
 # --------------------------------------------------------------------------- physical attention
 def _bn_train(sd, pre, x, training):
     w, b = sd[pre + ".weight"], sd[pre + ".bias"]
@@ -239,7 +257,10 @@ def generator_trunk(sd, in_xy, in_dxdy, sub_batches, img, training, social_mode=
     feats = [enc_h]
     if img is not None:
         feats.append(attention_global(sd, "scene_encoder", img, training))
-    social = social_attention(sd, "social", in_xy[-1], in_dxdy[-1], enc_h, sub_batches, social_mode)
+    if "social.mlp_pre_pool.0.weight" in sd:                               # --pool_type sgan (standard.py:63-71)
+        social = pool_hidden_net(sd, "social", in_xy[-1], enc_h, sub_batches)
+    else:
+        social = social_attention(sd, "social", in_xy[-1], in_dxdy[-1], enc_h, sub_batches, social_mode)
     feats.append(social)
     return torch.cat(feats, -1), social
 
@@ -311,7 +332,9 @@ def discriminator_forward(sd, in_xy, in_dxdy, pred_xy, pred_dxdy, sub_batches, i
         full[mask.repeat(k)] = pred_enc
         pred_enc = full
     enc = torch.cat([in_enc.repeat(k, 1), pred_enc], 1)                  # row = s*N + i
-    if social_mode == "reference":
+    if "social.mlp_pre_pool.0.weight" in sd:                               # --pool_type sgan (discriminators.py:59-69)
+        soc = pool_hidden_net(sd, "social", in_xy[-1].repeat(k, 1), enc, list(sub_batches) * k)
+    elif social_mode == "reference":
         soc = social_attention(sd, "social", in_xy[-1].repeat(k, 1), in_dxdy[-1].repeat(k, 1), enc,
                                list(sub_batches) * k, "reference")
     else:

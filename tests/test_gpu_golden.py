@@ -40,7 +40,8 @@ def make_config(g):
                                     "--scene_dim", "64" if g["meta"]["with_img"] else "0",
                                     "--gan_obj", g["meta"].get("gan_obj", "NS"),
                                     "--weighting_target", g["meta"].get("weighting_target", "ml"),
-                                    "--gan_type", g["meta"].get("gan_type", "mgan")])
+                                    "--gan_type", g["meta"].get("gan_type", "mgan"),
+                                    "--pool_type", g["meta"].get("pool_type", "sways")])
     args.gpus = True
     return args
 

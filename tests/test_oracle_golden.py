@@ -76,9 +76,11 @@ def test_training_iterations_objective_variants(golden_variant):
     _run_iterations(golden_variant)
 
 
-def test_training_iterations_gan_type_plain(golden_late_variant):
-    """gan_type "gan": no generator-id head, no classifier terms (discriminators.py:210-211, train.py:101,181)."""
-    assert golden_late_variant["meta"]["gan_type"] == "gan"
+def test_training_iterations_late_variants(golden_late_variant):
+    """gan_type "gan": no generator-id head, no classifier terms (discriminators.py:210-211, train.py:101,181);
+    pool_type "sgan": PoolHiddenNet in G and D (social_gan.py:157-229)."""
+    m = golden_late_variant["meta"]
+    assert m["gan_type"] == "gan" or m["pool_type"] == "sgan"
     _run_iterations(golden_late_variant)
 
 

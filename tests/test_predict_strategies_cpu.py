@@ -90,3 +90,36 @@ def test_gather_is_the_selected_decode():
     ref = flat[:, idx + offs * G, torch.arange(b).unsqueeze(1)].transpose(1, 2)
     mine = torch.stack([torch.stack([allp[:, offs[i, j], idx[i, j], i] for i in range(b)], 1) for j in range(num)], 1)
     assert torch.equal(ref, mine)
+
+
+def test_pool_hidden_net_host_logic_matches_oracle(monkeypatch):
+    """`--pool_type sgan`: the folded first layer, pair gather and segment max of the product's PoolHiddenNet (host logic;
+    `mggan_linear_*` replaced by torch here, the GPU path is checked by tests/test_gpu_zvariants.py) against the oracle's
+    literal restatement of the reference loop (social_gan.py:203-229), values and gradients."""
+    import torch
+    import torch.nn.functional as F
+    import mggan_oracle as O
+    from mggan import kernels as K
+    from mggan.model.modules.social_gan import PoolHiddenNet
+
+    def fake_linear(x, w, b=None, act=K.ACT_NONE, slope=0.0):
+        y = F.linear(x, w, b)
+        return torch.relu(y) if act == K.ACT_RELU else y
+
+    monkeypatch.setattr(K, "linear", fake_linear)
+    torch.manual_seed(5)
+    for h_dim, emb in ((32, 16), (64, 16)):
+        net = PoolHiddenNet(embedding_dim=emb, h_dim=h_dim, mlp_dim=h_dim, bottleneck_dim=h_dim)
+        sse = [(0, 3), (3, 4), (4, 9), (9, 11)]
+        in_xy = torch.randn(8, 11, 2) * 5
+        h = torch.randn(11, h_dim, requires_grad=True)
+        out = net(in_xy, None, h, sse)
+        sd = {"social." + k: v for k, v in net.state_dict().items()}
+        h2 = h.detach().clone().requires_grad_(True)
+        ref = O.pool_hidden_net(sd, "social", in_xy[-1], h2, sse)
+        assert out.shape == ref.shape == (11, h_dim)
+        assert torch.allclose(out, ref, rtol=1e-4, atol=1e-5), float((out - ref).abs().max())
+        g = torch.randn_like(ref)
+        out.backward(g)
+        ref.backward(g)
+        assert torch.allclose(h.grad, h2.grad, rtol=1e-4, atol=1e-5)
