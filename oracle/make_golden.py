@@ -45,6 +45,10 @@ CASES = {
     # --pool_type sgan: PoolHiddenNet instead of the Social-Ways attention in G and D (social_gan.py:157-229)
     "var_sgan_pool": dict(num_gens=3, sizes=[3, 1, 4, 2], with_img=False, nan_frac=0.0, k=5, iters=1, seed=88,
                           flags=["--pool_type", "sgan"], modules=False),
+    # --experiment discrete: DiscreteLatentGenerator, one decoder + a discrete latent code (standard_discrete.py:18-257);
+    # built by the reference's own construct_model (scene CNN on: model_factory.py:19 hard-codes scene_dim)
+    "var_discrete": dict(num_gens=3, sizes=[2, 3, 1], with_img=True, nan_frac=0.0, k=5, iters=1, seed=99,
+                         flags=["--experiment", "discrete"], modules=False),
     # gan_type "gan": plain discriminator, no generator-id head (discriminators.py:210-211, train.py:101,181)
     "var_gan_plain": dict(num_gens=3, sizes=[3, 1, 2], with_img=True, nan_frac=0.0, k=5, iters=1, seed=77,
                           flags=["--gan_type", "gan"], modules=False),
@@ -80,7 +84,9 @@ def build(ref, case):
     D = ref.discriminators.MultiDiscriminatorTrajectory(
         num_gens=case["num_gens"], num_discs=1, unbound_output=args.gan_obj in ["W", "LS"], h_dim=64, inp_format="rel",
         pred_len=12, gan_type=args.gan_type, global_disc=1, scene_dim=scene_dim, pool_type=args.pool_type)
-    if case["with_img"]:
+    if args.experiment == "discrete":
+        G, D = ref.model_factory.construct_model(args)
+    elif case["with_img"]:
         # the CLI path must build the very same thing (model_factory.py:7-86)
         G2, D2 = ref.model_factory.construct_model(args)
         assert [k for k in G2.state_dict()] == [k for k in G.state_dict()]
@@ -133,6 +139,7 @@ def run_case(ref, name, case):
 
     out = {"meta/gan_obj": np.array(args.gan_obj), "meta/weighting_target": np.array(args.weighting_target),
            "meta/gan_type": np.array(args.gan_type), "meta/pool_type": np.array(args.pool_type),
+           "meta/experiment": np.array(args.experiment),
            "meta/num_gens": np.int64(ng), "meta/k": np.int64(k), "meta/iters": np.int64(case["iters"]),
            "meta/with_img": np.int64(case["with_img"]), "meta/seq_start_end": np.array(sse, dtype=np.int64)}
     for n, v in b.items():
@@ -152,6 +159,10 @@ def run_case(ref, name, case):
         return logits, inj.idx.pop(0)
 
     ref.standard.MultiGenerator.get_samples = get_samples
+    # the discrete-latent generator lives in a module the shim does not expose: patch it through its globals
+    DLG = ref.model_factory.DiscreteLatentGenerator
+    DLG.forward.__globals__["get_global_noise"] = inj.global_noise
+    DLG.get_samples = get_samples
     rng = np.random.default_rng(case["seed"] + 1)
     gen = torch.Generator().manual_seed(case["seed"] + 2)
 
@@ -225,8 +236,9 @@ def run_case(ref, name, case):
     sd_np("G1", G, out)
     sd_np("D1", D, out)
     # AdamW state of one decoder tensor and one encoder tensor (step counters differ: SURVEY App. B)
+    dec_key = "gs.0.decoder.weight_hh_l0" if args.experiment != "discrete" else "decoder.decoder.weight_hh_l0"
     for tag, opt, mod, key in (("G", trainer.optimizerG, G, "encoder.embedding.weight"),
-                               ("G", trainer.optimizerG, G, "gs.0.decoder.weight_hh_l0"),
+                               ("G", trainer.optimizerG, G, dec_key),
                                ("D", trainer.optimizerD, D, "discs.0.0.weight")):
         p = dict(mod.named_parameters())[key]
         st = opt.state[p]

@@ -265,6 +265,61 @@ def generator_trunk(sd, in_xy, in_dxdy, sub_batches, img, training, social_mode=
     return torch.cat(feats, -1), social
 
 
+def discrete_generator_forward(sd, n_gens, in_xy, in_dxdy, sub_batches, noise, all_gen_out, img, num_samples,
+                               mask=None, gen_idxs=None, training=True, use_pinet=True, social_mode="scene",
+                               generator=None):
+    """DiscreteLatentGenerator.forward (`--experiment discrete`, standard_discrete.py:109-257): ONE decoder; the generator
+    index is a discrete latent code, one_hot -> Linear, ReLU, Linear (`one_hot_sample_encoder`), concatenated to the
+    encoding in front of the noise: h0 = enc_h_to_dec_h([enc | code(g) | z]) (:150-153,201-212,239-257)."""
+    N = in_xy.shape[1]
+    enc_cat, social = generator_trunk(sd, in_xy, in_dxdy, sub_batches, img, training, social_mode)
+    if noise is None:
+        noise = torch.stack([global_noise(8, sub_batches, generator) for _ in range(num_samples)])
+    assert noise.shape[:2] == (num_samples, N)
+    if mask is not None:
+        in_xy, in_dxdy = in_xy[:, mask], in_dxdy[:, mask]
+        enc_cat, social, noise = enc_cat[mask], social[mask], noise[:, mask]
+    n_act = enc_cat.shape[0]
+
+    def code(one_hot):
+        return _lin(sd, "one_hot_sample_encoder.2", torch.relu(_lin(sd, "one_hot_sample_encoder.0", one_hot)))
+
+    def decode(inp_h, z):
+        h0 = _lin(sd, "enc_h_to_dec_h.0", torch.cat([inp_h, z], -1))
+        return relative_decoder(sd, "decoder", in_xy[-1], in_dxdy[-1], social, h0)
+
+    def draw(logits):
+        if gen_idxs is not None:
+            return gen_idxs
+        p = torch.softmax(logits.detach(), 1)
+        return torch.multinomial(p, num_samples, replacement=True, generator=generator)
+
+    if all_gen_out:
+        A, R = [], []
+        with torch.no_grad():
+            for i in range(num_samples):
+                ga, gr = [], []
+                for j in range(n_gens):
+                    oh = F.one_hot(torch.tensor(j), n_gens)[None].repeat(n_act, 1).float()
+                    a, r = decode(torch.cat([enc_cat, code(oh)], 1), noise[i])
+                    ga.append(a)
+                    gr.append(r)
+                A.append(torch.stack(ga, 1))
+                R.append(torch.stack(gr, 1))
+        logits = pm_logits(sd, enc_cat, use_pinet)
+        return (torch.stack(R, 1), torch.stack(A, 1)), logits, draw(logits)
+    with torch.no_grad():
+        logits = pm_logits(sd, enc_cat, use_pinet)
+        idx = draw(logits)
+    oh = F.one_hot(idx, n_gens).float()
+    A, R = [], []
+    for i in range(num_samples):
+        a, r = decode(torch.cat([enc_cat, code(oh[:, i])], 1), noise[i])
+        A.append(a)
+        R.append(r)
+    return (torch.stack(R, 1), torch.stack(A, 1)), logits, idx
+
+
 def generator_forward(sd, n_gens, in_xy, in_dxdy, sub_batches, noise, all_gen_out, img,
                       num_samples, mask=None, gen_idxs=None, training=True, use_pinet=True,
                       social_mode="scene", generator=None):
@@ -274,6 +329,9 @@ def generator_forward(sd, n_gens, in_xy, in_dxdy, sub_batches, noise, all_gen_ou
     Categorical under no_grad, standard.py:187-188,223-224); None draws them here.
     Returns ((rel, abs), logits, gen_idxs).
     """
+    if "one_hot_sample_encoder.0.weight" in sd:                          # --experiment discrete (model_factory.py:50-65)
+        return discrete_generator_forward(sd, n_gens, in_xy, in_dxdy, sub_batches, noise, all_gen_out, img, num_samples,
+                                          mask, gen_idxs, training, use_pinet, social_mode, generator)
     N = in_xy.shape[1]
     enc_cat, social = generator_trunk(sd, in_xy, in_dxdy, sub_batches, img, training, social_mode)
     if noise is None:

@@ -41,7 +41,8 @@ def make_config(g):
                                     "--gan_obj", g["meta"].get("gan_obj", "NS"),
                                     "--weighting_target", g["meta"].get("weighting_target", "ml"),
                                     "--gan_type", g["meta"].get("gan_type", "mgan"),
-                                    "--pool_type", g["meta"].get("pool_type", "sways")])
+                                    "--pool_type", g["meta"].get("pool_type", "sways"),
+                                    "--experiment", g["meta"].get("experiment", "multi_generator")])
     args.gpus = True
     return args
 
@@ -158,6 +159,8 @@ def test_training_iterations_objective_variants(golden_variant, injected, tmp_pa
 
 
 def _run_iterations(g, inj, tmp_path):
+    # the one decoder tensor whose optimiser state is checked: generator 0's (or the single decoder of --experiment discrete)
+    dec_key = "decoder.decoder.weight_hh_l0" if g["meta"].get("experiment") == "discrete" else "gs.0.decoder.weight_hh_l0"
     from mggan.logging import Experiment
     from mggan.model.train import PiNetMultiGeneratorGAN
     G, D, cfg = build(g)
@@ -225,7 +228,7 @@ def _run_iterations(g, inj, tmp_path):
                 if key.endswith("Conv_1.bias"):
                     continue
                 check(gp[key[8:]], v, 2e-3, key, atol=1e-6)
-        assert "gs.0.decoder.weight_hh_l0" not in gp
+        assert dec_key not in gp
         check(metrics["train/net_chooser_loss"][0], r["metric/train/net_chooser_loss"], 1e-3, "pm loss")
         assert not inj.noise and not inj.idx and not inj.labels
 
@@ -239,11 +242,11 @@ def _run_iterations(g, inj, tmp_path):
                 check(sd[n].float(), v.float(), 1e-3, tag + " " + n, atol=5e-4 * iters)
             else:
                 check(sd[n].float(), v.float(), 1e-3, tag + " " + n, atol=2e-6)
-    p = dict(G.named_parameters())["gs.0.decoder.weight_hh_l0"]
+    p = dict(G.named_parameters())[dec_key]
     st = tr.optimizerG.state[p]
-    assert float(st["step"]) == g["optG"]["gs.0.decoder.weight_hh_l0/step"] == iters
+    assert float(st["step"]) == g["optG"][dec_key + "/step"] == iters
     assert float(tr.optimizerG.state[dict(G.named_parameters())["encoder.embedding.weight"]]["step"]) == 2 * iters
-    check(st["exp_avg"], g["optG"]["gs.0.decoder.weight_hh_l0/exp_avg"], 2e-3, "exp_avg", atol=1e-7)
+    check(st["exp_avg"], g["optG"][dec_key + "/exp_avg"], 2e-3, "exp_avg", atol=1e-7)
     pd_ = dict(D.named_parameters())["discs.0.0.weight"]
     check(tr.optimizerD.state[pd_]["exp_avg_sq"], g["optD"]["discs.0.0.weight/exp_avg_sq"], 4e-3, "exp_avg_sq", atol=1e-10)
 

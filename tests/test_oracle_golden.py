@@ -80,11 +80,13 @@ def test_training_iterations_late_variants(golden_late_variant):
     """gan_type "gan": no generator-id head, no classifier terms (discriminators.py:210-211, train.py:101,181);
     pool_type "sgan": PoolHiddenNet in G and D (social_gan.py:157-229)."""
     m = golden_late_variant["meta"]
-    assert m["gan_type"] == "gan" or m["pool_type"] == "sgan"
+    assert m["gan_type"] == "gan" or m["pool_type"] == "sgan" or m["experiment"] == "discrete"
     _run_iterations(golden_late_variant)
 
 
 def _run_iterations(g):
+    # the one decoder tensor whose optimiser state is checked: generator 0's (or the single decoder of --experiment discrete)
+    dec_key = "decoder.decoder.weight_hh_l0" if g["meta"].get("experiment") == "discrete" else "gs.0.decoder.weight_hh_l0"
     b = batch_of(g)
     ng, k = g["meta"]["num_gens"], g["meta"]["k"]
     tr = O.OracleTrainer(g["G0"], g["D0"], ng, num_samples=k, gan_obj=g["meta"].get("gan_obj", "NS"),
@@ -119,7 +121,7 @@ def _run_iterations(g):
         for n, v in r.items():
             if n.startswith("PM_grad/"):
                 close(pm["grads"][n[8:]], v, rtol=2e-3, atol=1e-6, what=n)
-        assert pm["grads"]["gs.0.decoder.weight_hh_l0"] is None
+        assert pm["grads"][dec_key] is None
     # A conv bias that feeds a train-mode BatchNorm has an exactly-zero true gradient; what
     # reaches AdamW is round-off noise, which Adam normalises to O(lr) steps of random sign.
     # Those tensors are only required to stay within the lr envelope.
@@ -132,10 +134,10 @@ def _run_iterations(g):
                 close(sd[n].detach().float(), v.float(), rtol=1e-3, atol=5e-4 * iters, what=tag + " " + n)
             else:
                 close(sd[n].detach().float(), v.float(), rtol=1e-3, atol=2e-6, what=tag + " " + n)
-    st = tr.optG.state["gs.0.decoder.weight_hh_l0"]
-    assert st["step"] == g["optG"]["gs.0.decoder.weight_hh_l0/step"] == g["meta"]["iters"]
+    st = tr.optG.state[dec_key]
+    assert st["step"] == g["optG"][dec_key + "/step"] == g["meta"]["iters"]
     assert tr.optG.state["encoder.embedding.weight"]["step"] == 2 * g["meta"]["iters"]
-    close(st["m"], g["optG"]["gs.0.decoder.weight_hh_l0/exp_avg"], rtol=2e-3, atol=1e-7, what="exp_avg")
+    close(st["m"], g["optG"][dec_key + "/exp_avg"], rtol=2e-3, atol=1e-7, what="exp_avg")
     close(tr.optD.state["discs.0.0.weight"]["v"], g["optD"]["discs.0.0.weight/exp_avg_sq"], rtol=4e-3, atol=1e-10, what="exp_avg_sq")
 
 

@@ -123,3 +123,96 @@ def test_pool_hidden_net_host_logic_matches_oracle(monkeypatch):
         out.backward(g)
         ref.backward(g)
         assert torch.allclose(h.grad, h2.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_discrete_latent_generator_host_logic_matches_oracle(monkeypatch):
+    """`--experiment discrete`: row layouts, code gather and autograd wiring of the product's DiscreteLatentGenerator (host
+    logic) with every kernel wrapper replaced by a plain torch stand-in; the real kernels are checked on the GPU
+    (tests/test_gpu_zvariants.py) against vectors frozen from the reference."""
+    import types
+    import torch
+    import torch.nn.functional as F
+    import mggan_oracle as O
+    from mggan import kernels as K
+    from mggan.model.modules.standard_discrete import DiscreteLatentGenerator
+
+    def fake_linear(x, w, b=None, act=K.ACT_NONE, slope=0.0):
+        y = F.linear(x, w, b)
+        return torch.relu(y) if act == K.ACT_RELU else y
+
+    def fake_lstm(x, w_emb, b_emb, w_ih, w_hh, b_ih, b_hh):
+        h = x.new_zeros(x.shape[1], w_hh.shape[1])
+        c = torch.zeros_like(h)
+        for t in range(x.shape[0]):
+            i, f, g, o = (F.linear(F.linear(x[t], w_emb, b_emb), w_ih, b_ih) + F.linear(h, w_hh, b_hh)).chunk(4, 1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+        return h
+
+    def fake_social(xy_last, dxdy_last, h, scenes, fc0, fc2, fc4, att_w):
+        sd = {"s.feature_embedder.fc.0.weight": fc0.weight, "s.feature_embedder.fc.0.bias": fc0.bias,
+              "s.feature_embedder.fc.2.weight": fc2.weight, "s.feature_embedder.fc.2.bias": fc2.bias,
+              "s.feature_embedder.fc.4.weight": fc4.weight, "s.feature_embedder.fc.4.bias": fc4.bias,
+              "s.attention.W.weight": att_w.weight, "s.attention.W.bias": att_w.bias}
+        return O.social_attention(sd, "s", xy_last, dxdy_last, h, scenes.sub_batches)
+
+    def fake_decode(A, social, last_xy, last_dxdy, noise, wz, gw, sel, pred_len):
+        g = {k: v[0] for k, v in gw.items()}
+        h, c, d, xy = A, torch.zeros_like(A), last_dxdy, last_xy
+        out_abs, out_rel = [], []
+        for _ in range(pred_len):
+            i, f, gg, o = (F.linear(d, g["wx"], g["b"]) + F.linear(h, g["whh"])).chunk(4, 1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            u = F.leaky_relu(F.linear(h, g["w1h"]) + F.linear(social, g["w1s"]) + g["b1"], 0.01)
+            d = F.linear(u, g["w2"], g["b2"])
+            xy = xy + d
+            out_abs.append(xy)
+            out_rel.append(d)
+        return torch.stack(out_abs), torch.stack(out_rel)
+
+    class FakeScenes:
+        def __init__(self, sub_batches):
+            self.sub_batches = [(int(a), int(b)) for a, b in sub_batches]
+            self.n_agents = self.sub_batches[-1][1]
+
+    monkeypatch.setattr(K, "linear", fake_linear)
+    monkeypatch.setattr(K, "lstm_encode", fake_lstm)
+    monkeypatch.setattr(K, "social_attention", fake_social)
+    monkeypatch.setattr(K, "decode", fake_decode)
+    monkeypatch.setattr(K.SceneIndex, "get", classmethod(lambda cls, sb, dev: sb if isinstance(sb, FakeScenes) else FakeScenes(sb)))
+    monkeypatch.setattr(K.Selection, "all_generators", staticmethod(lambda n, k, g, dev: types.SimpleNamespace()))
+
+    torch.manual_seed(3)
+    Gn, k = 3, 4
+    net = DiscreteLatentGenerator(z_size=8, encoder_h_dim=32, decoder_h_dim=32, social_feat_size=32, num_gens=Gn, pred_len=12,
+                                  embedding_dim=16, inp_format="rel", num_social_modules=1, pool_type="sways", scene_dim=0,
+                                  use_pinet=True)
+    sse = [(0, 3), (3, 4), (4, 6)]
+    in_xy = torch.randn(8, 6, 2).cumsum(0)
+    in_dxdy = in_xy[1:] - in_xy[:-1]
+    noise = torch.randn(k, 6, 8)
+    idx = torch.randint(0, Gn, (6, k))
+    sd = {n: v for n, v in net.state_dict().items()}
+
+    (rel, ab), logits, got_idx = net(in_xy, in_dxdy, sse, noise=noise, all_gen_out=False, num_samples=k, gen_idxs=idx)
+    (orel, oab), ologits, _ = O.generator_forward(sd, Gn, in_xy, in_dxdy, sse, noise, False, None, k, None, idx)
+    assert ab.shape == oab.shape == (12, k, 6, 2) and torch.equal(got_idx, idx)
+    assert torch.allclose(ab, oab, rtol=1e-4, atol=1e-5) and torch.allclose(rel, orel, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(logits, ologits, rtol=1e-4, atol=1e-5)
+    assert net.last_selection.totals.tolist() == torch.bincount(idx.flatten(), minlength=Gn).tolist()
+    # gradients reach the code encoder and the trunk
+    ab.square().mean().backward()
+    gw = net.one_hot_sample_encoder[0].weight.grad
+    params = {n: p for n, p in net.named_parameters()}
+    osd = {n: (v.detach().clone().requires_grad_(True) if n in params and params[n].requires_grad else v) for n, v in sd.items()}
+    (_, oab2), _, _ = O.generator_forward(osd, Gn, in_xy, in_dxdy, sse, noise, False, None, k, None, idx)
+    oab2.square().mean().backward()
+    assert gw is not None and torch.allclose(gw, osd["one_hot_sample_encoder.0.weight"].grad, rtol=1e-3, atol=1e-6)
+    assert torch.allclose(net.encoder.embedding.weight.grad, osd["encoder.embedding.weight"].grad, rtol=1e-3, atol=1e-6)
+
+    monkeypatch.setattr(DiscreteLatentGenerator, "get_samples", lambda self, enc_h, num_samples=5: (self.pm_logits(enc_h), idx))
+    (rel, ab), logits, _ = net(in_xy, in_dxdy, sse, noise=noise, all_gen_out=True, num_samples=k)
+    (orel, oab), _, _ = O.generator_forward(sd, Gn, in_xy, in_dxdy, sse, noise, True, None, k, None, idx)
+    assert ab.shape == oab.shape == (12, k, Gn, 6, 2)
+    assert torch.allclose(ab, oab, rtol=1e-4, atol=1e-5) and torch.allclose(rel, orel, rtol=1e-4, atol=1e-5)
