@@ -216,3 +216,93 @@ def test_discrete_latent_generator_host_logic_matches_oracle(monkeypatch):
     (orel, oab), _, _ = O.generator_forward(sd, Gn, in_xy, in_dxdy, sse, noise, True, None, k, None, idx)
     assert ab.shape == oab.shape == (12, k, Gn, 6, 2)
     assert torch.allclose(ab, oab, rtol=1e-4, atol=1e-5) and torch.allclose(rel, orel, rtol=1e-4, atol=1e-5)
+
+
+def test_discriminator_sgan_pooling_host_logic_matches_oracle(monkeypatch):
+    """`--pool_type sgan` in the discriminator: the replicated pooling block (one copy of the sample-0 pooling per sample,
+    social_gan.py:227-228 under `seq_start_end * n_samples`) in both forward paths of the product (trainable heads, and
+    the hoisted form used with frozen heads), with masked agents, against the oracle -- kernel wrappers replaced by torch."""
+    import torch
+    import torch.nn.functional as F
+    import mggan_oracle as O
+    from mggan import kernels as K
+    from mggan.model.modules.discriminators import MultiDiscriminatorTrajectory
+
+    def fake_linear(x, w, b=None, act=K.ACT_NONE, slope=0.0):
+        y = F.linear(x, w, b)
+        if act == K.ACT_RELU:
+            return torch.relu(y)
+        if act == K.ACT_LRELU:
+            return F.leaky_relu(y, slope)
+        if act == K.ACT_SIGMOID_EPS:
+            return torch.sigmoid(y) * (1 - 2e-7) + 1e-7
+        return y
+
+    def fake_lstm(x, w_emb, b_emb, w_ih, w_hh, b_ih, b_hh):
+        h = x.new_zeros(x.shape[1], w_hh.shape[1])
+        c = torch.zeros_like(h)
+        for t in range(x.shape[0]):
+            i, f, g, o = (F.linear(F.linear(x[t], w_emb, b_emb), w_ih, b_ih) + F.linear(h, w_hh, b_hh)).chunk(4, 1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+        return h
+
+    def fake_heads(pe, base, soc0, w1p, wd2, bd2, wg2, bg2, n, k):
+        HH = wd2.shape[1]
+        z = base.repeat(k, 1) + F.linear(pe, w1p)
+        z = z + torch.cat([soc0, soc0.new_zeros((k - 1) * n, soc0.shape[1])], 0)
+        a = F.leaky_relu(z, 0.2)
+        p = torch.sigmoid(F.linear(a[:, :HH], wd2, bd2)) * (1 - 2e-7) + 1e-7
+        return p.reshape(-1), (F.linear(a[:, HH:], wg2, bg2) if wg2 is not None else None)
+
+    class FakeScenes:
+        def __init__(self, sub_batches):
+            self.sub_batches = [(int(a), int(b)) for a, b in sub_batches]
+            self.n_agents = self.sub_batches[-1][1]
+
+        def pair_index(self):
+            ia = torch.cat([torch.arange(a, b).repeat_interleave(b - a) for a, b in self.sub_batches])
+            ib = torch.cat([torch.arange(a, b).repeat(b - a) for a, b in self.sub_batches])
+            return ia, ib
+
+    monkeypatch.setattr(K, "linear", fake_linear)
+    monkeypatch.setattr(K, "lstm_encode", fake_lstm)
+    monkeypatch.setattr(K, "disc_heads", fake_heads)
+    monkeypatch.setattr(K.SceneIndex, "get", classmethod(lambda cls, sb, dev: sb if isinstance(sb, FakeScenes) else FakeScenes(sb)))
+
+    torch.manual_seed(11)
+    Gn, k, N = 3, 4, 7
+    D = MultiDiscriminatorTrajectory(num_gens=Gn, num_discs=1, unbound_output=False, h_dim=64, inp_format="rel", pred_len=12,
+                                     gan_type="mgan", global_disc=1, scene_dim=0, pool_type="sgan")
+    sse = [(0, 3), (3, 4), (4, 7)]
+    in_xy = torch.randn(8, N, 2).cumsum(0)
+    in_dxdy = in_xy[1:] - in_xy[:-1]
+    mask = torch.tensor([True, True, False, True, True, False, True])
+    n_act = int(mask.sum())
+    pred_dxdy = torch.randn(12, k, n_act, 2) * 0.3
+    pred_xy = in_xy[-1, mask][None, None] + pred_dxdy.cumsum(0)
+    sd = dict(D.state_dict())
+    want, want_br = O.discriminator_forward(sd, in_xy, in_dxdy, pred_xy, pred_dxdy, sse, None, mask)
+    got, got_br = D(in_xy, in_dxdy, pred_xy, pred_dxdy, sse, mask=mask)                 # trainable heads: plain path
+    assert got.shape == want.shape == (n_act, k) and got_br.shape == want_br.shape == (n_act, k, Gn)
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-6) and torch.allclose(got_br, want_br, rtol=1e-4, atol=1e-5)
+    with torch.no_grad():                                                               # frozen heads: hoisted path
+        got, got_br = D(in_xy, in_dxdy, pred_xy, pred_dxdy, sse, mask=mask)
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-6) and torch.allclose(got_br, want_br, rtol=1e-4, atol=1e-5)
+    # and the default attention variant keeps its sample-0-only semantics through the same two paths
+    D2 = MultiDiscriminatorTrajectory(num_gens=Gn, num_discs=1, unbound_output=False, h_dim=64, inp_format="rel", pred_len=12,
+                                      gan_type="mgan", global_disc=1, scene_dim=0, pool_type="sways")
+
+    def fake_social(xy_last, dxdy_last, h, scenes, fc0, fc2, fc4, att_w):
+        s = {"s.feature_embedder.fc.0.weight": fc0.weight, "s.feature_embedder.fc.0.bias": fc0.bias,
+             "s.feature_embedder.fc.2.weight": fc2.weight, "s.feature_embedder.fc.2.bias": fc2.bias,
+             "s.feature_embedder.fc.4.weight": fc4.weight, "s.feature_embedder.fc.4.bias": fc4.bias,
+             "s.attention.W.weight": att_w.weight, "s.attention.W.bias": att_w.bias}
+        return O.social_attention(s, "s", xy_last, dxdy_last, h, scenes.sub_batches)
+
+    monkeypatch.setattr(K, "social_attention", fake_social)
+    want, want_br = O.discriminator_forward(dict(D2.state_dict()), in_xy, in_dxdy, pred_xy, pred_dxdy, sse, None, mask)
+    for frozen in (False, True):
+        with torch.set_grad_enabled(not frozen):
+            got, got_br = D2(in_xy, in_dxdy, pred_xy, pred_dxdy, sse, mask=mask)
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-6) and torch.allclose(got_br, want_br, rtol=1e-4, atol=1e-5), frozen
