@@ -32,7 +32,7 @@ def test_load_reference_checkpoint_predict_and_continue(tmp_path):
         S.MultiGenerator.get_samples = orig
     err = float((a.cpu() - torch.from_numpy(z["abs"])).abs().max()) / float(np.abs(z["abs"]).max())
     assert err <= 1e-3, err
-    assert np.abs(probs - z["probs"]).max() <= 1e-4
+    assert np.abs(probs - z["probs"]).max() <= 1e-3
 
     # the optimisers carry the reference's state: one more iteration advances its step counters from 1
     p = next(q for q in tr.D.parameters() if q.requires_grad)
