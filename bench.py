@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every iteration eagerly (no CUDA-graph replay)")
+    ap.add_argument("--gemm", type=int, default=1, choices=[1, 2],
+                    help="GEMM kernel behind mggan_linear_*: 1 default, 2 = 128x64 register-prefetch variant (A/B measurement)")
     ap.add_argument("--resident-images", action="store_true",
                     help="extra end-to-end leg: scene images resident in HBM, crops cut on the device (mggan_scene_crop); "
                          "the host batch carries image ids instead of the 17,424-byte crops")
@@ -189,6 +191,8 @@ def run_ours(a):
         ctx = DistContext()
     assert world == a.gpus or world == 1, (world, a.gpus)
 
+    if a.gemm != 1:
+        cuda_ext.set_gemm_variant(a.gemm)
     torch.manual_seed(1234)                         # identical initial weights on every rank
     cfg = get_parser().parse_args(["--num_gens", str(a.num_gens), "--num_samples", str(a.k)])
     cfg.gpus = True
@@ -390,7 +394,7 @@ def run_ours(a):
                           f"(~{n_local * a.k * 10.3e3 / 1e9:.1f} GB) exceed the 126 MB L2" if n_local * IMG_BYTES > 126e6 else
                           "working set fits the 126 MB L2 (latency point, not the judged workload)")},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-        "execution": {"cuda_graph": bool(graphed), "ms_per_step_eager": ms_eager,
+        "execution": {"cuda_graph": bool(graphed), "ms_per_step_eager": ms_eager, "gemm_variant": a.gemm,
                       "note": "gpu_launches = kernels of this library per iteration (counted in the eager pass); with "
                               "cuda_graph the iteration (these + autograd glue) is replayed as one graph"},
         "kernel_breakdown_ms": {n: round(t, 3) for n, (c, t) in top[:8]},

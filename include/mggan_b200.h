@@ -41,6 +41,10 @@ int mggan_linear_fwd(const float* X, int M, int K, const float* W, const float* 
 int mggan_linear_bwd(const float* X, int M, int K, const float* W, int O, int act, float slope, const float* Y,
                      const float* dY, float* dX, float* dW, float* db, cudaStream_t stream);
 
+/* GEMM kernel behind mggan_linear_*: 1 = 64 x 64 tile (default), 2 = 128 x 64 tile with register prefetch (opt-in until
+ * measured).  Process-wide switch; returns the previous variant, -1 for an unknown one. */
+int mggan_set_gemm_variant(int variant);
+
 /* ---- discriminator heads over k samples per agent, per-agent part hoisted: MultiDiscriminatorTrajectory.forward
  * mggan/model/modules/discriminators.py:178-219 (discs[0] :76-85,198-204; gen_id_reconstructor :103-108,209-217).
  * The classifier input of row (sample s, agent i) is [soc | in_enc | pred_enc | scene]: only pred_enc depends on s and

@@ -71,7 +71,8 @@ SIGNATURES = {
 }
 # plain (non status-returning) helpers
 _PLAIN = {"mggan_version": ("", ctypes.c_int), "mggan_device_check": ("", ctypes.c_int),
-          "mggan_selection_tiles": ("ii", ctypes.c_int), "mggan_last_error": ("", ctypes.c_char_p)}
+          "mggan_selection_tiles": ("ii", ctypes.c_int), "mggan_last_error": ("", ctypes.c_char_p),
+          "mggan_set_gemm_variant": ("i", ctypes.c_int)}
 
 EXPORTED = sorted(list(SIGNATURES) + list(_PLAIN))
 
@@ -103,6 +104,8 @@ def load():
         fn.argtypes = [_CT[c] for c in sig]
         fn.restype = res
     _lib = lib
+    if os.environ.get("MGGAN_GEMM", "1") == "2":
+        lib.mggan_set_gemm_variant(2)
     return lib
 
 
@@ -184,6 +187,15 @@ def call(name, *args):
     if rc != 0:
         raise MgganCudaError(f"{name} failed ({rc}): {lib.mggan_last_error().decode()}")
     launch_count += KERNELS_PER_CALL.get(name, 1)
+
+
+def set_gemm_variant(variant):
+    """GEMM kernel behind mggan_linear_*: 1 (default) or 2 (128 x 64 tile, register prefetch); returns the previous one.
+    MGGAN_GEMM=2 in the environment selects variant 2 at import."""
+    prev = load().mggan_set_gemm_variant(int(variant))
+    if prev < 0:
+        raise ValueError(f"unknown GEMM variant {variant}")
+    return prev
 
 
 def selection_tiles(n_seq, num_gens):
