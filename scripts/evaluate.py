@@ -1,99 +1,121 @@
 #!/usr/bin/env python
-"""Evaluate every `version_*` run under a model folder: ADE / FDE / Mode and Precision / Recall for
-k = 1 .. num_preds-1, written to one CSV (reference: scripts/evaluate.py:19-169, same arguments and
-output columns).  Prediction runs on the B200 kernels (`PiNetMultiGeneratorGAN.get_predictions`),
-metrics on the host.  Every prediction strategy of the reference (`get_predict_func`) runs on the B200 kernels."""
+"""Sweep every `version_*` run of a model folder over k = 1 .. num_preds-1 predictions and write ADE / FDE / Mode and
+Precision / Recall to one CSV -- the command line, file name and columns of the reference's scripts/evaluate.py:19-169.
+
+Predictions come from the B200 kernels (`PiNetMultiGeneratorGAN.get_predictions`, every strategy of `get_predict_func`);
+the metrics run on the host like the reference's, or on the device with `--metrics_device cuda`
+(`mggan_min_ade_fde`, `mggan_tube_inside`: same results).
+"""
+import argparse
+import collections
 import os
+import pathlib
 import sys
-from argparse import ArgumentParser
-from collections import defaultdict
-from pathlib import Path
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mg-gan_b200"))
 
 import pandas as pd  # noqa: E402
 import torch  # noqa: E402
 
+from mggan import evaluation  # noqa: E402
 from mggan.data_utils.data_loaders import get_dataloader  # noqa: E402
-from mggan.evaluation import (evaluate_ade_fde, evaluate_ade_fde_cuda, evaluate_precision_recall,  # noqa: E402
-                              evaluate_precision_recall_cuda)
 from mggan.model.train import PiNetMultiGeneratorGAN  # noqa: E402
 
-parser = ArgumentParser()
-parser.add_argument("--split", choices=["upper", "lower", "all"], default="all")
-parser.add_argument("--device", default="cuda")
-parser.add_argument("--radius", type=float, default=3.0)
-parser.add_argument("--model_path")
-parser.add_argument("--output_folder", required=True)
-parser.add_argument("--checkpoint", default="best")
-parser.add_argument("--phase", choices=["train", "val", "test"], default="test")
-parser.add_argument("--eval_set", default=None)
-parser.add_argument("--num_preds", default=20, type=int)
-parser.add_argument("--pred_strat", default="all", choices=["all", "sampling", "expected", "smart_expected", "rejection"])
-parser.add_argument("--no-precision-recall", action="store_true")
-parser.add_argument("--num_scenes", type=int, default=64, help="synthetic datasets: scenes to evaluate")
-parser.add_argument("--metrics_device", choices=["host", "cuda"], default="host",
-                    help="host: numpy metrics like the reference; cuda: mggan_min_ade_fde / mggan_tube_inside (same results)")
+STRATEGIES = ("sampling", "expected", "smart_expected", "rejection")
+SWEEP_ORDER = ("smart_expected", "expected", "sampling")          # what `--pred_strat all` runs, in the reference's order
 
-AVAILABLE = ("sampling", "expected", "smart_expected", "rejection")
+# flag -> argparse keywords (reference scripts/evaluate.py:19-69; the last two are additive)
+FLAGS = {
+    "--split": dict(default="all", choices=["upper", "lower", "all"]),
+    "--device": dict(default="cuda"),
+    "--radius": dict(default=3.0, type=float, help="tube radius of the Precision / Recall test"),
+    "--model_path": dict(help="folder holding the version_* directories to evaluate"),
+    "--output_folder": dict(required=True),
+    "--checkpoint": dict(default="best", help="epoch number or 'best'"),
+    "--phase": dict(default="test", choices=["train", "val", "test"]),
+    "--eval_set": dict(default=None, help="evaluate on this dataset instead of the training one"),
+    "--num_preds": dict(default=20, type=int),
+    "--pred_strat": dict(default="all", choices=["all", *STRATEGIES]),
+    "--no-precision-recall": dict(action="store_true"),
+    "--num_scenes": dict(default=64, type=int, help="synthetic datasets: scenes to evaluate"),
+    "--metrics_device": dict(default="host", choices=["host", "cuda"],
+                             help="host: numpy metrics like the reference; cuda: the device kernels (same results)"),
+}
+parser = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+for _flag, _kw in FLAGS.items():
+    parser.add_argument(_flag, **_kw)
+
+
+def applicable(config, strategy):
+    """Which strategies make sense for a run (reference :119-128)."""
+    if config.num_gens == 1:
+        return strategy in ("sampling", "rejection")
+    if strategy == "rejection":
+        return False
+    return not (config.weighting_target == "none" and "smart" in strategy)
+
+
+def describe(config, strategy):
+    """The descriptive CSV columns of one (run, strategy) row (reference :137-152)."""
+    return {
+        "Model": config.name, "# Generators": config.num_gens, "Decoder dim": config.decoder_h_dim,
+        "Generator params": getattr(config, "num_gen_parameters", None), "Prediction strategy": strategy,
+        "Mode": config.experiment, "Use Classifier": config.gan_type, "Prior": config.weighting_target,
+        "Dataset": config.dataset, "Maximization Samples": config.num_samples,
+        "Expectation Samples": config.num_expectation_samples, "L2 loss weight": config.l2_loss_weight,
+        "Clf loss weight": config.clf_loss_weight, "Sigma": config.sigma,
+    }
+
+
+def load_run(version_dir, checkpoint):
+    try:
+        return PiNetMultiGeneratorGAN.load_from_path(version_dir, checkpoint)
+    except Exception as exc:             # like the reference: fall back to the best checkpoint of the run
+        print(exc)
+        return PiNetMultiGeneratorGAN.load_from_path(version_dir, "best")
+
+
+def score(dataset, preds, ks, args):
+    on_device = args.metrics_device == "cuda"
+    ade_fde = evaluation.evaluate_ade_fde_cuda if on_device else evaluation.evaluate_ade_fde
+    metrics = dict(ade_fde(dataset, preds, ks))
+    if not args.no_precision_recall:
+        prec_rec = evaluation.evaluate_precision_recall_cuda if on_device else evaluation.evaluate_precision_recall
+        metrics.update(prec_rec(dataset, preds, args.radius, ks))
+    return metrics
 
 
 def main(argv=None):
     args = parser.parse_args(argv)
-    num_preds_list = list(range(1, args.num_preds))           # k = 1 .. num_preds-1, like the reference (:77)
-    wanted = ["smart_expected", "expected", "sampling"] if args.pred_strat == "all" else [args.pred_strat]
-    pred_strats = [s for s in wanted if s in AVAILABLE]
-    for s in wanted:
-        if s not in AVAILABLE:
-            print(f"prediction strategy '{s}' is not on the B200 path yet; skipped")
-    model = Path(args.model_path).stem
-    out_dir = Path(args.output_folder)
+    ks = list(range(1, args.num_preds))                      # k = 1 .. num_preds-1, like the reference (:77)
+    strategies = SWEEP_ORDER if args.pred_strat == "all" else (args.pred_strat,)
+    root = pathlib.Path(args.model_path)
+    out_dir = pathlib.Path(args.output_folder)
     out_dir.mkdir(parents=True, exist_ok=True)
-    output_csv = out_dir / f"{model}_{args.phase}_{args.checkpoint}_{args.split}_{args.pred_strat}_radius_{args.radius}.csv"
-    print(output_csv)
+    csv = out_dir / f"{root.stem}_{args.phase}_{args.checkpoint}_{args.split}_{args.pred_strat}_radius_{args.radius}.csv"
+    print(csv)
     torch.set_grad_enabled(False)
-    model_dirs = sorted(d for d in Path(args.model_path).iterdir() if "version" in d.stem)
-    all_results = defaultdict(list)
-    for pred_strat in pred_strats:
-        for model_dir in model_dirs:
-            try:
-                m, config = PiNetMultiGeneratorGAN.load_from_path(model_dir, args.checkpoint)
-            except Exception as e:
-                print(e)
-                m, config = PiNetMultiGeneratorGAN.load_from_path(model_dir, "best")
-            if config.num_gens == 1 and pred_strat not in ("sampling", "rejection"):      # reference :119-123
+    runs = sorted(d for d in root.iterdir() if "version" in d.stem)
+    table = collections.defaultdict(list)
+    for strategy in strategies:
+        for version_dir in runs:
+            trainer, config = load_run(version_dir, args.checkpoint)
+            if not applicable(config, strategy):
                 continue
-            if config.weighting_target == "none" and "smart" in pred_strat:
-                continue
-            if pred_strat == "rejection" and config.num_gens != 1:
-                continue
-            m.G.eval()
+            trainer.G.eval()
             config.augment = False
             if args.eval_set is not None:
-                all_results["Training dataset"].append(config.dataset)
+                table["Training dataset"].append(config.dataset)
                 config.dataset = args.eval_set
             loader = get_dataloader(config.dataset, args.phase, batch_size=32, split=args.split,
                                     num_scenes=args.num_scenes, with_img=getattr(config, "scene_dim", 64) > 0)
-            for col, val in (("Model", config.name), ("# Generators", config.num_gens),
-                             ("Decoder dim", config.decoder_h_dim),
-                             ("Generator params", getattr(config, "num_gen_parameters", None)),
-                             ("Prediction strategy", pred_strat), ("Mode", config.experiment),
-                             ("Use Classifier", config.gan_type), ("Prior", config.weighting_target),
-                             ("Dataset", config.dataset), ("Maximization Samples", config.num_samples),
-                             ("Expectation Samples", config.num_expectation_samples),
-                             ("L2 loss weight", config.l2_loss_weight), ("Clf loss weight", config.clf_loss_weight),
-                             ("Sigma", config.sigma)):
-                all_results[col].append(val)
-            preds = m.get_predictions(loader, max(num_preds_list), strategy=pred_strat)
-            ade_fde, prec_rec = ((evaluate_ade_fde_cuda, evaluate_precision_recall_cuda) if args.metrics_device == "cuda"
-                                 else (evaluate_ade_fde, evaluate_precision_recall))
-            metric_dict = dict(ade_fde(loader.dataset, preds, num_preds_list))
-            if not args.no_precision_recall:
-                metric_dict.update(prec_rec(loader.dataset, preds, args.radius, num_preds_list))
-            for k, v in metric_dict.items():
-                all_results[k].append(v)
-            pd.DataFrame(all_results).to_csv(output_csv)
-    return output_csv
+            row = describe(config, strategy)
+            preds = trainer.get_predictions(loader, max(ks), strategy=strategy)
+            row.update(score(loader.dataset, preds, ks, args))
+            for column, value in row.items():
+                table[column].append(value)
+            pd.DataFrame(table).to_csv(csv)                  # rewritten after every run, like the reference
+    return csv
 
 
 if __name__ == "__main__":
