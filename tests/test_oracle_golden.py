@@ -144,3 +144,30 @@ def _run_iterations(g):
 def test_selection_indices():
     idx = torch.tensor([[1, 2, 3, 1], [0, 0, 0, 0], [2, 1, 2, 1]])
     assert O.selection_indices(idx).tolist() == [[0, 0, 0, 1], [0, 1, 2, 3], [0, 0, 1, 1]]
+
+
+def test_train_then_evaluate_20_iterations():
+    """ADE / FDE after TRAINING from identical weights on identical data.  20 D + G + PM iterations of the
+    oracle with the reference's injected draws (tests/golden/train20.npz, oracle/make_golden_train.py), then k = 20
+    predictions in eval mode: coordinates and metrics against what the unmodified reference produced."""
+    from conftest import load_golden
+    g = load_golden("train20")
+    b = batch_of(g)
+    ng, k, iters = g["meta"]["num_gens"], g["meta"]["k"], g["meta"]["iters"]
+    tr = O.OracleTrainer(g["G0"], g["D0"], ng, num_samples=k)
+    d = g["draws"]
+    for it in range(iters):
+        lab = d["labels"][it].tolist()
+        tr.discriminator_step(b, d["d_noise"][it][None], d["d_idx"][it], lab[0], lab[1])
+        tr.generator_step(b, d["g_noise"][it], d["g_idx"][it], lab[2])
+        tr.net_chooser_step(b, d["pm_noise"][it][None])
+    e = g["eval"]
+    with torch.no_grad():
+        (rel, ab), logits, _ = O.generator_forward(tr.G, ng, b["in_xy"], b["in_dxdy"], b["seq_start_end"], e["noise"], False,
+                                                   b["features"], g["meta"]["k_eval"], None, e["idx"], training=False)
+    drift = float((ab - e["abs"]).abs().max() / e["abs"].abs().max())
+    assert drift <= 1e-3, drift                       # fp32 round-off through 20 Adam steps stays far below the 1e-3 bar
+    m = O.ade_fde(ab, b["gt_xy"], b["seq_start_end"])
+    for key in ("ADE", "FDE"):
+        value, count = m[key]
+        assert abs(float(value) / float(count) - float(e[key])) <= 1e-3, key
