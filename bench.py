@@ -38,8 +38,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every iteration eagerly (no CUDA-graph replay)")
-    ap.add_argument("--gemm", type=int, default=1, choices=[1, 2],
-                    help="GEMM kernel behind mggan_linear_*: 1 default, 2 = 128x64 register-prefetch variant (A/B measurement)")
+    ap.add_argument("--gemm", type=int, default=1, choices=[1, 2, 3],
+                    help="GEMM kernel behind mggan_linear_*: 1 default, 2 = FP32 128x64 register-prefetch variant, "
+                         "3 = tcgen05 3xTF32 variant (A/B measurement)")
     ap.add_argument("--resident-images", action="store_true",
                     help="extra end-to-end leg: scene images resident in HBM, crops cut on the device (mggan_scene_crop); "
                          "the host batch carries image ids instead of the 17,424-byte crops")

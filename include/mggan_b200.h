@@ -41,8 +41,9 @@ int mggan_linear_fwd(const float* X, int M, int K, const float* W, const float* 
 int mggan_linear_bwd(const float* X, int M, int K, const float* W, int O, int act, float slope, const float* Y,
                      const float* dY, float* dX, float* dW, float* db, cudaStream_t stream);
 
-/* GEMM kernel behind mggan_linear_*: 1 = 64 x 64 tile (default), 2 = 128 x 64 tile with register prefetch (opt-in until
- * measured).  Process-wide switch; returns the previous variant, -1 for an unknown one. */
+/* GEMM kernel behind mggan_linear_*: 1 = FP32 64 x 64 tile (default), 2 = FP32 128 x 64 tile with register prefetch,
+ * 3 = tcgen05 tensor cores, 3 x TF32 with fp32-level accuracy (2 and 3 are opt-in until measured).  Process-wide switch;
+ * returns the previous variant, -1 for an unknown one. */
 int mggan_set_gemm_variant(int variant);
 
 /* ---- discriminator heads over k samples per agent, per-agent part hoisted: MultiDiscriminatorTrajectory.forward

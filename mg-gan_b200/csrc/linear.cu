@@ -8,47 +8,12 @@
 // register micro-tile, operands transposed into shared memory so the inner loop is two
 // LDS.128 per 16 FMAs.
 #include "common.cuh"
+#include "gemm_args.cuh"
 
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16;
 constexpr int LDT = BM + 4;
-
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_SIGMOID_EPS = 3 };
-constexpr float D_EPS = 1e-7f;      // discriminators.py:110, :203-204
-
-__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
-    switch (act) {
-        case ACT_RELU: return fmaxf(z, 0.f);
-        case ACT_LRELU: return z > 0.f ? z : slope * z;
-        case ACT_SIGMOID_EPS: return (1.f / (1.f + expf(-z))) * (1.f - 2.f * D_EPS) + D_EPS;
-        default: return z;
-    }
-}
-// derivative expressed through the stored output y
-__device__ __forceinline__ float act_bwd(float y, int act, float slope) {
-    switch (act) {
-        case ACT_RELU: return y > 0.f ? 1.f : 0.f;
-        case ACT_LRELU: return y > 0.f ? 1.f : slope;
-        case ACT_SIGMOID_EPS: {
-            float s = (y - D_EPS) / (1.f - 2.f * D_EPS);
-            return (1.f - 2.f * D_EPS) * s * (1.f - s);
-        }
-        default: return 1.f;
-    }
-}
-
-struct GemmArgs {
-    const float* A; long long sam, sak;      // A(m, k) = A[m*sam + k*sak]
-    const float* Ay; int act_in;             // optional: multiply A(m,k) by act_in'(Ay(m,k)) (same indexing)
-    const float* B; long long sbn, sbk;      // B(n, k) = B[n*sbn + k*sbk]
-    float* C; long long scm, scn;            // C(m, n)
-    const float* bias;                       // per n (forward)
-    float* colsum;                           // per m: sum_k A(m,k)  (db in the weight-gradient call)
-    int M, N, K;
-    int act; float slope;
-    int splitk;                              // >1: K split over blockIdx.z, atomicAdd epilogue
-};
 
 __global__ void __launch_bounds__(MGGAN_THREADS)
 gemm_kernel(GemmArgs g) {
@@ -249,10 +214,14 @@ gemm_kernel_v2(GemmArgs g) {
 int g_gemm_variant = 1;
 
 // rows of the output tile of the selected variant for a GEMM with M output rows
-int tile_rows(int M) { return g_gemm_variant == 2 ? (M > 64 ? 128 : 64) : BM; }
+int tile_rows(int M) { return g_gemm_variant == 3 ? 128 : g_gemm_variant == 2 ? (M > 64 ? 128 : 64) : BM; }
 
 int launch(const GemmArgs& g, cudaStream_t s) {
-    const int bm = tile_rows(g.M);
+    if (g_gemm_variant == 3) {                       // tensor cores (linear_tc.cu); -1 = shape it does not build
+        const int rc = mggan_gemm_tc_launch(g, s);
+        if (rc != -1) return rc;
+    }
+    const int bm = g_gemm_variant == 3 ? BM : tile_rows(g.M);
     dim3 grid((g.M + bm - 1) / bm, (g.N + BN - 1) / BN, g.splitk > 1 ? g.splitk : 1);
     if (g_gemm_variant == 2) {
         if (bm == 128) gemm_kernel_v2<8><<<grid, MGGAN_THREADS, 0, s>>>(g);
@@ -311,10 +280,10 @@ extern "C" int mggan_linear_bwd(const float* X, int M, int K, const float* W, in
     return MGGAN_OK;
 }
 
-// 1 = the 64 x 64 tile kernel (default), 2 = the 128 x 64 register-prefetch kernel (opt-in until measured).  Process-wide;
-// returns the previous value, or -1 for an unknown variant.
+// 1 = the 64 x 64 tile kernel (default), 2 = the 128 x 64 register-prefetch kernel, 3 = tcgen05 3 x TF32 (linear_tc.cu); 2 and
+// 3 are opt-in until measured.  Process-wide; returns the previous value, or -1 for an unknown variant.
 extern "C" int mggan_set_gemm_variant(int variant) {
-    if (variant != 1 && variant != 2) return -1;
+    if (variant < 1 || variant > 3) return -1;
     const int prev = g_gemm_variant;
     g_gemm_variant = variant;
     return prev;

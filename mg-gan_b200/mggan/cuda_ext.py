@@ -104,8 +104,8 @@ def load():
         fn.argtypes = [_CT[c] for c in sig]
         fn.restype = res
     _lib = lib
-    if os.environ.get("MGGAN_GEMM", "1") == "2":
-        lib.mggan_set_gemm_variant(2)
+    if os.environ.get("MGGAN_GEMM", "1") in ("2", "3"):
+        lib.mggan_set_gemm_variant(int(os.environ["MGGAN_GEMM"]))
     return lib
 
 
@@ -190,8 +190,8 @@ def call(name, *args):
 
 
 def set_gemm_variant(variant):
-    """GEMM kernel behind mggan_linear_*: 1 (default) or 2 (128 x 64 tile, register prefetch); returns the previous one.
-    MGGAN_GEMM=2 in the environment selects variant 2 at import."""
+    """GEMM kernel behind mggan_linear_*: 1 (default), 2 (FP32 128 x 64 tile, register prefetch) or 3 (tcgen05 tensor
+    cores, 3 x TF32); returns the previous one.  MGGAN_GEMM=2 / 3 in the environment selects a variant at import."""
     prev = load().mggan_set_gemm_variant(int(variant))
     if prev < 0:
         raise ValueError(f"unknown GEMM variant {variant}")

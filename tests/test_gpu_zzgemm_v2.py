@@ -1,7 +1,7 @@
-"""GPU parity of the opt-in GEMM variant 2 behind `mggan_linear_*` (128 x 64 tile, register prefetch; csrc/linear.cu
-`gemm_kernel_v2`): the dense-layer cases of tests/test_gpu_kernels.py, larger shapes of the bench workload, and a whole
-reference-frozen training iteration, all with `mggan_set_gemm_variant(2)`.  The variant was written after this round's GPU
-budget was spent and is not the default."""
+"""GPU parity of the opt-in GEMM variants behind `mggan_linear_*` -- 2: FP32 128 x 64 tile with register prefetch
+(csrc/linear.cu `gemm_kernel_v2`), 3: tcgen05 tensor cores, 3 x TF32 (csrc/linear_tc.cu) -- on the dense-layer cases of
+tests/test_gpu_kernels.py, larger shapes of the bench workload, and a whole reference-frozen training iteration.  Both
+variants were written after this round's GPU budget was spent and neither is the default."""
 import pytest
 import torch
 
@@ -13,10 +13,10 @@ from test_gpu_golden import injected  # noqa: F401  (fixture)
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def gemm_v2():
+@pytest.fixture(params=[2, 3])
+def gemm_v2(request):
     from mggan import cuda_ext
-    prev = cuda_ext.set_gemm_variant(2)
+    prev = cuda_ext.set_gemm_variant(request.param)
     try:
         yield
     finally:
@@ -38,9 +38,9 @@ def test_variants_agree_on_a_bench_shape(gemm_v2):
     w = (torch.randn(96, 192, generator=g) * 0.1).cuda()
     b = torch.randn(96, generator=g).cuda()
     y2 = K.linear(x, w, b, K.ACT_LRELU, 0.2)
-    cuda_ext.set_gemm_variant(1)
+    variant = cuda_ext.set_gemm_variant(1)
     y1 = K.linear(x, w, b, K.ACT_LRELU, 0.2)
-    cuda_ext.set_gemm_variant(2)
+    cuda_ext.set_gemm_variant(variant)
     assert float((y1 - y2).abs().max()) <= 1e-5 * float(y1.abs().max())
 
 
