@@ -8,14 +8,6 @@ from test_gpu_golden import _run_iterations, injected  # noqa: F401  (fixture)
 pytestmark = pytest.mark.gpu
 
 
-def test_training_iterations_late_variants(golden_late_variant, injected, tmp_path, monkeypatch):  # noqa: F811
-    import mggan.model.modules.standard_discrete as SD
-    monkeypatch.setattr(SD, "get_global_noise", injected.global_noise)     # the discrete generator draws through its own import
-    m = golden_late_variant["meta"]
-    assert m["gan_type"] == "gan" or m["pool_type"] == "sgan" or m["experiment"] == "discrete"
-    _run_iterations(golden_late_variant, injected, tmp_path)
-
-
 @pytest.mark.parametrize("R", [1, 70, 300])
 def test_single_relative_decoder_forward_backward(R):
     """`RelativeDecoder.forward` on its own (one decoder, given initial hidden states) -- the call the discrete-latent
@@ -45,3 +37,11 @@ def test_single_relative_decoder_forward_backward(R):
                             (dec.hidden2pos[0].weight.grad, sd["d.hidden2pos.0.weight"].grad, "d hidden2pos.0")):
         err = float((got.detach().cpu() - want).abs().max() / (want.abs().max() + 1e-12))
         assert err <= 2e-3, (what, err)
+
+
+def test_training_iterations_late_variants(golden_late_variant, injected, tmp_path, monkeypatch):  # noqa: F811
+    import mggan.model.modules.standard_discrete as SD
+    monkeypatch.setattr(SD, "get_global_noise", injected.global_noise)     # the discrete generator draws through its own import
+    m = golden_late_variant["meta"]
+    assert m["gan_type"] == "gan" or m["pool_type"] == "sgan" or m["experiment"] == "discrete"
+    _run_iterations(golden_late_variant, injected, tmp_path)
