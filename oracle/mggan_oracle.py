@@ -547,7 +547,10 @@ class OracleTrainer:
                 "fake": fake_loss.detach(), "grads": grads, "grad_norm": norm,
                 "d_real": real.detach(), "d_fake": fake.detach(), "fake_abs": ab}
 
-    def generator_step(self, b, noise, gen_idxs, labels):
+    def generator_step(self, b, noise, gen_idxs, labels, count_scale=1):
+        """count_scale (tests only): multiplies the per-generator draw counts of the reweighting (train.py:92-96), as if
+        the batch were `count_scale` copies of itself -- the reweighted terms are sums of loss / count divided by the number
+        of draws, so they are NOT invariant under replicating the batch (they shrink by 1 / copies)."""
         mask, gt_xy, gt_dxdy = self.loss_mask(b)
         N = b["in_xy"].shape[1]
         (rel, ab), _, idx = self._G(b, noise, False, self.k, mask, gen_idxs)
@@ -557,7 +560,7 @@ class OracleTrainer:
             min_l2 = min_l2 + l2[:, a:e].sum(1).min()
         min_l2 = min_l2 / N
         out, branch = self._D(b, ab, rel, mask)
-        counts = torch.bincount(idx.flatten(), minlength=self.n_gens).to(out.dtype)
+        counts = torch.bincount(idx.flatten(), minlength=self.n_gens).to(out.dtype) * count_scale
         w = 1.0 / counts[idx]                                            # train.py:92-96
         adv = (self._phi(3, out, *labels) * w).mean()
         clf = ((F.cross_entropy(branch.flatten(0, 1), idx.reshape(-1), reduction="none").reshape(idx.shape) * w).mean()

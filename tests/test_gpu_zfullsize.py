@@ -1,10 +1,11 @@
 """GPU parity at BASELINE.json's full size (cfg 4: num_gens=8, k=20, 512 scenes x 32 agents = 16,384 agents) through a
 size-independent property: REPLICATION INVARIANCE.  The full batch is 64 copies of an 8-scene batch (same scenes, same
 scene noise, same PM-Network draws, same labels).  Every per-scene quantity of a copy then equals the one of the small
-batch, train-mode BatchNorm sees the same batch statistics, and every loss of the iteration is a mean (or a per-scene sum
-over the global agent count, or count-reweighted), so losses AND gradients of the 16,384-agent iteration must equal those
-of the 256-agent batch -- which the CPU oracle (pinned to the reference by tests/test_oracle_golden.py) computes in
-seconds.  Tolerances as in tests/test_gpu_golden.py: losses 1e-3, gradients 2e-3 of the tensor's max."""
+batch, train-mode BatchNorm sees the same batch statistics, and every loss of the iteration is a mean or a per-scene sum
+over the global agent count -- except the two count-reweighted generator terms, which shrink by exactly 1 / copies and are
+evaluated with the replicated counts on the small side -- so losses AND gradients of the 16,384-agent iteration must equal
+those of the 256-agent batch, which the CPU oracle (pinned to the reference by tests/test_oracle_golden.py, premise checked
+by ::test_replication_invariance_of_the_iteration) computes in seconds.  Tolerances as in tests/test_gpu_golden.py: losses 1e-3, gradients 2e-3 of the tensor's max."""
 import math
 from collections import defaultdict
 
@@ -90,7 +91,9 @@ def test_full_size_iteration_equals_oracle_on_replicated_scenes(injected, tmp_pa
     ob["seq_start_end"] = sse_s
     orc = O.OracleTrainer(sdG, sdD, NUM_GENS, num_samples=K)
     od = orc.discriminator_step(ob, d_noise[None], d_idx, lab[0], lab[1])
-    og = orc.generator_step(ob, g_noise, g_idx, lab[2])
+    # the two count-reweighted generator terms (loss / per-generator count, then mean) shrink by 1 / copies under
+    # replication: the single-copy oracle is given the replicated counts (tests/test_oracle_golden.py checks this premise)
+    og = orc.generator_step(ob, g_noise, g_idx, lab[2], count_scale=COPIES)
     opm = orc.net_chooser_step(ob, pm_noise[None])
 
     # ---- the 16,384-agent batch on the B200 path

@@ -171,3 +171,56 @@ def test_train_then_evaluate_20_iterations():
     for key in ("ADE", "FDE"):
         value, count = m[key]
         assert abs(float(value) / float(count) - float(e[key])) <= 1e-3, key
+
+
+def test_replication_invariance_of_the_iteration():
+    """The premise of tests/test_gpu_zfullsize.py, checked on the oracle itself: a batch made of C copies of the same scenes
+    (same noise, same PM-Network draws, same labels) has the losses AND gradients of the single copy -- the losses are means
+    (or per-scene sums over the agent count) and train-mode BatchNorm sees the same statistics -- EXCEPT the two
+    count-reweighted generator terms (train.py:92-113: loss / per-generator count, then mean), which shrink by 1 / C; the
+    single-copy side reproduces that with `count_scale=C`."""
+    import numpy as np
+    from mggan.model.config import get_parser
+    from mggan.model.model_factory import construct_model
+    from mggan.synthetic import make_batch
+    C, G, k = 3, 3, 4
+    torch.manual_seed(2)
+    cfg = get_parser().parse_args(["--num_gens", str(G), "--num_samples", str(k)])
+    Gm, Dm = construct_model(cfg)
+    sdG = {n: v.detach().clone() for n, v in Gm.state_dict().items() if not n.startswith("G_")}
+    sdD = {n: v.detach().clone() for n, v in Dm.state_dict().items()}
+    small = make_batch([3, 5, 2], seed=3, with_img=True)
+    sse = small.pop("seq_start_end")
+    small = {n: torch.from_numpy(v) for n, v in small.items()}
+    n = small["in_xy"].shape[1]
+    big = {n_: (v.repeat(C, 1, 1, 1) if n_ == "features" else v.repeat(1, C, 1)) for n_, v in small.items()}
+    big["seq_start_end"] = [[c * n + a, c * n + b] for c in range(C) for a, b in sse]
+    small["seq_start_end"] = sse
+    gen, rng = torch.Generator().manual_seed(4), np.random.default_rng(5)
+
+    def scene_noise():
+        return torch.cat([torch.randn(1, 8, generator=gen).repeat(b - a, 1) for a, b in sse])
+
+    d_noise, pm_noise, g_noise = scene_noise(), scene_noise(), torch.stack([scene_noise() for _ in range(k)])
+    d_idx = torch.from_numpy(rng.integers(0, G, size=(n, 1)))
+    g_idx = torch.from_numpy(rng.integers(0, G, size=(n, k)))
+    lab = [(0.95, 0.04), (0.92, 0.07), (0.97, 0.02)]
+    res = []
+    for b, rep in ((small, 1), (big, C)):
+        tr = O.OracleTrainer(sdG, sdD, G, num_samples=k)
+        d = tr.discriminator_step(b, d_noise.repeat(rep, 1)[None], d_idx.repeat(rep, 1), lab[0], lab[1])
+        g = tr.generator_step(b, g_noise.repeat(1, rep, 1), g_idx.repeat(rep, 1), lab[2], count_scale=C // rep)
+        pm = tr.net_chooser_step(b, pm_noise.repeat(rep, 1)[None])
+        res.append((d, g, pm))
+    (d1, g1, p1), (d2, g2, p2) = res
+    for key in ("ce", "real", "fake"):
+        close(d2[key], d1[key], rtol=1e-5, atol=1e-7, what=key)
+    for key in ("l2", "adv", "clf"):
+        close(g2[key], g1[key], rtol=1e-5, atol=1e-7, what=key)
+    close(p2["loss"], p1["loss"], rtol=1e-5, atol=1e-7, what="pm")
+    for a, b, what in ((d1, d2, "D"), (g1, g2, "G"), (p1, p2, "PM")):
+        for name, v in a["grads"].items():
+            if v is None or name.endswith("Conv_1.bias"):
+                assert (b["grads"][name] is None) == (v is None)
+                continue
+            close(b["grads"][name], v, rtol=2e-3, atol=2e-6, what=f"{what} {name}")
