@@ -48,3 +48,22 @@ def test_reference_checkpoint_loads_strictly():
         i = next(iter(sd["state"]))
         assert set(sd["state"][i]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][i]["step"]) >= 1
         assert sd["param_groups"][0]["betas"] == ref_groups[0]["betas"] and sd["param_groups"][0]["weight_decay"] == 0.01
+
+
+def test_oracle_on_the_reference_checkpoint_reproduces_its_predictions():
+    """The weights stored in the reference-written checkpoint, run through the oracle generator in eval mode with the
+    fixture's noise and PM-Network draws, give the predictions the reference trainer made after saving."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import mggan_oracle as O
+    ck = torch.load(os.path.join(VERSION_DIR, "checkpoints", "checkpoint_best.pth"), map_location="cpu")
+    z = np.load(os.path.join(GOLD, "expected.npz"))
+    sd = {k: v for k, v in ck["generator"].items() if not k.startswith("G_")}
+    sse = [tuple(int(x) for x in r) for r in z["seq_start_end"]]
+    with torch.no_grad():
+        (_, ab), logits, _ = O.generator_forward(sd, 2, torch.from_numpy(z["in_xy"]), torch.from_numpy(z["in_dxdy"]), sse,
+                                                 torch.from_numpy(z["noise"]), False, torch.from_numpy(z["features"]), 4, None,
+                                                 torch.from_numpy(z["idx"]), training=False)
+    assert float((ab - torch.from_numpy(z["abs"])).abs().max()) <= 1e-5 * float(np.abs(z["abs"]).max())
+    assert float((torch.softmax(logits, 1) - torch.from_numpy(z["probs"])).abs().max()) <= 1e-6

@@ -142,3 +142,18 @@ def test_synthetic_scene_image_modes():
         for a in range(0, len(ids), 5):
             want = DO.image_features_small(imgs[ids[a]], bh["in_xy"][-1, a].numpy(), SCALING_SMALL)
             assert np.array_equal(want, bh["features"][a].numpy())
+
+
+def test_oracle_reproduces_the_fixture_predictions(ev):
+    """The evaluation fixture's predictions came from the reference's `predict` (eval mode, injected noise and PM-Network
+    draws): the oracle generator reproduces them, so the GPU test built on the fixture asks the right thing."""
+    import mggan_oracle as O
+    sd = {k[2:]: torch.from_numpy(v) for k, v in ev.items() if k.startswith("G/")}
+    sse = [tuple(int(x) for x in r) for r in ev["batch/seq_start_end"]]
+    with torch.no_grad():
+        (_, ab), logits, _ = O.generator_forward(
+            sd, 4, torch.from_numpy(ev["batch/in_xy"]), torch.from_numpy(ev["batch/in_dxdy"]), sse,
+            torch.from_numpy(ev["pred/noise"]), False, None, int(ev["meta/K"]), None, torch.from_numpy(ev["pred/idx"]),
+            training=False)
+    assert float((ab - torch.from_numpy(ev["pred/abs"])).abs().max()) <= 1e-5 * float(np.abs(ev["pred/abs"]).max())
+    assert float((torch.softmax(logits, 1) - torch.from_numpy(ev["pred/probs"])).abs().max()) <= 1e-6
