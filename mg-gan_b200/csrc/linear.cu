@@ -104,7 +104,7 @@ gemm_kernel(GemmArgs g) {
 // ---- variant 2 (opt-in, mggan_set_gemm_variant(2)): same contract as gemm_kernel, (16 TM) x 64 output tile with a
 // TM x 4 register micro-tile (TM = 8: three LDS.128 feed 32 FMAs instead of two feeding 16) and the next K-slab's global
 // loads issued into registers before the current slab is computed (one memory latency overlapped per slab instead of
-// exposed).  Written after the round's GPU budget was spent: NOT the default until tests/test_gpu_zzgemm_v2.py has run.
+// exposed).  Written after the round's GPU budget was spent: NOT the default until tests/test_gpu_zf_gemm_variants.py has run.
 template <int TM>
 __global__ void __launch_bounds__(MGGAN_THREADS)
 gemm_kernel_v2(GemmArgs g) {

@@ -8,7 +8,7 @@
 // accumulate the slab into one TMEM tile.  One CTA = one warpgroup = one 128-row tile of C; thread r stages row r of A
 // (its own 128-byte line of a K-fast operand, or a coalesced column of an M-fast one), rows r and r + 128 of B, and owns
 // TMEM lane r in the epilogue (bias, activation, store or split-K atomicAdd; column sums of A for the bias gradient are
-// thread-local).  Written after the round's GPU budget was spent: NOT the default until tests/test_gpu_zzgemm_v2.py has
+// thread-local).  Written after the round's GPU budget was spent: NOT the default until tests/test_gpu_zf_gemm_variants.py has
 // run on a B200.  The PTX wrappers are copies of decoder_tc.cu's on purpose (that file is measured and stays untouched).
 #include "gemm_args.cuh"
 

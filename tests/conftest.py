@@ -15,7 +15,7 @@ GOLDEN_CASES = ["cfg1_g1_tiny", "cfg2_g4_eth_noimg", "cfg3_g8_sdd_masked"]
 # objective variants (gan_obj LS / MM, weighting_target l2 / endpoint / mgan): whole-iteration vectors only
 VARIANT_CASES = ["var_ls_l2", "var_mm_endpoint", "var_ns_mgan"]
 # variants frozen after the round's GPU budget was spent: checked against the oracle on the CPU, and on the GPU from a
-# late-sorting test file (tests/test_gpu_zvariants.py) so that a surprise there cannot mask the parity tests that ran
+# late-sorting test file (tests/test_gpu_ze_variants.py) so that a surprise there cannot mask the parity tests that ran
 LATE_VARIANT_CASES = ["var_gan_plain", "var_sgan_pool", "var_discrete"]
 
 

@@ -80,7 +80,7 @@ def test_crop_oracle_matches_reference(crops):
 def test_device_metric_host_logic_matches_reference(ev, monkeypatch):
     """The descriptor / offset construction and the reductions of `evaluate_*_cuda` (host logic), with the two kernels
     replaced by straightforward torch / numpy stand-ins; the kernels themselves are checked on the GPU
-    (tests/test_gpu_zdata_eval.py)."""
+    (tests/test_gpu_zd_data_eval.py)."""
     from mggan import evaluation as E
     from mggan import kernels as K
 

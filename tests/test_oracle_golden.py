@@ -174,7 +174,7 @@ def test_train_then_evaluate_20_iterations():
 
 
 def test_replication_invariance_of_the_iteration():
-    """The premise of tests/test_gpu_zfullsize.py, checked on the oracle itself: a batch made of C copies of the same scenes
+    """The premise of tests/test_gpu_zb_fullsize.py, checked on the oracle itself: a batch made of C copies of the same scenes
     (same noise, same PM-Network draws, same labels) has the losses AND gradients of the single copy -- the losses are means
     (or per-scene sums over the agent count) and train-mode BatchNorm sees the same statistics -- EXCEPT the two
     count-reweighted generator terms (train.py:92-113: loss / per-generator count, then mean), which shrink by 1 / C; the

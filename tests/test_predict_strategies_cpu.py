@@ -94,7 +94,7 @@ def test_gather_is_the_selected_decode():
 
 def test_pool_hidden_net_host_logic_matches_oracle(monkeypatch):
     """`--pool_type sgan`: the folded first layer, pair gather and segment max of the product's PoolHiddenNet (host logic;
-    `mggan_linear_*` replaced by torch here, the GPU path is checked by tests/test_gpu_zvariants.py) against the oracle's
+    `mggan_linear_*` replaced by torch here, the GPU path is checked by tests/test_gpu_ze_variants.py) against the oracle's
     literal restatement of the reference loop (social_gan.py:203-229), values and gradients."""
     import torch
     import torch.nn.functional as F
@@ -128,7 +128,7 @@ def test_pool_hidden_net_host_logic_matches_oracle(monkeypatch):
 def test_discrete_latent_generator_host_logic_matches_oracle(monkeypatch):
     """`--experiment discrete`: row layouts, code gather and autograd wiring of the product's DiscreteLatentGenerator (host
     logic) with every kernel wrapper replaced by a plain torch stand-in; the real kernels are checked on the GPU
-    (tests/test_gpu_zvariants.py) against vectors frozen from the reference."""
+    (tests/test_gpu_ze_variants.py) against vectors frozen from the reference."""
     import types
     import torch
     import torch.nn.functional as F
