@@ -3,7 +3,9 @@
 `evaluate_ade_fde` implements the reference's *intent*: as written the reference passes
 `(…, None, "raw")` positionally into `(…, mode, mode_thresh)` and raises TypeError
 (SURVEY.md 8a a17); the intended call is `mode="raw"` and that is what happens here.
-Precision / Recall (manifold test, evaluation.py:101-156) is a "next" row of the scope table.
+`evaluate_precision_recall` is the manifold (growing-radius tube) test of evaluation.py:101-156.  Both host functions are
+checked against outputs of the unmodified reference (tests/test_eval_crop_cpu.py); the `*_cuda` functions at the end of
+the file return the same dicts with the arithmetic in `mggan_min_ade_fde` / `mggan_tube_inside`.
 """
 from collections import defaultdict
 
