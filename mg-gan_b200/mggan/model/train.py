@@ -9,10 +9,11 @@ their gradients are single kernels (`mggan_l2_scene_min`, `mggan_bce_scalar_labe
 `mggan_ce_generators`, `mggan_pm_ml_loss`), the per-generator reweighting uses the draw counts
 the selection kernel already produced, and no step synchronises with the host.
 
-Only the default configuration is on the path: gan_type in {mgan, gan}, gan_obj NS,
-weighting_target in {ml, none}, l2_loss_type not in {none, mse} (the non-default branches are
-"next" rows in SURVEY.md 8f and raise NotImplementedError).  All prediction strategies of
-`get_predict_func` (train.py:291-576) are built: they decode only the sequences they keep.
+On the path: gan_type in {mgan, gan}, gan_obj in {NS, MM, LS}, weighting_target in {ml, l2, endpoint, mgan, none},
+l2_loss_type != mse, both experiments (multi_generator, discrete) and both pooling types (sways, sgan).  What the
+reference cannot run either raises NotImplementedError (gan_obj W, gan_type infogan / probgan, weighting_target
+disc_scores, num_unrolling_steps > 0).  All prediction strategies of `get_predict_func` (train.py:291-576) are built:
+they decode only the sequences they keep.
 """
 import random
 import time
