@@ -1,7 +1,8 @@
 // tcgen05 feature probe for the next kernels: which operand forms of tcgen05.mma kind::tf32 work on
 // this part and how they are encoded, answered by exact integer-valued products checked on the host.
 //
-//   ss_kmajor     A, B in shared memory, K-major canonical no-swizzle layout (the form decoder_tc.cu uses), N = 128/32/16
+//   ss_kmajor     A, B in shared memory, K-major canonical no-swizzle layout (the form decoder_tc.cu uses), N = 128/32/16,
+//                 and the same with core matrices 144 B apart (padded LBO) for conflict-free transposed staging
 //   ts_tmem_a     A read from tensor memory (written by tcgen05.st, thread r = lane r), B K-major in shared memory:
 //                 the form a thread-per-row backward needs for dh = dG . W_hh without a 64 KB shared-memory operand
 //   mn_major      A and/or B MN-major (the reduction index K is the slow one: [k][m] storage), both readings of the
@@ -172,6 +173,14 @@ static std::vector<Named> probes() {
     v.push_back({"ss_kmajor_n32_k32", kmaj(32, 32)});
     v.push_back({"ss_kmajor_n16_k32", kmaj(16, 32)});
     v.push_back({"ss_kmajor_n32_k128", kmaj(32, 128)});
+    {   // K-major with padded core-matrix spacing (LBO = 144 B): lets a thread-per-row kernel write TRANSPOSED operands
+        // (4-byte stores, k fastest across lanes) without 8-way bank conflicts
+        Probe p = kmaj(32, 32);
+        p.a_k_group = p.b_k_group = 144; p.a_lbo = p.b_lbo = 144;
+        p.a_mn_group = p.b_mn_group = (32 / 4) * 144; p.a_sbo = p.b_sbo = (32 / 4) * 144;
+        p.a_kstep = p.b_kstep = 2 * 144;
+        v.push_back({"ss_kmajor_lbo144", p});
+    }
     for (int N : {32, 128}) {
         Probe p = kmaj(N, 128);
         p.a_mode = 2;
