@@ -144,7 +144,7 @@ class GraphedIteration:
             b1, b2 = group["betas"]
             f[off] = group["lr"]
             for j, p in enumerate(params):
-                st = opt.state[p]
+                st = opt._init_state(p)
                 st["step"] += 1
                 t = int(st["step"].item())
                 f[off + 1 + j] = 1.0 - b1 ** t

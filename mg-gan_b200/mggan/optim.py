@@ -24,6 +24,9 @@ class FusedAdamW(torch.optim.Optimizer):
             st["step"] = torch.tensor(0.0)
             st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        elif not torch.is_tensor(st["step"]):
+            # checkpoints written by the reference's pinned torch 1.6 store `step` as a Python int
+            st["step"] = torch.tensor(float(st["step"]))
         return st
 
     @torch.no_grad()

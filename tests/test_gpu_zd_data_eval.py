@@ -113,7 +113,7 @@ def test_tube_inside_matches_oracle(m, n):
     desc = torch.tensor([(m + i, 0, m) for i in range(n)], dtype=torch.int32, device=DEV)
     got = K.tube_inside(pool, radius, desc, torch.arange(m, dtype=torch.int32, device=DEV)).cpu().numpy()
     assert np.array_equal(got, want)
-    if m:
+    if m and n // 2:          # near-copies were planted only when n // 2 > 0
         assert 0 < want.sum()
 
 
