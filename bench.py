@@ -41,9 +41,11 @@ def parse():
     ap.add_argument("--gemm", type=int, default=1, choices=[1, 2, 3],
                     help="GEMM kernel behind mggan_linear_*: 1 default, 2 = FP32 128x64 register-prefetch variant, "
                          "3 = tcgen05 3xTF32 variant (A/B measurement)")
-    ap.add_argument("--resident-images", action="store_true",
-                    help="extra end-to-end leg: scene images resident in HBM, crops cut on the device (mggan_scene_crop); "
-                         "the host batch carries image ids instead of the 17,424-byte crops")
+    ap.add_argument("--resident-images", action="store_true", help="(kept for compatibility: now the default e2e leg)")
+    ap.add_argument("--no-host-crops-e2e", action="store_true",
+                    help="skip the second end-to-end leg that ships host-built 17,424-byte crops per agent over PCIe")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg (global 512 scenes sharded)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the cfg-2 / cfg-3 / latency-point legs (N = 1 only)")
     ap.add_argument("--roofline-kernel", default=None, help="entry point whose launches are timed in the timed region")
     ap.add_argument("--breakdown", action="store_true", help="print a per-kernel time table to stderr")
     ap.add_argument("--breakdown-detail", action="store_true", help="per-(entry point, shape) time table to stderr")
@@ -324,41 +326,67 @@ def run_ours(a):
         ms_step = ms_eager
     clocks = sampler.stop() if sampler else None
 
-    # ---- end-to-end through the public API with host buffers
-    e2e = None
+    # ---- end-to-end through the public API with HOST batches.  Headline `e2e`: the dataset's scene images are resident in
+    # HBM (u8 atlas) and the pinned host batch carries trajectories + one image id per agent; the crops
+    # are cut on the device by mggan_scene_crop inside the timed region.  Second leg `e2e_host_crops`: the reference's
+    # loader layout, host-built (N, 4, 33, 33) fp32 crops shipped over PCIe every step.
+    e2e = e2e_host = None
     if not a.no_e2e:
-        ms_e2e, _, _ = timed(run_e2e, a.steps, max(a.warmup, 3))
-        h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "seq_start_end")
-        e2e = {"value": 20.0 * n_total / (ms_e2e / 1e3), "unit": "agent-timesteps/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 6 * 4,
-               "api": "PiNetMultiGeneratorGAN.train_iterations(host batches): H2D of step i+1 overlaps step i"}
+        import numpy as np
+        from mggan.data_utils.scene_images import SceneImageStore
+        from mggan.synthetic import SCALING_SMALL, make_scene_image
+        images = [make_scene_image(9000 + rank * a.scenes + i) for i in range(a.scenes)]
+        tr.attach_scene_images(SceneImageStore(images, SCALING_SMALL, dev))
+        ids = np.concatenate([np.full(e - s, i, np.int32) for i, (s, e) in enumerate(sse)])
+        host_res = {k: v for k, v in host.items() if k != "features"}
+        host_res["image_ids"] = torch.from_numpy(ids).pin_memory()
 
-    # ---- optional: end to end with the scene images resident in HBM.  Reported beside `e2e`, which
-    # keeps shipping host-built crops like the reference's loader does.
-    e2e_res = None
-    if a.resident_images and not a.no_e2e:
-        try:
-            import numpy as np
-            from mggan.data_utils.scene_images import SceneImageStore
-            from mggan.synthetic import SCALING_SMALL, make_scene_image
-            images = [make_scene_image(9000 + rank * a.scenes + i) for i in range(a.scenes)]
-            tr.attach_scene_images(SceneImageStore(images, SCALING_SMALL, dev))
-            ids = np.concatenate([np.full(e - s, i, np.int32) for i, (s, e) in enumerate(sse)])
-            host_res = {k: v for k, v in host.items() if k != "features"}
-            host_res["image_ids"] = torch.from_numpy(ids).pin_memory()
+        def run_e2e_res(n):
+            m = defaultdict(list)
 
-            def run_e2e_res(n):
-                m = defaultdict(list)
-                tr.train_iterations((host_res for _ in range(n)), m, on_step=lambda i, mm: mm.clear())
+            def read_back(i, mm):
+                keys = sorted(kk for kk in mm if kk.startswith("train/"))
+                vals = torch.stack([mm[kk][-1].float().reshape(()) for kk in keys])
+                loss_ring[i, :vals.numel()].copy_(vals, non_blocking=True)
+                mm.clear()
 
-            ms_res, _, _ = timed(run_e2e_res, a.steps, max(a.warmup, 3))
-            h2d_res = sum(v.numel() * v.element_size() for k, v in host_res.items() if k != "seq_start_end")
-            e2e_res = {"value": 20.0 * n_total / (ms_res / 1e3), "unit": "agent-timesteps/s", "ms_per_step": ms_res,
-                       "h2d_bytes_per_step": int(h2d_res), "d2h_bytes_per_step": 0,
-                       "resident_image_bytes": tr.scene_images.nbytes(),
-                       "api": "train_iterations(host batches with image_ids); crops cut by mggan_scene_crop"}
-        except Exception as exc:            # an optional leg never costs the main line
-            e2e_res = {"error": repr(exc)}
+            tr.train_iterations((host_res for _ in range(n)), m, on_step=read_back)
+
+        ms_res, _, _ = timed(run_e2e_res, a.steps, max(a.warmup, 3))
+        h2d_res = sum(v.numel() * v.element_size() for k, v in host_res.items() if k != "seq_start_end")
+        e2e = {"value": 20.0 * n_total / (ms_res / 1e3), "unit": "agent-timesteps/s", "ms_per_step": ms_res,
+               "h2d_bytes_per_step": int(h2d_res), "d2h_bytes_per_step": 6 * 4,
+               "resident_image_bytes": tr.scene_images.nbytes(),
+               "api": "PiNetMultiGeneratorGAN.train_iterations(pinned host batches: trajectories + image_ids); scene images "
+                      "resident in HBM, crops cut by mggan_scene_crop inside the timed region; H2D of step i+1 overlaps step i"}
+        if not a.no_host_crops_e2e:
+            ms_e2e, _, _ = timed(run_e2e, a.steps, max(a.warmup, 3))
+            h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "seq_start_end")
+            e2e_host = {"value": 20.0 * n_total / (ms_e2e / 1e3), "unit": "agent-timesteps/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 6 * 4,
+                        "api": "train_iterations(host batches with host-built fp32 crops, the reference loader's layout)"}
+
+    # ---- strong scaling (global batch 512 scenes = 16,384 agents sharded over the ranks)
+    strong = None
+    if world > 1 and not a.no_strong:
+        from mggan.distributed import shard_batch
+        full = make_inputs(a.scenes, a.agents, seed=4000, pin=False)           # the SAME global batch on every rank
+        mine = shard_batch(full, world, rank)
+        sse_s = mine["seq_start_end"]
+        devs = {k: v.to(dev) for k, v in mine.items() if k != "seq_start_end"}
+        prep_s = (devs["in_xy"], devs["in_dxdy"], devs["gt_xy"], devs["gt_dxdy"], sse_s, devs["features"], None)
+
+        def run_strong(n):
+            for _ in range(n):
+                tr._run_iteration(prep_s, metrics)
+                metrics.clear()
+
+        ms_s, _, _ = timed(run_strong, a.steps, max(a.warmup, 3))
+        n_glob = full["in_xy"].shape[1]
+        strong = {"scaling": "strong", "value": 20.0 * n_glob / (ms_s / 1e3), "unit": "agent-timesteps/s",
+                  "ms_per_step": ms_s, "global_agents": n_glob, "agents_per_gpu": devs["in_xy"].shape[1],
+                  "note": "global batch of %d scenes sharded by scene over %d ranks; compare with the N=1 `value` "
+                          "(same global batch on one GPU)" % (a.scenes, world)}
 
     hbm_peak, peak_kind = peaks()
     b_iter = algorithmic_bytes_per_iter(n_local, True, pg, pd, pm)
@@ -381,6 +409,7 @@ def run_ours(a):
                            "frac_hbm": b_iter / (ms_step / 1e3) / 1e9 / hbm_peak},
             "fp32": {"algorithmic_gflop_per_step": flops / 1e9, "achieved_tflops": flops / (ms_step / 1e3) / 1e12,
                      "peak_tflops": FP32_PEAK_TFLOPS, "frac": flops / (ms_step / 1e3) / 1e12 / FP32_PEAK_TFLOPS,
+                     "peak_source": "NOMINAL (148 SMs x 128 FMA lanes x 2 x 1.965 GHz), not a measured peak",
                      "note": "the path is FP32-FMA bound (970 FLOP/B), not HBM bound: this is the fraction that measures kernel quality"}}
 
     line = {
@@ -400,8 +429,15 @@ def run_ours(a):
                               "cuda_graph the iteration (these + autograd glue) is replayed as one graph"},
         "kernel_breakdown_ms": {n: round(t, 3) for n, (c, t) in top[:8]},
     }
-    if e2e_res is not None:
-        line["e2e_resident_images"] = e2e_res
+    if e2e_host is not None:
+        line["e2e_host_crops"] = e2e_host
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if rank == 0 and world == 1 and not a.no_extra_configs:
+        try:
+            line["other_configs"] = extra_configs(a, dev)
+        except Exception as exc:                      # an extra leg never costs the main line
+            line["other_configs"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, budget_s=20.0)
     if rank == 0:
@@ -418,6 +454,76 @@ def run_ours(a):
         dist.barrier()
         dist.destroy_process_group()
         os._exit(0)
+
+
+def extra_configs(a, dev):
+    """BASELINE.json configs[1] (cfg-2: G=4, eth-shape, no scene CNN), configs[2] (cfg-3: G=8, SDD-shape, scene CNN) and
+    the reference-default latency point of cfg-4 (2 scenes x 32 agents) on one GPU: parity cases, reported beside the
+    headline with their own whole-step roofline entries (SURVEY.md 8d byte / FLOP formulas).  Each is timed eagerly and
+    as the trainer runs a repeating batch structure (CUDA-graph replay)."""
+    import contextlib, io
+    import numpy as np
+    import torch
+    from collections import defaultdict
+    from mggan import kernels as _K
+    from mggan.logging import Experiment
+    from mggan.model.config import get_parser
+    from mggan.model.model_factory import construct_model
+    from mggan.model.train import PiNetMultiGeneratorGAN
+    from mggan.synthetic import make_config_batch, make_batch
+    hbm_peak, _ = peaks()
+    out = {}
+    cases = [("cfg2_eth_g4_noimg", "eth", 64, 4, False), ("cfg3_sdd_g8_img", "sdd", 64, 8, True),
+             ("cfg4_latency_point", "univ", 2, a.num_gens, True)]
+    for name, shape, scenes, G_, with_img in cases:
+        torch.manual_seed(1234)
+        cfg = get_parser().parse_args(["--num_gens", str(G_), "--num_samples", str(a.k), "--scene_dim", "64" if with_img else "0"])
+        cfg.gpus = True
+        with contextlib.redirect_stdout(io.StringIO()):
+            G, D = construct_model(cfg)
+        tr = PiNetMultiGeneratorGAN(G, D, cfg, Experiment(tempfile.mkdtemp(prefix="mggan_bench_"), name, version=0))
+        tr.epoch = 1
+        tr.G.train(); tr.D.train()
+        b = make_config_batch(shape, scenes, seed=77, with_img=with_img)
+        sse = b.pop("seq_start_end")
+        d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in b.items()}
+        prepared = (d["in_xy"], d["in_dxdy"], d["gt_xy"], d["gt_dxdy"], sse, d.get("features"), None)
+        n = d["in_xy"].shape[1]
+        m = defaultdict(list)
+
+        def eager(k_):
+            for _ in range(k_):
+                _K.PatchStats._cache.clear()
+                tr._run_prepared(prepared, m)
+                m.clear()
+
+        def loop(k_):
+            for _ in range(k_):
+                tr._run_iteration(prepared, m)
+                m.clear()
+
+        res = {}
+        for tag, fn in (("eager", eager), ("graph", loop)):
+            fn(4)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = max(a.steps, 10)
+            e0.record(); fn(steps); e1.record()
+            torch.cuda.synchronize()
+            res[tag] = e0.elapsed_time(e1) / steps
+        pg, pd, pm = param_counts(tr.G, tr.D)
+        b_iter = algorithmic_bytes_per_iter(n, with_img, pg, pd, pm)
+        ms = res["graph"]
+        out[name] = {"agents": n, "scenes": len(sse), "num_gens": G_, "scene_cnn": with_img, "ms_per_step": ms,
+                     "ms_per_step_eager": res["eager"], "value": 20.0 * n / (ms / 1e3), "unit": "agent-timesteps/s",
+                     "roofline": {"bound": "hbm", "scope": "whole step", "algorithmic_bytes": int(b_iter),
+                                  "achieved": b_iter / (ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": b_iter / (ms / 1e3) / 1e9 / hbm_peak,
+                                  "note": "latency-bound at this batch size (a few hundred agents): ~20 dependent kernels per "
+                                          "step function; the working set fits the L2"}}
+        tr._graphs.clear()
+        del tr
+    return out
 
 
 # ------------------------------------------------------------------------------------------ CPU arm

@@ -60,6 +60,7 @@ class MultiGeneratorGAN(abc.ABC):
         self._graph = None                 # mggan.graph.GraphedIteration while capturing
         self._graphs = []                  # captured iterations (one per batch structure, most recent first)
         self._graph_seen = None            # structure key of the previous eager iteration
+        self._graph_failed = set()         # structures whose capture raised: they stay eager
         self.scene_images = None           # SceneImageStore: crops are cut on the device for batches carrying `image_ids`
         # GAN objective (reference abstract_train.py:61-85): phi_1 (D on real), phi_2 (D on fake), phi_3 (G on fake), each a
         # (loss kernel, which label, sign) triple applied to the discriminator output with a scalar smoothed label
@@ -173,9 +174,16 @@ class MultiGeneratorGAN(abc.ABC):
             return
         self._graph_seen = key if eligible else None
         self._run_prepared(prepared, metrics, total_iterations, sums)       # this batch runs eagerly
-        if ready:
+        if ready and key not in self._graph_failed:
             from mggan.graph import GraphedIteration
-            new = GraphedIteration(self, prepared, total_iterations)
+            try:
+                new = GraphedIteration(self, prepared, total_iterations)
+            except Exception as exc:        # the eager iteration above already ran: keep training, never capture this structure again
+                # (data-parallel: a rank without a graph answers "no graph" in the per-iteration exchange, so no rank replays)
+                self._graph_failed.add(key)
+                torch.cuda.synchronize(self.device)
+                print(f"[mggan] CUDA-graph capture failed ({exc!r}); this batch structure keeps running eagerly")
+                return
             new.global_counts = (sums["agents"][1], sums["active"][1]) if sums is not None else None
             self._graphs.insert(0, new)
             del self._graphs[2:]

@@ -90,6 +90,12 @@ class DistContext:
         self._replay = list(self._log) if on else None
 
     def attach(self, G, D):
+        # Called after the (identically seeded) weight initialisation: from here on every rank draws its own scene noise
+        # (torch's CUDA generator) and generator indices (the Gumbel sampler is keyed on torch.initial_seed()), so the
+        # shards of one global batch are statistically independent like the scenes of a single-GPU batch.
+        if self.world_size > 1 and not getattr(self, "_reseeded", False):
+            self._reseeded = True
+            torch.manual_seed((torch.initial_seed() + 1000003 * (self.rank + 1)) % (1 << 63))
         for m in (G, D):
             enc = getattr(m, "scene_encoder", None)
             if enc is not None:

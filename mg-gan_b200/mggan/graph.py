@@ -68,6 +68,8 @@ class ScalarFeed:
 class GraphedIteration:
     """One captured training iteration of `trainer` for batches shaped like `prepared`."""
 
+    _uid = 0
+
     def __init__(self, trainer, prepared, total_iterations=0):
         in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img, loss_mask = prepared
         assert loss_mask is None, "batches with NaN-masked futures run eagerly"
@@ -84,6 +86,8 @@ class GraphedIteration:
         self.metrics = defaultdict(list)
         self.total_iterations = total_iterations
         self.global_counts = None      # data-parallel: (sum of agents, sum of unmasked agents) the normalisers were baked with
+        GraphedIteration._uid += 1
+        self.uid = GraphedIteration._uid
 
         trainer._graph = self
         for m in (trainer.G, trainer.D):
@@ -125,6 +129,7 @@ class GraphedIteration:
 
     def sampler_offset(self):
         self.sampler_calls += 1
+        assert self.sampler_calls <= 4, "the replay offset layout reserves 2 bits for the sampler call index"
         return self.feed.di[0:1]
 
     # ---- replay ----------------------------------------------------------------------------------------
@@ -150,7 +155,9 @@ class GraphedIteration:
                 f[off + 1 + j] = 1.0 - b1 ** t
                 f[off + 65 + j] = math.sqrt(1.0 - b2 ** t)
         self.replays += 1
-        self.feed.i[0] = self.replays << 32                    # a fresh Philox offset range per replay
+        # a fresh Philox offset range per replay, disjoint from the eager draws (bit 62) and from other captured
+        # structures (uid); the 2 bits under it hold the sampler call's index inside the iteration
+        self.feed.i[0] = (1 << 62) | ((self.uid & 0xFFFF) << 46) | ((self.replays & 0xFFFFFF) << 22)
 
     def run(self, prepared):
         """Copy the batch into the static buffers, refresh the per-iteration scalars, replay.  Returns the metrics

@@ -131,10 +131,15 @@ class MultiGenerator(nn.Module):
         Categorical(logits).sample (standard.py:217-225); here a device Gumbel-max sampler keyed on
         torch's seed and a call counter draws from the same distribution."""
         logits = self.pm_logits(enc_h)
-        self._sample_calls += 1
         graph = getattr(self, "_graph", None)          # captured iteration: the Philox offset advances on the device
-        idx = K.gumbel_sample(logits, num_samples, torch.initial_seed() & ((1 << 63) - 1), self._sample_calls << 20,
-                              graph.sampler_offset() if graph is not None else None)
+        seed = torch.initial_seed() & ((1 << 63) - 1)
+        if graph is not None:
+            # replayed draws live in their own offset space (bit 62 set by the graph's device-side offset; the static part is
+            # the call's index inside the iteration), so they never meet the eager draws' `_sample_calls << 20`
+            idx = K.gumbel_sample(logits, num_samples, seed, graph.sampler_calls << 20, graph.sampler_offset())
+        else:
+            self._sample_calls += 1
+            idx = K.gumbel_sample(logits, num_samples, seed, self._sample_calls << 20, None)
         return logits, idx
 
     def _decode(self, in_xy, in_dxdy, enc_h, noise, social_feats, sel):
@@ -180,6 +185,12 @@ class MultiGenerator(nn.Module):
                     sampled_gen_idxs = gen_idxs(net_chooser_out) if callable(gen_idxs) else gen_idxs
                     sampled_gen_idxs = sampled_gen_idxs.to(device=enc_h.device, dtype=torch.int64)
                     assert sampled_gen_idxs.shape == (batch_size, num_samples), sampled_gen_idxs.shape
+                    # caller-supplied indices (prediction strategies, tests): the selection kernel would decode an
+                    # out-of-range index with generator 0; this path may synchronise, so check on the host
+                    if sampled_gen_idxs.numel() and not torch.cuda.is_current_stream_capturing():
+                        lo, hi = int(sampled_gen_idxs.min()), int(sampled_gen_idxs.max())
+                        if lo < 0 or hi >= self.n_gs:
+                            raise ValueError(f"gen_idxs out of range [0, {self.n_gs}): min {lo}, max {hi}")
             sel = K.Selection.from_indices(sampled_gen_idxs, self.n_gs)
             self.last_selection = sel           # per-generator draw counts for the trainer's reweighting
             pred_xy, pred_dxdy = self._decode(in_xy, in_dxdy, enc_h, noise, social_feats, sel)

@@ -19,7 +19,7 @@ def _check_base(line):
 
 
 def test_committed_b200_bench_lines_have_every_contract_key():
-    ours = sorted(p for p in glob.glob(os.path.join(ROOT, "profiles", "r1*_bench.json")))
+    ours = sorted(p for p in glob.glob(os.path.join(ROOT, "profiles", "r[0-9]*_bench.json")))
     assert ours, "no bench line captured on a B200 under profiles/"
     line = json.load(open(ours[-1]))
     _check_base(line)
@@ -49,4 +49,10 @@ def test_reference_arm_line_live():
     _check_base(line)
     assert line["impl"] == "reference"
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    cpu = line["cpu_baseline"]
+    assert cpu["value"] == line["value"] and cpu["cores"] >= 1 and cpu["sample"]
+    staged = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "mggan")) or os.path.isdir("/root/reference/mggan")
+    # the unmodified reference trainer when a copy is present (staged by __graft_entry__.build()), else the oracle port
+    assert cpu["kind"] == ("reference" if staged else "port")
+    if staged:
+        assert cpu["port"]["kind"] == "port" and cpu["port"]["value"] > 0

@@ -34,6 +34,19 @@ def check(a, b, tol, what, atol=0.0):
     assert math.isfinite(err) and err <= bound, f"{what}: max abs err {err:.3e} > {bound:.3e} (ref max {float(b.abs().max()):.3e})"
 
 
+def check_elementwise(a, b, what, rtol=1e-3, atol=1e-3):
+    """north_star bar read element by element: |got - ref| <= atol + rtol |ref| for EVERY predicted coordinate (metres;
+    atol = 1 mm), not only against the largest coordinate of the tensor."""
+    a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.numel() == 0:
+        return
+    excess = (a - b).abs() - (atol + rtol * b.abs())
+    worst = int(excess.argmax())
+    assert float(excess.max()) <= 0.0, (f"{what}: element {worst}: got {float(a.flatten()[worst]):.6f} ref "
+                                        f"{float(b.flatten()[worst]):.6f} (max abs err {float((a - b).abs().max()):.3e})")
+
+
 def make_config(g):
     from mggan.model.config import get_parser
     args = get_parser().parse_args(["--num_gens", str(g["meta"]["num_gens"]), "--num_samples", str(g["meta"]["k"]),
@@ -124,13 +137,17 @@ def test_module_outputs(golden, injected):
         (rel, ab), logits, _ = G(b["in_xy"], b["in_dxdy"], sse, noise=m["all_noise"].to(DEV), all_gen_out=True,
                                  img=img, num_samples=3, mask=mask)
         check(ab, m["all_abs"], 1e-3, "all_abs")
+        check_elementwise(ab, m["all_abs"], "all_abs")
         check(rel, m["all_rel"], 1e-3, "all_rel")
+        check_elementwise(rel, m["all_rel"], "all_rel", atol=1e-4)
         check(logits, m["logits"], 1e-3, "logits")
         inj.idx.append(m["sel_idx"])
         (rel, ab), _, _ = G(b["in_xy"], b["in_dxdy"], sse, noise=m["sel_noise"].to(DEV), all_gen_out=False, img=img,
                             num_samples=k, mask=mask)
         check(ab, m["sel_abs"], 1e-3, "sel_abs")
+        check_elementwise(ab, m["sel_abs"], "sel_abs")
         check(rel, m["sel_rel"], 1e-3, "sel_rel")
+        check_elementwise(rel, m["sel_rel"], "sel_rel", atol=1e-4)
         o, br = D(b["in_xy"], b["in_dxdy"], m["sel_abs"].to(DEV), m["sel_rel"].to(DEV), sse, img=img, mask=mask)
         check(o, m["d_fake_out"], 1e-3, "d_fake_out")
         check(br, m["d_fake_branch"], 1e-3, "d_fake_branch")
@@ -142,6 +159,7 @@ def test_module_outputs(golden, injected):
         (rel, ab), _, _ = G(b["in_xy"], b["in_dxdy"], sse, noise=m["sel_noise"][:5].to(DEV), all_gen_out=False,
                             img=img, num_samples=5, mask=mask)
         check(ab, m["eval_abs"], 1e-3, "eval_abs")
+        check_elementwise(ab, m["eval_abs"], "eval_abs")
     # BatchNorm running statistics after the same number of train-mode forwards (G: 2, D: 2 here; the
     # reference ran 3 G forwards in train mode before the eval one -> compare D only, and G's count)
     for n, v in g["Dmod"].items():
