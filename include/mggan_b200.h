@@ -174,10 +174,10 @@ int mggan_scene_bn1_bwd_finalize(const double* sums_global, const double* sums_l
                                  cudaStream_t stream);
 
 /* ---- losses: mggan/model/train.py:55-113 (G step), :148-200 (D step), :626-639 (PM step) */
-/* abs (T,k,n,2), gt (T,n,2); loss += sum_scenes min_s sum_{i in scene} sum_t |abs-gt| * inv_norm;
- * best (S) argmin sample; d_abs (T,k,n,2) zero-filled by the caller, or NULL. */
+/* abs (T,k,n,2), gt (T,n,2); loss += sum_scenes min_s sum_{i in scene} sum_t |abs-gt| * inv_norm  (squared != 0:
+ * |abs-gt|^2, l2_loss_type "mse", train.py:62-63); best (S) argmin sample; d_abs (T,k,n,2) zero-filled by the caller, or NULL. */
 int mggan_l2_scene_min(const float* abs_, const float* gt, int T, int k, int n, const int* scene_off, int n_scenes,
-                       float inv_norm, float* loss, int* best, float* d_abs, cudaStream_t stream);
+                       float inv_norm, int squared, float* loss, int* best, float* d_abs, cudaStream_t stream);
 /* loss += inv_denom * sum_i w_i BCE(p_i, label), w_i = 1/counts[gen_idx[i]] or 1; dp (n) or NULL.
  * (gan_obj NS; gan_obj MM's generator term -BCE(d_fake, l_fake) is the same call with a negative inv_denom.) */
 int mggan_bce_scalar_label(const float* p, int n, float label, const long long* gen_idx, const int* counts,

@@ -23,11 +23,12 @@ __device__ __forceinline__ void block_add(float v, float* dst) {
 
 // ---- scene-level min-over-samples L2 (train.py:57-75) ---------------------------------------
 // abs (T, k, n, 2), gt (T, n, 2); scene ranges are the *un-adjusted* seq_start_end clipped to n
-// (reference quirk).  One CTA per scene, one warp per sample.
+// (reference quirk).  One CTA per scene, one warp per sample.  squared: l2_loss_type "mse"
+// (train.py:62-63: the per-step distances are squared before the sum over time).
 __global__ void __launch_bounds__(MGGAN_THREADS)
 l2_scene_min_kernel(const float* __restrict__ abs_, const float* __restrict__ gt, int T, int k, int n,
-                    const int* __restrict__ scene_off, int n_scenes, float inv_norm, float* __restrict__ loss,
-                    int* __restrict__ best, float* __restrict__ d_abs) {
+                    const int* __restrict__ scene_off, int n_scenes, float inv_norm, int squared,
+                    float* __restrict__ loss, int* __restrict__ best, float* __restrict__ d_abs) {
     extern __shared__ float stot[];      // [k]
     const int sc = blockIdx.x;
     const int a = min(scene_off[sc], n), e = min(scene_off[sc + 1], n);
@@ -40,7 +41,8 @@ l2_scene_min_kernel(const float* __restrict__ abs_, const float* __restrict__ gt
                 float2 p = __ldg(reinterpret_cast<const float2*>(abs_) + ((size_t)t * k + s) * n + i);
                 float2 q = __ldg(reinterpret_cast<const float2*>(gt) + (size_t)t * n + i);
                 float dx = p.x - q.x, dy = p.y - q.y;
-                d += sqrtf(dx * dx + dy * dy);
+                const float sq = dx * dx + dy * dy;
+                d += squared ? sq : sqrtf(sq);
             }
             acc += d;
         }
@@ -68,7 +70,7 @@ l2_scene_min_kernel(const float* __restrict__ abs_, const float* __restrict__ gt
         float2 g = __ldg(reinterpret_cast<const float2*>(gt) + (size_t)t * n + i);
         float dx = p.x - g.x, dy = p.y - g.y;
         float nr = sqrtf(dx * dx + dy * dy);
-        float sc_ = nr > 0.f ? inv_norm / nr : 0.f;
+        float sc_ = squared ? 2.f * inv_norm : (nr > 0.f ? inv_norm / nr : 0.f);     // d/dp of |p - g|^2 or |p - g|
         reinterpret_cast<float2*>(d_abs)[o] = make_float2(dx * sc_, dy * sc_);
     }
 }
@@ -178,12 +180,12 @@ pm_ml_kernel(const float* __restrict__ abs_all, const float* __restrict__ gt, in
 }  // namespace
 
 extern "C" int mggan_l2_scene_min(const float* abs_, const float* gt, int T, int k, int n, const int* scene_off,
-                                  int n_scenes, float inv_norm, float* loss, int* best, float* d_abs,
+                                  int n_scenes, float inv_norm, int squared, float* loss, int* best, float* d_abs,
                                   cudaStream_t stream) {
     MGGAN_REQUIRE(k >= 1 && T >= 1, "mggan_l2_scene_min: bad arguments");
     if (n_scenes <= 0) return MGGAN_OK;
     l2_scene_min_kernel<<<n_scenes, MGGAN_THREADS, sizeof(float) * k, stream>>>(abs_, gt, T, k, n, scene_off, n_scenes,
-                                                                                inv_norm, loss, best, d_abs);
+                                                                                inv_norm, squared, loss, best, d_abs);
     return mggan_check_launch("l2_scene_min");
 }
 

@@ -61,6 +61,7 @@ class MultiGeneratorGAN(abc.ABC):
         self._graphs = []                  # captured iterations (one per batch structure, most recent first)
         self._graph_seen = None            # structure key of the previous eager iteration
         self._graph_failed = set()         # structures whose capture raised: they stay eager
+        self._stage_ring = {}              # slot -> {name: persistent device staging buffer} (train_iterations prefetch)
         self.scene_images = None           # SceneImageStore: crops are cut on the device for batches carrying `image_ids`
         # GAN objective (reference abstract_train.py:61-85): phi_1 (D on real), phi_2 (D on fake), phi_3 (G on fake), each a
         # (loss kernel, which label, sign) triple applied to the discriminator output with a scalar smoothed label
@@ -77,34 +78,55 @@ class MultiGeneratorGAN(abc.ABC):
             dist_ctx.attach(self.G, self.D)
 
     # ------------------------------------------------------------------ loop
-    def _to_device(self, batch):
-        in_xy = batch["in_xy"].to(self.device, non_blocking=True)
-        in_dxdy = batch["in_dxdy"].to(self.device, non_blocking=True)
+    def _to_device(self, batch, slot=None):
+        """Host (or device) batch -> device tensors.  `slot` (0 / 1): copy into the persistent staging buffers of that ring
+        slot instead of allocating (the loop's prefetch: a fresh 285 MB allocation per step on the copy stream keeps the
+        caching allocator growing for many iterations and costs milliseconds per step until it settles)."""
+        ring = None
+        if slot is not None:
+            ring = self._stage_ring.setdefault(slot, {})
+
+        def put(name, src, dtype=None):
+            if ring is None:
+                return src.to(self.device, non_blocking=True)
+            buf = ring.get(name)
+            if buf is None or buf.shape != src.shape or buf.dtype != (dtype or src.dtype):
+                buf = ring[name] = torch.empty(src.shape, device=self.device, dtype=dtype or src.dtype)
+            buf.copy_(src, non_blocking=True)
+            return buf
+
+        in_xy = put("in_xy", batch["in_xy"])
+        in_dxdy = put("in_dxdy", batch["in_dxdy"])
         b = in_xy.size(1)
         sub_batches = batch["seq_start_end"] if "seq_start_end" in batch else list(zip(range(b), range(1, b + 1)))
-        gt_xy = batch["gt_xy"].to(self.device, non_blocking=True)
-        gt_dxdy = batch["gt_dxdy"].to(self.device, non_blocking=True)
-        img = batch["features"].to(self.device, non_blocking=True) if "features" in batch else None
+        gt_xy = put("gt_xy", batch["gt_xy"])
+        gt_dxdy = put("gt_dxdy", batch["gt_dxdy"])
+        img = put("features", batch["features"]) if "features" in batch else None
         if img is None and "image_ids" in batch:
             # crops cut on the device from the resident scene images (mggan_scene_crop) instead of a host-built
             # `features` tensor: 4 bytes per agent cross PCIe instead of 17,424
             if self.scene_images is None:
                 raise RuntimeError("the batch carries image_ids but no SceneImageStore is attached "
                                    "(trainer.attach_scene_images(dataset.scene_image_store()))")
-            img = self.scene_images.crop(batch["image_ids"], in_xy[-1])
+            out = None
+            if ring is not None:
+                out = ring.get("crop")
+                if out is None or out.shape[0] != b:
+                    out = ring["crop"] = torch.empty(b, 4, 33, 33, device=self.device, dtype=torch.float32)
+            img = self.scene_images.crop(batch["image_ids"], in_xy[-1], out=out)
         return in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img
 
     def attach_scene_images(self, store):
         """Keep a dataset's scene images resident in HBM (mggan/data_utils/scene_images.py)."""
         self.scene_images = store
 
-    def _prepare(self, batch):
+    def _prepare(self, batch, slot=None):
         """Collated batch (host or device tensors) -> device tensors + NaN loss mask.  The reference always
         builds the mask (abstract_train.py:130-132); when no future is masked it is dropped so the step runs
         without boolean-index gathers.  For host batches the NaN test runs on the host copy (no device sync)."""
         gt_host = batch["gt_xy"]
         has_nan = bool(torch.isnan(gt_host).any()) if not gt_host.is_cuda else None
-        in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img = self._to_device(batch)
+        in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img = self._to_device(batch, slot)
         if has_nan is None:
             has_nan = bool(torch.isnan(gt_xy).any())
         loss_mask = None
@@ -121,12 +143,20 @@ class MultiGeneratorGAN(abc.ABC):
                 self.dist.set_sums(sums)           # already exchanged by _run_iteration
             else:
                 self.dist.prefetch_sums(self._local_counts(prepared))
+        backup = None
         if (total_iterations % self.config.num_gen_steps == 0) or (self.epoch >= self.config.keep_gen_steps):
-            if self.config.num_unrolling_steps > 0:
-                raise NotImplementedError("num_unrolling_steps > 0 is outside the B200 hot path")
-            self.discriminator_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
+            # reference abstract_train.py:139-153: num_unrolling_steps + 1 discriminator steps
+            for u in range(self.config.num_unrolling_steps + 1):
+                self.discriminator_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
+                if u == 0 and self.config.num_unrolling_steps > 0:
+                    backup = self.D.state_dict()
         self.generator_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
         self.net_chooser_step(in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, metrics, loss_mask, img)
+        if backup is not None:
+            # reference :161-162.  As executed there this restores nothing: state_dict() returns the live tensors, so the
+            # "backup" follows the unrolled steps and is copied onto itself (frozen from the unmodified reference in
+            # tests/golden/var_mse_unroll.npz: D after the iteration = D after num_unrolling_steps + 1 steps).  Kept as written.
+            self.D.load_state_dict(backup)
 
     @staticmethod
     def _local_counts(prepared):
@@ -198,30 +228,36 @@ class MultiGeneratorGAN(abc.ABC):
             copy_stream = self._copy_stream = torch.cuda.Stream(self.device)
         main = torch.cuda.current_stream(self.device)
 
-        def stage(batch):
+        done = [None, None]                 # per ring slot: main-stream event after the iteration that consumed it
+
+        def stage(batch, slot):
             with torch.cuda.stream(copy_stream):
-                prepared = self._prepare(batch)
+                if done[slot] is not None:
+                    copy_stream.wait_event(done[slot])        # the iteration that read this slot's buffers has finished
+                prepared = self._prepare(batch, slot)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
             return prepared, ev
 
         it = iter(batches)
         try:
-            nxt = stage(next(it))
+            nxt = stage(next(it), 0)
         except StopIteration:
             return 0
         n = 0
         while nxt is not None:
             prepared, ev = nxt
             main.wait_event(ev)
-            for t in prepared:
+            for t in prepared:               # tensors made on the copy stream (NaN-mask gathers) are read on the main one
                 if torch.is_tensor(t):
                     t.record_stream(main)
             try:
-                nxt = stage(next(it))
+                nxt = stage(next(it), (n + 1) & 1)
             except StopIteration:
                 nxt = None
             self._run_iteration(prepared, metrics, total_iterations + n)
+            done[n & 1] = torch.cuda.Event()
+            done[n & 1].record(main)
             if on_step is not None:
                 on_step(n, metrics)
             n += 1

@@ -57,7 +57,7 @@ SIGNATURES = {
     "mggan_scene_bn_bwd_finalize": "pdippps",
     "mggan_scene_fused12_bwd": "ppiippppppppppppppps",
     "mggan_scene_bn1_bwd_finalize": "ppdipppppppppps",
-    "mggan_l2_scene_min": "ppiiipifppps",
+    "mggan_l2_scene_min": "ppiiipifippps",
     "mggan_bce_scalar_label": "pifppfpps",
     "mggan_mse_scalar_label": "pifppfpps",
     "mggan_ce_generators": "piippfpps",

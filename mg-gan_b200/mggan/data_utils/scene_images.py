@@ -41,10 +41,11 @@ class SceneImageStore:
     def nbytes(self):
         return int(self.atlas.numel())
 
-    def crop(self, image_ids, last_xy):
-        """image_ids (N) int (host or device), last_xy (N, 2) device fp32 = in_xy[-1] -> features (N, 4, 33, 33)."""
+    def crop(self, image_ids, last_xy, out=None):
+        """image_ids (N) int (host or device), last_xy (N, 2) device fp32 = in_xy[-1] -> features (N, 4, 33, 33)
+        (written into `out` when given)."""
         ids = torch.as_tensor(image_ids)
         if ids.dtype != torch.int32:
             ids = ids.to(torch.int32)
         ids = ids.to(self.device, non_blocking=True)
-        return K.scene_crop(self.atlas, self.img_off, self.img_wh, self.img_scale, ids, last_xy)
+        return K.scene_crop(self.atlas, self.img_off, self.img_wh, self.img_scale, ids, last_xy, out=out)

@@ -512,26 +512,27 @@ def decode(A, social, last_xy, last_dxdy, noise, wz, gen_weights, sel, pred_len)
 # --------------------------------------------------------------------------- losses
 class _L2SceneMin(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, abs_, gt, scenes, inv_norm):
+    def forward(ctx, abs_, gt, scenes, inv_norm, squared=False):
         abs_, gt = _f32(abs_), _f32(gt)
         T, k, n, _ = abs_.shape
         loss = torch.zeros(1, device=abs_.device)
         best = torch.empty(max(scenes.n_scenes, 1), device=abs_.device, dtype=torch.int32)
         d_abs = torch.zeros_like(abs_) if ctx.needs_input_grad[0] else None
         call("mggan_l2_scene_min", ptr(abs_), ptr(gt), T, k, n, ptr(scenes.scene_off), scenes.n_scenes,
-             float(inv_norm), ptr(loss), ptr(best), ptr(d_abs))
+             float(inv_norm), 1 if squared else 0, ptr(loss), ptr(best), ptr(d_abs))
         ctx.save_for_backward(d_abs)
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         (d_abs,) = ctx.saved_tensors
-        return d_abs * g, None, None, None
+        return d_abs * g, None, None, None, None
 
 
-def l2_scene_min(abs_, gt, scenes, inv_norm):
-    """(1/N) sum_scenes min_s sum_{i in scene, t} |abs - gt|  (train.py:57-75); inv_norm = 1/N."""
-    return _L2SceneMin.apply(abs_, gt, scenes, inv_norm)
+def l2_scene_min(abs_, gt, scenes, inv_norm, squared=False):
+    """(1/N) sum_scenes min_s sum_{i in scene, t} |abs - gt|  (train.py:57-75); inv_norm = 1/N.
+    squared: l2_loss_type "mse" (the per-step distances are squared, train.py:62-63)."""
+    return _L2SceneMin.apply(abs_, gt, scenes, inv_norm, squared)
 
 
 def _scalar_label_loss(entry):
@@ -672,14 +673,17 @@ def multi_copy(dsts, srcs):
 
 
 # --------------------------------------------------------------------------- data side / evaluation (no autograd)
-def scene_crop(atlas, img_off, img_wh, img_scale, agent_img, last_xy):
+def scene_crop(atlas, img_off, img_wh, img_scale, agent_img, last_xy, out=None):
     """(N, 4, 33, 33) crop features cut from the resident u8 scene-image atlas (mggan_scene_crop)."""
     n = int(agent_img.numel())
     last_xy = _f32(last_xy)
     assert last_xy.shape == (n, 2) and agent_img.dtype == torch.int32 and atlas.dtype == torch.uint8
-    out = torch.empty(n, 4, 33, 33, device=last_xy.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(n, 4, 33, 33, device=last_xy.device, dtype=torch.float32)
+    assert out.shape == (n, 4, 33, 33) and out.dtype == torch.float32 and out.is_contiguous()
     call("mggan_scene_crop", ptr(atlas), ptr(img_off), ptr(img_wh), ptr(img_scale), int(img_scale.numel()),
          ptr(agent_img.contiguous()), ptr(last_xy), n, ptr(out))
+    torch.autograd.graph.increment_version(out)      # written through a raw pointer: caches keyed on `_version` must see it
     return out
 
 

@@ -10,9 +10,9 @@ their gradients are single kernels (`mggan_l2_scene_min`, `mggan_bce_scalar_labe
 the selection kernel already produced, and no step synchronises with the host.
 
 On the path: gan_type in {mgan, gan}, gan_obj in {NS, MM, LS}, weighting_target in {ml, l2, endpoint, mgan, none},
-l2_loss_type != mse, both experiments (multi_generator, discrete) and both pooling types (sways, sgan).  What the
+every l2_loss_type (mse squares the per-step distances), num_unrolling_steps >= 0, both experiments (multi_generator, discrete) and both pooling types (sways, sgan).  What the
 reference cannot run either raises NotImplementedError (gan_obj W, gan_type infogan / probgan, weighting_target
-disc_scores, num_unrolling_steps > 0).  All prediction strategies of `get_predict_func` (train.py:291-576) are built:
+disc_scores).  All prediction strategies of `get_predict_func` (train.py:291-576) are built:
 they decode only the sequences they keep.
 """
 import random
@@ -63,8 +63,6 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
             raise NotImplementedError("weighting_target='%s' is outside the B200 hot path" % config.weighting_target)
         if config.weighting_target == "mgan":
             assert self.gan_type == "mgan"
-        if config.l2_loss_type == "mse":
-            raise NotImplementedError("l2_loss_type='mse' is outside the B200 hot path")
 
     # ------------------------------------------------------------------ helpers
     def _noise(self, sub_batches, num_samples=None):
@@ -122,7 +120,8 @@ class PiNetMultiGeneratorGAN(MultiGeneratorGAN):
         loss = None
         if cfg.l2_loss_type != "none":
             scenes = K.SceneIndex.get(sub_batches, self.device)
-            min_l2 = K.l2_scene_min(gen_out.abs, gt_xy, scenes, 1.0 / self._global(b, "agents"))
+            min_l2 = K.l2_scene_min(gen_out.abs, gt_xy, scenes, 1.0 / self._global(b, "agents"),
+                                    squared=cfg.l2_loss_type == "mse")
             train_metrics["train/L2_loss"].append(min_l2.detach())
             loss = cfg.l2_loss_weight * min_l2
         with _frozen(self.D):

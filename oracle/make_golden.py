@@ -49,6 +49,11 @@ CASES = {
     # built by the reference's own construct_model (scene CNN on: model_factory.py:19 hard-codes scene_dim)
     "var_discrete": dict(num_gens=3, sizes=[2, 3, 1], with_img=True, nan_frac=0.0, k=5, iters=1, seed=99,
                          flags=["--experiment", "discrete"], modules=False),
+    # l2_loss_type "mse" (train.py:58-65: squared per-step distances) + num_unrolling_steps 1 (abstract_train.py:139-165: two
+    # discriminator steps per iteration; `backup = self.D.state_dict()` aliases the live tensors, so the restore after the
+    # PM step is a no-op -- executed here exactly as the reference loop does)
+    "var_mse_unroll": dict(num_gens=3, sizes=[2, 3, 1], with_img=True, nan_frac=0.0, k=5, iters=1, seed=111,
+                           flags=["--l2_loss_type", "mse", "--num_unrolling_steps", "1"], modules=False),
     # gan_type "gan": plain discriminator, no generator-id head (discriminators.py:210-211, train.py:101,181)
     "var_gan_plain": dict(num_gens=3, sizes=[3, 1, 2], with_img=True, nan_frac=0.0, k=5, iters=1, seed=77,
                           flags=["--gan_type", "gan"], modules=False),
@@ -139,7 +144,8 @@ def run_case(ref, name, case):
 
     out = {"meta/gan_obj": np.array(args.gan_obj), "meta/weighting_target": np.array(args.weighting_target),
            "meta/gan_type": np.array(args.gan_type), "meta/pool_type": np.array(args.pool_type),
-           "meta/experiment": np.array(args.experiment),
+           "meta/experiment": np.array(args.experiment), "meta/l2_loss_type": np.array(args.l2_loss_type),
+           "meta/num_unrolling_steps": np.int64(args.num_unrolling_steps),
            "meta/num_gens": np.int64(ng), "meta/k": np.int64(k), "meta/iters": np.int64(case["iters"]),
            "meta/with_img": np.int64(case["with_img"]), "meta/seq_start_end": np.array(sse, dtype=np.int64)}
     for n, v in b.items():
@@ -220,6 +226,17 @@ def run_case(ref, name, case):
         inj.noise, inj.idx, inj.labels = [d_noise.clone()], [d_idx], [lab[0], lab[1]]
         trainer.discriminator_step(t["in_xy"], t["in_dxdy"], gt_xy, gt_dxdy, sse, metrics, mask, img)
         grads_np(f"{P}/D_grad", D, out)
+        backup = None
+        for u in range(1, args.num_unrolling_steps + 1):          # abstract_train.py:139-153
+            if u == 1:
+                backup = trainer.D.state_dict()
+            un, ui = scene_noise(), torch.from_numpy(rng.integers(0, ng, size=(n_act, 1)))
+            ul = [(float(rng.uniform(0.9, 1.0)), float(rng.uniform(0.0, 0.1))) for _ in range(2)]
+            out[f"{P}/d_noise_u{u}"], out[f"{P}/d_idx_u{u}"] = un.numpy(), ui.numpy()
+            out[f"{P}/labels_u{u}"] = np.array(ul, dtype=np.float64)
+            inj.noise, inj.idx, inj.labels = [un.clone()], [ui], [ul[0], ul[1]]
+            trainer.discriminator_step(t["in_xy"], t["in_dxdy"], gt_xy, gt_dxdy, sse, metrics, mask, img)
+            grads_np(f"{P}/D_grad_u{u}", D, out)
 
         inj.noise, inj.idx, inj.labels = [z.clone() for z in g_noise], [g_idx], [lab[2]]
         trainer.generator_step(t["in_xy"], t["in_dxdy"], gt_xy, gt_dxdy, sse, metrics, mask, img)
@@ -228,9 +245,13 @@ def run_case(ref, name, case):
         inj.noise, inj.idx, inj.labels = [pm_noise.clone()], [torch.zeros(n_act, 1, dtype=torch.long)], []
         trainer.net_chooser_step(t["in_xy"], t["in_dxdy"], gt_xy, gt_dxdy, sse, metrics, mask, img)
         grads_np(f"{P}/PM_grad", G, out)
+        if backup is not None:
+            trainer.D.load_state_dict(backup)                         # abstract_train.py:161-162
         for mk, mv in metrics.items():
             if not mk.startswith("probs/"):
                 out[f"{P}/metric/{mk}"] = np.float64(mv[0])
+                for u in range(1, len(mv)):                           # the unrolled discriminator steps log again
+                    out[f"{P}/metric_u{u}/{mk}"] = np.float64(mv[u])
         assert not inj.noise and not inj.idx and not inj.labels
 
     sd_np("G1", G, out)

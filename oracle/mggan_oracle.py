@@ -477,7 +477,8 @@ class OracleTrainer:
 
     def __init__(self, sdG, sdD, n_gens, num_samples=20, sigma=1.0, l2_w=1.0, clf_w=1.0,
                  pi_w=1.0, clip_g=500, clip_d=100, lr=1e-3, beta1=0.5, use_pinet=True,
-                 social_mode="scene", gan_obj="NS", weighting_target="ml", epoch=1):
+                 social_mode="scene", gan_obj="NS", weighting_target="ml", epoch=1, l2_loss_type="min_g_z"):
+        self.l2_loss_type = l2_loss_type         # "mse": squared per-step distances (train.py:62-63)
         # non-default objectives (abstract_train.py:61-79) and PM-step targets (train.py:604-647)
         self.gan_obj, self.weighting_target, self.epoch = gan_obj, weighting_target, epoch
         self.G = {k: v.clone() for k, v in sdG.items() if not k.startswith("G_")}
@@ -554,7 +555,10 @@ class OracleTrainer:
         mask, gt_xy, gt_dxdy = self.loss_mask(b)
         N = b["in_xy"].shape[1]
         (rel, ab), _, idx = self._G(b, noise, False, self.k, mask, gen_idxs)
-        l2 = (ab - gt_xy[:, None]).norm(dim=-1).sum(0)                   # (k, N_act)
+        l2 = (ab - gt_xy[:, None]).norm(dim=-1)
+        if self.l2_loss_type == "mse":
+            l2 = l2 ** 2
+        l2 = l2.sum(0)                                                   # (k, N_act)
         min_l2 = 0.0
         for a, e in b["seq_start_end"]:                                  # un-adjusted ranges, train.py:67-71
             min_l2 = min_l2 + l2[:, a:e].sum(1).min()

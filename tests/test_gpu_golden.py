@@ -55,7 +55,9 @@ def make_config(g):
                                     "--weighting_target", g["meta"].get("weighting_target", "ml"),
                                     "--gan_type", g["meta"].get("gan_type", "mgan"),
                                     "--pool_type", g["meta"].get("pool_type", "sways"),
-                                    "--experiment", g["meta"].get("experiment", "multi_generator")])
+                                    "--experiment", g["meta"].get("experiment", "multi_generator"),
+                                    "--l2_loss_type", g["meta"].get("l2_loss_type", "min_g_z"),
+                                    "--num_unrolling_steps", str(g["meta"].get("num_unrolling_steps", 0))])
     args.gpus = True
     return args
 
@@ -212,6 +214,15 @@ def _run_iterations(g, inj, tmp_path):
                 check(gd[key[7:]], v, 2e-3, key, atol=1e-6)
                 n += 1
         assert n >= 25
+        for u in range(1, int(g["meta"].get("num_unrolling_steps", 0)) + 1):       # abstract_train.py:139-153
+            ul = r[f"labels_u{u}"].tolist()
+            inj.noise, inj.idx, inj.labels = [r[f"d_noise_u{u}"]], [r[f"d_idx_u{u}"]], [ul[0], ul[1]]
+            tr.discriminator_step(b["in_xy"], b["in_dxdy"], gt_xy, gt_dxdy, sse, metrics, mask, img)
+            gd = grads_of(D)
+            for key, v in r.items():
+                if key.startswith(f"D_grad_u{u}/") and not key.endswith("Conv_1.bias"):
+                    check(gd[key.split("/", 1)[1]], v, 2e-3, key, atol=1e-6)
+            check(metrics["train/discr_loss"][u], r[f"metric_u{u}/train/discr_loss"], 1e-3, f"discr_loss u{u}")
         plain = g["meta"].get("gan_type", "mgan") == "gan"           # no generator-id head, no classifier terms
         if plain:
             assert "train/info_mgan_disc_loss" not in metrics

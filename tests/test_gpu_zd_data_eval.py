@@ -207,7 +207,9 @@ def test_training_iteration_resident_images_equals_host_features():
         tr.train_iteration(batch, metrics)
         torch.cuda.synchronize()
         results.append((prepared[5].cpu(), {k: float(v[0]) for k, v in metrics.items()},
-                        [p.detach().cpu().clone() for p in tr.G.parameters()]))
+                        # conv biases in front of train-mode BatchNorm have a zero true gradient: AdamW turns the kernels'
+                        # atomic round-off into +-lr steps, so they are not compared
+                        [p.detach().cpu().clone() for n, p in tr.G.named_parameters() if not n.endswith("Conv_1.bias")]))
     assert torch.equal(results[0][0], results[1][0])
     # identical inputs; the kernels' floating-point atomics make two runs agree to round-off, not bit for bit
     assert set(results[0][1]) == set(results[1][1])

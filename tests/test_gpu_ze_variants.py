@@ -43,5 +43,6 @@ def test_training_iterations_late_variants(golden_late_variant, injected, tmp_pa
     import mggan.model.modules.standard_discrete as SD
     monkeypatch.setattr(SD, "get_global_noise", injected.global_noise)     # the discrete generator draws through its own import
     m = golden_late_variant["meta"]
-    assert m["gan_type"] == "gan" or m["pool_type"] == "sgan" or m["experiment"] == "discrete"
+    assert (m["gan_type"] == "gan" or m["pool_type"] == "sgan" or m["experiment"] == "discrete"
+            or m.get("l2_loss_type") == "mse")
     _run_iterations(golden_late_variant, injected, tmp_path)

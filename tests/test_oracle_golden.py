@@ -80,7 +80,8 @@ def test_training_iterations_late_variants(golden_late_variant):
     """gan_type "gan": no generator-id head, no classifier terms (discriminators.py:210-211, train.py:101,181);
     pool_type "sgan": PoolHiddenNet in G and D (social_gan.py:157-229)."""
     m = golden_late_variant["meta"]
-    assert m["gan_type"] == "gan" or m["pool_type"] == "sgan" or m["experiment"] == "discrete"
+    assert (m["gan_type"] == "gan" or m["pool_type"] == "sgan" or m["experiment"] == "discrete"
+            or m.get("l2_loss_type") == "mse")
     _run_iterations(golden_late_variant)
 
 
@@ -90,7 +91,8 @@ def _run_iterations(g):
     b = batch_of(g)
     ng, k = g["meta"]["num_gens"], g["meta"]["k"]
     tr = O.OracleTrainer(g["G0"], g["D0"], ng, num_samples=k, gan_obj=g["meta"].get("gan_obj", "NS"),
-                         weighting_target=g["meta"].get("weighting_target", "ml"))
+                         weighting_target=g["meta"].get("weighting_target", "ml"),
+                         l2_loss_type=g["meta"].get("l2_loss_type", "min_g_z"))
     for it in range(g["meta"]["iters"]):
         r = g[f"it{it}"]
         lab = r["labels"].tolist()
@@ -104,6 +106,13 @@ def _run_iterations(g):
         for n, v in r.items():
             if n.startswith("D_grad/"):
                 close(d["grads"][n[7:]], v, rtol=2e-3, atol=1e-6, what=n)
+        for u in range(1, int(g["meta"].get("num_unrolling_steps", 0)) + 1):       # abstract_train.py:139-153
+            ul = r[f"labels_u{u}"].tolist()
+            du = tr.discriminator_step(b, r[f"d_noise_u{u}"][None], r[f"d_idx_u{u}"], ul[0], ul[1])
+            close(du["real"] + du["fake"], r[f"metric_u{u}/train/discr_loss"], what=f"discr_loss u{u}")
+            for n, v in r.items():
+                if n.startswith(f"D_grad_u{u}/"):
+                    close(du["grads"][n.split("/", 1)[1]], v, rtol=2e-3, atol=1e-6, what=n)
         gs = tr.generator_step(b, r["g_noise"], r["g_idx"], lab[2])
         close(gs["l2"], r["metric/train/L2_loss"], what="l2")
         close(gs["adv"], r["metric/train/gen_loss"], what="adv")
