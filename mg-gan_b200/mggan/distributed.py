@@ -51,6 +51,39 @@ def shard_batch(batch, world_size, rank, balance="agents"):
     return out
 
 
+def shard_items(n_items, world_size, rank):
+    """Contiguous [lo, hi) range of dataset items (scenes) of `rank`: sizes differ by at most one, order preserved."""
+    base, extra = divmod(int(n_items), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_predictions(preds, group, rank, world_size):
+    """Per-rank prediction arrays (pred_len, k, n_rank, 2) (None for an empty shard) -> the dataset-order concatenation
+    along the agent axis on rank 0, None elsewhere.  Object gather over the host group: evaluation sets are small (a few
+    MB) and the ranks hold different agent counts."""
+    import numpy as np
+    cpu_group = _host_group(group)
+    bucket = [None] * world_size if rank == 0 else None
+    dist.gather_object(preds, bucket, dst=dist.get_global_rank(cpu_group, 0) if cpu_group is not None else 0, group=cpu_group)
+    if rank != 0:
+        return None
+    parts = [p for p in bucket if p is not None]
+    return np.concatenate(parts, 2) if parts else None
+
+
+def _host_group(group):
+    """The gloo companion of an NCCL group (the group itself when it is not NCCL)."""
+    if dist.get_backend(group) != "nccl":
+        return group
+    key = id(group) if group is not None else None
+    cpu = _CPU_GROUPS.get(key)
+    if cpu is None:
+        ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
+        cpu = _CPU_GROUPS[key] = dist.new_group(ranks=ranks, backend="gloo")
+    return cpu
+
+
 _CPU_GROUPS = {}
 
 
@@ -60,15 +93,7 @@ def host_sum(values, group=None):
     synchronisation per call (and a host<->device copy that queues behind the batch's H2D transfer on the copy engine).
     Collective: every rank of `group` must call it at the same point."""
     t = torch.tensor([float(v) for v in values], dtype=torch.float64)
-    if dist.get_backend(group) == "nccl":
-        key = id(group) if group is not None else None
-        cpu = _CPU_GROUPS.get(key)
-        if cpu is None:
-            ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
-            cpu = _CPU_GROUPS[key] = dist.new_group(ranks=ranks, backend="gloo")
-        dist.all_reduce(t, group=cpu)
-    else:
-        dist.all_reduce(t, group=group)
+    dist.all_reduce(t, group=_host_group(group))
     return t.tolist()
 
 

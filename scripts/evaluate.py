@@ -5,6 +5,12 @@ Precision / Recall to one CSV -- the command line, file name and columns of the 
 Predictions come from the B200 kernels (`PiNetMultiGeneratorGAN.get_predictions`, every strategy of `get_predict_func`);
 the metrics run on the host like the reference's, or on the device with `--metrics_device cuda`
 (`mggan_min_ade_fde`, `mggan_tube_inside`: same results).
+
+Multi-GPU (BASELINE.json configs[4]): launched under torchrun, e.g.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 scripts/evaluate.py <flags>
+every rank predicts a contiguous range of the dataset's scenes (`mggan.distributed.shard_items`), the predictions are
+gathered to rank 0 in dataset order (`gather_predictions`) and rank 0 alone scores them and writes the CSV -- the same file a
+single process writes (scenes are independent units; the Precision / Recall grouping runs on the gathered set).
 """
 import argparse
 import collections
@@ -85,8 +91,27 @@ def score(dataset, preds, ks, args):
     return metrics
 
 
+def predict_sharded(trainer, dataset, ks, strategy, ctx, batch_size=32):
+    """This rank's scenes -> predictions of the WHOLE dataset on rank 0 (None elsewhere)."""
+    from torch.utils.data import DataLoader, Subset
+    from mggan.data_utils.data_loaders import seq_collate_scene
+    from mggan.distributed import gather_predictions, shard_items
+    lo, hi = shard_items(len(dataset), ctx.world_size, ctx.rank)
+    loader = DataLoader(Subset(dataset, range(lo, hi)), batch_size=batch_size, shuffle=False, collate_fn=seq_collate_scene)
+    preds = trainer.get_predictions(loader, max(ks), strategy=strategy) if hi > lo else None
+    return gather_predictions(preds, ctx.group, ctx.rank, ctx.world_size)
+
+
 def main(argv=None):
     args = parser.parse_args(argv)
+    ctx = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        from mggan.distributed import DistContext
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if args.device == "cuda" else "gloo")
+        ctx = DistContext()
     ks = list(range(1, args.num_preds))                      # k = 1 .. num_preds-1, like the reference (:77)
     strategies = SWEEP_ORDER if args.pred_strat == "all" else (args.pred_strat,)
     root = pathlib.Path(args.model_path)
@@ -110,11 +135,19 @@ def main(argv=None):
             loader = get_dataloader(config.dataset, args.phase, batch_size=32, split=args.split,
                                     num_scenes=args.num_scenes, with_img=getattr(config, "scene_dim", 64) > 0)
             row = describe(config, strategy)
-            preds = trainer.get_predictions(loader, max(ks), strategy=strategy)
+            if ctx is None:
+                preds = trainer.get_predictions(loader, max(ks), strategy=strategy)
+            else:
+                preds = predict_sharded(trainer, loader.dataset, ks, strategy, ctx)
+                if ctx.rank != 0:
+                    continue                                 # rank 0 scores and writes
             row.update(score(loader.dataset, preds, ks, args))
             for column, value in row.items():
                 table[column].append(value)
             pd.DataFrame(table).to_csv(csv)                  # rewritten after every run, like the reference
+    if ctx is not None:
+        import torch.distributed as dist
+        dist.barrier()
     return csv
 
 

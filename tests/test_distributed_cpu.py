@@ -70,6 +70,35 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _gather_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mggan.distributed import gather_predictions, shard_items
+    n_items, agents_per_item = 5, [3, 1, 4, 2, 6]
+    full = np.arange(12 * 2 * sum(agents_per_item) * 2, dtype=np.float32).reshape(12, 2, sum(agents_per_item), 2)
+    lo, hi = shard_items(n_items, world, rank)
+    a_lo, a_hi = sum(agents_per_item[:lo]), sum(agents_per_item[:hi])
+    got = gather_predictions(full[:, :, a_lo:a_hi] if hi > lo else None, None, rank, world)
+    ret[rank] = bool(np.array_equal(got, full)) if rank == 0 else got is None
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_gathers_dataset_order_world2():
+    """scripts/evaluate.py under torchrun (cfg-5): item ranges partition the dataset, rank 0 receives the predictions in
+    dataset order."""
+    from mggan.distributed import shard_items
+    for n, w in ((5, 2), (8, 8), (3, 8), (64, 8)):
+        cover = []
+        for r in range(w):
+            lo, hi = shard_items(n, w, r)
+            cover += list(range(lo, hi))
+        assert cover == list(range(n))
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gather_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
+
+
 def test_gloo_allreduce_world2():
     mgr = mp.Manager()
     ret = mgr.dict()

@@ -190,13 +190,21 @@ def _run_iterations(g, inj, tmp_path):
     img = b.get("features")
     n_act = int(mask.sum())
 
-    def grads_of(mod):
+    def grads_of(mod, max_norm=None):
+        """.grad of every parameter.  max_norm: the reference's clip_grad_norm_ rescales .grad IN PLACE before the optimiser
+        step (train.py:131-134, :209-212), so its frozen gradients are the clipped ones; the fused optimiser applies the
+        same coefficient inside the AdamW kernel and leaves .grad untouched -- apply it here before comparing."""
         out, seen = {}, set()
         for k, p in mod.named_parameters():
             key = k if not k.startswith("G_") else "gs." + k[2:]
             if key not in seen and p.grad is not None:
                 out[key] = p.grad.detach().clone()
             seen.add(key)
+        if max_norm:
+            total = float(torch.sqrt(sum((v.double() ** 2).sum() for v in out.values())))
+            coef = min(1.0, max_norm / (total + 1e-6))
+            if coef < 1.0:
+                out = {k: v * coef for k, v in out.items()}
         return out
 
     for it in range(g["meta"]["iters"]):
@@ -205,7 +213,7 @@ def _run_iterations(g, inj, tmp_path):
         metrics = defaultdict(list)
         inj.noise, inj.idx, inj.labels = [r["d_noise"]], [r["d_idx"]], [lab[0], lab[1]]
         tr.discriminator_step(b["in_xy"], b["in_dxdy"], gt_xy, gt_dxdy, sse, metrics, mask, img)
-        gd = grads_of(D)
+        gd = grads_of(D, cfg.clipping_threshold_d)
         n = 0
         for key, v in r.items():
             if key.startswith("D_grad/"):
@@ -218,7 +226,7 @@ def _run_iterations(g, inj, tmp_path):
             ul = r[f"labels_u{u}"].tolist()
             inj.noise, inj.idx, inj.labels = [r[f"d_noise_u{u}"]], [r[f"d_idx_u{u}"]], [ul[0], ul[1]]
             tr.discriminator_step(b["in_xy"], b["in_dxdy"], gt_xy, gt_dxdy, sse, metrics, mask, img)
-            gd = grads_of(D)
+            gd = grads_of(D, cfg.clipping_threshold_d)
             for key, v in r.items():
                 if key.startswith(f"D_grad_u{u}/") and not key.endswith("Conv_1.bias"):
                     check(gd[key.split("/", 1)[1]], v, 2e-3, key, atol=1e-6)
@@ -232,7 +240,7 @@ def _run_iterations(g, inj, tmp_path):
 
         inj.noise, inj.idx, inj.labels = [r["g_noise"]], [r["g_idx"]], [lab[2]]
         tr.generator_step(b["in_xy"], b["in_dxdy"], gt_xy, gt_dxdy, sse, metrics, mask, img)
-        gg = grads_of(G)
+        gg = grads_of(G, cfg.clipping_threshold_g)
         n = 0
         for key, v in r.items():
             if key.startswith("G_grad/"):
