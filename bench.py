@@ -433,6 +433,10 @@ def run_ours(a):
         line["e2e_host_crops"] = e2e_host
     if strong is not None:
         line["strong_scaling"] = strong
+    if ctx is not None:
+        line["exchange"] = {"kind": "one-shot all-reduce kernel over NVLink peer memory (mggan_peer_allreduce), gradient "
+                                    "norm fused" if ctx.peer is not None else "nccl all_reduce",
+                            "peer_error": ctx.peer_error}
     if rank == 0 and world == 1 and not a.no_extra_configs:
         try:
             line["other_configs"] = extra_configs(a, dev)

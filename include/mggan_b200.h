@@ -238,6 +238,24 @@ int mggan_clip_adamw(const MgganTensorTable* table, int count, const double* sqn
                      cudaStream_t stream);
 int mggan_multi_copy(const MgganTensorTable* table, int count, cudaStream_t stream); /* p[t] <- g[t] */
 
+/* ---- data-parallel exchange (new; the reference is single-device): one-shot all-reduce over
+ * NVLink peer memory, fused with the squared gradient norm that mggan_clip_adamw clips with.  `region[r]` is THIS call's
+ * region of rank r's symmetric arena and `flags[r]` rank r's flag array ([64][16] uint32, zero-initialised once), both as
+ * peer-mapped device pointers (torch.distributed._symmetric_memory buffer_ptrs + offsets).  The kernel copies `in` (n
+ * elements; NULL when a packing kernel already wrote the operand into region[rank]) into its own region, meets the same
+ * block of every rank at a flag barrier, and writes out[i] = sum_r region[r][i] in fixed rank order (bit-identical on every
+ * rank); for float32 it also adds sum_i out[i]^2 to *sqnorm when sqnorm != NULL.  dtype: 0 float32, 1 float64, 2 int32.
+ * Every rank must issue the same sequence of calls; a region may be reused only after another call of the sequence. */
+#define MGGAN_PEER_MAX 16
+typedef struct MgganPeerTable {
+    void* region[MGGAN_PEER_MAX];
+    unsigned int* flags[MGGAN_PEER_MAX];
+    int rank, world;
+} MgganPeerTable;
+/* table is a HOST pointer (copied into kernel-parameter space). */
+int mggan_peer_allreduce(const MgganPeerTable* table, int dtype, const void* in, long long n, void* out, double* sqnorm,
+                         cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

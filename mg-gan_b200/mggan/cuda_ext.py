@@ -28,10 +28,18 @@ class TensorTable(ctypes.Structure):
     ]
 
 
-_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "d": ctypes.c_double,
+PEER_MAX = 16
+
+
+class PeerTable(ctypes.Structure):
+    _fields_ = [("region", ctypes.c_void_p * PEER_MAX), ("flags", ctypes.c_void_p * PEER_MAX),
+                ("rank", ctypes.c_int), ("world", ctypes.c_int)]
+
+
+_CT = {"T": ctypes.POINTER(PeerTable), "q": ctypes.c_longlong, "p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "d": ctypes.c_double,
        "Q": ctypes.c_ulonglong, "s": ctypes.c_void_p, "t": ctypes.POINTER(TensorTable)}
 
-# name -> argument codes (p pointer, i int, f float, d double, Q uint64, s stream, t table*)
+# name -> argument codes (p pointer, i int, q long long, f float, d double, Q uint64, s stream, t tensor table*, T peer table*)
 SIGNATURES = {
     "mggan_lstm_seq_fwd": "piiippppps",
     "mggan_lstm_seq_bwd": "piiipppppps",
@@ -68,6 +76,7 @@ SIGNATURES = {
     "mggan_grad_sqnorm": "tips",
     "mggan_clip_adamw": "tipfffffffs",
     "mggan_multi_copy": "tis",
+    "mggan_peer_allreduce": "Tipqpps",
 }
 # plain (non status-returning) helpers
 _PLAIN = {"mggan_version": ("", ctypes.c_int), "mggan_device_check": ("", ctypes.c_int),

@@ -97,17 +97,124 @@ def host_sum(values, group=None):
     return t.tolist()
 
 
+class PeerReducer:
+    """The exchanges of the data-parallel step as ONE kernel each over NVLink peer memory (csrc/peer_reduce.cu,
+    `mggan_peer_allreduce`): every rank maps every peer's symmetric arena (torch.distributed._symmetric_memory), writes
+    its operand into its own region, meets the peers at an in-kernel flag barrier and sums all regions in rank order.
+    No NCCL call, no staging `torch.cat`, and for gradients the squared norm of the clip comes out of the same launch.
+
+    Regions are bump-allocated per call and the cursor is reset every iteration, so a region is reused one iteration
+    later at the earliest (the kernel has no exit barrier; see peer_reduce.cu).  All ranks issue the same call sequence."""
+    FLAG_BYTES = 64 * 16 * 4
+    _CODES = {torch.float32: 0, torch.float64: 1, torch.int32: 2}
+
+    def __init__(self, group, device, arena_bytes=16 << 20):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.arena = symm.empty(arena_bytes // 4, dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.arena, self.group)
+        self.arena.zero_()                                   # flags start at 0 on every rank ...
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)                             # ... before any rank launches
+        self.base = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(self.base) == self.world and self.base[self.rank] == self.arena.data_ptr()
+        self.bytes, self.off = arena_bytes, self.FLAG_BYTES
+        self.calls = 0
+
+    def begin_iteration(self):
+        self.off = self.FLAG_BYTES
+
+    def _region(self, nbytes):
+        from .cuda_ext import PeerTable
+        off = self.off
+        self.off = (off + nbytes + 255) & ~255
+        if self.off > self.bytes:
+            raise RuntimeError(f"peer arena exhausted ({self.off} > {self.bytes} bytes in one iteration)")
+        tb = PeerTable()
+        for r in range(self.world):
+            tb.region[r] = self.base[r] + off
+            tb.flags[r] = self.base[r]
+        tb.rank, tb.world = self.rank, self.world
+        self.calls += 1
+        return tb, off
+
+    def allreduce_(self, t):
+        """In-place sum of a contiguous float32 / float64 / int32 tensor over the ranks."""
+        from .cuda_ext import call, ptr
+        assert t.is_contiguous() and t.dtype in self._CODES, (t.dtype, t.is_contiguous())
+        if t.numel() == 0:
+            return t
+        tb, _ = self._region(t.numel() * t.element_size())
+        call("mggan_peer_allreduce", tb, self._CODES[t.dtype], ptr(t), t.numel(), ptr(t), None)
+        return t
+
+    def allreduce_grads(self, grads, want_sqnorm=True):
+        """Gradient tensors -> (views of the reduced flat buffer in the same order, squared L2 norm of the reduced
+        gradient as a device double or None).  The gradients are packed straight into this rank's region by one
+        pointer-table copy kernel per 64 tensors; the reduce kernel reads the regions of all ranks."""
+        from . import kernels as K
+        from .cuda_ext import call, ptr
+        sizes = [g.numel() for g in grads]
+        total = sum(sizes)
+        tb, off = self._region(total * 4)
+        mine = self.arena[off // 4: off // 4 + total]
+        dsts, o = [], 0
+        for n in sizes:
+            dsts.append(mine[o:o + n])
+            o += n
+        K.multi_copy(dsts, [g.reshape(-1) for g in grads])
+        flat = torch.empty(total, device=mine.device, dtype=torch.float32)
+        sq = torch.zeros(1, device=mine.device, dtype=torch.float64) if want_sqnorm else None
+        call("mggan_peer_allreduce", tb, 0, None, total, ptr(flat), ptr(sq))
+        out, o = [], 0
+        for g, n in zip(grads, sizes):
+            out.append(flat[o:o + n].view_as(g))
+            o += n
+        return out, sq
+
+
+_REDUCERS = {}          # id(process group) -> PeerReducer
+
+
+def allreduce_tensor(t, group):
+    """In-place sum over `group`: the peer-memory kernel when the group has a PeerReducer, else the backend's all_reduce."""
+    red = _REDUCERS.get(id(group if group is not None else dist.group.WORLD))
+    if red is not None and t.is_cuda and t.dtype in PeerReducer._CODES and t.is_contiguous():
+        return red.allreduce_(t)
+    dist.all_reduce(t, group=group)
+    return t
+
+
 class DistContext:
-    def __init__(self, group=None):
+    def __init__(self, group=None, peer=None):
+        """peer: None = use the peer-memory reducer when the backend is NCCL and symmetric memory can be set up on every
+        rank (MGGAN_PEER_REDUCE=0 disables it); False = NCCL collectives only."""
+        import os
         assert dist.is_initialized()
         self.group = group
         self.rank = dist.get_rank(group)
         self.world_size = dist.get_world_size(group)
         self._log = []          # (local value, global sum) of every sum_scalar call of the current iteration
         self._replay = None     # while an iteration is captured as a CUDA graph: the previous iteration's log
+        self.peer, self.peer_error = None, None
+        want = peer is not False and os.environ.get("MGGAN_PEER_REDUCE", "1") != "0"
+        if want and self.world_size > 1 and dist.get_backend(group) == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            try:
+                red = PeerReducer(group, dev)
+            except Exception as exc:                    # no fabric / symmetric-memory support: NCCL carries the exchanges
+                red, self.peer_error = None, repr(exc)
+            ok = torch.tensor([1.0 if red is not None else 0.0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)          # the choice is collective
+            if float(ok.item()) == 1.0:
+                self.peer = red
+                _REDUCERS[id(group if group is not None else dist.group.WORLD)] = red
 
     def begin_iteration(self):
         self._log = []
+        if self.peer is not None:
+            self.peer.begin_iteration()
 
     def freeze(self, on):
         """Capture mode: `sum_scalar` has a host read-back, which cannot run inside a CUDA-graph capture; the captured
@@ -157,15 +264,16 @@ class DistContext:
         return pref[name][1]
 
     def sum_tensor(self, t):
-        dist.all_reduce(t, group=self.group)
-        return t
+        return allreduce_tensor(t, self.group)
 
     def _device(self):
         return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else "cpu"
 
-    def allreduce_grads(self, grads):
-        """Sum a list of gradient tensors over ranks with one collective; returns views of the
-        reduced flat buffer in the same order."""
+    def allreduce_grads(self, grads, want_sqnorm=True):
+        """Sum a list of gradient tensors over ranks with one exchange; returns views of the reduced flat buffer in the
+        same order -- or (views, squared norm) from the peer-memory kernel, which produces the clip norm in the same pass."""
+        if self.peer is not None:
+            return self.peer.allreduce_grads(grads, want_sqnorm)
         flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat, group=self.group)
         out, off = [], 0

@@ -246,8 +246,8 @@ BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
 def _allreduce(t, group):
     if group is not None:
-        import torch.distributed as dist
-        dist.all_reduce(t, group=group)
+        from .distributed import allreduce_tensor
+        allreduce_tensor(t, group)
 
 
 class PatchStats:

@@ -43,9 +43,16 @@ class FusedAdamW(torch.optim.Optimizer):
         if not work:
             return
         grads = [p.grad.contiguous() for _, p in work]
+        sq = None
         if reduce_fn is not None:
-            grads = reduce_fn(grads) or grads
-        sq = K.grad_sqnorm(grads) if max_norm and max_norm > 0 else None
+            red = reduce_fn(grads)
+            if isinstance(red, tuple):          # the peer-memory reducer returns the squared norm of the reduced gradient too
+                red, sq = red
+            grads = red or grads
+        if not (max_norm and max_norm > 0):
+            sq = None
+        elif sq is None:
+            sq = K.grad_sqnorm(grads)
         self.last_grad_sqnorm = sq
         start = 0
         while start < len(work):             # one launch set per param group

@@ -21,16 +21,19 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_two_gpu_iterations_equal_one_gpu(graph):
+@pytest.mark.parametrize("graph,nccl", [(False, False), (True, False), (False, True), (True, True)])
+def test_two_gpu_iterations_equal_one_gpu(graph, nccl):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "check_dp.py"), "--iters", "4" if graph else "2"]
     if graph:
         cmd.append("--graph")
+    if nccl:
+        cmd.append("--nccl")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert out.returncode == 0 and lines, (out.stdout[-2000:], out.stderr[-3000:])
     rep = json.loads(lines[-1])
     assert rep["ok"] and rep["max_abs_diff"] <= rep["tol"], rep
+    assert rep["exchange"] == ("nccl" if nccl else "peer-memory kernel"), rep

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--num_gens", type=int, default=4)
     ap.add_argument("--k", type=int, default=6)
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="NCCL collectives instead of the peer-memory kernel")
     ap.add_argument("--tol", type=float, default=1e-5)
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -119,7 +120,10 @@ def main():
                {("Dbuf." + n): p.detach().clone().float() for n, p in tr.D.named_buffers()}
 
     _, _, a_lo, a_hi, _ = shard_scenes(sse, world, rank)
-    sharded = run(DistContext(), shard_batch(full, world, rank), a_lo, a_hi)
+    ctx = DistContext(peer=False if a.nccl else None)
+    if not a.nccl and ctx.peer is None:
+        print(f"[rank {rank}] peer-memory reducer unavailable ({ctx.peer_error}); NCCL carries the exchanges", file=sys.stderr)
+    sharded = run(ctx, shard_batch(full, world, rank), a_lo, a_hi)
     ok, report = True, {}
     if rank == 0:
         single = run(None, full, 0, N)
@@ -131,7 +135,8 @@ def main():
             if dlt > worst:
                 worst, worst_name = dlt, n
         ok = worst <= a.tol
-        report = {"ok": ok, "world": world, "iters": a.iters, "graph": a.graph, "max_abs_diff": worst, "worst": worst_name,
+        report = {"ok": ok, "exchange": "peer-memory kernel" if ctx.peer is not None else "nccl",
+                  "peer_calls": ctx.peer.calls if ctx.peer is not None else 0, "world": world, "iters": a.iters, "graph": a.graph, "max_abs_diff": worst, "worst": worst_name,
                   "tol": a.tol, "tensors": len(single), "agents": N, "scenes": len(sse)}
         print(json.dumps(report))
         sys.stdout.flush()

@@ -15,6 +15,10 @@ def parse(path=HEADER):
         for a in [x.strip() for x in args.split(",") if x.strip() and x.strip() != "void"]:
             if "MgganTensorTable" in a:
                 codes += "t"
+            elif "MgganPeerTable" in a:
+                codes += "T"
+            elif a.startswith("long long") and "*" not in a:
+                codes += "q"
             elif "*" in a:
                 codes += "p"
             elif a.startswith("cudaStream_t"):
