@@ -16,6 +16,7 @@
 // Partial BatchNorm sums are accumulated in fp32 per thread, reduced per CTA and added to the
 // global statistics as doubles (one atomicAdd per channel per CTA).
 #include "common.cuh"
+#include <cstdint>
 
 namespace {
 
@@ -44,6 +45,43 @@ struct BwdPad {
 };
 template <int C>
 struct FwdLdw2 { static constexpr int value = C == 16 ? 24 : 8; };            // 24 t + g / 8 t + g: 32 distinct banks
+
+// ---- bulk (TMA-engine) staging of one agent's crop --------------------------------------------------------------
+// A crop is 4 x 33 x 33 fp32 = 17,424 contiguous bytes (16-byte multiple, 16-byte aligned for every agent of a 16-byte
+// aligned batch), so one `cp.async.bulk` (SASS UBLKCP) moves it global -> shared without touching registers and signals an
+// mbarrier when the bytes have landed.  The fused conv kernels double-buffer it: agent n+1's crop streams in while agent n
+// is convolved, and the kernels read the UNPADDED [4][33][33] layout directly (only row / column -1 of a 3 x 3 window can
+// fall outside; it is predicated to zero).
+constexpr int RAW = CIN * IMG2;                // floats per crop
+constexpr uint32_t RAW_BYTES = RAW * 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void sbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void sbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (spins > (1u << 24)) __trap();       // a lost copy traps (reported by the C ABI) instead of hanging the device
+    }
+}
+// One thread: arm the barrier and start the copy of agent `src`'s crop into `dst`.
+__device__ __forceinline__ void stage_crop(const float* __restrict__ img, int src, float* dst, uint64_t* bar) {
+    const uint32_t b = smem_addr(bar);
+    sbar_expect_tx(b, RAW_BYTES);
+    bulk_g2s(smem_addr(dst), img + (size_t)src * RAW, RAW_BYTES, b);
+}
 
 int sm_count() {
     static int n = 0;
@@ -320,12 +358,18 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     constexpr int PPAD = FwdPad::PPAD;           // channel stride of the pooled map: 8 mod 32 (conflict-free A fragments)
     constexpr int LDW2 = FwdLdw2<C>::value;        // row stride of the conv2 weights [tap][ci][co]: 8 t + g distinct banks
     extern __shared__ __align__(16) float smem[];
-    float* sImg = smem;                          // [4][35][36]
-    float* sW1 = sImg + CIN * IMGPAD;            // [36 taps][C]
+    float* sRaw = smem;                          // [2][4][33][33]  double-buffered crop, filled by cp.async.bulk
+    float* sW1 = sRaw + 2 * RAW;                 // [36 taps][C]
     float* sP = sW1 + NTAP * C;                  // [C][PPAD]
     float* sW2 = sP + ((C * PPAD + 3) & ~3);     // [9 taps][C in][LDW2]   (C out used)
     float* sAB = sW2 + 9 * C * LDW2;             // [2C]
     float* sred = sAB + 2 * C;                   // [8][2C]
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sred + 8 * 2 * C);      // [2] one mbarrier per crop buffer
+    if (threadIdx.x == 0) {
+        sbar_init(smem_addr(sBar), 1);
+        sbar_init(smem_addr(sBar + 1), 1);
+        sbar_fence_init();
+    }
     for (int i = threadIdx.x; i < NTAP * C; i += MGGAN_THREADS) {
         int c = i / NTAP, tap = i - c * NTAP;
         sW1[tap * C + c] = __ldg(W1 + i);
@@ -335,8 +379,9 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
         sW2[(tap * C + ci) * LDW2 + co] = __ldg(W2 + i);
     }
     if (threadIdx.x < 2 * C) sAB[threadIdx.x] = __ldg(ab1 + threadIdx.x);
-    for (int i = threadIdx.x; i < CIN * IMGPAD; i += MGGAN_THREADS) sImg[i] = 0.f;
     for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) sP[i] = 0.f;
+    __syncthreads();                              // barriers initialised before anyone arms or polls them
+    if (threadIdx.x == 0 && (int)blockIdx.x < N) stage_crop(img, rows ? rows[blockIdx.x] : blockIdx.x, sRaw, sBar);
     constexpr int NT = C / 8;                     // conv2 n-tiles (8 output channels each) = k-steps per tap (8 input channels)
     float st[4 * NT];                             // BatchNorm-2 partial sums: channels 8 j + 2 t + {0, 1}: sum [2j + e], squares [2NT + 2j + e]
 #pragma unroll
@@ -344,15 +389,15 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
     const int warp = threadIdx.x >> 5, g8 = (threadIdx.x & 31) >> 2, t4 = threadIdx.x & 3;
 
-    for (int n = blockIdx.x; n < N; n += gridDim.x) {
-        const int src = rows ? rows[n] : n;
-        __syncthreads();
-        const float* ip = img + (size_t)src * CIN * IMG2;
-        for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
-            int ci = i / IMG2, p = i - ci * IMG2, y = p / IMG, x = p - y * IMG;
-            sImg[ci * IMGPAD + (y + 1) * LDI + x + 1] = __ldg(ip + i);
+    int j = 0;                                    // agents this CTA has processed: buffer j & 1, barrier phase (j >> 1) & 1
+    for (int n = blockIdx.x; n < N; n += gridDim.x, ++j) {
+        __syncthreads();                          // previous agent: conv2 has read sP, conv1 has read the other crop buffer
+        const float* sImg = sRaw + (j & 1) * RAW;
+        if (threadIdx.x == 0 && n + (int)gridDim.x < N) {
+            const int nn = n + gridDim.x;
+            stage_crop(img, rows ? rows[nn] : nn, sRaw + ((j + 1) & 1) * RAW, sBar + ((j + 1) & 1));
         }
-        __syncthreads();
+        sbar_wait(smem_addr(sBar + (j & 1)), (j >> 1) & 1);
         {
             float acc[4][C];
 #pragma unroll
@@ -362,14 +407,13 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             }
 #pragma unroll 1
             for (int ci = 0; ci < CIN; ++ci) {
-                float pt[4][4];
-                const float* bp = sImg + ci * IMGPAD + (2 * py) * LDI + 2 * px;
+                float pt[4][4];                   // rows 2 py - 1 .. 2 py + 2, columns 2 px - 1 .. 2 px + 2 of the crop
+                const float* bp = sImg + ci * IMG2 + (2 * py - 1) * IMG + 2 * px - 1;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    float2 u = *reinterpret_cast<const float2*>(bp + r * LDI);
-                    float2 v = *reinterpret_cast<const float2*>(bp + r * LDI + 2);
-                    pt[r][0] = u.x; pt[r][1] = u.y; pt[r][2] = v.x; pt[r][3] = v.y;
-                }
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        pt[r][cc] = ((r > 0 || py > 0) && (cc > 0 || px > 0)) ? bp[r * IMG + cc] : 0.f;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -499,10 +543,16 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     float* sP = sDX + C * PPAD;                          // [C][PPAD]  p1 with zero halo
     float* sWT = sP + ((C * PPAD + 3) & ~3);             // [tap][co][LDWD]  (ci used)
     float* sDY = sWT + 9 * C * LDWD;                     // [C][LDY] dy1 (sparse values, dense layout)
-    float* sImg = sDY + C * LDY;                         // [4][35][36]
-    float* sPar = sImg + CIN * IMGPAD_BWD;                   // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
+    float* sRaw = sDY + C * LDY;                         // [2][4][33][33] double-buffered crop, filled by cp.async.bulk
+    float* sPar = sRaw + 2 * RAW;                        // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
     float* sred = sPar + 10 * C;                         // [8][2C]
-    unsigned char* sIdx = reinterpret_cast<unsigned char*>(sred + 8 * 2 * C);    // [C][256]
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sred + 8 * 2 * C);              // [2] one mbarrier per crop buffer
+    unsigned char* sIdx = reinterpret_cast<unsigned char*>(sBar + 2);            // [C][256]
+    if (threadIdx.x == 0) {
+        sbar_init(smem_addr(sBar), 1);
+        sbar_init(smem_addr(sBar + 1), 1);
+        sbar_fence_init();
+    }
     for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
         int co = i / (9 * C), r = i - co * 9 * C, ci = r / 9, tap = r - ci * 9;
         sWT[(tap * C + co) * LDWD + ci] = __ldg(W2 + i);
@@ -515,7 +565,8 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
         sPar[8 * C + threadIdx.x] = __ldg(m12_2 + threadIdx.x);
     }
     for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) { sDX[i] = 0.f; sP[i] = 0.f; }
-    for (int i = threadIdx.x; i < CIN * IMGPAD_BWD; i += MGGAN_THREADS) sImg[i] = 0.f;
+    __syncthreads();                                      // barriers initialised before anyone arms or polls them
+    if (threadIdx.x == 0 && (int)blockIdx.x < N) stage_crop(img, rows ? rows[blockIdx.x] : blockIdx.x, sRaw, sBar);
     const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
     const int warp = threadIdx.x >> 5, g8 = (threadIdx.x & 31) >> 2, t4 = threadIdx.x & 3;     // MMA fragment coordinates
     const int s_c = threadIdx.x / (CIN * QG), s_ci = (threadIdx.x / QG) % CIN, s_qg = threadIdx.x % QG;
@@ -530,15 +581,15 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
 #pragma unroll
     for (int c = 0; c < 4 * NT; ++c) st[c] = 0.f;
 
-    for (int n = blockIdx.x; n < N; n += gridDim.x) {
-        const int src = rows ? rows[n] : n;
-        __syncthreads();
+    int j = 0;                                           // agents this CTA has processed: crop buffer j & 1, phase (j >> 1) & 1
+    for (int n = blockIdx.x; n < N; n += gridDim.x, ++j) {
+        __syncthreads();                                 // the previous agent's last stage has read the other crop buffer
+        const float* sImg = sRaw + (j & 1) * RAW;
+        if (threadIdx.x == 0 && n + (int)gridDim.x < N) {
+            const int nn = n + gridDim.x;
+            stage_crop(img, rows ? rows[nn] : nn, sRaw + ((j + 1) & 1) * RAW, sBar + ((j + 1) & 1));
+        }
         {
-            const float* ip = img + (size_t)src * CIN * IMG2;
-            for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
-                int ci = i / IMG2, p = i - ci * IMG2, yy = p / IMG, xx = p - yy * IMG;
-                sImg[ci * IMGPAD_BWD + (yy + 1) * LDI + xx + 1] = __ldg(ip + i);
-            }
             const int win = (y >> 1) * P2 + (x >> 1), loc = (y & 1) * 2 + (x & 1);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -627,18 +678,25 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
         __syncthreads();
         {   // sparse half of the conv1 weight gradient: thread = (c, ci, lane group); lane groups take interleaved
             // pooled pixels (q = it * QG + group) so that neighbouring lanes read neighbouring banks
-            const float* ipc = sImg + s_ci * IMGPAD_BWD;
+            sbar_wait(smem_addr(sBar + (j & 1)), (j >> 1) & 1);          // the crop landed long ago: it was requested one agent earlier
+            const float* ipc = sImg + s_ci * IMG2;
 #pragma unroll 2
             for (int it = 0; it < Q_PER; ++it) {
                 const int q = it * QG + s_qg;
                 const float d = sDY[s_c * LDY + q];
                 if (d == 0.f) continue;
                 const int code = sIdx[s_c * P1SQ + q] & 3;
-                const float* bp = ipc + (2 * (q >> 4) + (code >> 1)) * LDI + 2 * (q & 15) + (code & 1);
+                // 3 x 3 window around conv1 output (2 qy + ay, 2 qx + ax): crop rows y0 .. y0 + 2, columns x0 .. x0 + 2; only
+                // row / column -1 can fall outside the unpadded crop
+                const int y0 = 2 * (q >> 4) + (code >> 1) - 1, x0 = 2 * (q & 15) + (code & 1) - 1;
+                const float* bp = ipc + y0 * IMG + x0;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) sacc[ky * 3 + kx] = fmaf(d, bp[ky * LDI + kx], sacc[ky * 3 + kx]);
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float v = ((ky > 0 || y0 >= 0) && (kx > 0 || x0 >= 0)) ? bp[ky * IMG + kx] : 0.f;
+                        sacc[ky * 3 + kx] = fmaf(d, v, sacc[ky * 3 + kx]);
+                    }
             }
         }
     }
@@ -936,11 +994,11 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
 
 
 template <int C>
-size_t fused_fwd_smem() { constexpr int PPAD = FwdPad::PPAD; return sizeof(float) * (CIN * IMGPAD + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * FwdLdw2<C>::value + 2 * C + 8 * 2 * C); }
+size_t fused_fwd_smem() { constexpr int PPAD = FwdPad::PPAD; return sizeof(float) * (2 * RAW + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * FwdLdw2<C>::value + 2 * C + 8 * 2 * C) + 16; }
 template <int C>
 size_t fused_bwd_smem() {
     constexpr int PPAD = BwdPad::PPAD;
-    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * BwdPad::LDWD + C * (P1SQ + 4) + CIN * IMGPAD_BWD + 10 * C + 8 * 2 * C) + C * P1SQ;
+    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * BwdPad::LDWD + C * (P1SQ + 4) + 2 * RAW + 10 * C + 8 * 2 * C) + 16 + C * P1SQ;
 }
 template <int C>
 size_t attn_w_floats() { return 2 * AH * C + AH + C + 2 * C; }
@@ -1046,6 +1104,7 @@ extern "C" int mggan_scene_fused12_fwd(const float* img, const int* rows, int N,
                                        float* e1, unsigned char* idx1, cudaStream_t stream) {
     if (N <= 0) return MGGAN_OK;
     MGGAN_REQUIRE((e1 == nullptr) == (idx1 == nullptr), "mggan_scene_fused12_fwd: e1 and idx1 must both be set or both NULL");
+    MGGAN_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0, "mggan_scene_fused12_fwd: img must be 16-byte aligned (bulk copy)");
     SCENE_DISPATCH(C, return fused_fwd<16>(img, rows, N, W1, b1, ab1, W2, b2, x2, stats2, e1, idx1, stream),
                    return fused_fwd<8>(img, rows, N, W1, b1, ab1, W2, b2, x2, stats2, e1, idx1, stream));
 }
@@ -1072,6 +1131,7 @@ extern "C" int mggan_scene_fused12_bwd(const float* img, const int* rows, int N,
                                        const float* dy2, const unsigned char* idx2, float* dW2, float* dbias2, float* S1,
                                        double* sums1, cudaStream_t stream) {
     if (N <= 0) return MGGAN_OK;
+    MGGAN_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0, "mggan_scene_fused12_bwd: img must be 16-byte aligned (bulk copy)");
     SCENE_DISPATCH(C, return fused_bwd<16>(img, rows, N, x2, e1, idx1, ab1, mean_istd1, ab2, mean_istd2, m12_2, W2, dy2, idx2, dW2, dbias2, S1, sums1, stream),
                    return fused_bwd<8>(img, rows, N, x2, e1, idx1, ab1, mean_istd1, ab2, mean_istd2, m12_2, W2, dy2, idx2, dW2, dbias2, S1, sums1, stream));
 }
