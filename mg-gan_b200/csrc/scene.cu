@@ -543,16 +543,10 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     float* sP = sDX + C * PPAD;                          // [C][PPAD]  p1 with zero halo
     float* sWT = sP + ((C * PPAD + 3) & ~3);             // [tap][co][LDWD]  (ci used)
     float* sDY = sWT + 9 * C * LDWD;                     // [C][LDY] dy1 (sparse values, dense layout)
-    float* sRaw = sDY + C * LDY;                         // [2][4][33][33] double-buffered crop, filled by cp.async.bulk
-    float* sPar = sRaw + 2 * RAW;                        // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
+    float* sImg = sDY + C * LDY;                         // [4][35][36]
+    float* sPar = sImg + CIN * IMGPAD_BWD;                   // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
     float* sred = sPar + 10 * C;                         // [8][2C]
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sred + 8 * 2 * C);              // [2] one mbarrier per crop buffer
-    unsigned char* sIdx = reinterpret_cast<unsigned char*>(sBar + 2);            // [C][256]
-    if (threadIdx.x == 0) {
-        sbar_init(smem_addr(sBar), 1);
-        sbar_init(smem_addr(sBar + 1), 1);
-        sbar_fence_init();
-    }
+    unsigned char* sIdx = reinterpret_cast<unsigned char*>(sred + 8 * 2 * C);    // [C][256]
     for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
         int co = i / (9 * C), r = i - co * 9 * C, ci = r / 9, tap = r - ci * 9;
         sWT[(tap * C + co) * LDWD + ci] = __ldg(W2 + i);
@@ -565,8 +559,7 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
         sPar[8 * C + threadIdx.x] = __ldg(m12_2 + threadIdx.x);
     }
     for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) { sDX[i] = 0.f; sP[i] = 0.f; }
-    __syncthreads();                                      // barriers initialised before anyone arms or polls them
-    if (threadIdx.x == 0 && (int)blockIdx.x < N) stage_crop(img, rows ? rows[blockIdx.x] : blockIdx.x, sRaw, sBar);
+    for (int i = threadIdx.x; i < CIN * IMGPAD_BWD; i += MGGAN_THREADS) sImg[i] = 0.f;
     const int y = threadIdx.x >> 4, x = threadIdx.x & 15;
     const int warp = threadIdx.x >> 5, g8 = (threadIdx.x & 31) >> 2, t4 = threadIdx.x & 3;     // MMA fragment coordinates
     const int s_c = threadIdx.x / (CIN * QG), s_ci = (threadIdx.x / QG) % CIN, s_qg = threadIdx.x % QG;
@@ -581,15 +574,18 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
 #pragma unroll
     for (int c = 0; c < 4 * NT; ++c) st[c] = 0.f;
 
-    int j = 0;                                           // agents this CTA has processed: crop buffer j & 1, phase (j >> 1) & 1
-    for (int n = blockIdx.x; n < N; n += gridDim.x, ++j) {
-        __syncthreads();                                 // the previous agent's last stage has read the other crop buffer
-        const float* sImg = sRaw + (j & 1) * RAW;
-        if (threadIdx.x == 0 && n + (int)gridDim.x < N) {
-            const int nn = n + gridDim.x;
-            stage_crop(img, rows ? rows[nn] : nn, sRaw + ((j + 1) & 1) * RAW, sBar + ((j + 1) & 1));
-        }
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        const int src = rows ? rows[n] : n;
+        __syncthreads();
         {
+            // the crop is only read by the last stage (sparse conv1 weight gradient): cp.async (LDGSTS) it into the padded
+            // layout now and wait for it there, behind the two tensor-core stages
+            const float* ip = img + (size_t)src * CIN * IMG2;
+            for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
+                int ci = i / IMG2, p = i - ci * IMG2, yy = p / IMG, xx = p - yy * IMG;
+                cp_async4(&sImg[ci * IMGPAD_BWD + (yy + 1) * LDI + xx + 1], ip + i);
+            }
+            cp_async_commit();
             const int win = (y >> 1) * P2 + (x >> 1), loc = (y & 1) * 2 + (x & 1);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -675,28 +671,22 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                     }
             }
         }
+        cp_async_wait<0>();
         __syncthreads();
         {   // sparse half of the conv1 weight gradient: thread = (c, ci, lane group); lane groups take interleaved
             // pooled pixels (q = it * QG + group) so that neighbouring lanes read neighbouring banks
-            sbar_wait(smem_addr(sBar + (j & 1)), (j >> 1) & 1);          // the crop landed long ago: it was requested one agent earlier
-            const float* ipc = sImg + s_ci * IMG2;
+            const float* ipc = sImg + s_ci * IMGPAD_BWD;
 #pragma unroll 2
             for (int it = 0; it < Q_PER; ++it) {
                 const int q = it * QG + s_qg;
                 const float d = sDY[s_c * LDY + q];
                 if (d == 0.f) continue;
                 const int code = sIdx[s_c * P1SQ + q] & 3;
-                // 3 x 3 window around conv1 output (2 qy + ay, 2 qx + ax): crop rows y0 .. y0 + 2, columns x0 .. x0 + 2; only
-                // row / column -1 can fall outside the unpadded crop
-                const int y0 = 2 * (q >> 4) + (code >> 1) - 1, x0 = 2 * (q & 15) + (code & 1) - 1;
-                const float* bp = ipc + y0 * IMG + x0;
+                const float* bp = ipc + (2 * (q >> 4) + (code >> 1)) * LDI + 2 * (q & 15) + (code & 1);
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float v = ((ky > 0 || y0 >= 0) && (kx > 0 || x0 >= 0)) ? bp[ky * IMG + kx] : 0.f;
-                        sacc[ky * 3 + kx] = fmaf(d, v, sacc[ky * 3 + kx]);
-                    }
+                    for (int kx = 0; kx < 3; ++kx) sacc[ky * 3 + kx] = fmaf(d, bp[ky * LDI + kx], sacc[ky * 3 + kx]);
             }
         }
     }
@@ -998,7 +988,7 @@ size_t fused_fwd_smem() { constexpr int PPAD = FwdPad::PPAD; return sizeof(float
 template <int C>
 size_t fused_bwd_smem() {
     constexpr int PPAD = BwdPad::PPAD;
-    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * BwdPad::LDWD + C * (P1SQ + 4) + 2 * RAW + 10 * C + 8 * 2 * C) + 16 + C * P1SQ;
+    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * BwdPad::LDWD + C * (P1SQ + 4) + CIN * IMGPAD_BWD + 10 * C + 8 * 2 * C) + C * P1SQ;
 }
 template <int C>
 size_t attn_w_floats() { return 2 * AH * C + AH + C + 2 * C; }
@@ -1131,7 +1121,6 @@ extern "C" int mggan_scene_fused12_bwd(const float* img, const int* rows, int N,
                                        const float* dy2, const unsigned char* idx2, float* dW2, float* dbias2, float* S1,
                                        double* sums1, cudaStream_t stream) {
     if (N <= 0) return MGGAN_OK;
-    MGGAN_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0, "mggan_scene_fused12_bwd: img must be 16-byte aligned (bulk copy)");
     SCENE_DISPATCH(C, return fused_bwd<16>(img, rows, N, x2, e1, idx1, ab1, mean_istd1, ab2, mean_istd2, m12_2, W2, dy2, idx2, dW2, dbias2, S1, sums1, stream),
                    return fused_bwd<8>(img, rows, N, x2, e1, idx1, ab1, mean_istd1, ab2, mean_istd2, m12_2, W2, dy2, idx2, dW2, dbias2, S1, sums1, stream));
 }

@@ -16,12 +16,16 @@ disc_scores).  All prediction strategies of `get_predict_func` (train.py:291-576
 they decode only the sequences they keep.
 """
 import random
+import sys
 import time
 from functools import partial
 from pathlib import Path
 
 import numpy as np
 import torch
+
+if __package__ in (None, ""):          # `python mggan/model/train.py <flags>` (the reference's README command line)
+    sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 
 from mggan import kernels as K
 from mggan.abstract_train import MultiGeneratorGAN
