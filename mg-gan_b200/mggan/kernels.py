@@ -231,12 +231,13 @@ def social_attention(xy_last, dxdy_last, h, scenes, fc0, fc2, fc4, att_w):
     """SocialAttention.forward on the rows covered by `scenes`.
 
     fc0/fc2/fc4: the three Linear layers of EmbedSocialFeatures, att_w: AttentionPooling.W.
-    The last embedding layer and W are folded into per-agent vectors with two dense-layer
-    kernels: q = W h + b (N,F); Us = [fc4.weight^T ; fc4.bias] q (N,65)."""
+    The last embedding layer and W are folded into per-agent vectors with one dense-layer
+    kernel: Us = [fc4.weight^T ; fc4.bias] (W h + b) (N,65)."""
     x4 = torch.cat([xy_last, dxdy_last], -1)
-    q = linear(h, att_w.weight, att_w.bias)
+    # us = [fc4.weight^T ; fc4.bias] (W h + b): the two weight matrices are folded on the host side (a (65, F) x (F, H) product,
+    # tracked by autograd), so the per-agent work is ONE dense layer instead of two
     wc3 = torch.cat([fc4.weight.t(), fc4.bias[None]], 0)        # (65, F)
-    us = linear(q, wc3)
+    us = linear(h, wc3 @ att_w.weight, wc3 @ att_w.bias)
     return _SocialAttn.apply(x4, h, us, fc0.weight, fc0.bias, fc2.weight, fc2.bias, scenes, torch.is_grad_enabled())
 
 

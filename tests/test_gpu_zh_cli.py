@@ -25,7 +25,7 @@ def trained(tmp_path_factory):
     log = tmp_path_factory.mktemp("cli_logs")
     _run([sys.executable, os.path.join(ROOT, "mg-gan_b200", "mggan", "model", "train.py"), "--dataset", "synthetic_gofp",
           "--synthetic_scenes", "6", "--epochs", "2", "--batch_size", "3", "--num_gens", "2", "--num_samples", "4",
-          "--top_k_test", "4", "--save_every", "1", "--log_dir", str(log), "--name", "cli", "--num_unrolling_steps", "1",
+          "--save_every", "1", "--log_dir", str(log), "--name", "cli", "--num_unrolling_steps", "1",
           "--l2_loss_type", "mse"])
     model_dir = log / "multi_generator" / "cli"
     versions = [d for d in model_dir.iterdir() if d.name.startswith("version_")]
@@ -33,6 +33,7 @@ def trained(tmp_path_factory):
     v = versions[0]
     assert (v / "meta_tags.csv").is_file()
     names = sorted(p.name for p in (v / "checkpoints").iterdir())
+    # best-checkpoint tracking follows "val/ADE k=20" (abstract_train.py:104-107,184-191): needs the default --top_k_test 20
     assert "checkpoint_best.pth" in names and "checkpoint_1.pth" in names and "checkpoint_2.pth" in names
     ck = torch.load(v / "checkpoints" / "checkpoint_2.pth", map_location="cpu")
     assert set(ck) == {"generator", "discriminator", "gen_opt", "disc_opt"}          # abstract_train.py:236-244
