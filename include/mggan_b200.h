@@ -238,6 +238,18 @@ int mggan_clip_adamw(const MgganTensorTable* table, int count, const double* sqn
                      cudaStream_t stream);
 int mggan_multi_copy(const MgganTensorTable* table, int count, cudaStream_t stream); /* p[t] <- g[t] */
 
+/* ---- fused two-layer perceptron Y = act2(W2 act1(W1 x + b1) + b2): the dense chains of the path in one launch each
+ * (discriminators.py:46-56 in_encoder_fc / pred_encoder, :76-108 the two heads; standard.py:99-105 PM-Network layers 1-2).
+ * X (M,K) row-major 16-byte aligned, K % 4 == 0, K <= 192; W1 (H,K), H % 4 == 0, H <= 96; W2 (O,H), O <= 32; biases may be
+ * NULL; act codes as mggan_linear_* (0 none, 1 ReLU, 2 LeakyReLU(slope), 3 sigmoid * (1 - 2e-7) + 1e-7).  The hidden layer
+ * stays in shared memory (forward) / is recomputed from X (backward).  Backward: dX (M,K) overwritten or NULL; dW1, db1, dW2,
+ * db2 ACCUMULATED into (caller zero-fills), all set or all NULL (frozen weights -> input gradient only). */
+int mggan_mlp2_fwd(const float* X, long long M, int K, const float* W1, const float* b1, int H, int act1, float slope1,
+                   const float* W2, const float* b2, int O, int act2, float slope2, float* Y, cudaStream_t stream);
+int mggan_mlp2_bwd(const float* X, long long M, int K, const float* W1, const float* b1, int H, int act1, float slope1,
+                   const float* W2, int O, int act2, float slope2, const float* Y, const float* dY, float* dX,
+                   float* dW1, float* db1, float* dW2, float* db2, cudaStream_t stream);
+
 /* ---- data-parallel exchange (new; the reference is single-device): one-shot all-reduce over
  * NVLink peer memory, fused with the squared gradient norm that mggan_clip_adamw clips with.  `region[r]` is THIS call's
  * region of rank r's symmetric arena and `flags[r]` rank r's flag array ([64][16] uint32, zero-initialised once), both as

@@ -8,7 +8,7 @@ SRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "mggan", "_C")
 OUT = os.path.join(OUT_DIR, "libmggan_b200.so")
 SOURCES = ["api.cu", "lstm_enc.cu", "decoder.cu", "decoder_tc.cu", "social.cu", "scene.cu", "linear.cu", "disc_heads.cu", "select.cu", "losses.cu",
-           "optim.cu", "data_eval.cu", "linear_tc.cu", "peer_reduce.cu"]
+           "optim.cu", "data_eval.cu", "linear_tc.cu", "peer_reduce.cu", "mlp2.cu"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
          "--use_fast_math" if False else "-Xptxas", "-v" if os.environ.get("MGGAN_PTXAS_V") else "-O3"]
 

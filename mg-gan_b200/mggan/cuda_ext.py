@@ -77,6 +77,8 @@ SIGNATURES = {
     "mggan_clip_adamw": "tipfffffffs",
     "mggan_multi_copy": "tis",
     "mggan_peer_allreduce": "Tipqpps",
+    "mggan_mlp2_fwd": "pqippiifppiifps",
+    "mggan_mlp2_bwd": "pqippiifpiifppppppps",
 }
 # plain (non status-returning) helpers
 _PLAIN = {"mggan_version": ("", ctypes.c_int), "mggan_device_check": ("", ctypes.c_int),

@@ -67,6 +67,57 @@ def linear(x, w, b=None, act=ACT_NONE, slope=0.0):
     return _Linear.apply(x, w, b, act, slope, torch.is_grad_enabled())
 
 
+# --------------------------------------------------------------------------- fused two-layer perceptron
+class _Mlp2(torch.autograd.Function):
+    """act2(W2 act1(W1 x + b1) + b2) in one launch; the backward recomputes the hidden layer (csrc/mlp2.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, act1, slope1, act2, slope2, grad_on):
+        x, w1, w2 = _f32(x), _f32(w1), _f32(w2)
+        b1 = _f32(b1) if b1 is not None else None
+        b2 = _f32(b2) if b2 is not None else None
+        M, K = x.shape
+        H, O = w1.shape[0], w2.shape[0]
+        y = torch.empty(M, O, device=x.device, dtype=torch.float32)
+        call("mggan_mlp2_fwd", ptr(x), M, K, ptr(w1), ptr(b1), H, act1, float(slope1), ptr(w2), ptr(b2), O, act2,
+             float(slope2), ptr(y))
+        if grad_on:
+            ctx.save_for_backward(x, w1, b1, w2, y)
+        ctx.cfg = (act1, float(slope1), act2, float(slope2), b1 is not None, b2 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, b1, w2, y = ctx.saved_tensors
+        act1, slope1, act2, slope2, has_b1, has_b2 = ctx.cfg
+        M, K = x.shape
+        H, O = w1.shape[0], w2.shape[0]
+        need_x = ctx.needs_input_grad[0]
+        need_w = any(ctx.needs_input_grad[1:5])
+        dx = torch.empty_like(x) if need_x else None
+        dw1 = db1 = dw2 = db2 = None
+        if need_w:
+            dw1, db1, dw2, db2 = _zeros(x.device, w1.shape, (H,), w2.shape, (O,))
+        if need_x or need_w:
+            call("mggan_mlp2_bwd", ptr(x), M, K, ptr(w1), ptr(b1), H, act1, slope1, ptr(w2), O, act2, slope2, ptr(y),
+                 ptr(_f32(dy)), ptr(dx), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2))
+        g = ctx.needs_input_grad
+        return (dx, dw1 if g[1] else None, db1 if (g[2] and has_b1) else None, dw2 if g[3] else None,
+                db2 if (g[4] and has_b2) else None, None, None, None, None, None)
+
+
+def mlp2_supported(K, H, O):
+    return 4 <= K <= 192 and K % 4 == 0 and 4 <= H <= 96 and H % 4 == 0 and 1 <= O <= 32
+
+
+def mlp2(x, w1, b1, w2, b2, act1=ACT_NONE, slope1=0.0, act2=ACT_NONE, slope2=0.0):
+    """act2(act1(x @ w1.T + b1) @ w2.T + b2) for 2-D x: one fused launch when the sizes fit the kernel (they do for every
+    chain of the default model), else two dense-layer launches."""
+    if not mlp2_supported(x.shape[1], w1.shape[0], w2.shape[0]) or x.shape[0] == 0:
+        return linear(linear(x, w1, b1, act1, slope1), w2, b2, act2, slope2)
+    return _Mlp2.apply(x, w1, b1, w2, b2, act1, slope1, act2, slope2, torch.is_grad_enabled())
+
+
 # --------------------------------------------------------------------------- discriminator heads (frozen weights)
 class _DiscHeads(torch.autograd.Function):
     """p, branch = heads(base[i] + (s == 0) soc0[i] + W1p pe[s, i]) -- see include/mggan_b200.h.  Gradients flow to

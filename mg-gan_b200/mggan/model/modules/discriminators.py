@@ -84,8 +84,7 @@ class MultiDiscriminatorTrajectory(nn.Module):
 
     @staticmethod
     def _mlp2(seq, x, last_act=K.ACT_NONE):
-        h = K.linear(x, seq[0].weight, seq[0].bias, K.ACT_LRELU, 0.2)
-        return K.linear(h, seq[2].weight, seq[2].bias, last_act)
+        return K.mlp2(x, seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, K.ACT_LRELU, 0.2, last_act)
 
     def _in_enc(self, in_dxdy):
         key = (id(in_dxdy), in_dxdy._version, torch.is_grad_enabled())

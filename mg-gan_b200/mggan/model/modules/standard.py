@@ -122,8 +122,7 @@ class MultiGenerator(nn.Module):
         if not self.use_pinet:
             return self.net_prior.expand(enc_h.size(0), -1)
         nc = self.net_chooser
-        x = K.linear(enc_h, nc[0].weight, nc[0].bias, K.ACT_RELU)
-        x = K.linear(x, nc[2].weight, nc[2].bias, K.ACT_RELU)
+        x = K.mlp2(enc_h, nc[0].weight, nc[0].bias, nc[2].weight, nc[2].bias, K.ACT_RELU, 0.0, K.ACT_RELU)
         return K.linear(x, nc[4].weight, nc[4].bias)
 
     def get_samples(self, enc_h, num_samples=5):

@@ -40,6 +40,56 @@ def K():
     return kernels
 
 
+# ------------------------------------------------------------------------------------ fused two-layer perceptron
+def _act_ref(z, act, slope):
+    if act == 1:
+        return torch.relu(z)
+    if act == 2:
+        return torch.where(z > 0, z, slope * z)
+    if act == 3:
+        return torch.sigmoid(z) * (1 - 2e-7) + 1e-7
+    return z
+
+
+@pytest.mark.parametrize("M,Kd,Hd,Od,act1,act2,frozen", [
+    (300, 24, 64, 32, 2, 0, False),        # pred_encoder (discriminators.py:46-50)
+    (5000, 64, 32, 32, 2, 0, False),       # in_encoder_fc (:52-56)
+    (1000, 192, 96, 1, 2, 3, False),       # discriminator head (:76-85): sigmoid with the eps squash
+    (333, 192, 96, 8, 2, 0, False),        # generator-id head (:103-108)
+    (130, 128, 64, 3, 2, 0, False),        # heads without the scene CNN, G = 3
+    (77, 128, 16, 16, 1, 1, False),        # PM-Network layers 1-2 (standard.py:99-105)
+    (1, 64, 16, 16, 1, 1, False),
+    (4099, 24, 64, 32, 2, 0, True),        # generator step: frozen discriminator, input gradient only
+])
+def test_mlp2_matches_pytorch_fp32(K, M, Kd, Hd, Od, act1, act2, frozen):
+    """Plain PyTorch fp32 reference of the same two dense layers (CPU), outputs and every gradient."""
+    g = torch.Generator().manual_seed(M * 7 + Kd)
+    x = torch.randn(M, Kd, generator=g)
+    w1, b1 = torch.randn(Hd, Kd, generator=g) * 0.2, torch.randn(Hd, generator=g) * 0.1
+    w2, b2 = torch.randn(Od, Hd, generator=g) * 0.2, torch.randn(Od, generator=g) * 0.1
+    dy = torch.randn(M, Od, generator=g)
+    ref_in = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    yr = _act_ref(_act_ref(ref_in[0] @ ref_in[1].t() + ref_in[2], act1, 0.2) @ ref_in[3].t() + ref_in[4], act2, 0.2)
+    (yr * dy).sum().backward()
+    got_in = [t.clone().to(DEV).requires_grad_(not frozen or i == 0) for i, t in enumerate((x, w1, b1, w2, b2))]
+    yg = K.mlp2(got_in[0], got_in[1], got_in[2], got_in[3], got_in[4], act1, 0.2, act2, 0.2)
+    (yg * dy.to(DEV)).sum().backward()
+    check(yg, yr, 2e-5, "y")
+    names = ["dx", "dw1", "db1", "dw2", "db2"]
+    for i, (a, b) in enumerate(zip(got_in, ref_in)):
+        if frozen and i > 0:
+            assert a.grad is None
+        else:
+            check(a.grad, b.grad, 1e-4, names[i])
+
+
+def test_mlp2_falls_back_to_two_layers_for_unsupported_sizes(K):
+    g = torch.Generator().manual_seed(3)
+    x, w1, w2 = torch.randn(20, 65, generator=g), torch.randn(200, 65, generator=g) * 0.1, torch.randn(5, 200, generator=g) * 0.1
+    y = K.mlp2(x.to(DEV), w1.to(DEV), None, w2.to(DEV), None, 1, 0.0, 0)
+    check(y, torch.relu(x @ w1.t()) @ w2.t(), 2e-5, "y")
+
+
 # ------------------------------------------------------------------------------------ linear
 @pytest.mark.parametrize("M,Kd,Od,act", [(1, 16, 16, 0), (37, 24, 64, 2), (300, 192, 96, 2), (129, 96, 1, 3),
                                           (1000, 128, 16, 1), (65, 65, 8, 0)])
