@@ -362,6 +362,10 @@ class MultiGeneratorGAN(abc.ABC):
         config = load_hparams_from_tags_csv(version_dir / "meta_tags.csv")
         defaults = get_argparse_defaults(get_parser())
         defaults.update(config)
+        # `--gpus` is a STRING flag used for truthiness (config.py:24: the default "0" selects the GPU); meta_tags.csv
+        # round-trips it through `convert`, which turns "0" into the falsy int 0 -- read it back as the string it was
+        if defaults.get("gpus") is not None and not isinstance(defaults["gpus"], bool):
+            defaults["gpus"] = str(defaults["gpus"])
         config = Namespace(**defaults)
         g, d = cls.construct_model(config)
         writer = Experiment(log_path, name=exp_name, version=version)
