@@ -30,7 +30,11 @@ def main():
     ap.add_argument("--k", type=int, default=6)
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--nccl", action="store_true", help="NCCL collectives instead of the peer-memory kernel")
-    ap.add_argument("--tol", type=float, default=1e-5)
+    ap.add_argument("--tol", type=float, default=5e-5,
+                    help="parameters after ITERS iterations: 5 %% of one AdamW step (lr 1e-3).  AdamW's first steps are "
+                         "lr * g / (|g| + 1e-8): for weight elements whose gradient is ~1e-8 the update depends on the "
+                         "gradient's round-off (summation order differs between 1 and W shards), measured 1.3e-5 on one "
+                         "decoder tensor; the gradients themselves are compared at 1e-5 relative")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -114,6 +118,16 @@ def main():
             else:
                 tr._run_prepared(prepared, defaultdict(list), it)
         torch.cuda.synchronize()
+        # gradients left by the last optimiser step of the run (PM-Network step: encoder, scene CNN, social attention,
+        # PM-Network); data-parallel ranks hold their shard's part, summed here exactly as the step summed it
+        grads = {}
+        for n, p in tr.G.named_parameters():
+            if p.grad is not None and not n.startswith("G_"):
+                g = p.grad.detach().clone()
+                if ctx is not None:
+                    dist.all_reduce(g)
+                grads["Ggrad." + n] = g
+        run.grads = grads
         return {("G." + n): p.detach().clone() for n, p in tr.G.named_parameters() if not n.startswith("G_")} | \
                {("D." + n): p.detach().clone() for n, p in tr.D.named_parameters()} | \
                {("Gbuf." + n): p.detach().clone().float() for n, p in tr.G.named_buffers() if not n.startswith("G_")} | \
@@ -124,10 +138,19 @@ def main():
     if not a.nccl and ctx.peer is None:
         print(f"[rank {rank}] peer-memory reducer unavailable ({ctx.peer_error}); NCCL carries the exchanges", file=sys.stderr)
     sharded = run(ctx, shard_batch(full, world, rank), a_lo, a_hi)
+    sharded_grads = run.grads
     ok, report = True, {}
     if rank == 0:
         single = run(None, full, 0, N)
+        grad_err, grad_worst = 0.0, None
+        for n, v in run.grads.items():
+            if n.endswith("Conv_1.bias"):
+                continue
+            e = float((sharded_grads[n] - v).abs().max() / (v.abs().max() + 1e-12))
+            if e > grad_err:
+                grad_err, grad_worst = e, n
         worst, worst_name, worst_rm = 0.0, None, 0.0
+        ranked = sorted(((float((sharded[n] - v).abs().max()) if v.numel() else 0.0, n) for n, v in single.items()), reverse=True)
         for n, v in single.items():
             if n.endswith("Conv_1.bias"):
                 continue          # zero true gradient under train-mode BatchNorm: AdamW amplifies round-off to +-lr
@@ -137,10 +160,11 @@ def main():
                 continue
             if dlt > worst:
                 worst, worst_name = dlt, n
-        ok = worst <= a.tol and worst_rm <= 5e-4 * a.iters
+        ok = worst <= a.tol and worst_rm <= 5e-4 * a.iters and grad_err <= 1e-5 and len(run.grads) >= 20
         report = {"ok": ok, "exchange": "peer-memory kernel" if ctx.peer is not None else "nccl",
                   "peer_calls": ctx.peer.calls if ctx.peer is not None else 0, "world": world, "iters": a.iters, "graph": a.graph, "max_abs_diff": worst, "worst": worst_name, "running_mean_max_abs_diff": worst_rm,
-                  "tol": a.tol, "tensors": len(single), "agents": N, "scenes": len(sse)}
+                  "tol": a.tol, "grad_rel_err": grad_err, "grad_worst": grad_worst, "grads_compared": len(run.grads),
+                  "top5": ranked[:5], "tensors": len(single), "agents": N, "scenes": len(sse)}
         print(json.dumps(report))
         sys.stdout.flush()
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
