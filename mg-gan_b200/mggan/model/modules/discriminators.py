@@ -97,7 +97,7 @@ class MultiDiscriminatorTrajectory(nn.Module):
 
     def _pred_enc(self, pred_dxdy):
         pred_len, n_samples, b, _ = pred_dxdy.shape
-        pv = pred_dxdy.permute(1, 2, 0, 3).reshape(n_samples * b, -1)
+        pv = pred_dxdy.permute(1, 2, 0, 3).reshape(n_samples * b, pred_len * 2)
         return self._mlp2(self.pred_encoder, pv)
 
     def encode(self, in_xy, in_dxdy, pred_xy, pred_dxdy, mask=None):

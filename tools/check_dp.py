@@ -50,7 +50,7 @@ def main():
     from mggan.model.model_factory import construct_model
     from mggan.synthetic import make_batch
 
-    sizes = [3, 1, 5, 2, 4, 6, 2, 3]                      # ragged, including a singleton scene
+    sizes = [3, 1, 5, 2, 4, 6, 2, 3] * max(1, world // 2)  # ragged, including singleton scenes; >= 4 scenes per rank
     b = make_batch(sizes, seed=21, with_img=True)
     sse = b["seq_start_end"]
     N = b["in_xy"].shape[1]
