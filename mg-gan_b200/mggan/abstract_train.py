@@ -58,8 +58,10 @@ class MultiGeneratorGAN(abc.ABC):
         self.lr_schedulerG = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizerG, config.epochs, eta_min=0)
         self.epoch = 0
         self._graph = None                 # mggan.graph.GraphedIteration while capturing
-        self._graphs = []                  # captured iterations (one per batch structure, most recent first)
-        self._graph_seen = None            # structure key of the previous eager iteration
+        self._graphs = []                  # captured iterations, one per batch structure, most recently used first (LRU)
+        self._graph_seen = {}              # structure key -> eager iterations seen (a structure is captured on its 2nd one)
+        self._graph_pool = None            # one memory pool shared by all captures (they never run concurrently)
+        self.graph_hits = self.graph_misses = 0
         self._graph_failed = set()         # structures whose capture raised: they stay eager
         self._stage_ring = {}              # slot -> {name: persistent device staging buffer} (train_iterations prefetch)
         self.scene_images = None           # SceneImageStore: crops are cut on the device for batches carrying `image_ids`
@@ -177,8 +179,9 @@ class MultiGeneratorGAN(abc.ABC):
                 and cfg.num_gen_steps == 1 and cfg.num_unrolling_steps == 0)
 
     def _run_iteration(self, prepared, metrics, total_iterations=0):
-        """Eager iteration, or the replay of a captured one when this batch has the structure (scene sizes, no masked
-        futures) of the previous one: the iteration is captured the second time a structure repeats (mggan/graph.py).
+        """Eager iteration, or the replay of a captured one when this batch has a structure (scene sizes, no masked
+        futures) that was captured before: a structure is captured the second time it is seen (mggan/graph.py) and the
+        captures live in an LRU cache of `--graph_cache` entries sharing one memory pool.
         Data-parallel: the choice is collective.  One host-side exchange per iteration tells every rank whether ALL
         ranks hold a matching graph (replay), whether all could capture now (eager + capture), or not (eager); it also
         carries the global agent counts, and a graph is replayed only under the counts it was captured with (its loss
@@ -186,7 +189,7 @@ class MultiGeneratorGAN(abc.ABC):
         eligible = self._graph_eligible(prepared)
         g = next((x for x in self._graphs if x.matches(prepared)), None) if eligible else None
         key = (tuple(prepared[0].shape), prepared[5] is None, tuple(tuple(s) for s in prepared[4]))
-        ready = eligible and (g is not None or self._graph_seen == key)
+        ready = eligible and (g is not None or self._graph_seen.get(key, 0) >= 1)
         sums = None
         if self.dist is not None:
             from mggan.distributed import host_sum
@@ -199,10 +202,18 @@ class MultiGeneratorGAN(abc.ABC):
                 g = None
             ready = v[1] == world
         if g is not None:
+            self.graph_hits += 1
+            if self._graphs[0] is not g:                     # LRU order
+                self._graphs.remove(g)
+                self._graphs.insert(0, g)
             for k, v_ in g.run(prepared).items():
                 metrics[k].extend(t.clone() for t in v_)           # the graph's own tensors are overwritten by the next replay
             return
-        self._graph_seen = key if eligible else None
+        self.graph_misses += 1
+        if eligible:
+            if len(self._graph_seen) > 4096:
+                self._graph_seen.clear()
+            self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
         self._run_prepared(prepared, metrics, total_iterations, sums)       # this batch runs eagerly
         if ready and key not in self._graph_failed:
             from mggan.graph import GraphedIteration
@@ -216,7 +227,9 @@ class MultiGeneratorGAN(abc.ABC):
                 return
             new.global_counts = (sums["agents"][1], sums["active"][1]) if sums is not None else None
             self._graphs.insert(0, new)
-            del self._graphs[2:]
+            # Ragged datasets: with the reference-default batch of 2 scenes a shuffled epoch has only a few dozen distinct
+            # structures (pairs of scene sizes), so a modest LRU cache turns almost every iteration into a replay.
+            del self._graphs[max(1, int(getattr(self.config, "graph_cache", 64))):]
 
     def train_iterations(self, batches, metrics, total_iterations=0, on_step=None):
         """The reference loop `for batch in loader: <D, G, PM step>` (abstract_train.py:114-168) with the

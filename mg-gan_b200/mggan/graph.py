@@ -99,7 +99,9 @@ class GraphedIteration:
         try:
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
+            if trainer._graph_pool is None:
+                trainer._graph_pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(self.graph, pool=trainer._graph_pool, capture_error_mode="relaxed"):
                 s = self.static
                 trainer._run_prepared((s[0], s[1], s[2], s[3], sub_batches, s[4], None), self.metrics, total_iterations)
         finally:

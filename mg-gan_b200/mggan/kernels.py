@@ -125,6 +125,7 @@ class _DiscHeads(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pe, base, soc0, w1p, wd2, bd2, wg2, bg2, n, k, grad_on):
+        ctx.set_materialize_grads(False)        # an unused output's gradient arrives as None (the kernel takes NULL), not as a zero fill
         assert not (grad_on and any(ctx.needs_input_grad[3:8])), \
             "disc_heads: weight gradients are not produced (frozen discriminator only)"
         pe, base, soc0, w1p, wd2, bd2 = map(_f32, (pe, base, soc0, w1p, wd2, bd2))
@@ -148,6 +149,8 @@ class _DiscHeads(torch.autograd.Function):
     def backward(ctx, dp, dbranch):
         pe, base, soc0, w1p, wd2, wg2, p = ctx.saved_tensors
         n, k, HH, G = ctx.dims
+        if dp is None and dbranch is None:
+            return (None,) * 11
         d_pe = torch.empty_like(pe)
         d_soc0 = torch.empty_like(soc0)
         d_base = torch.zeros_like(base) if ctx.needs_input_grad[1] else None
@@ -515,6 +518,7 @@ DECODER_FWD = "mggan_decoder_fwd" if os.environ.get("MGGAN_DECODER", "tc") == "f
 class _Decoder(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, social, last_xy, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2, sel, pred_len, grad_on):
+        ctx.set_materialize_grads(False)        # d_abs / d_rel of an unused output arrive as None (the kernel takes NULL)
         ts = [_f32(t) for t in (A, social, last_xy, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2)]
         A, social, last_xy, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2 = ts
         dev = A.device
@@ -538,6 +542,8 @@ class _Decoder(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_abs, d_rel):
+        if d_abs is None and d_rel is None:
+            return (None,) * 17
         social, last_dxdy, noise, wz, wx, b, whh, w1h, w1s, b1, w2, b2, out_rel, acts, u1, h0 = ctx.saved_tensors
         sel = ctx.sel
         Z = wz.shape[1]

@@ -89,7 +89,8 @@ _EXTRA_FLAGS = [
                                help="synthetic_* datasets: keep one image per scene resident in HBM and cut the agents' "
                                     "33x33 crops on the device (mggan_scene_crop) instead of shipping host-built features")),
     ("--cuda_graph", dict(type=int, default=1, choices=[0, 1],
-                          help="replay the training iteration as a CUDA graph when consecutive batches have the same structure")),
+                          help="replay the training iteration as a CUDA graph for batch structures seen before")),
+    ("--graph_cache", dict(type=int, default=64, help="captured iterations kept (LRU), one per batch structure")),
 ]
 
 

@@ -113,3 +113,26 @@ def test_graph_replay_matches_eager(monkeypatch):
         assert (se is None or len(se) == 0) == (sg is None or len(sg) == 0)
         if se:
             assert float(se["step"]) == float(sg["step"])
+
+
+def test_graph_cache_serves_a_shuffled_ragged_epoch():
+    """Ragged scenes (eth shape: 1..6 agents) at the reference-default batch of 2 scenes, shuffled every epoch: the
+    structures (ordered pairs of scene sizes) repeat, every one is captured the second time it is seen and kept in the LRU
+    cache, so after a few epochs almost every iteration is a graph replay (abstract_train._run_iteration)."""
+    from mggan.data_utils.data_loaders import get_dataloader
+    torch.manual_seed(7)
+    np.random.seed(7)
+    tr = make_trainer(1)
+    loader = get_dataloader("synthetic_eth", "train", batch_size=2, shuffle=True, num_scenes=48, with_img=True, seed=3)
+    rates = []
+    for epoch in range(7):
+        h0, m0 = tr.graph_hits, tr.graph_misses
+        m = defaultdict(list)
+        tr.train_iterations(loader, m)
+        torch.cuda.synchronize()
+        assert all(np.isfinite(float(v[-1])) for k, v in m.items() if k.startswith("train/"))
+        rates.append((tr.graph_hits - h0) / max(1, tr.graph_hits - h0 + tr.graph_misses - m0))
+    assert len(tr._graphs) <= 36                       # at most one capture per ordered pair of sizes 1..6
+    assert rates[0] == 0.0 and rates[-1] >= 0.75, rates
+    for p in list(tr.G.parameters()) + list(tr.D.parameters()):
+        assert torch.isfinite(p).all()
