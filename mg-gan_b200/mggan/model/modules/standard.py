@@ -7,6 +7,8 @@ the decoding of exactly the selected (agent, sample, generator) sequences are sm
 the reference's `forward_all` over G x M x N sequences followed by a gather becomes one decoder
 launch over k x N sequences grouped by generator.
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -115,8 +117,31 @@ class MultiGenerator(nn.Module):
 
     # ------------------------------------------------------------------ pieces
     def _stacked_decoder_weights(self):
-        per = [g.folded() for g in self.gs]
-        return {k: torch.stack([p[k] for p in per]) for k in per[0]}
+        """Kernel-layout decoder weights of all generators, stacked along dim 0.  The spatial embedding is folded into the
+        input projection with two batched products over the generator axis (instead of a product per generator).  While
+        the trainer shares the trunk (constant weights between the discriminator step's and the generator step's
+        forward) the folded set is built once, with its autograd graph, and reused."""
+        if self._shared is not None and "dec_w" in self._shared:
+            w = self._shared["dec_w"]
+            return w if torch.is_grad_enabled() else {k: v.detach() for k, v in w.items()}
+        with torch.enable_grad() if self._shared is not None else contextlib.nullcontext():
+            st = lambda f: torch.stack([f(g) for g in self.gs])
+            H = self.decoder_h_dim
+            w_ih, w_s = st(lambda g: g.decoder.weight_ih_l0), st(lambda g: g.spatial_embedding.weight)
+            b_s = st(lambda g: g.spatial_embedding.bias)
+            w1 = st(lambda g: g.hidden2pos[0].weight)
+            w = {
+                "wx": torch.bmm(w_ih, w_s),
+                "b": torch.bmm(w_ih, b_s[:, :, None])[:, :, 0] + st(lambda g: g.decoder.bias_ih_l0) + st(lambda g: g.decoder.bias_hh_l0),
+                "whh": st(lambda g: g.decoder.weight_hh_l0), "w1h": w1[:, :, :H], "w1s": w1[:, :, H:],
+                "b1": st(lambda g: g.hidden2pos[0].bias), "w2": st(lambda g: g.hidden2pos[2].weight),
+                "b2": st(lambda g: g.hidden2pos[2].bias),
+            }
+        if self._shared is not None:
+            self._shared["dec_w"] = w
+            if not torch.is_grad_enabled():
+                return {k: v.detach() for k, v in w.items()}
+        return w
 
     def pm_logits(self, enc_h):
         if not self.use_pinet:
