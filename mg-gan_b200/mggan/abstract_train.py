@@ -60,7 +60,6 @@ class MultiGeneratorGAN(abc.ABC):
         self._graph = None                 # mggan.graph.GraphedIteration while capturing
         self._graphs = []                  # captured iterations, one per batch structure, most recently used first (LRU)
         self._graph_seen = {}              # structure key -> eager iterations seen (a structure is captured on its 2nd one)
-        self._graph_pool = None            # one memory pool shared by all captures (they never run concurrently)
         self.graph_hits = self.graph_misses = 0
         self._graph_failed = set()         # structures whose capture raised: they stay eager
         self._stage_ring = {}              # slot -> {name: persistent device staging buffer} (train_iterations prefetch)
@@ -181,7 +180,7 @@ class MultiGeneratorGAN(abc.ABC):
     def _run_iteration(self, prepared, metrics, total_iterations=0):
         """Eager iteration, or the replay of a captured one when this batch has a structure (scene sizes, no masked
         futures) that was captured before: a structure is captured the second time it is seen (mggan/graph.py) and the
-        captures live in an LRU cache of `--graph_cache` entries sharing one memory pool.
+        captures live in an LRU cache of `--graph_cache` entries.
         Data-parallel: the choice is collective.  One host-side exchange per iteration tells every rank whether ALL
         ranks hold a matching graph (replay), whether all could capture now (eager + capture), or not (eager); it also
         carries the global agent counts, and a graph is replayed only under the counts it was captured with (its loss

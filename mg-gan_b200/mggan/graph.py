@@ -76,6 +76,12 @@ class GraphedIteration:
         self.tr = trainer
         dev = in_xy.device
         self.sub_batches = sub_batches
+        # the captured kernels read the scene CSR arrays of this structure: keep them alive for as long as the graph
+        # (kernels.SceneIndex caches them, but that cache is bounded and cleared)
+        from . import kernels as K
+        self.scene_index = K.SceneIndex.get(sub_batches, dev)
+        from .utils import _scene_ids
+        self.scene_ids = _scene_ids(sub_batches, dev)       # same for the scene-id gather of the scene-shared noise
         self.static = [t.clone() if torch.is_tensor(t) else t for t in (in_xy, in_dxdy, gt_xy, gt_dxdy, img)]
         self.feed = ScalarFeed(dev)
         self.label_off = self.feed.alloc(8)
@@ -99,9 +105,10 @@ class GraphedIteration:
         try:
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
-            if trainer._graph_pool is None:
-                trainer._graph_pool = torch.cuda.graph_pool_handle()
-            with torch.cuda.graph(self.graph, pool=trainer._graph_pool, capture_error_mode="relaxed"):
+            # every capture keeps its own memory pool: tensors a capture leaves behind (parameter .grad, metrics) are
+            # freed by later eager iterations, and a shared pool would hand those blocks to the next capture while this
+            # graph still writes them on replay
+            with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
                 s = self.static
                 trainer._run_prepared((s[0], s[1], s[2], s[3], sub_batches, s[4], None), self.metrics, total_iterations)
         finally:

@@ -247,7 +247,7 @@ class SceneIndex:
         key = (tuple((int(a), int(b)) for a, b in sub_batches), str(device))
         hit = cls._cache.get(key)
         if hit is None:
-            if len(cls._cache) > 16:
+            if len(cls._cache) > 1024:       # ragged datasets: one entry per batch structure (a few hundred bytes each)
                 cls._cache.clear()
             hit = cls._cache[key] = SceneIndex(sub_batches, device)
         return hit

@@ -98,7 +98,7 @@ def _scene_ids(sub_batches, device):
     key = (tuple((int(s), int(e)) for s, e in sub_batches), str(device))
     ids = _SCENE_IDS.get(key)
     if ids is None:
-        if len(_SCENE_IDS) > 16:
+        if len(_SCENE_IDS) > 1024:        # ragged datasets: one small entry per batch structure
             _SCENE_IDS.clear()
         sizes = torch.tensor([e - s for s, e in sub_batches], device=device)
         ids = torch.repeat_interleave(torch.arange(len(sub_batches), device=device), sizes)
