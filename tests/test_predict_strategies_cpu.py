@@ -176,7 +176,11 @@ def test_discrete_latent_generator_host_logic_matches_oracle(monkeypatch):
             self.sub_batches = [(int(a), int(b)) for a, b in sub_batches]
             self.n_agents = self.sub_batches[-1][1]
 
+    def fake_mlp2(x, w1, b1, w2, b2, act1=K.ACT_NONE, slope1=0.0, act2=K.ACT_NONE, slope2=0.0):
+        return fake_linear(fake_linear(x, w1, b1, act1, slope1), w2, b2, act2, slope2)
+
     monkeypatch.setattr(K, "linear", fake_linear)
+    monkeypatch.setattr(K, "mlp2", fake_mlp2)
     monkeypatch.setattr(K, "lstm_encode", fake_lstm)
     monkeypatch.setattr(K, "social_attention", fake_social)
     monkeypatch.setattr(K, "decode", fake_decode)
@@ -265,7 +269,11 @@ def test_discriminator_sgan_pooling_host_logic_matches_oracle(monkeypatch):
             ib = torch.cat([torch.arange(a, b).repeat(b - a) for a, b in self.sub_batches])
             return ia, ib
 
+    def fake_mlp2(x, w1, b1, w2, b2, act1=K.ACT_NONE, slope1=0.0, act2=K.ACT_NONE, slope2=0.0):
+        return fake_linear(fake_linear(x, w1, b1, act1, slope1), w2, b2, act2, slope2)
+
     monkeypatch.setattr(K, "linear", fake_linear)
+    monkeypatch.setattr(K, "mlp2", fake_mlp2)
     monkeypatch.setattr(K, "lstm_encode", fake_lstm)
     monkeypatch.setattr(K, "disc_heads", fake_heads)
     monkeypatch.setattr(K.SceneIndex, "get", classmethod(lambda cls, sb, dev: sb if isinstance(sb, FakeScenes) else FakeScenes(sb)))
