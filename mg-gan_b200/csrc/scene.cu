@@ -67,6 +67,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// contiguous chunk -> L2 through the bulk-copy engine (no registers, no completion tracking); bytes % 16 == 0
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0;; ++spins) {
         uint32_t ok;
@@ -183,13 +187,20 @@ __global__ void scene_bn_bwd_finalize_kernel(const double* __restrict__ sums, do
 // mean(x1_c) = (W_c . P) / n + b_c,  E[x1_c^2] = (W_c^T R W_c + 2 b_c W_c . P) / n + b_c^2, and
 // sum x1_c * patch_a = (R W_c)_a + b_c P_a.  They depend on the crops only, so one launch serves every
 // scene-CNN forward / backward of a training iteration (G and D, three optimiser steps).
-// A CTA owns ONE pair of input channels (A <= B, 10 pairs) for a strided subset of the agents: it stages the two
-// padded channels, threads own pixels, and each thread keeps the full 9 x 9 tap block of R for that channel pair in
-// registers across all its agents (18 shared-memory loads feed 81 FMAs per pixel), reduced once at the end.
+// The statistics are a Gram matrix X X^T of the (tap x pixel) patch matrix X of every crop, i.e. a tensor-pipe product
+// with the contraction over pixels: warp-level m16n8k8 TF32 MMAs (common.cuh) whose A and B fragments are the SAME
+// loads (both index X[tap][pixel]: 8 consecutive taps x 8 consecutive pixels per group), so one k-step of 8 pixels is
+// 10 conflict-free LDS.32 per lane feeding the 9 upper-triangular (16 x 8) tiles of the 40 x 40 product (36 taps, a
+// constant-1 tap whose column yields P, 3 zero taps).  Crops cut from 8-bit images (-1 + u8 / 128, the reference's
+// BaseTrajectories.py:278-286, and the synthetic batches) are exactly representable in TF32, so their products are
+// exact with ONE MMA per tile; the kernel tests every staged crop (low 13 mantissa bits) and falls back to the
+// 3 x TF32 split products for arbitrary fp32 input.  FP32 thread-per-pixel form before: 1.11 ms per batch of 16,384.
 constexpr int NTAP = 36;
-constexpr int NPAIRS_CH = CIN * (CIN + 1) / 2;     // 10
-
-constexpr int PS_THREADS = 128;                    // ~150 registers per thread (81 accumulators): 3 CTAs per SM
+constexpr int G_LDR = 38;                          // padded row: the 8 taps x 4 pixels of a fragment load fall on distinct banks
+constexpr int G_CHS = 35 * G_LDR;                  // padded channel [35][38], zero halo
+constexpr int G_BUF = CIN * G_CHS + 24;            // + slack: masked reads of the tail k-step stay inside the buffer
+constexpr int G_KSTEPS = (IMG2 + 7) / 8;           // 137 k-steps of 8 pixels (the last holds one pixel)
+constexpr int G_NT = 40;                           // taps padded to 5 groups of 8
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -199,91 +210,140 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NPENDING>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory"); }
 
-__global__ void __launch_bounds__(PS_THREADS, 3)
-scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N, int slots,
-                         double* __restrict__ R, double* __restrict__ P) {
-    __shared__ __align__(16) float sImg[2][2 * IMGPAD];       // double buffer x channels A and B, [35][36] each, zero halo
-    const int bp = blockIdx.x % NPAIRS_CH, slot = blockIdx.x / NPAIRS_CH;
-    int cA = 0, cB = 0;
-    {
-        int q = bp;
-        for (cA = 0; cA < CIN; ++cA) {
-            if (q < CIN - cA) { cB = cA + q; break; }
-            q -= CIN - cA;
+// one k-step of the Gram product: SPLIT = false feeds the raw fp32 bits (exact TF32 operands), true the (hi, lo) split
+template <bool SPLIT>
+__device__ __forceinline__ void gram_kstep(float (&acc)[9][4], const float (&x)[5][2]) {
+    uint32_t hi[5][2], lo[5][2];
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (SPLIT) tf32_split(x[j][h], hi[j][h], lo[j][h]);
+            else { hi[j][h] = __float_as_uint(x[j][h]); lo[j][h] = 0u; }
+        }
+    int tile = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        // m-tile i = tap groups 2i (rows g) and 2i + 1 (rows g + 8; absent for i = 2)
+        const uint32_t ah[4] = {hi[2 * i][0], i < 2 ? hi[2 * i + 1][0] : 0u, hi[2 * i][1], i < 2 ? hi[2 * i + 1][1] : 0u};
+        const uint32_t al[4] = {lo[2 * i][0], i < 2 ? lo[2 * i + 1][0] : 0u, lo[2 * i][1], i < 2 ? lo[2 * i + 1][1] : 0u};
+#pragma unroll
+        for (int j = 2 * i; j < 5; ++j, ++tile) {
+            mma_tf32_16x8x8(acc[tile], ah, hi[j][0], hi[j][1]);
+            if (SPLIT) {
+                mma_tf32_16x8x8(acc[tile], al, hi[j][0], hi[j][1]);
+                mma_tf32_16x8x8(acc[tile], ah, lo[j][0], lo[j][1]);
+            }
         }
     }
-    const bool diag = cA == cB;
-    for (int i = threadIdx.x; i < 4 * IMGPAD; i += PS_THREADS) (&sImg[0][0])[i] = 0.f;
-    float acc[81], ps[9];
+}
+
+__global__ void __launch_bounds__(MGGAN_THREADS, 2)
+scene_patch_stats_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N,
+                         double* __restrict__ R, double* __restrict__ P) {
+    extern __shared__ __align__(16) float smem[];
+    float* sImg = smem;                                                   // [2][G_BUF] double-buffered padded crop
+    double* sD = reinterpret_cast<double*>(smem + 2 * G_BUF);             // [G_NT][G_NT] CTA reduction
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int i = threadIdx.x; i < 2 * G_BUF; i += MGGAN_THREADS) sImg[i] = 0.f;
+    for (int i = threadIdx.x; i < G_NT * G_NT; i += MGGAN_THREADS) sD[i] = 0.0;
+    int toff[5];                                       // tap 8 j + g of this lane: offset of its window corner
 #pragma unroll
-    for (int q = 0; q < 81; ++q) acc[q] = 0.f;
+    for (int j = 0; j < 5; ++j) {
+        const int tap = 8 * j + g;
+        const int ci = tap / 9, r = tap - ci * 9;
+        toff[j] = tap < NTAP ? ci * G_CHS + (r / 3) * G_LDR + r % 3 : 0;
+    }
+    const bool tail_tap = g < 4;                       // group 4: taps 32..35, then the constant-1 tap, then zeros
+    const float tail_const = g == 4 ? 1.f : 0.f;
+    float acc[9][4];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) ps[q] = 0.f;
+    for (int q = 0; q < 9; ++q) { acc[q][0] = 0.f; acc[q][1] = 0.f; acc[q][2] = 0.f; acc[q][3] = 0.f; }
     __syncthreads();
 
-    // asynchronous staging (cp.async, 4-byte: channel rows are only 4-byte aligned) of the next agent's two channels
-    // while the current one is processed
+    // warp w copies rows w, w + 8, ... of the crop (row = (channel, y): 33 floats, only 4-byte aligned) into the padded
+    // layout: lanes = consecutive x (coalesced; a lane-per-row mapping touched 32 lines per instruction and made the
+    // staging, not the products, the kernel's critical path), lane 0 also takes x = 32
     auto stage = [&](int n, int buf) {
         const int src = rows ? rows[n] : n;
-        const float* ipA = img + ((size_t)src * CIN + cA) * IMG2;
-        const float* ipB = img + ((size_t)src * CIN + cB) * IMG2;
-        for (int i = threadIdx.x; i < IMG2; i += PS_THREADS) {
-            int y = i / IMG, x = i - y * IMG;
-            cp_async4(&sImg[buf][(y + 1) * LDI + x + 1], ipA + i);
-            if (!diag) cp_async4(&sImg[buf][IMGPAD + (y + 1) * LDI + x + 1], ipB + i);
+        const float* ip = img + (size_t)src * RAW;
+        float* base = sImg + buf * G_BUF + G_LDR + 1;
+        for (int r = warp; r < CIN * IMG; r += MGGAN_THREADS / 32) {
+            const int ci = r / IMG, y = r - ci * IMG;
+            float* d = base + ci * G_CHS + y * G_LDR;
+            cp_async4(d + lane, ip + r * IMG + lane);
+            if (lane == 0) cp_async4(d + 32, ip + r * IMG + 32);
         }
         cp_async_commit();
     };
     int buf = 0;
-    if (slot < N) stage(slot, 0);
-    for (int n = slot; n < N; n += slots) {
-        const bool more = n + slots < N;
-        if (more) stage(n + slots, buf ^ 1);
-        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
-        __syncthreads();
-        const float* sA = sImg[buf];
-        const float* sB = diag ? sA : sA + IMGPAD;
-        // lanes = 32 consecutive pixels of one row (conflict-free shared-memory reads), warps = rows; the 33rd
-        // column is swept afterwards by the first 33 threads
-        for (int it = threadIdx.x >> 5; it < IMG + 2; it += PS_THREADS / 32) {
-            int y, x;
-            if (it < IMG) { y = it; x = threadIdx.x & 31; }
-            else { y = (it - IMG) * 32 + (threadIdx.x & 31); x = IMG - 1; if (y >= IMG) continue; }
-            const int base = y * LDI + x;
-            float va[9], vb[9];
+    if ((int)blockIdx.x < N) stage(blockIdx.x, 0);
+    for (int n = blockIdx.x; n < N; n += gridDim.x, buf ^= 1) {
+        cp_async_wait<0>();
+        __syncthreads();                               // crop n has landed; every warp is done with the other buffer
+        if (n + (int)gridDim.x < N) stage(n + gridDim.x, buf ^ 1);
+        const float* sI = sImg + buf * G_BUF;
+        uint32_t low = 0u;                             // any low mantissa bit set -> not a TF32 number
+        for (int i = threadIdx.x; i < CIN * G_CHS / 4; i += MGGAN_THREADS) {
+            const float4 v = ld4(sI + 4 * i);
+            low |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
+        }
+        const bool split = __syncthreads_or((low & 0x1FFFu) != 0u);
+        // The tensor pipe adds into its fp32 accumulator with truncation (measured: a one-sided -3.5e-6 on the all-positive
+        // diagonal sums after ~100 accumulations), so an accumulator only ever holds ONE crop's 17 k-steps; the sum over
+        // the CTA's crops is carried in a second register set with round-to-nearest adds.
+        float cur[9][4];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) va[t] = sA[base + (t / 3) * LDI + (t % 3)];
-            if (diag) {
+        for (int q = 0; q < 9; ++q) { cur[q][0] = 0.f; cur[q][1] = 0.f; cur[q][2] = 0.f; cur[q][3] = 0.f; }
+        for (int ks = warp; ks < G_KSTEPS; ks += MGGAN_THREADS / 32) {
+            const int p0 = ks * 8 + t, p1 = p0 + 4;    // the lane's two pixels (k = t, t + 4)
+            const int y0 = p0 / IMG, y1 = p1 / IMG;
+            const int a0 = p0 + y0 * (G_LDR - IMG), a1 = p1 + y1 * (G_LDR - IMG);
+            float x[5][2];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) { vb[t] = va[t]; ps[t] += va[t]; }
-            } else {
+            for (int j = 0; j < 4; ++j) { x[j][0] = sI[toff[j] + a0]; x[j][1] = sI[toff[j] + a1]; }
+            x[4][0] = tail_tap ? sI[toff[4] + a0] : tail_const;
+            x[4][1] = tail_tap ? sI[toff[4] + a1] : tail_const;
+            if (ks == G_KSTEPS - 1) {
 #pragma unroll
-                for (int t = 0; t < 9; ++t) vb[t] = sB[base + (t / 3) * LDI + (t % 3)];
+                for (int j = 0; j < 5; ++j) {
+                    if (p0 >= IMG2) x[j][0] = 0.f;
+                    if (p1 >= IMG2) x[j][1] = 0.f;
+                }
             }
-#pragma unroll
-            for (int i = 0; i < 9; ++i)
-#pragma unroll
-                for (int j = 0; j < 9; ++j) acc[i * 9 + j] = fmaf(va[i], vb[j], acc[i * 9 + j]);
+            if (split) gram_kstep<true>(cur, x); else gram_kstep<false>(cur, x);
         }
-        __syncthreads();                    // this buffer is overwritten by the staging of the iteration after next
-        buf ^= 1;
-    }
-    // CTA reduction: warp shuffles in double, then one atomicAdd per entry per warp
-    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int q = 0; q < 81; ++q) {
-        double v = warp_sum_d((double)acc[q]);
-        if (lane == 0) {
-            const int a = cA * 9 + q / 9, b = cB * 9 + q % 9;
-            atomicAdd(R + a * NTAP + b, v);
-            if (!diag) atomicAdd(R + b * NTAP + a, v);
+        for (int q = 0; q < 9; ++q) { acc[q][0] += cur[q][0]; acc[q][1] += cur[q][1]; acc[q][2] += cur[q][2]; acc[q][3] += cur[q][3]; }
+    }
+    cp_async_wait<0>();
+    // CTA reduction in double, one warp after the other (distinct lanes own distinct entries), then one atomic per entry
+    for (int w = 0; w < MGGAN_THREADS / 32; ++w) {
+        __syncthreads();
+        if (warp == w) {
+            int tile = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 2 * i; j < 5; ++j, ++tile) {
+                    const int ra = 16 * i + g, cb = 8 * j + 2 * t;
+                    sD[ra * G_NT + cb] += (double)acc[tile][0];
+                    sD[ra * G_NT + cb + 1] += (double)acc[tile][1];
+                    if (i < 2) {
+                        sD[(ra + 8) * G_NT + cb] += (double)acc[tile][2];
+                        sD[(ra + 8) * G_NT + cb + 1] += (double)acc[tile][3];
+                    }
+                }
         }
     }
-    if (diag) {
-#pragma unroll
-        for (int q = 0; q < 9; ++q) {
-            double v = warp_sum_d((double)ps[q]);
-            if (lane == 0) atomicAdd(P + cA * 9 + q, v);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NTAP * G_NT; i += MGGAN_THREADS) {
+        const int a = i / G_NT, b = i - a * G_NT;
+        const double v = sD[i];
+        if (b == NTAP) atomicAdd(P + a, v);
+        else if (b < NTAP && a <= b) {                 // upper triangle (the blocks below the diagonal were not all computed;
+            atomicAdd(R + a * NTAP + b, v);            // mirroring keeps R exactly symmetric under the split products too)
+            if (a < b) atomicAdd(R + b * NTAP + a, v);
         }
     }
 }
@@ -346,9 +406,31 @@ scene_bn1_from_patches_kernel(const double* __restrict__ R, const double* __rest
 
 // ------------------------------------------------------------------------------------------
 // fused forward of both conv blocks: img -> conv1 -> BN1 -> ReLU -> pool -> conv2 -> x2 (+ BN2 sums).
-// thread = pooled pixel: its 2x2 window of conv1 outputs is computed from a 4x4 register patch per input
-// channel (16 loads feed 36*C FMAs), so conv1 never touches global memory.  Optionally saves the pre-BN
-// value at the pool arg (e1) and the arg index | active bit (idx1) for the backward.
+// Both convolutions run on the tensor pipe as warp-level m16n8k8 TF32 products (common.cuh).  The FP32 form of conv1
+// (thread = pooled pixel, 36 C FMAs per input pixel) made the kernel ISSUE-bound: ~35 k warp instructions per crop, 18 k
+// of them FFMA; as an implicit GEMM it is ~1.3 k MMAs and as many LDS.
+//   conv1   M = conv output positions, K = 36 taps (ci, ky, kx) padded to 40, N = C.  One PAIR of m-tiles covers 8 pooled
+//           pixels of a row: tile 0 holds window row 0, tile 1 window row 1, fragment rows g / g + 8 are window columns
+//           0 / 1 of pooled pixel px0 + g -- so lane (g, t) ends up with the whole 2 x 2 window of its pooled pixel for the
+//           channels 8 q + 2 t + {0, 1} and BN1 / ReLU / max-pool / arg are thread-local.  The A operand is read straight
+//           from the zero-padded crop in shared memory (im2col by address: tap offset + position); the K index is permuted
+//           (TAP_PERM) so that the 8 positions x 4 taps of every fragment load fall on 32 distinct banks with row stride 35
+//           and channel stride 1231.  W1 stays in registers as pre-split (hi, lo) B fragments.
+//           Crops cut from 8-bit images are exact TF32 numbers (see scene_patch_stats): then the products are exact with
+//           two MMAs per tile (x W1_hi + x W1_lo); any other fp32 crop takes the three split products.
+//   conv2   m-tile = one output row (16 pixels), n-tile = 8 output channels, k-step = 8 input channels of one tap, 3 x TF32;
+//           the pooled map and W2 are kept PRE-SPLIT as (hi, lo) planes in shared memory, so a fragment is plain LDS.32s
+//           (splitting on the fly cost 5 ALU instructions per MMA).
+// The next crop is staged (cp.async into the padded layout) while conv2 runs.  Optionally saves the pre-BN value at the
+// pool arg (e1) and the arg index | active bit (idx1) for the backward.
+constexpr int F_LDR = 35;                        // padded crop row (33 + halo)
+constexpr int F_CHS = 1231;                      // padded crop channel: 35 * 35 + 6 (bank spread of the permuted taps)
+constexpr int F_CROP = CIN * F_CHS + 5;          // floats per staged crop, rounded up to a multiple of 4 below
+constexpr int F_CROP4 = (F_CROP + 3) & ~3;
+// K order of conv1: k-step s holds taps TAP_PERM[8 s .. 8 s + 7] (k = t -> entry t, k = t + 4 -> entry 4 + t); 36.. = zero taps
+__constant__ int TAP_PERM[40] = {0, 1, 2, 11, 3, 4, 5, 14, 6, 7, 8, 17, 9, 10, 19, 20, 12, 13, 22, 23,
+                                 15, 16, 25, 26, 18, 21, 28, 31, 24, 27, 29, 34, 30, 32, 33, 35, 36, 37, 38, 39};
+
 template <int C>
 __global__ void __launch_bounds__(MGGAN_THREADS, 2)
 scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N,
@@ -357,143 +439,198 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                          double* __restrict__ stats2, float* __restrict__ e1, unsigned char* __restrict__ idx1) {
     constexpr int PPAD = FwdPad::PPAD;           // channel stride of the pooled map: 8 mod 32 (conflict-free A fragments)
     constexpr int LDW2 = FwdLdw2<C>::value;        // row stride of the conv2 weights [tap][ci][co]: 8 t + g distinct banks
+    constexpr int PBUF = (C * PPAD + 3) & ~3;      // one plane of the pooled map
+    constexpr int NT = C / 8;                     // n-tiles (8 output channels each) = conv2 k-steps per tap
     extern __shared__ __align__(16) float smem[];
-    float* sRaw = smem;                          // [2][4][33][33]  double-buffered crop, filled by cp.async.bulk
-    float* sW1 = sRaw + 2 * RAW;                 // [36 taps][C]
-    float* sP = sW1 + NTAP * C;                  // [C][PPAD]
-    float* sW2 = sP + ((C * PPAD + 3) & ~3);     // [9 taps][C in][LDW2]   (C out used)
-    float* sAB = sW2 + 9 * C * LDW2;             // [2C]
-    float* sred = sAB + 2 * C;                   // [8][2C]
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sred + 8 * 2 * C);      // [2] one mbarrier per crop buffer
-    if (threadIdx.x == 0) {
-        sbar_init(smem_addr(sBar), 1);
-        sbar_init(smem_addr(sBar + 1), 1);
-        sbar_fence_init();
-    }
-    for (int i = threadIdx.x; i < NTAP * C; i += MGGAN_THREADS) {
-        int c = i / NTAP, tap = i - c * NTAP;
-        sW1[tap * C + c] = __ldg(W1 + i);
-    }
+    float* sCrop = smem;                         // [4][35][35]+   zero-padded crop
+    float* sPh = sCrop + F_CROP4;                // [C][PPAD]      pooled map, TF32 hi plane (zero halo)
+    float* sPl = sPh + PBUF;                     //                lo plane
+    float* sW2h = sPl + PBUF;                    // [9 taps][C in][LDW2]   (C out used), hi plane
+    float* sW2l = sW2h + 9 * C * LDW2;           //                lo plane
+    float* sAB = sW2l + 9 * C * LDW2;            // [2C]  BatchNorm-1 as an affine map
+    float* sB1 = sAB + 2 * C;                    // [C]   conv1 bias
+    float* sW1f = sB1 + C;                       // [5][NT][2][2][32] conv1 B fragments
+    float* sred = sW1f + 5 * NT * 2 * 64;        // [8][2C]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g8 = lane >> 2, t4 = lane & 3;
     for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
         int co = i / (9 * C), r = i - co * 9 * C, ci = r / 9, tap = r - ci * 9;
-        sW2[(tap * C + ci) * LDW2 + co] = __ldg(W2 + i);
+        uint32_t hi, lo;
+        tf32_split(__ldg(W2 + i), hi, lo);
+        sW2h[(tap * C + ci) * LDW2 + co] = __uint_as_float(hi);
+        sW2l[(tap * C + ci) * LDW2 + co] = __uint_as_float(lo);
     }
     if (threadIdx.x < 2 * C) sAB[threadIdx.x] = __ldg(ab1 + threadIdx.x);
-    for (int i = threadIdx.x; i < C * PPAD; i += MGGAN_THREADS) sP[i] = 0.f;
-    __syncthreads();                              // barriers initialised before anyone arms or polls them
-    if (threadIdx.x == 0 && (int)blockIdx.x < N) stage_crop(img, rows ? rows[blockIdx.x] : blockIdx.x, sRaw, sBar);
-    constexpr int NT = C / 8;                     // conv2 n-tiles (8 output channels each) = k-steps per tap (8 input channels)
+    for (int i = threadIdx.x; i < 2 * PBUF; i += MGGAN_THREADS) sPh[i] = 0.f;
+    for (int i = threadIdx.x; i < F_CROP4; i += MGGAN_THREADS) sCrop[i] = 0.f;
+    // conv1 B fragments, pre-split and stored per lane ([s][q][h][hi | lo][lane]: conflict-free LDS.32; in registers they
+    // pushed the C = 16 instance over 128): b0 = W1[8 q + g][tap(s, t)], b1 = W1[8 q + g][tap(s, 4 + t)]
+    for (int i = threadIdx.x; i < 5 * NT * 2 * 32; i += MGGAN_THREADS) {
+        const int ln = i & 31, h = (i >> 5) & 1, q = (i >> 6) % NT, sidx = i / (64 * NT);
+        const int tap = TAP_PERM[8 * sidx + 4 * h + (ln & 3)];
+        const float w = tap < NTAP ? __ldg(W1 + (8 * q + (ln >> 2)) * NTAP + tap) : 0.f;
+        uint32_t hi, lo;
+        tf32_split(w, hi, lo);
+        sW1f[((sidx * NT + q) * 2 + h) * 64 + ln] = __uint_as_float(hi);
+        sW1f[((sidx * NT + q) * 2 + h) * 64 + 32 + ln] = __uint_as_float(lo);
+    }
+    int toff[5][2];                               // tap offsets in the padded crop (zero taps: offset 0, weight 0)
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int tap = TAP_PERM[8 * s + 4 * h + t4];
+            const int ci = tap / 9, r = tap - ci * 9;
+            toff[s][h] = tap < NTAP ? ci * F_CHS + (r / 3) * F_LDR + r % 3 : 0;
+        }
+    if (threadIdx.x < C) sB1[threadIdx.x] = __ldg(b1 + threadIdx.x);
+    __syncthreads();
+
+    // warp w copies rows w, w + 8, ... of the crop (row = (channel, y)): lanes = consecutive x, lane 0 also takes x = 32
+    auto stage = [&](int n) {
+        const int src = rows ? rows[n] : n;
+        const float* ip = img + (size_t)src * RAW;
+        for (int r = warp; r < CIN * IMG; r += MGGAN_THREADS / 32) {
+            const int ci = r / IMG, y = r - ci * IMG;
+            float* d = sCrop + ci * F_CHS + (y + 1) * F_LDR + 1;
+            cp_async4(d + lane, ip + r * IMG + lane);
+            if (lane == 0) cp_async4(d + 32, ip + r * IMG + 32);
+        }
+        cp_async_commit();
+    };
+    if ((int)blockIdx.x < N) stage(blockIdx.x);
     float st[4 * NT];                             // BatchNorm-2 partial sums: channels 8 j + 2 t + {0, 1}: sum [2j + e], squares [2NT + 2j + e]
 #pragma unroll
     for (int c = 0; c < 4 * NT; ++c) st[c] = 0.f;
-    const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
-    const int warp = threadIdx.x >> 5, g8 = (threadIdx.x & 31) >> 2, t4 = threadIdx.x & 3;
 
-    int j = 0;                                    // agents this CTA has processed: buffer j & 1, barrier phase (j >> 1) & 1
-    for (int n = blockIdx.x; n < N; n += gridDim.x, ++j) {
-        __syncthreads();                          // previous agent: conv2 has read sP, conv1 has read the other crop buffer
-        const float* sImg = sRaw + (j & 1) * RAW;
-        if (threadIdx.x == 0 && n + (int)gridDim.x < N) {
-            const int nn = n + gridDim.x;
-            stage_crop(img, rows ? rows[nn] : nn, sRaw + ((j + 1) & 1) * RAW, sBar + ((j + 1) & 1));
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        cp_async_wait<0>();
+        __syncthreads();                          // the crop has landed; the previous agent's conv2 has read the pooled map
+        uint32_t low = 0u;                        // any low mantissa bit set -> the crop is not made of TF32 numbers
+        for (int i = threadIdx.x; i < F_CROP4 / 4; i += MGGAN_THREADS) {
+            const float4 v = ld4(sCrop + 4 * i);
+            low |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
         }
-        sbar_wait(smem_addr(sBar + (j & 1)), (j >> 1) & 1);
-        {
-            float acc[4][C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float bv = __ldg(b1 + c);
-                acc[0][c] = bv; acc[1][c] = bv; acc[2][c] = bv; acc[3][c] = bv;
-            }
+        const bool split = __syncthreads_or((low & 0x1FFFu) != 0u);
+        // ---- conv1 -> BN1 -> ReLU -> pool: tile pairs (pooled row py, half row) warp, warp + 8, ...
 #pragma unroll 1
-            for (int ci = 0; ci < CIN; ++ci) {
-                float pt[4][4];                   // rows 2 py - 1 .. 2 py + 2, columns 2 px - 1 .. 2 px + 2 of the crop
-                const float* bp = sImg + ci * IMG2 + (2 * py - 1) * IMG + 2 * px - 1;
+        for (int tp = warp; tp < 32; tp += MGGAN_THREADS / 32) {
+            const int py = tp >> 1, px0 = (tp & 1) * 8;
+            const float* pos = sCrop + (2 * py) * F_LDR + 2 * (px0 + g8);      // window (0, 0) of pooled pixel (py, px0 + g)
+            float acc[2][NT][4];                  // [window row][n-tile][c0 c1 | c2 c3] = [.][.][col 0: ch e | col 1: ch e]
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
+            for (int wy = 0; wy < 2; ++wy)
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-                        pt[r][cc] = ((r > 0 || py > 0) && (cc > 0 || px > 0)) ? bp[r * IMG + cc] : 0.f;
+                for (int q = 0; q < NT; ++q) {
+                    const float2 bv = *reinterpret_cast<const float2*>(sB1 + 8 * q + 2 * t4);
+                    acc[wy][q][0] = bv.x; acc[wy][q][1] = bv.y; acc[wy][q][2] = bv.x; acc[wy][q][3] = bv.y;
+                }
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+            for (int s = 0; s < 5; ++s) {
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float* wp = sW1 + (ci * 9 + ky * 3 + kx) * C;
+                for (int wy = 0; wy < 2; ++wy) {
+                    const float* pa = pos + wy * F_LDR;
+                    float a[4];
+                    a[0] = pa[toff[s][0]]; a[1] = pa[toff[s][0] + 1];
+                    if (s < 4) { a[2] = pa[toff[s][1]]; a[3] = pa[toff[s][1] + 1]; } else { a[2] = 0.f; a[3] = 0.f; }
+                    uint32_t ah[4], al[4];
+                    if (split) {
 #pragma unroll
-                        for (int c = 0; c < C; c += 4) {
-                            float4 w = ld4(wp + c);
+                        for (int i = 0; i < 4; ++i) tf32_split(a[i], ah[i], al[i]);
+                    } else {
 #pragma unroll
-                            for (int d = 0; d < 4; ++d) {
-                                const float v = pt[(d >> 1) + ky][(d & 1) + kx];
-                                acc[d][c] = fmaf(v, w.x, acc[d][c]); acc[d][c + 1] = fmaf(v, w.y, acc[d][c + 1]);
-                                acc[d][c + 2] = fmaf(v, w.z, acc[d][c + 2]); acc[d][c + 3] = fmaf(v, w.w, acc[d][c + 3]);
-                            }
-                        }
+                        for (int i = 0; i < 4; ++i) ah[i] = __float_as_uint(a[i]);
                     }
-            }
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float a = sAB[c], b = sAB[C + c];
-                float m = fmaf(a, acc[0][c], b), e = acc[0][c]; int arg = 0;
-#pragma unroll
-                for (int d = 1; d < 4; ++d) {
-                    float v = fmaf(a, acc[d][c], b);
-                    if (v > m) { m = v; e = acc[d][c]; arg = d; }
-                }
-                sP[c * PPAD + (py + 1) * LDP + px + 1] = fmaxf(m, 0.f);
-                if (e1 != nullptr) {
-                    e1[((size_t)n * C + c) * P1SQ + threadIdx.x] = e;
-                    idx1[((size_t)n * C + c) * P1SQ + threadIdx.x] = (unsigned char)(arg | (m > 0.f ? 4 : 0));
+                    for (int q = 0; q < NT; ++q) {
+                        const float* wf = sW1f + (s * NT + q) * 128 + lane;
+                        const uint32_t bh0 = __float_as_uint(wf[0]), bl0 = __float_as_uint(wf[32]);
+                        const uint32_t bh1 = __float_as_uint(wf[64]), bl1 = __float_as_uint(wf[96]);
+                        mma_tf32_16x8x8(acc[wy][q], ah, bh0, bh1);
+                        mma_tf32_16x8x8(acc[wy][q], ah, bl0, bl1);
+                        if (split) mma_tf32_16x8x8(acc[wy][q], al, bh0, bh1);
+                    }
                 }
             }
+            const int pix = py * P1 + px0 + g8;
+#pragma unroll
+            for (int q = 0; q < NT; ++q)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 8 * q + 2 * t4 + e;
+                    const float a = sAB[c], b = sAB[C + c];
+                    // window order (0,0) (0,1) (1,0) (1,1), first maximum wins (as the FP32 kernel and the oracle's max_pool2d)
+                    const float x0 = acc[0][q][e], x1 = acc[0][q][2 + e], x2v = acc[1][q][e], x3 = acc[1][q][2 + e];
+                    float m = fmaf(a, x0, b), ev = x0; int arg = 0;
+                    float v = fmaf(a, x1, b);
+                    if (v > m) { m = v; ev = x1; arg = 1; }
+                    v = fmaf(a, x2v, b);
+                    if (v > m) { m = v; ev = x2v; arg = 2; }
+                    v = fmaf(a, x3, b);
+                    if (v > m) { m = v; ev = x3; arg = 3; }
+                    uint32_t hi, lo;
+                    tf32_split(fmaxf(m, 0.f), hi, lo);
+                    const int o = c * PPAD + (py + 1) * LDP + px0 + g8 + 1;
+                    sPh[o] = __uint_as_float(hi);
+                    sPl[o] = __uint_as_float(lo);
+                    if (e1 != nullptr) {
+                        e1[((size_t)n * C + c) * P1SQ + pix] = ev;
+                        idx1[((size_t)n * C + c) * P1SQ + pix] = (unsigned char)(arg | (m > 0.f ? 4 : 0));
+                    }
+                }
         }
-        __syncthreads();
-        {   // conv2 as warp-level 3 x TF32 tensor-core products (common.cuh): m-tile = one output row (16 pixels), n-tile =
-            // 8 output channels, k-step = 8 input channels of one tap; every fragment element is a conflict-free LDS.32.
-            // The FP32 register-tile form of this stage was half of the kernel's FMA issue and most of its LDS traffic.
-            {
-                const int y = warp * 2;                   // the warp's two rows are interleaved: 2 NT independent accumulator chains
-                float acc[2][NT][4];
+        __syncthreads();                          // pooled map complete; the crop buffer is free
+        if (n + (int)gridDim.x < N) stage(n + gridDim.x);
+        {   // ---- conv2: the warp's two rows are interleaved (2 NT independent accumulator chains)
+            const int y = warp * 2;
+            float acc[2][NT][4];
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    const float ba = __ldg(b2 + 8 * j + 2 * t4), bb = __ldg(b2 + 8 * j + 2 * t4 + 1);
+            for (int j = 0; j < NT; ++j) {
+                const float ba = __ldg(b2 + 8 * j + 2 * t4), bb = __ldg(b2 + 8 * j + 2 * t4 + 1);
 #pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) { acc[rr][j][0] = ba; acc[rr][j][1] = bb; acc[rr][j][2] = ba; acc[rr][j][3] = bb; }
-                }
+                for (int rr = 0; rr < 2; ++rr) { acc[rr][j][0] = ba; acc[rr][j][1] = bb; acc[rr][j][2] = ba; acc[rr][j][3] = bb; }
+            }
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                    for (int ks = 0; ks < NT; ++ks) {
-                        const float* pb = sW2 + (tap * C + ks * 8 + t4) * LDW2 + g8;
-                        float b0[NT], b1[NT];
-#pragma unroll
-                        for (int j = 0; j < NT; ++j) { b0[j] = pb[8 * j]; b1[j] = pb[4 * LDW2 + 8 * j]; }
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const float* pa = sP + (ks * 8 + t4) * PPAD + (y + rr + tap / 3) * LDP + g8 + tap % 3;
-                            uint32_t ah[4], al[4];
-                            tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8], ah[1], al[1]);
-                            tf32_split(pa[4 * PPAD], ah[2], al[2]); tf32_split(pa[4 * PPAD + 8], ah[3], al[3]);
-#pragma unroll
-                            for (int j = 0; j < NT; ++j) mma_3xtf32(acc[rr][j], ah, al, b0[j], b1[j]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
+                for (int ks = 0; ks < NT; ++ks) {
+                    const int ob = (tap * C + ks * 8 + t4) * LDW2 + g8;
+                    uint32_t bh0[NT], bh1[NT], bl0[NT], bl1[NT];
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
-                        float* o = x2 + ((size_t)n * C + 8 * j + 2 * t4) * P1SQ + (y + rr) * P1 + g8;
-                        const float* a = acc[rr][j];
-                        o[0] = a[0]; o[8] = a[2]; o[P1SQ] = a[1]; o[P1SQ + 8] = a[3];
-                        st[2 * j] += a[0] + a[2];
-                        st[2 * j + 1] += a[1] + a[3];
-                        st[2 * NT + 2 * j] = fmaf(a[0], a[0], fmaf(a[2], a[2], st[2 * NT + 2 * j]));
-                        st[2 * NT + 2 * j + 1] = fmaf(a[1], a[1], fmaf(a[3], a[3], st[2 * NT + 2 * j + 1]));
+                        bh0[j] = __float_as_uint(sW2h[ob + 8 * j]); bh1[j] = __float_as_uint(sW2h[ob + 4 * LDW2 + 8 * j]);
+                        bl0[j] = __float_as_uint(sW2l[ob + 8 * j]); bl1[j] = __float_as_uint(sW2l[ob + 4 * LDW2 + 8 * j]);
                     }
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int oa = (ks * 8 + t4) * PPAD + (y + rr + tap / 3) * LDP + g8 + tap % 3;
+                        const uint32_t ah[4] = {__float_as_uint(sPh[oa]), __float_as_uint(sPh[oa + 8]),
+                                                __float_as_uint(sPh[oa + 4 * PPAD]), __float_as_uint(sPh[oa + 4 * PPAD + 8])};
+                        const uint32_t al[4] = {__float_as_uint(sPl[oa]), __float_as_uint(sPl[oa + 8]),
+                                                __float_as_uint(sPl[oa + 4 * PPAD]), __float_as_uint(sPl[oa + 4 * PPAD + 8])};
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            mma_tf32_16x8x8(acc[rr][j], ah, bh0[j], bh1[j]);
+                            mma_tf32_16x8x8(acc[rr][j], al, bh0[j], bh1[j]);
+                            mma_tf32_16x8x8(acc[rr][j], ah, bl0[j], bl1[j]);
+                        }
+                    }
+                }
             }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    float* o = x2 + ((size_t)n * C + 8 * j + 2 * t4) * P1SQ + (y + rr) * P1 + g8;
+                    const float* a = acc[rr][j];
+                    o[0] = a[0]; o[8] = a[2]; o[P1SQ] = a[1]; o[P1SQ + 8] = a[3];
+                    st[2 * j] += a[0] + a[2];
+                    st[2 * j + 1] += a[1] + a[3];
+                    st[2 * NT + 2 * j] = fmaf(a[0], a[0], fmaf(a[2], a[2], st[2 * NT + 2 * j]));
+                    st[2 * NT + 2 * j + 1] = fmaf(a[1], a[1], fmaf(a[3], a[3], st[2 * NT + 2 * j + 1]));
+                }
         }
     }
+    cp_async_wait<0>();
     if (stats2 != nullptr) {     // lanes that differ in g hold the same channels: shuffle, then shared / global double atomics
         double* sd = reinterpret_cast<double*>(sred);
         __syncthreads();
@@ -579,30 +716,67 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
         const int src = rows ? rows[n] : n;
         __syncthreads();
         {
+            // the next agent's inputs are requested into the L2 now (this stage waits on global loads with 16 warps per SM:
+            // long-scoreboard stalls were a quarter of the kernel's samples)
+            if (threadIdx.x < 6 && n + (int)gridDim.x < N) {
+                const size_t nn = (size_t)n + gridDim.x;
+                if (threadIdx.x == 0) prefetch_l2_bulk(x2 + nn * C * P1SQ, C * P1SQ * 4);
+                else if (threadIdx.x == 1) prefetch_l2_bulk(e1 + nn * C * P1SQ, C * P1SQ * 4);
+                else if (threadIdx.x == 2) prefetch_l2_bulk(idx1 + nn * C * P1SQ, C * P1SQ);
+                else if (threadIdx.x == 3) prefetch_l2_bulk(dy2 + nn * C * P2SQ, C * P2SQ * 4);
+                else if (threadIdx.x == 4) prefetch_l2_bulk(idx2 + nn * C * P2SQ, C * P2SQ);
+                else prefetch_l2_bulk(img + (size_t)(rows ? rows[nn] : (int)nn) * RAW, RAW_BYTES);
+            }
             // the crop is only read by the last stage (sparse conv1 weight gradient): cp.async (LDGSTS) it into the padded
-            // layout now and wait for it there, behind the two tensor-core stages
-            const float* ip = img + (size_t)src * CIN * IMG2;
-            for (int i = threadIdx.x; i < CIN * IMG2; i += MGGAN_THREADS) {
-                int ci = i / IMG2, p = i - ci * IMG2, yy = p / IMG, xx = p - yy * IMG;
-                cp_async4(&sImg[ci * IMGPAD_BWD + (yy + 1) * LDI + xx + 1], ip + i);
+            // layout now and wait for it there, behind the two tensor-core stages.  Warp = rows (channel, y), lanes = x.
+            const float* ip = img + (size_t)src * RAW;
+            for (int r = warp; r < CIN * IMG; r += MGGAN_THREADS / 32) {
+                const int ci = r / IMG, yy = r - ci * IMG;
+                float* d = sImg + ci * IMGPAD_BWD + (yy + 1) * LDI + 1;
+                cp_async4(d + (threadIdx.x & 31), ip + r * IMG + (threadIdx.x & 31));
+                if ((threadIdx.x & 31) == 0) cp_async4(d + 32, ip + r * IMG + 32);
             }
             cp_async_commit();
             const int win = (y >> 1) * P2 + (x >> 1), loc = (y & 1) * 2 + (x & 1);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float xv = __ldg(x2 + ((size_t)n * C + c) * P1SQ + threadIdx.x);
-                float xh = (xv - sPar[6 * C + c]) * sPar[7 * C + c];
-                float d = 0.f;
-                if (idx2[((size_t)n * C + c) * P2SQ + win] == loc) d = __ldg(dy2 + ((size_t)n * C + c) * P2SQ + win);
-                float dx = sPar[4 * C + c] * (d - sPar[8 * C + c] - xh * sPar[9 * C + c]);
-                sDX[c * PPAD + (y + 1) * LDP + x + 1] = dx;
-                dbs[c] += dx;
+            for (int c0 = 0; c0 < C; c0 += 8) {       // 8 channels per batch: independent loads first, one latency per batch
+                float xv[8], dv[8];
+                unsigned char iv[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int c = c0 + cc;
+                    xv[cc] = __ldg(x2 + ((size_t)n * C + c) * P1SQ + threadIdx.x);
+                    iv[cc] = idx2[((size_t)n * C + c) * P2SQ + win];
+                    dv[cc] = __ldg(dy2 + ((size_t)n * C + c) * P2SQ + win);
+                }
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int c = c0 + cc;
+                    const float xh = (xv[cc] - sPar[6 * C + c]) * sPar[7 * C + c];
+                    const float d = iv[cc] == loc ? dv[cc] : 0.f;
+                    const float dx = sPar[4 * C + c] * (d - sPar[8 * C + c] - xh * sPar[9 * C + c]);
+                    sDX[c * PPAD + (y + 1) * LDP + x + 1] = dx;
+                    dbs[c] += dx;
+                }
             }
-            for (int i = threadIdx.x; i < C * P1SQ; i += MGGAN_THREADS) {
-                int c = i >> 8, pp = i & 255;
-                float e = __ldg(e1 + (size_t)n * C * P1SQ + i);
-                sIdx[i] = idx1[(size_t)n * C * P1SQ + i];
-                sP[c * PPAD + ((pp >> 4) + 1) * LDP + (pp & 15) + 1] = fmaxf(fmaf(sPar[c], e, sPar[C + c]), 0.f);
+            // e1 / idx1: 4 consecutive pooled pixels of one channel per thread and trip (float4 / 32-bit loads)
+            const float4* e4 = reinterpret_cast<const float4*>(e1 + (size_t)n * C * P1SQ);
+            const uint32_t* i4 = reinterpret_cast<const uint32_t*>(idx1 + (size_t)n * C * P1SQ);
+            float4 ev[C / 4];
+            uint32_t iw[C / 4];
+#pragma unroll
+            for (int k = 0; k < C / 4; ++k) {
+                ev[k] = __ldg(e4 + threadIdx.x + k * MGGAN_THREADS);
+                iw[k] = __ldg(i4 + threadIdx.x + k * MGGAN_THREADS);
+            }
+#pragma unroll
+            for (int k = 0; k < C / 4; ++k) {
+                const int q = threadIdx.x + k * MGGAN_THREADS, c = q >> 6, pp = (q & 63) * 4;
+                reinterpret_cast<uint32_t*>(sIdx)[q] = iw[k];
+                float* o = sP + c * PPAD + ((pp >> 4) + 1) * LDP + (pp & 15) + 1;
+                const float a = sPar[c], b = sPar[C + c];
+                o[0] = fmaxf(fmaf(a, ev[k].x, b), 0.f); o[1] = fmaxf(fmaf(a, ev[k].y, b), 0.f);
+                o[2] = fmaxf(fmaf(a, ev[k].z, b), 0.f); o[3] = fmaxf(fmaf(a, ev[k].w, b), 0.f);
             }
         }
         __syncthreads();
@@ -905,7 +1079,8 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) wacc[i][j] = 0.f;
-    float bacc = 0.f;            // dba2[c] for t < C ; dba1[k] for C <= t < C + AH
+    const int bcol = threadIdx.x & 63, bpart = threadIdx.x >> 6;
+    float bacc = 0.f;            // dba2[bcol] for bcol < C ; dba1[bcol - C] for C <= bcol < C + AH (rows of quarter bpart)
     float st[2 * C];
 #pragma unroll
     for (int c = 0; c < 2 * C; ++c) st[c] = 0.f;
@@ -915,6 +1090,10 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
         float v[C], hp[AH], att[C], e[C], ds[C], dv[C]; int arg[C];
         float dhid[AH];
         __syncthreads();
+        if (threadIdx.x == 0) {               // the next trip's four agents -> L2 (8 warps per SM: every global latency is exposed)
+            const int nn = n0 + gridDim.x * 4;
+            if (nn < N) prefetch_l2_bulk(x2 + (size_t)nn * C * P1SQ, (uint32_t)min(4, N - nn) * C * P1SQ * 4);
+        }
         if (n < N) {
             pool_block2<C, true>(x2 + (size_t)n * C * P1SQ, w.sAB, pos, v, arg, e);
             attn_mlp<C>(w, v, hp, att);
@@ -982,10 +1161,14 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
             int oq = b2 % (AH / 4), kq = b2 / (AH / 4);
             tile_wgrad<RPG>(wacc, sDH + rg * RPG * LDA, LDA, oq * 4, sV + rg * RPG * LDC, LDC, kq * 4);
         }
-        if (threadIdx.x < C) {
-            for (int r = 0; r < MGGAN_THREADS; ++r) bacc += sDS[r * LDC + threadIdx.x];
-        } else if (threadIdx.x < C + AH) {
-            for (int r = 0; r < MGGAN_THREADS; ++r) bacc += sDH[r * LDA + threadIdx.x - C];
+        // bias gradients: column bcol over the 64 rows of quarter bpart (a 256-row chain in C + AH threads kept the other
+        // warps at the next barrier: 17 % of the kernel's stall samples)
+        if (bcol < C) {
+#pragma unroll 8
+            for (int r = bpart * 64; r < bpart * 64 + 64; ++r) bacc += sDS[r * LDC + bcol];
+        } else if (bcol < C + AH) {
+#pragma unroll 8
+            for (int r = bpart * 64; r < bpart * 64 + 64; ++r) bacc += sDH[r * LDA + bcol - C];
         }
     }
     if (blk < NBLK / 2) {
@@ -996,14 +1179,14 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
         int oq = b2 % (AH / 4), kq = b2 / (AH / 4);
         atomic_block44(dWa1, C, oq * 4, kq * 4, wacc);
     }
-    if (threadIdx.x < C) atomicAdd(dba2 + threadIdx.x, bacc);
-    else if (threadIdx.x < C + AH) atomicAdd(dba1 + threadIdx.x - C, bacc);
+    if (bcol < C) atomicAdd(dba2 + bcol, bacc);
+    else if (bcol < C + AH) atomicAdd(dba1 + bcol - C, bacc);
     block_reduce_to_global<2 * C>(st, sums2, sred);
 }
 
 
 template <int C>
-size_t fused_fwd_smem() { constexpr int PPAD = FwdPad::PPAD; return sizeof(float) * (2 * RAW + NTAP * C + ((C * PPAD + 3) & ~3) + 9 * C * FwdLdw2<C>::value + 2 * C + 8 * 2 * C) + 16; }
+size_t fused_fwd_smem() { constexpr int PPAD = FwdPad::PPAD; return sizeof(float) * (F_CROP4 + 2 * ((C * PPAD + 3) & ~3) + 2 * 9 * C * FwdLdw2<C>::value + 3 * C + 5 * (C / 8) * 128 + 8 * 2 * C); }
 template <int C>
 size_t fused_bwd_smem() {
     constexpr int PPAD = BwdPad::PPAD;
@@ -1074,9 +1257,9 @@ int attn_bwd(const float* x2, int N, const float* ab2, const float* mi2, const f
 extern "C" int mggan_scene_patch_stats(const float* img, const int* rows, int N, double* R, double* P,
                                        cudaStream_t stream) {
     if (N <= 0) return MGGAN_OK;
-    int slots = sm_count() * 3 / NPAIRS_CH;          // 44 agent slots x 10 channel pairs = 440 CTAs, 3 per SM
-    if (slots > N) slots = N;
-    scene_patch_stats_kernel<<<slots * NPAIRS_CH, PS_THREADS, 0, stream>>>(img, rows, N, slots, R, P);
+    const size_t sm = sizeof(float) * 2 * G_BUF + sizeof(double) * G_NT * G_NT;
+    cudaFuncSetAttribute(scene_patch_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    scene_patch_stats_kernel<<<agent_grid(N, 2), MGGAN_THREADS, sm, stream>>>(img, rows, N, R, P);
     return mggan_check_launch("scene_patch_stats");
 }
 

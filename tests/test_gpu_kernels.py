@@ -182,6 +182,42 @@ def test_social_attention(K, HD, sizes):
 
 
 # ------------------------------------------------------------------------------------ scene attention
+def _patch_stats_reference(img):
+    """R = sum patch patch^T, P = sum patch over (agent, pixel) in float64: the 36 taps (ci, ky, kx) of the zero-padded
+    3 x 3 window (csrc/scene.cu; the quantities BatchNorm-1 of cnn.py:137-158 is derived from)."""
+    x = np.pad(img.astype(np.float64), ((0, 0), (0, 0), (1, 1), (1, 1)))
+    taps = np.stack([x[:, ci, ky:ky + 33, kx:kx + 33] for ci in range(4) for ky in range(3) for kx in range(3)], 0)
+    taps = taps.reshape(36, -1)
+    return taps @ taps.T, taps.sum(1)
+
+
+@pytest.mark.parametrize("N,exact", [(1, True), (7, True), (700, True), (5, False), (333, False)])
+def test_scene_patch_stats(K, N, exact):
+    """Tensor-pipe Gram kernel against float64: crops cut from 8-bit images (TF32-exact operands, one MMA per tile) and
+    arbitrary fp32 crops (3 x TF32 split products), with and without the row gather."""
+    from mggan.cuda_ext import call, ptr
+    from mggan.synthetic import make_batch
+    rng = np.random.default_rng(N)
+    if exact:
+        img = make_batch([N], seed=N, with_img=True)["features"]
+    else:
+        img = rng.standard_normal((N, 4, 33, 33)).astype(np.float32) * rng.uniform(0.1, 3.0, (N, 4, 1, 1)).astype(np.float32)
+    for rows in (None, rng.permutation(N)[: max(1, N // 2)].astype(np.int32)):
+        sel = img if rows is None else img[rows]
+        Rr, Pr = _patch_stats_reference(sel)
+        buf = torch.zeros(36 * 36 + 36, device=DEV, dtype=torch.float64)
+        d_img = torch.from_numpy(img).to(DEV)
+        d_rows = None if rows is None else torch.from_numpy(rows).to(DEV)
+        call("mggan_scene_patch_stats", ptr(d_img), ptr(d_rows), sel.shape[0], ptr(buf[:1296]), ptr(buf[1296:]))
+        R, P = buf[:1296].reshape(36, 36).cpu().numpy(), buf[1296:].cpu().numpy()
+        assert np.array_equal(R, R.T)
+        # the tensor pipe accumulates with truncation: a one-sided error of ~2^-24 per accumulation on the all-positive diagonal
+        # sums, 17 accumulations per crop with exact operands and 51 with the split products (measured 1e-6 / 3e-6)
+        tol = 2e-6 if exact else 8e-6
+        assert np.abs(R - Rr).max() <= tol * np.abs(Rr).max(), np.abs(R - Rr).max() / np.abs(Rr).max()
+        assert np.abs(P - Pr).max() <= tol * max(np.abs(Pr).max(), np.sqrt(np.abs(Rr).max() * sel.shape[0] * 1089))
+
+
 @pytest.mark.parametrize("C,N", [(16, 3), (8, 5), (16, 70)])
 def test_scene_attention(K, C, N):
     from mggan.model.modules.cnn import AttentionGlobal

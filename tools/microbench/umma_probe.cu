@@ -36,6 +36,7 @@ struct Probe {
     int a_kstep, b_kstep;                  // descriptor start-address advance per K = 8 step (bytes)
     int a_shift_rows;                      // shifted_rows: A staged with M + shift rows, descriptor starts at row `shift`
     int repeat;                            // rate probe: number of times the K loop is issued
+    int acc_sets;                          // rate probe: accumulators (TMEM column blocks of N) the MMAs rotate over (0 / 1 = one)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -122,16 +123,17 @@ probe_kernel(Probe p, const float* __restrict__ A, const float* __restrict__ B, 
         for (int rep = 0; rep < p.repeat; ++rep)
             for (int kk = 0; kk < p.K / 8; ++kk) {
                 const uint32_t acc = (rep > 0 || kk > 0) ? 1u : 0u;
+                const uint32_t d_tmem = tmem_base + (p.acc_sets > 1 ? static_cast<uint32_t>(((rep * (p.K / 8) + kk) % p.acc_sets) * p.N) : 0u);
                 const uint64_t bd = bdesc + static_cast<uint64_t>((kk * p.b_kstep) >> 4);
                 if (p.a_mode == 2) {
                     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
                                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, q;\n\t}"
-                                 ::"r"(tmem_base), "r"(tmem_base + A_COL0 + kk * 8), "l"(bd), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+                                 ::"r"(d_tmem), "r"(tmem_base + A_COL0 + kk * 8), "l"(bd), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
                 } else {
                     const uint64_t ad = adesc + static_cast<uint64_t>((kk * p.a_kstep) >> 4);
                     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
                                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, q;\n\t}"
-                                 ::"r"(tmem_base), "l"(ad), "l"(bd), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+                                 ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
                 }
             }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -220,6 +222,18 @@ static std::vector<Named> probes() {
             static char names[8][32];
             static int n = 0;
             snprintf(names[n], 32, "rate_%s_n%d", ts ? "ts" : "ss", N);
+            v.push_back({names[n++], p});
+        }
+    // the same with the MMAs rotating over 4 independent accumulators: issue rate without the accumulate dependency
+    for (int N : {16, 32, 64})
+        for (int ts = 0; ts < 2; ++ts) {
+            Probe p = kmaj(N, 32);
+            p.a_mode = ts ? 2 : 0;
+            p.repeat = 512;
+            p.acc_sets = 4;
+            static char names[6][32];
+            static int n = 0;
+            snprintf(names[n], 32, "rate4_%s_n%d", ts ? "ts" : "ss", N);
             v.push_back({names[n++], p});
         }
     return v;
