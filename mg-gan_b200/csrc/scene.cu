@@ -431,6 +431,59 @@ constexpr int F_CROP4 = (F_CROP + 3) & ~3;
 __constant__ int TAP_PERM[40] = {0, 1, 2, 11, 3, 4, 5, 14, 6, 7, 8, 17, 9, 10, 19, 20, 12, 13, 22, 23,
                                  15, 16, 25, 26, 18, 21, 28, 31, 24, 27, 29, 34, 30, 32, 33, 35, 36, 37, 38, 39};
 
+// conv1 products of NTP tile pairs (8 pooled pixels each): acc[p][window row][n-tile][c0 c1 | c2 c3].  The MMAs are issued
+// product-major over the 2 NTP NT independent accumulators (back-to-back MMAs on one accumulator wait for each other:
+// "wait" was the top stall reason of the first tensor-pipe version).  SPLIT = false: the crop holds TF32 numbers.
+template <int NT, int NTP, bool SPLIT>
+__device__ __forceinline__ void conv1_mma(const float* const (&pos)[NTP], const int (&toff)[5][2], const float* __restrict__ sW1f,
+                                          int lane, float (&acc)[NTP][2][NT][4]) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+            const float* wf = sW1f + (s * NT + q) * 128 + lane;
+            bh[q][0] = __float_as_uint(wf[0]); bl[q][0] = __float_as_uint(wf[32]);
+            bh[q][1] = __float_as_uint(wf[64]); bl[q][1] = __float_as_uint(wf[96]);
+        }
+        uint32_t ah[NTP][2][4], al[NTP][2][4];
+#pragma unroll
+        for (int p = 0; p < NTP; ++p)
+#pragma unroll
+            for (int wy = 0; wy < 2; ++wy) {
+                const float* pa = pos[p] + wy * F_LDR;
+                float a[4];
+                a[0] = pa[toff[s][0]]; a[1] = pa[toff[s][0] + 1];
+                if (s < 4) { a[2] = pa[toff[s][1]]; a[3] = pa[toff[s][1] + 1]; } else { a[2] = 0.f; a[3] = 0.f; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (SPLIT) tf32_split(a[i], ah[p][wy][i], al[p][wy][i]);
+                    else { ah[p][wy][i] = __float_as_uint(a[i]); al[p][wy][i] = 0u; }
+                }
+            }
+#pragma unroll
+        for (int p = 0; p < NTP; ++p)
+#pragma unroll
+            for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+                for (int q = 0; q < NT; ++q) mma_tf32_16x8x8(acc[p][wy][q], ah[p][wy], bh[q][0], bh[q][1]);
+#pragma unroll
+        for (int p = 0; p < NTP; ++p)
+#pragma unroll
+            for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+                for (int q = 0; q < NT; ++q) mma_tf32_16x8x8(acc[p][wy][q], ah[p][wy], bl[q][0], bl[q][1]);
+        if (SPLIT) {
+#pragma unroll
+            for (int p = 0; p < NTP; ++p)
+#pragma unroll
+                for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+                    for (int q = 0; q < NT; ++q) mma_tf32_16x8x8(acc[p][wy][q], al[p][wy], bh[q][0], bh[q][1]);
+        }
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(MGGAN_THREADS, 2)
 scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ rows, int N,
@@ -511,90 +564,80 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             low |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
         }
         const bool split = __syncthreads_or((low & 0x1FFFu) != 0u);
-        // ---- conv1 -> BN1 -> ReLU -> pool: tile pairs (pooled row py, half row) warp, warp + 8, ...
+        // ---- conv1 -> BN1 -> ReLU -> pool: tile pairs (pooled row py, half row) warp, warp + 8, ..., NTP at a time
+        constexpr int NTP = NT == 1 ? 2 : 1;      // 4 independent accumulators per k-step either way
 #pragma unroll 1
-        for (int tp = warp; tp < 32; tp += MGGAN_THREADS / 32) {
-            const int py = tp >> 1, px0 = (tp & 1) * 8;
-            const float* pos = sCrop + (2 * py) * F_LDR + 2 * (px0 + g8);      // window (0, 0) of pooled pixel (py, px0 + g)
-            float acc[2][NT][4];                  // [window row][n-tile][c0 c1 | c2 c3] = [.][.][col 0: ch e | col 1: ch e]
+        for (int tp0 = warp; tp0 < 32; tp0 += NTP * (MGGAN_THREADS / 32)) {
+            const float* pos[NTP];                // window (0, 0) of pooled pixel (py, px0 + g) of tile pair p
+            float acc[NTP][2][NT][4];             // [pair][window row][n-tile][col 0: ch e | col 1: ch e]
 #pragma unroll
-            for (int wy = 0; wy < 2; ++wy)
+            for (int p = 0; p < NTP; ++p) {
+                const int tp = tp0 + p * (MGGAN_THREADS / 32);
+                pos[p] = sCrop + (2 * (tp >> 1)) * F_LDR + 2 * ((tp & 1) * 8 + g8);
 #pragma unroll
-                for (int q = 0; q < NT; ++q) {
-                    const float2 bv = *reinterpret_cast<const float2*>(sB1 + 8 * q + 2 * t4);
-                    acc[wy][q][0] = bv.x; acc[wy][q][1] = bv.y; acc[wy][q][2] = bv.x; acc[wy][q][3] = bv.y;
-                }
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-#pragma unroll
-                for (int wy = 0; wy < 2; ++wy) {
-                    const float* pa = pos + wy * F_LDR;
-                    float a[4];
-                    a[0] = pa[toff[s][0]]; a[1] = pa[toff[s][0] + 1];
-                    if (s < 4) { a[2] = pa[toff[s][1]]; a[3] = pa[toff[s][1] + 1]; } else { a[2] = 0.f; a[3] = 0.f; }
-                    uint32_t ah[4], al[4];
-                    if (split) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) tf32_split(a[i], ah[i], al[i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) ah[i] = __float_as_uint(a[i]);
-                    }
+                for (int wy = 0; wy < 2; ++wy)
 #pragma unroll
                     for (int q = 0; q < NT; ++q) {
-                        const float* wf = sW1f + (s * NT + q) * 128 + lane;
-                        const uint32_t bh0 = __float_as_uint(wf[0]), bl0 = __float_as_uint(wf[32]);
-                        const uint32_t bh1 = __float_as_uint(wf[64]), bl1 = __float_as_uint(wf[96]);
-                        mma_tf32_16x8x8(acc[wy][q], ah, bh0, bh1);
-                        mma_tf32_16x8x8(acc[wy][q], ah, bl0, bl1);
-                        if (split) mma_tf32_16x8x8(acc[wy][q], al, bh0, bh1);
+                        const float2 bv = *reinterpret_cast<const float2*>(sB1 + 8 * q + 2 * t4);
+                        acc[p][wy][q][0] = bv.x; acc[p][wy][q][1] = bv.y; acc[p][wy][q][2] = bv.x; acc[p][wy][q][3] = bv.y;
                     }
-                }
             }
-            const int pix = py * P1 + px0 + g8;
+            if (split) conv1_mma<NT, NTP, true>(pos, toff, sW1f, lane, acc);
+            else conv1_mma<NT, NTP, false>(pos, toff, sW1f, lane, acc);
 #pragma unroll
-            for (int q = 0; q < NT; ++q)
+            for (int p = 0; p < NTP; ++p) {
+                const int tp = tp0 + p * (MGGAN_THREADS / 32);
+                const int py = tp >> 1, px0 = (tp & 1) * 8;
+                const int pix = py * P1 + px0 + g8;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = 8 * q + 2 * t4 + e;
-                    const float a = sAB[c], b = sAB[C + c];
-                    // window order (0,0) (0,1) (1,0) (1,1), first maximum wins (as the FP32 kernel and the oracle's max_pool2d)
-                    const float x0 = acc[0][q][e], x1 = acc[0][q][2 + e], x2v = acc[1][q][e], x3 = acc[1][q][2 + e];
-                    float m = fmaf(a, x0, b), ev = x0; int arg = 0;
-                    float v = fmaf(a, x1, b);
-                    if (v > m) { m = v; ev = x1; arg = 1; }
-                    v = fmaf(a, x2v, b);
-                    if (v > m) { m = v; ev = x2v; arg = 2; }
-                    v = fmaf(a, x3, b);
-                    if (v > m) { m = v; ev = x3; arg = 3; }
-                    uint32_t hi, lo;
-                    tf32_split(fmaxf(m, 0.f), hi, lo);
-                    const int o = c * PPAD + (py + 1) * LDP + px0 + g8 + 1;
-                    sPh[o] = __uint_as_float(hi);
-                    sPl[o] = __uint_as_float(lo);
-                    if (e1 != nullptr) {
-                        e1[((size_t)n * C + c) * P1SQ + pix] = ev;
-                        idx1[((size_t)n * C + c) * P1SQ + pix] = (unsigned char)(arg | (m > 0.f ? 4 : 0));
+                for (int q = 0; q < NT; ++q)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = 8 * q + 2 * t4 + e;
+                        const float a = sAB[c], b = sAB[C + c];
+                        // window order (0,0) (0,1) (1,0) (1,1), first maximum wins (as the FP32 kernel and the oracle's max_pool2d)
+                        const float x0 = acc[p][0][q][e], x1 = acc[p][0][q][2 + e], x2v = acc[p][1][q][e], x3 = acc[p][1][q][2 + e];
+                        float m = fmaf(a, x0, b), ev = x0; int arg = 0;
+                        float v = fmaf(a, x1, b);
+                        if (v > m) { m = v; ev = x1; arg = 1; }
+                        v = fmaf(a, x2v, b);
+                        if (v > m) { m = v; ev = x2v; arg = 2; }
+                        v = fmaf(a, x3, b);
+                        if (v > m) { m = v; ev = x3; arg = 3; }
+                        uint32_t hi, lo;
+                        tf32_split(fmaxf(m, 0.f), hi, lo);
+                        const int o = c * PPAD + (py + 1) * LDP + px0 + g8 + 1;
+                        sPh[o] = __uint_as_float(hi);
+                        sPl[o] = __uint_as_float(lo);
+                        if (e1 != nullptr) {
+                            e1[((size_t)n * C + c) * P1SQ + pix] = ev;
+                            idx1[((size_t)n * C + c) * P1SQ + pix] = (unsigned char)(arg | (m > 0.f ? 4 : 0));
+                        }
                     }
-                }
+            }
         }
         __syncthreads();                          // pooled map complete; the crop buffer is free
         if (n + (int)gridDim.x < N) stage(n + gridDim.x);
-        {   // ---- conv2: the warp's two rows are interleaved (2 NT independent accumulator chains)
+        {   // ---- conv2: the warp's two rows, MMAs issued product-major over 4 independent accumulators (C = 8: even / odd
+            // taps accumulate separately and are added at the end)
+            constexpr int NSET = NT == 1 ? 2 : 1;
             const int y = warp * 2;
-            float acc[2][NT][4];
+            float acc[NSET][2][NT][4];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const float ba = __ldg(b2 + 8 * j + 2 * t4), bb = __ldg(b2 + 8 * j + 2 * t4 + 1);
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) { acc[rr][j][0] = ba; acc[rr][j][1] = bb; acc[rr][j][2] = ba; acc[rr][j][3] = bb; }
+                for (int rr = 0; rr < 2; ++rr) {
+                    acc[0][rr][j][0] = ba; acc[0][rr][j][1] = bb; acc[0][rr][j][2] = ba; acc[0][rr][j][3] = bb;
+                    if (NSET == 2) { acc[NSET - 1][rr][j][0] = 0.f; acc[NSET - 1][rr][j][1] = 0.f; acc[NSET - 1][rr][j][2] = 0.f; acc[NSET - 1][rr][j][3] = 0.f; }
+                }
             }
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
                 for (int ks = 0; ks < NT; ++ks) {
                     const int ob = (tap * C + ks * 8 + t4) * LDW2 + g8;
-                    uint32_t bh0[NT], bh1[NT], bl0[NT], bl1[NT];
+                    uint32_t bh0[NT], bh1[NT], bl0[NT], bl1[NT], ah[2][4], al[2][4];
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
                         bh0[j] = __float_as_uint(sW2h[ob + 8 * j]); bh1[j] = __float_as_uint(sW2h[ob + 4 * LDW2 + 8 * j]);
@@ -603,17 +646,24 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
                         const int oa = (ks * 8 + t4) * PPAD + (y + rr + tap / 3) * LDP + g8 + tap % 3;
-                        const uint32_t ah[4] = {__float_as_uint(sPh[oa]), __float_as_uint(sPh[oa + 8]),
-                                                __float_as_uint(sPh[oa + 4 * PPAD]), __float_as_uint(sPh[oa + 4 * PPAD + 8])};
-                        const uint32_t al[4] = {__float_as_uint(sPl[oa]), __float_as_uint(sPl[oa + 8]),
-                                                __float_as_uint(sPl[oa + 4 * PPAD]), __float_as_uint(sPl[oa + 4 * PPAD + 8])};
-#pragma unroll
-                        for (int j = 0; j < NT; ++j) {
-                            mma_tf32_16x8x8(acc[rr][j], ah, bh0[j], bh1[j]);
-                            mma_tf32_16x8x8(acc[rr][j], al, bh0[j], bh1[j]);
-                            mma_tf32_16x8x8(acc[rr][j], ah, bl0[j], bl1[j]);
-                        }
+                        ah[rr][0] = __float_as_uint(sPh[oa]); ah[rr][1] = __float_as_uint(sPh[oa + 8]);
+                        ah[rr][2] = __float_as_uint(sPh[oa + 4 * PPAD]); ah[rr][3] = __float_as_uint(sPh[oa + 4 * PPAD + 8]);
+                        al[rr][0] = __float_as_uint(sPl[oa]); al[rr][1] = __float_as_uint(sPl[oa + 8]);
+                        al[rr][2] = __float_as_uint(sPl[oa + 4 * PPAD]); al[rr][3] = __float_as_uint(sPl[oa + 4 * PPAD + 8]);
                     }
+                    float (&ac)[2][NT][4] = acc[NSET == 2 ? (tap & 1) : 0];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) mma_tf32_16x8x8(ac[rr][j], ah[rr], bh0[j], bh1[j]);
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) mma_tf32_16x8x8(ac[rr][j], al[rr], bh0[j], bh1[j]);
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) mma_tf32_16x8x8(ac[rr][j], ah[rr], bl0[j], bl1[j]);
                 }
             }
 #pragma unroll
@@ -621,7 +671,9 @@ scene_fused12_fwd_kernel(const float* __restrict__ img, const int* __restrict__ 
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     float* o = x2 + ((size_t)n * C + 8 * j + 2 * t4) * P1SQ + (y + rr) * P1 + g8;
-                    const float* a = acc[rr][j];
+                    float a[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = NSET == 2 ? acc[0][rr][j][i] + acc[NSET - 1][rr][j][i] : acc[0][rr][j][i];
                     o[0] = a[0]; o[8] = a[2]; o[P1SQ] = a[1]; o[P1SQ + 8] = a[3];
                     st[2 * j] += a[0] + a[2];
                     st[2 * j + 1] += a[1] + a[3];
