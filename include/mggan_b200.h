@@ -85,7 +85,8 @@ int mggan_selection_all(int n, int k, int G, int* tile_gen, int* seq_agent, int*
  * per generator: Wx (G,128,2), b (G,128), Whh (G,128,32), W1h/W1s (G,16,32) = halves of hidden2pos.0,
  * b1 (G,16), W2 (G,2,16), b2 (G,2).  out_abs/out_rel (pred_len, n_cols, 2).
  * Saved for the backward (all three or all NULL), n_tiles even, rows grouped in 128-row tiles with the row index second-fastest
- * (a warp's rows are contiguous): acts (pred_len, n_tiles/2, 3 pairs, 16 unit-pairs, 128 rows, 4) with pairs (i,f | g,o | c,tanh c),
+ * (a warp's rows are contiguous): acts (pred_len, n_tiles/2, 16 unit-pairs, 128 rows, 4) = the recurrent state (h, c | h, c) of the
+ * pair's two units after the step -- the backward recomputes the gates from h_{t-1} (one more tensor-pipe product per step),
  * u1save (pred_len, n_tiles/2, 4, 128 rows, 4), h0save (n_tiles/2, 8, 128 rows, 4)  -- csrc/common.cuh dec_*_off. */
 int mggan_decoder_fwd(int n_tiles, const int* tile_gen, const int* seq_agent, const int* seq_noise,
                       const int* seq_out, const float* A, const float* social, const float* last_xy,

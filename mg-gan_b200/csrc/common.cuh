@@ -170,15 +170,17 @@ __device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4
 }
 
 // ---- decoder saved-activation layouts (decoder.cu, decoder_tc.cu) -----------------------------------------------
+// The forward saves only the recurrent state (h_t, c_t) of every step; the backward recomputes the gates from h_{t-1}
+// with one more tensor-pipe product per step (round 1 saved the six gate / cell values per unit and step: 3.5 GB written
+// and 4.1 GB re-read per generator step, and the backward was bound by the latency of those loads).
 // Rows are grouped in 128-row tiles and the row index is the second-fastest dimension, so that the 32 rows a warp of
-// the thread-per-row tensor-core kernel writes for one (pair, unit-pair) are 512 contiguous bytes (4 lines per
-// 16-byte store instead of 32), and the (4 rows x 8 units) float2 accesses of the FP32 kernels stay 64-byte segments.
-//   acts   (T, rows/128, 3 pairs, 16 unit-pairs, 128 rows, 4)   4 floats = pair values of units 2j, 2j+1;
-//                                                               pairs: (i, f) | (g, o) | (c, tanh c)
+// the thread-per-row tensor-core kernel writes for one unit pair are 512 contiguous bytes (4 lines per 16-byte store
+// instead of 32), and a 64-row tile of one unit pair is one contiguous 1 KB chunk for the backward's float4 loads.
+//   acts   (T, rows/128, 16 unit-pairs, 128 rows, 4)            4 floats = (h, c) of unit 2j, (h, c) of unit 2j+1
 //   u1save (T, rows/128, 4, 128 rows, 4)                        hidden2pos.0 pre-activations m = 4 q + (0..3)
 //   h0save (rows/128, 8, 128 rows, 4)                           initial hidden state, units 4 q + (0..3)
-__device__ __forceinline__ size_t dec_acts_off(size_t n_super, int t, size_t row, int pair, int u) {
-    return ((((size_t)t * n_super + (row >> 7)) * 3 + pair) * 16 + (u >> 1)) * 512 + (row & 127) * 4 + (u & 1) * 2;
+__device__ __forceinline__ size_t dec_acts_off(size_t n_super, int t, size_t row, int u) {
+    return (((size_t)t * n_super + (row >> 7)) * 16 + (u >> 1)) * 512 + (row & 127) * 4 + (u & 1) * 2;
 }
 __device__ __forceinline__ size_t dec_u1_off(size_t n_super, int t, size_t row, int m) {
     return (((size_t)t * n_super + (row >> 7)) * 4 + (m >> 2)) * 512 + (row & 127) * 4 + (m & 3);

@@ -172,10 +172,7 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
                 hnext[r * LDH + u] = og * tc;
                 if (acts != nullptr && sAgent[r] >= 0) {
                     // layout: dec_acts_off (common.cuh); a warp's float2 stores cover 64-byte segments
-                    float* a = acts + dec_acts_off(Rpad >> 7, t, row0 + r, 0, u);
-                    *reinterpret_cast<float2*>(a) = make_float2(ig, fg);
-                    *reinterpret_cast<float2*>(a + 16 * 512) = make_float2(gg, og);
-                    *reinterpret_cast<float2*>(a + 2 * 16 * 512) = make_float2(c[i], tc);
+                    *reinterpret_cast<float2*>(acts + dec_acts_off(Rpad >> 7, t, row0 + r, u)) = make_float2(og * tc, c[i]);
                 }
             }
             __syncthreads();
@@ -215,17 +212,25 @@ decoder_fwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ A, const fl
     }
 }
 
-// Backward.  Inputs: the forward's saved activations, d_abs / d_rel (either may be null).
-// Per step and 64-row tile:  phase 0 hidden2pos backward (thread = row x 4 mid units), phase 1 LSTM cell backward
-// (thread = 8 rows x 1 unit; activations read as (i,f | g,o | c,tanh c) float2 triples, layout dec_acts_off in common.cuh), phase 2 tile products:
+// Backward.  Inputs: the forward's saved recurrent state (h_t, c_t per step), d_abs / d_rel (either may be null).
+// Per step and 64-row tile:
+//   phase 0  hidden2pos backward (thread = row x 4 mid units); the tile's h_{t-1}, c_{t-1} (16 contiguous 1 KB chunks,
+//            float4 loads issued before the phase's arithmetic) -> shared memory, with (x0, x1, 1) in the pad columns
+//   phase G  the gate pre-activations are RECOMPUTED on the tensor pipe:  Z = [h_{t-1} | x | 1] [W_hh | Wx | b]^T
+//            (64 x 128, K = 40) -- round 1 re-read the six saved gate / cell values per unit and step (4.1 GB per
+//            generator step at 21 % of the HBM peak, long-scoreboard stalls 28 % of the kernel) where this reads two
+//   phase 1  LSTM cell backward (thread = 8 rows x 1 unit): gates from Z, c_t = f c_{t-1} + i g, d(gates) in place of Z
+//   phase 2  tile products:
 //   dh_{t-1} = dG W_hh (64 x 32, K = 128)          dW_hh += dG^T h_{t-1} (128 x 32, K = 64 rows)
 //       -- these two are 80 % of the step's MACs and made the kernel shared-memory-wavefront bound (lsu 86 %) as FP32
 //          register tiles; they run as warp-level 3 x TF32 mma.sync products (common.cuh), 5-6x fewer wavefronts per MAC
 //   (dWx | db) += dG^T (x | 1)   via the pad columns 32..34 of the h_{t-1} tile, rows split over the k-quad lanes
 //   dW1h += dU^T h_t (16 x 32)   rows split over the 8 warps
-//   d(dxdy_{t-1}) = dG Wx        thread = (row, quarter of the 128 gates), Wx kept transposed
+//   d(dxdy_{t-1}) = dG Wx        thread = (row, quarter of the 128 gates), Wx kept transposed (rows 32, 33 of the W_hh^T tile)
 // All weight-gradient tiles stay in registers across steps and tiles of one generator and are flushed with one
 // atomicAdd per element per CTA.
+constexpr int KG = H + 8;     // contraction length of the gate recompute: 32 units, x0, x1, 1, 5 zero columns
+
 __global__ void __launch_bounds__(MGGAN_THREADS, 2)
 decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, const float* __restrict__ last_dxdy,
                    const float* __restrict__ noise, int Z, DecWeights w, int T, int n_cols,
@@ -233,15 +238,17 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                    const float* __restrict__ u1save, const float* __restrict__ h0save,
                    const float* __restrict__ d_abs, const float* __restrict__ d_rel, DecGrads gr) {
     extern __shared__ __align__(16) float smem[];
-    float* sWT = smem;                      // [H][LDG]    W_hh transposed (unit-major): B operand of dh = dG W_hh
-    float* sW1 = sWT + H * LDG;             // [M1][LDH]   W1s (epilogue)
+    float* sWT = smem;                      // [KG][LDG]   rows 0..31 W_hh transposed (unit-major): B operand of dh = dG W_hh and of the
+                                            //             gate recompute; rows 32, 33 Wx transposed, row 34 b, rows 35..39 zero
+    float* sW1 = sWT + KG * LDG;            // [M1][LDH]   W1s (epilogue)
     float* sG = sW1 + M1 * LDH;             // [ROWS][LDG] gate pre-activation gradients
     float* sHp = sG + ROWS * LDG;           // [ROWS][LDH] h_{t-1} | x0 x1 1 0
     float* sHt = sHp + ROWS * LDH;          // [ROWS][LDH] h_t   (social tile after the loop)
     float* sDh = sHt + ROWS * LDH;          // [ROWS][LDH] dL/dh from the later step
     float* sDu = sDh + ROWS * LDH;          // [ROWS][LDU] d(hidden2pos.0 pre-activation)
-    float* sWxT = sDu + ROWS * LDU;         // [2][4H]     Wx transposed
-    float* sZ = sWxT + 2 * 4 * H;           // [ROWS][ZMAX] noise rows of the tile
+    float* sCp = sDu + ROWS * LDU;          // [ROWS][LDH] c_{t-1}
+    float* sWxT = sWT + H * LDG;            //             Wx transposed = rows 32, 33 of sWT (row stride LDG)
+    float* sZ = sCp + ROWS * LDH;           // [ROWS][ZMAX] noise rows of the tile
     float* sW1sAcc = sZ + ROWS * ZMAX;      // [M1][H]     dW1s of the current generator (per-tile shared-memory adds)
     float* sW1h = sW1sAcc + M1 * H;         // [M1][LDH]   W1h
     float* sW2 = sW1h + M1 * LDH;           // [2][M1]     hidden2pos.2
@@ -251,19 +258,18 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
     const int u = (warp & 3) * 8 + (lane & 7);
     const int rl = (warp >> 2) * 32 + (lane >> 3);
     const int prow = threadIdx.x >> 2, mq = threadIdx.x & 3;
-    const int w_oq = (warp & 3) * 8 + (lane & 7), w_kq = (warp >> 2) * 4 + (lane >> 3);
     const int e_mq = lane & 3, e_kq = lane >> 2;                    // dW1h / dW1s 4x4 block, rows split over warps
     const int z_u = threadIdx.x & 31, z_g = threadIdx.x >> 5;       // dWz: unit, noise-column group (z_g, z_g + 8)
     const size_t Rpad = (size_t)n_tiles * ROWS;
 
-    float wacc[4][4], xacc[4][3], w1acc[4][4];
+    float wacc[5][4], w1acc[4][4];      // wacc[0..3]: dW_hh n-tiles; wacc[4]: the pad columns (x0, x1, 1) = (dWx | db)
     float aw2a[4], aw2b[4], ab2a, ab2b, ab1[4], awz0, awz1;
     auto zero_acc = [&]() {
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) { wacc[a][b] = 0.f; w1acc[a][b] = 0.f; }
-            xacc[a][0] = xacc[a][1] = xacc[a][2] = 0.f;
+            wacc[4][a] = 0.f;
             aw2a[a] = aw2b[a] = ab1[a] = 0.f;
         }
         ab2a = ab2b = awz0 = awz1 = 0.f;
@@ -278,12 +284,14 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 atomicAdd(dst + H + j, wacc[j][2]); atomicAdd(dst + H + 4 + j, wacc[j][3]);
             }
         }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const size_t o = (size_t)g * 4 * H + w_oq * 4 + a;
-            atomicAdd(gr.dWx + o * 2, xacc[a][0]);
-            atomicAdd(gr.dWx + o * 2 + 1, xacc[a][1]);
-            atomicAdd(gr.db + o, xacc[a][2]);
+        {   // wacc[4]: c0, c1 -> gate m0 + 2g, pad columns 2t, 2t + 1 (0: x0, 1: x1, 2: the constant 1); c2, c3 -> gate m0 + 2g + 1
+            const size_t o = (size_t)g * 4 * H + warp * 16 + 2 * (lane >> 2);
+            if ((lane & 3) == 0) {
+                atomicAdd(gr.dWx + o * 2, wacc[4][0]); atomicAdd(gr.dWx + o * 2 + 1, wacc[4][1]);
+                atomicAdd(gr.dWx + o * 2 + 2, wacc[4][2]); atomicAdd(gr.dWx + o * 2 + 3, wacc[4][3]);
+            } else if ((lane & 3) == 1) {
+                atomicAdd(gr.db + o, wacc[4][0]); atomicAdd(gr.db + o + 1, wacc[4][2]);
+            }
         }
         atomic_block44(gr.dW1h + (size_t)g * M1 * H, H, e_mq * 4, e_kq * 4, w1acc);
         for (int i = threadIdx.x; i < M1 * H; i += MGGAN_THREADS) atomicAdd(gr.dW1s + (size_t)g * M1 * H + i, sW1sAcc[i]);
@@ -301,6 +309,8 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
         if (z_g + 8 < Z) atomicAdd(gr.dWz + z_u * Z + z_g + 8, awz1);
     };
     zero_acc();
+    for (int i = threadIdx.x; i < (KG - H - 3) * LDG; i += MGGAN_THREADS) sWT[(H + 3) * LDG + i] = 0.f;     // zero rows of the K extension
+    for (int i = threadIdx.x; i < ROWS * (LDH - H); i += MGGAN_THREADS) sHp[(i / (LDH - H)) * LDH + H + i % (LDH - H)] = 0.f;
 
     const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
     const int t_begin = blockIdx.x * per, t_end = min(n_tiles, t_begin + per);
@@ -315,7 +325,8 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
             for (int i = threadIdx.x; i < 4 * H * H; i += MGGAN_THREADS)
                 sWT[(i & (H - 1)) * LDG + (i >> 5)] = __ldg(w.Whh + (size_t)g * 4 * H * H + i);
             for (int i = threadIdx.x; i < 4 * H * 2; i += MGGAN_THREADS)
-                sWxT[(i & 1) * 4 * H + (i >> 1)] = __ldg(w.Wx + (size_t)g * 4 * H * 2 + i);
+                sWxT[(i & 1) * LDG + (i >> 1)] = __ldg(w.Wx + (size_t)g * 4 * H * 2 + i);
+            for (int i = threadIdx.x; i < 4 * H; i += MGGAN_THREADS) sWT[(H + 2) * LDG + i] = __ldg(w.b + (size_t)g * 4 * H + i);
             stage_matrix(sW1h, LDH, w.W1h + (size_t)g * M1 * H, M1, H);
             if (threadIdx.x < 2 * M1) sW2[threadIdx.x] = __ldg(w.W2 + (size_t)g * 2 * M1 + threadIdx.x);
         }
@@ -332,6 +343,14 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
             const float* zp = noise + (size_t)(ag >= 0 ? sq.seq_noise[row0 + r] : 0) * Z;
             for (int z = threadIdx.x & 3; z < ZMAX; z += 4) sZ[r * ZMAX + z] = (ag >= 0 && z < Z) ? __ldg(zp + z) : 0.f;
         }
+        // output gradients of the row: the values of step t - 1 are requested during step t (they are 8-byte gathers by output
+        // column whose latency sat in front of every step: 6 % of the kernel's stall samples)
+        float2 g_abs = make_float2(0.f, 0.f), g_rel = make_float2(0.f, 0.f);
+        if (pcol >= 0) {
+            const size_t o = ((size_t)(T - 1) * n_cols + pcol) * 2;
+            if (d_abs != nullptr) g_abs = __ldg(reinterpret_cast<const float2*>(d_abs + o));
+            if (d_rel != nullptr) g_rel = __ldg(reinterpret_cast<const float2*>(d_rel + o));
+        }
         float dxy0 = 0.f, dxy1 = 0.f;       // sum_{tau >= t} d_abs[tau]
         float dn0 = 0.f, dn1 = 0.f;         // gradient reaching dxdy_t through step t+1's input
         float dbs[4] = {0.f, 0.f, 0.f, 0.f};
@@ -340,6 +359,18 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
         for (int i = 0; i < 8; ++i) dc[i] = 0.f;
 
         for (int t = T - 1; t >= 0; --t) {
+            // the tile's recurrent state of the previous step: 4 float4 per thread = (h, c) of two units, requested first so
+            // that the latency runs under the hidden2pos arithmetic (t = 0: h_0 from its own buffer, c_0 = 0)
+            float4 hc[4];
+            {
+                const size_t ns = Rpad >> 7;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int idx = threadIdx.x + q * MGGAN_THREADS, r = idx & (ROWS - 1), j = idx >> 6;
+                    if (t > 0) hc[q] = __ldg(reinterpret_cast<const float4*>(acts + dec_acts_off(ns, t - 1, row0 + r, 2 * j)));
+                    else if (q < 2) hc[q] = __ldg(reinterpret_cast<const float4*>(h0save + dec_h0_off(row0 + r, 4 * j)));
+                }
+            }
             // ---- phase 0: hidden2pos backward (thread = row x 4 mid units)
             {
                 float dr0 = dn0, dr1 = dn1;
@@ -348,15 +379,12 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { w2a[q] = sW2[mq + 4 * q]; w2b[q] = sW2[M1 + mq + 4 * q]; }
                 if (pcol >= 0) {
-                    size_t o = ((size_t)t * n_cols + pcol) * 2;
-                    if (d_abs != nullptr) {
-                        float2 v = __ldg(reinterpret_cast<const float2*>(d_abs + o));
-                        dxy0 += v.x; dxy1 += v.y;
-                    }
-                    dr0 += dxy0; dr1 += dxy1;
-                    if (d_rel != nullptr) {
-                        float2 v = __ldg(reinterpret_cast<const float2*>(d_rel + o));
-                        dr0 += v.x; dr1 += v.y;
+                    dxy0 += g_abs.x; dxy1 += g_abs.y;
+                    dr0 += dxy0 + g_rel.x; dr1 += dxy1 + g_rel.y;
+                    if (t > 0) {
+                        const size_t o = ((size_t)(t - 1) * n_cols + pcol) * 2;
+                        if (d_abs != nullptr) g_abs = __ldg(reinterpret_cast<const float2*>(d_abs + o));
+                        if (d_rel != nullptr) g_rel = __ldg(reinterpret_cast<const float2*>(d_rel + o));
                     }
                     const float* us = u1save + dec_u1_off(Rpad >> 7, t, row0 + prow, mq);
 #pragma unroll
@@ -379,62 +407,111 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                         xv = t > 0 ? __ldg(reinterpret_cast<const float2*>(out_rel + ((size_t)(t - 1) * n_cols + pcol) * 2))
                                    : __ldg(reinterpret_cast<const float2*>(last_dxdy + (size_t)pag * 2));
                     }
-                    st4(sHp + prow * LDH + H, make_float4(xv.x, xv.y, 1.f, 0.f));
+                    st4(sHp + prow * LDH + H, make_float4(xv.x, xv.y, pcol >= 0 ? 1.f : 0.f, 0.f));
+                }
+                // h_{t-1}, c_{t-1} -> shared memory (padding rows: zeros)
+                if (t > 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int idx = threadIdx.x + q * MGGAN_THREADS, r = idx & (ROWS - 1), j = idx >> 6;
+                        const bool ok = sAgent[r] >= 0;
+                        *reinterpret_cast<float2*>(sHp + r * LDH + 2 * j) = ok ? make_float2(hc[q].x, hc[q].z) : make_float2(0.f, 0.f);
+                        *reinterpret_cast<float2*>(sCp + r * LDH + 2 * j) = ok ? make_float2(hc[q].y, hc[q].w) : make_float2(0.f, 0.f);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int idx = threadIdx.x + q * MGGAN_THREADS, r = idx & (ROWS - 1), j = idx >> 6;
+                        if (q < 2) st4(sHp + r * LDH + 4 * j, sAgent[r] >= 0 ? hc[q] : make_float4(0.f, 0.f, 0.f, 0.f));
+                        *reinterpret_cast<float2*>(sCp + r * LDH + 2 * j) = make_float2(0.f, 0.f);
+                    }
                 }
             }
             __syncthreads();
-            // ---- phase 1: dh_t, LSTM cell backward (thread = 8 rows x 1 unit).  The saved activations are read with
-            // unconditional, batched loads (NB rows at a time: one memory latency per batch instead of one per row);
-            // padding rows read their own, never-written slots and are masked afterwards.
-            constexpr int NB = 4;            // rows per load batch (register budget: 5 float2 per row in flight)
-            float w1col[M1];
+            // ---- phase G: gate pre-activations Z = [h_{t-1} | x | 1] [W_hh | Wx | b]^T as warp-level 3 x TF32 products:
+            // warp = 16 rows x 64 gates (4 n-tiles at a time: register budget), K = 40; B fragment (k = t, n = g) =
+            // sWT[(k0 + t) LDG + n0 + g] (row stride = 8 mod 32: 32 distinct banks); MMAs product-major over the n-tiles
+            {
+                const int g8 = lane >> 2, t4 = lane & 3;
+                const int m0 = (warp & 3) * 16;
+#pragma unroll 1
+                for (int nh = 0; nh < 2; ++nh) {
+                    const int nb = (warp >> 2) * 64 + nh * 32;
+                    float acc[4][4];
 #pragma unroll
-            for (int m = 0; m < M1; ++m) w1col[m] = sW1h[m * LDH + u];
+                    for (int j = 0; j < 4; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
 #pragma unroll
-            for (int half = 0; half < 8 / NB; ++half) {
-                float2 q0[NB], q1[NB], q2[NB], p1[NB], p2[NB];
-                float h0v[NB];
+                    for (int k0 = 0; k0 < KG; k0 += 8) {
+                        const float* pa = sHp + (m0 + g8) * LDH + k0 + t4;
+                        uint32_t ah[4], al[4], bh[4][2], bl[4][2];
+                        tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDH], ah[1], al[1]);
+                        tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDH + 4], ah[3], al[3]);
+                        const float* pb = sWT + (k0 + t4) * LDG + nb + g8;
 #pragma unroll
-                for (int ii = 0; ii < NB; ++ii) {
-                    const int r = rl + 4 * (half * NB + ii);
-                    const float* a = acts + dec_acts_off(Rpad >> 7, t, row0 + r, 0, u);
-                    q0[ii] = __ldg(reinterpret_cast<const float2*>(a));
-                    q1[ii] = __ldg(reinterpret_cast<const float2*>(a + 16 * 512));
-                    q2[ii] = __ldg(reinterpret_cast<const float2*>(a + 2 * 16 * 512));
-                    if (t > 0) {
-                        const float* ap = a - (Rpad >> 7) * (3 * 16 * 512);
-                        p1[ii] = __ldg(reinterpret_cast<const float2*>(ap + 16 * 512));
-                        p2[ii] = __ldg(reinterpret_cast<const float2*>(ap + 2 * 16 * 512));
-                    } else {
-                        h0v[ii] = __ldg(h0save + dec_h0_off(row0 + r, u));
+                        for (int j = 0; j < 4; ++j) {
+                            tf32_split(pb[8 * j], bh[j][0], bl[j][0]);
+                            tf32_split(pb[4 * LDG + 8 * j], bh[j][1], bl[j][1]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j], ah, bh[j][0], bh[j][1]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j], ah, bl[j][0], bl[j][1]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float* o = sG + (m0 + g8) * LDG + nb + 8 * j + 2 * t4;
+                        *reinterpret_cast<float2*>(o) = make_float2(acc[j][0], acc[j][1]);
+                        *reinterpret_cast<float2*>(o + 8 * LDG) = make_float2(acc[j][2], acc[j][3]);
                     }
                 }
+                {   // dh_t += dU_t W1h (64 x 32, K = 16), the hidden2pos path into h_t: warp = 16 rows x 16 units.  As FP32
+                    // (8 rows x 16 FMAs behind 32 LDS.128 per thread in phase 1) it was 10 % of the kernel's stall samples.
+                    const int n0 = (warp >> 2) * 16;
+                    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-                for (int ii = 0; ii < NB; ++ii) {
-                    const int i = half * NB + ii;
-                    const int r = rl + 4 * i;
-                    const bool valid = sAgent[r] >= 0;
-                    const float ig = q0[ii].x, fg = q0[ii].y, gg = q1[ii].x, og = q1[ii].y, tc = q2[ii].y;
-                    const float cp = t > 0 ? p2[ii].x : 0.f;
-                    const float hp = t > 0 ? p1[ii].y * p2[ii].y : h0v[ii];
-                    const float ht = og * tc;
-                    float dh = sDh[r * LDH + u];
-#pragma unroll
-                    for (int m = 0; m < M1; m += 4) {
-                        float4 d4 = ld4(sDu + r * LDU + m);
-                        dh = fmaf(w1col[m], d4.x, fmaf(w1col[m + 1], d4.y, fmaf(w1col[m + 2], d4.z, fmaf(w1col[m + 3], d4.w, dh))));
+                    for (int k0 = 0; k0 < M1; k0 += 8) {
+                        const float* pa = sDu + (m0 + g8) * LDU + k0 + t4;
+                        uint32_t ah[4], al[4];
+                        tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDU], ah[1], al[1]);
+                        tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDU + 4], ah[3], al[3]);
+                        const float* pb = sW1h + (k0 + t4) * LDH + n0 + g8;
+                        mma_3xtf32(acc[0], ah, al, pb[0], pb[4 * LDH]);
+                        mma_3xtf32(acc[1], ah, al, pb[8], pb[4 * LDH + 8]);
                     }
-                    const float dcc = fmaf(dh * og, 1.f - tc * tc, dc[i]);
-                    const float dao = dh * tc * og * (1.f - og);
-                    const float dai = dcc * gg * ig * (1.f - ig);
-                    const float dag = dcc * ig * (1.f - gg * gg);
-                    const float daf = dcc * cp * fg * (1.f - fg);
-                    dc[i] = valid ? dcc * fg : 0.f;
-                    sG[r * LDG + u] = valid ? dai : 0.f; sG[r * LDG + H + u] = valid ? daf : 0.f;
-                    sG[r * LDG + 2 * H + u] = valid ? dag : 0.f; sG[r * LDG + 3 * H + u] = valid ? dao : 0.f;
-                    sHp[r * LDH + u] = valid ? hp : 0.f;
-                    sHt[r * LDH + u] = valid ? ht : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float2* o0 = reinterpret_cast<float2*>(sDh + (m0 + g8) * LDH + n0 + 8 * j + 2 * t4);
+                        float2* o1 = reinterpret_cast<float2*>(sDh + (m0 + g8 + 8) * LDH + n0 + 8 * j + 2 * t4);
+                        float2 v0 = *o0, v1 = *o1;
+                        *o0 = make_float2(v0.x + acc[j][0], v0.y + acc[j][1]);
+                        *o1 = make_float2(v1.x + acc[j][2], v1.y + acc[j][3]);
+                    }
                 }
+            }
+            __syncthreads();
+            // ---- phase 1: dh_t, LSTM cell backward (thread = 8 rows x 1 unit): gates from the recomputed pre-activations,
+            // c_t = f c_{t-1} + i g, gate gradients written in place of the pre-activations
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rl + 4 * i;
+                const bool valid = sAgent[r] >= 0;
+                const float ig = sigmoidf_(sG[r * LDG + u]), fg = sigmoidf_(sG[r * LDG + H + u]);
+                const float gg = tanhf_(sG[r * LDG + 2 * H + u]), og = sigmoidf_(sG[r * LDG + 3 * H + u]);
+                const float cp = sCp[r * LDH + u];
+                const float tc = tanhf_(fmaf(fg, cp, ig * gg));
+                const float ht = og * tc;
+                const float dh = sDh[r * LDH + u];
+                const float dcc = fmaf(dh * og, 1.f - tc * tc, dc[i]);
+                const float dao = dh * tc * og * (1.f - og);
+                const float dai = dcc * gg * ig * (1.f - ig);
+                const float dag = dcc * ig * (1.f - gg * gg);
+                const float daf = dcc * cp * fg * (1.f - fg);
+                dc[i] = valid ? dcc * fg : 0.f;
+                sG[r * LDG + u] = valid ? dai : 0.f; sG[r * LDG + H + u] = valid ? daf : 0.f;
+                sG[r * LDG + 2 * H + u] = valid ? dag : 0.f; sG[r * LDG + 3 * H + u] = valid ? dao : 0.f;
+                sHt[r * LDH + u] = valid ? ht : 0.f;
             }
             __syncthreads();
             // ---- phase 2: tile products
@@ -489,19 +566,9 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                         mma_3xtf32(wacc[1], ah, al, y0.y, y1.y);
                         mma_3xtf32(wacc[2], ah, al, y0.z, y1.z);
                         mma_3xtf32(wacc[3], ah, al, y0.w, y1.w);
+                        // (dWx | db) += dG^T (x0 x1 1): a fifth n-tile over the pad columns of the h_{t-1} tile
+                        mma_3xtf32(wacc[4], ah, al, pb[k0 * LDH + H - 3 * g8], pb[(k0 + 4) * LDH + H - 3 * g8]);
                     }
-                }
-            }
-            {   // (dWx | db): rows [8 w_kq, 8 w_kq + 8) of dG^T (x0 x1 1)
-#pragma unroll
-                for (int rr = 0; rr < 8; ++rr) {
-                    const int r = w_kq * 8 + rr;
-                    const float4 gq = ld4(sG + r * LDG + w_oq * 4);
-                    const float4 xq = ld4(sHp + r * LDH + H);
-                    xacc[0][0] = fmaf(gq.x, xq.x, xacc[0][0]); xacc[0][1] = fmaf(gq.x, xq.y, xacc[0][1]); xacc[0][2] = fmaf(gq.x, xq.z, xacc[0][2]);
-                    xacc[1][0] = fmaf(gq.y, xq.x, xacc[1][0]); xacc[1][1] = fmaf(gq.y, xq.y, xacc[1][1]); xacc[1][2] = fmaf(gq.y, xq.z, xacc[1][2]);
-                    xacc[2][0] = fmaf(gq.z, xq.x, xacc[2][0]); xacc[2][1] = fmaf(gq.z, xq.y, xacc[2][1]); xacc[2][2] = fmaf(gq.z, xq.z, xacc[2][2]);
-                    xacc[3][0] = fmaf(gq.w, xq.x, xacc[3][0]); xacc[3][1] = fmaf(gq.w, xq.y, xacc[3][1]); xacc[3][2] = fmaf(gq.w, xq.z, xacc[3][2]);
                 }
             }
             // dW1h: rows [8 warp, 8 warp + 8) of dU^T h_t
@@ -514,7 +581,7 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 for (int oo = 0; oo < H; oo += 4) {
                     const int o = oo * 4 + mq * 4;
                     const float4 gq = ld4(sG + prow * LDG + o);
-                    const float4 wa = ld4(sWxT + o), wb = ld4(sWxT + 4 * H + o);
+                    const float4 wa = ld4(sWxT + o), wb = ld4(sWxT + LDG + o);
                     s0 = fmaf(gq.x, wa.x, fmaf(gq.y, wa.y, fmaf(gq.z, wa.z, fmaf(gq.w, wa.w, s0))));
                     s1 = fmaf(gq.x, wb.x, fmaf(gq.y, wb.y, fmaf(gq.z, wb.z, fmaf(gq.w, wb.w, s1))));
                 }
@@ -579,7 +646,7 @@ size_t dec_fwd_smem() {
     return sizeof(float) * (4 * H * LDH + 2 * M1 * LDH + 2 * ROWS * LDH + ROWS * LDU + ROWS * 2 + H * (ZMAX + 1));
 }
 size_t dec_bwd_smem() {
-    return sizeof(float) * (H * LDG + M1 * LDH + ROWS * LDG + 3 * ROWS * LDH + ROWS * LDU + 2 * 4 * H + ROWS * ZMAX + M1 * H + M1 * LDH + 2 * M1);
+    return sizeof(float) * (KG * LDG + M1 * LDH + ROWS * LDG + 4 * ROWS * LDH + ROWS * LDU + ROWS * ZMAX + M1 * H + M1 * LDH + 2 * M1);
 }
 
 int sm_count() {

@@ -302,12 +302,12 @@ decoder_fwd_tc_kernel(DecSeq sq, int n_super, const float* __restrict__ A, const
             float uacc[M1];
 #pragma unroll
             for (int m = 0; m < M1; ++m) uacc[m] = bs[m];
-            float* arow = (acts != nullptr && valid) ? acts + dec_acts_off(n_super, t, row, 0, 0) : nullptr;
+            float* arow = (acts != nullptr && valid) ? acts + dec_acts_off(n_super, t, row, 0) : nullptr;
 #pragma unroll
             for (int u4 = 0; u4 < H / 4; ++u4) {
                 float v[16];
                 tmem_ld16(tmem_row + u4 * 16, v);
-                float hq[4], pif[8], pgo[8], pct[8];
+                float hq[4];
 #pragma unroll
                 for (int uu = 0; uu < 4; ++uu) {
                     const int u = u4 * 4 + uu;
@@ -320,9 +320,6 @@ decoder_fwd_tc_kernel(DecSeq sq, int n_super, const float* __restrict__ A, const
                     const float tc = tanh_tc(c[u]);
                     const float h = og * tc;
                     hq[uu] = h;
-                    pif[uu * 2] = ig; pif[uu * 2 + 1] = fg;
-                    pgo[uu * 2] = gg; pgo[uu * 2 + 1] = og;
-                    pct[uu * 2] = c[u]; pct[uu * 2 + 1] = tc;
 #pragma unroll
                     for (int m4 = 0; m4 < M1 / 4; ++m4) {
                         const float4 w1 = ld4(sW1hT + u * M1 + m4 * 4);
@@ -332,9 +329,8 @@ decoder_fwd_tc_kernel(DecSeq sq, int n_super, const float* __restrict__ A, const
                 }
                 if (arow != nullptr) {     // dec_acts_off layout: each st4 of a warp is 512 contiguous bytes (unit pair 2 u4 + {0, 1})
                     float* a = arow + (u4 * 2) * 512;
-                    st4(a, make_float4(pif[0], pif[1], pif[2], pif[3])); st4(a + 512, make_float4(pif[4], pif[5], pif[6], pif[7]));
-                    st4(a + 16 * 512, make_float4(pgo[0], pgo[1], pgo[2], pgo[3])); st4(a + 17 * 512, make_float4(pgo[4], pgo[5], pgo[6], pgo[7]));
-                    st4(a + 32 * 512, make_float4(pct[0], pct[1], pct[2], pct[3])); st4(a + 33 * 512, make_float4(pct[4], pct[5], pct[6], pct[7]));
+                    st4(a, make_float4(hq[0], c[u4 * 4], hq[1], c[u4 * 4 + 1]));
+                    st4(a + 512, make_float4(hq[2], c[u4 * 4 + 2], hq[3], c[u4 * 4 + 3]));
                 }
                 if (t + 1 < T) {
                     const float4 hi = make_float4(tf32_hi(hq[0]), tf32_hi(hq[1]), tf32_hi(hq[2]), tf32_hi(hq[3]));

@@ -528,7 +528,7 @@ class _Decoder(torch.autograd.Function):
         out_rel = torch.empty_like(out_abs)
         need = grad_on and any(ctx.needs_input_grad)
         R = sel.n_tiles * TILE
-        acts = torch.empty(pred_len, R, 3, 32, 2, device=dev) if need else None
+        acts = torch.empty(pred_len, R, 32, 2, device=dev) if need else None       # (h_t, c_t): the backward recomputes the gates
         u1 = torch.empty(pred_len, R, 16, device=dev) if need else None
         h0 = torch.empty(R, 32, device=dev) if need else None
         call(DECODER_FWD, sel.n_tiles, ptr(sel.tile_gen), ptr(sel.seq_agent), ptr(sel.seq_noise),
