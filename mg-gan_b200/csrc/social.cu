@@ -146,11 +146,14 @@ social_fwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
 
 // Backward.  Phase 1 (per scene): softmax backward -> d sigma (scratch `dsig`) and dh_j = sum_i att_ij dS_i as a
 // small matrix product (no atomics).  Phase 2: the pair MLP backward over tiles of PT pairs in j-major order
-// (pair p -> j = p / n, i = p % n), every dense piece as a register-blocked shared-memory tile product:
-//     S  = A1 W2^T + b2        (PT x 64, K = 32)     recomputed pre-activation of layer 2
-//     D2 = [S > 0] ds u_j ,  dU_j += ds relu(S)      (run-length accumulated per thread, flushed with atomics)
-//     dA1 = D2 W2 [A1 > 0]     (PT x 32, K = 64)
-//     dW2 += D2^T A1, db2 += colsum D2, dW1 += dA1^T F, db1 += colsum dA1   (kept in registers across tiles)
+// (pair p -> j = p / n, i = p % n); the three dense pieces are warp-level 3 x TF32 tensor-pipe products (common.cuh;
+// as FP32 register tiles they were 85 % of the kernel's samples at the FMA-issue floor):
+//     S  = A1 W2^T + b2        (PT x 64, K = 32)     recomputed pre-activation of layer 2; warp = 16 pairs x 64
+//     D2 = [S > 0] ds u_j ,  dU_j += ds relu(S)      (16-row tiles of one neighbour j: shuffle-reduced, one atomic per column)
+//     dA1 = D2 W2 [A1 > 0]     (PT x 32, K = 64)     warp = 16 pairs x 32
+//     dW2 += D2^T A1           (64 x 32, K = PT)     warp = 16 outputs x 16 inputs, C fragments kept across tiles
+//     db2 += colsum D2, dW1 += dA1^T F, db1 += colsum dA1   (FP32, kept in registers across tiles)
+// W2 is staged pre-split as (hi, lo) planes; the activations are split where they are read.
 template <int HD>
 __global__ void __launch_bounds__(MGGAN_THREADS, 2)
 social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, const float* __restrict__ Us,
@@ -161,8 +164,9 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
                   float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
     constexpr int LDHS = HD + 1;
     extern __shared__ __align__(16) float smem[];
-    float* sW2 = smem;                       // [F2][LDW2]
-    float* sW1 = sW2 + F2 * LDW2;            // [F1][4]
+    float* sW2 = smem;                       // [F2][LDW2]  TF32 hi plane of W2
+    float* sW2l = sW2 + F2 * LDW2;           // [F2][LDW2]  lo plane (W2 - hi)
+    float* sW1 = sW2l + F2 * LDW2;           // [F1][4]
     float* sb2 = sW1 + F1 * 4;               // [F2]
     float* sX = sb2 + F2;                    // [NMAX][4]
     float* sU = sX + NMAX * 4;               // [NMAX][LDU]
@@ -175,18 +179,20 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
     float* sHh = sA1;
     float* sdS = sD2;
     stage_pair_weights(sW1, sW2, sb2, W1, b1, W2, b2);
+    __syncthreads();
+    for (int i = threadIdx.x; i < F2 * LDW2; i += MGGAN_THREADS) {       // split W2 in place: (hi, lo) planes
+        uint32_t hi, lo;
+        tf32_split(sW2[i], hi, lo);
+        sW2[i] = __uint_as_float(hi);
+        sW2l[i] = __uint_as_float(lo);
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // layer-2 tile product: warp pair -> 32 rows, thread -> rows rl + 4 i (i < 8), columns u + 16 jj (jj < 4)
-    const int u = (warp & 1) * 8 + (lane & 7);
-    const int rl = (warp >> 1) * 32 + (lane >> 3);
-    // input-gradient tile product: rows d_r0 + 32 i (i < 4), columns 4 d_kq .. +3
-    const int d_kq = threadIdx.x & 7, d_r0 = threadIdx.x >> 3;
-    // weight-gradient blocks
-    const int wb = threadIdx.x & 127, whalf = threadIdx.x >> 7;
-    const int w_oq = wb & 15, w_kq = wb >> 4;
-    float wacc[4][4];
+    const int g8 = lane >> 2, t4 = lane & 3;                // MMA fragment coordinates
+    const int m0 = warp * 16;                               // the warp's 16 pairs of a tile
+    const int wm0 = (warp >> 1) * 16, wn0 = (warp & 1) * 16;    // dW2 block of the warp: outputs wm0.., inputs wn0..
+    float wacc[2][4];                                       // dW2 C fragments (n-tiles wn0, wn0 + 8), kept across tiles
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) wacc[i][j] = 0.f;
     float acc_small = 0.f;       // db2[c] (t<64) | dW1[k][f] (64<=t<160) | db1[k] (160<=t<192)
@@ -268,89 +274,156 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
                     sJ[pl] = jl;
                 }
             }
-            __syncthreads();
-            {   // S = A1 W2^T + b2 -> D2, dU
+            __syncwarp();                        // warp w produced exactly the 16 pairs (rows m0 ..) it consumes next
+            {   // S = A1 W2^T + b2 -> D2, dU.  warp = pairs m0 .. m0 + 15; A (row g, k t) = sA1[(m0 + g) LDA1 + k0 + t],
+                // B (k t, n g) = W2[n0 + g][k0 + t]: both on banks 4 g + t
                 float acc[8][4];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const float bv = sb2[u + 16 * jj];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i][jj] = bv;
+                for (int j = 0; j < 8; ++j) {
+                    const float ba = sb2[8 * j + 2 * t4], bb = sb2[8 * j + 2 * t4 + 1];
+                    acc[j][0] = ba; acc[j][1] = bb; acc[j][2] = ba; acc[j][3] = bb;
                 }
-                tile_rowdot<8, 4, F1>(acc, sA1, LDA1, rl, 4, sW2, LDW2, u, 16);
-                int curj = -1;
-                float uj[4] = {0.f, 0.f, 0.f, 0.f}, run[4] = {0.f, 0.f, 0.f, 0.f}, run_s = 0.f;
-                const bool sown = u == 0;             // one column owner per row also carries the s_j term
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rl + 4 * i;
-                    const int jl = sJ[r];
-                    const float ds = sDs[r];
-                    if (jl != curj) {
-                        if (curj >= 0) {
-                            float* du = dUs + (size_t)(a + curj) * LDU;
+                for (int k0 = 0; k0 < F1; k0 += 8) {
+                    const float* pa = sA1 + (m0 + g8) * LDA1 + k0 + t4;
+                    uint32_t ah[4], al[4];
+                    tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDA1], ah[1], al[1]);
+                    tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDA1 + 4], ah[3], al[3]);
+                    const int ob = g8 * LDW2 + k0 + t4;
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj)
-                                if (run[jj] != 0.f) atomicAdd(du + u + 16 * jj, run[jj]);
-                            if (sown && run_s != 0.f) atomicAdd(du + F2, run_s);
-                        }
-                        curj = jl;
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) { run[jj] = 0.f; uj[jj] = jl >= 0 ? pU[(size_t)jl * LDU + u + 16 * jj] : 0.f; }
-                        run_s = 0.f;
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t bh0 = __float_as_uint(sW2[ob + 8 * j * LDW2]), bh1 = __float_as_uint(sW2[ob + 8 * j * LDW2 + 4]);
+                        const uint32_t bl0 = __float_as_uint(sW2l[ob + 8 * j * LDW2]), bl1 = __float_as_uint(sW2l[ob + 8 * j * LDW2 + 4]);
+                        mma_tf32_16x8x8(acc[j], ah, bh0, bh1);
+                        mma_tf32_16x8x8(acc[j], al, bh0, bh1);
+                        mma_tf32_16x8x8(acc[j], ah, bl0, bl1);
                     }
-                    float d2[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float sv = acc[i][jj];
-                        run[jj] = fmaf(ds, fmaxf(sv, 0.f), run[jj]);
-                        d2[jj] = sv > 0.f ? ds * uj[jj] : 0.f;
-                        sD2[r * LDA2 + u + 16 * jj] = d2[jj];
-                    }
-                    run_s += ds;
                 }
-                if (curj >= 0) {
-                    float* du = dUs + (size_t)(a + curj) * LDU;
+                // the thread holds rows m0 + g, m0 + g + 8 and columns 8 j + 2 t + {0, 1}
+                const int ra = m0 + g8, rb = ra + 8;
+                const int ja = sJ[ra], jb = sJ[rb];
+                const float dsa = sDs[ra], dsb = sDs[rb];
+                const bool one_j = sJ[m0] == sJ[m0 + 15] && sJ[m0] >= 0;      // the tile's 16 pairs share their neighbour (warp-uniform)
+                const float* ua = pU + (size_t)(ja >= 0 ? ja : 0) * LDU;
+                const float* ub = pU + (size_t)(jb >= 0 ? jb : 0) * LDU;
+                float* dua = dUs + (size_t)(a + (ja >= 0 ? ja : 0)) * LDU;
+                float* dub = dUs + (size_t)(a + (jb >= 0 ? jb : 0)) * LDU;
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
-                        if (run[jj] != 0.f) atomicAdd(du + u + 16 * jj, run[jj]);
-                    if (sown && run_s != 0.f) atomicAdd(du + F2, run_s);
+                for (int j = 0; j < 8; ++j) {
+                    const int c = 8 * j + 2 * t4;
+                    const float s0 = acc[j][0], s1 = acc[j][1], s2 = acc[j][2], s3 = acc[j][3];
+                    *reinterpret_cast<float2*>(sD2 + ra * LDA2 + c) =
+                        make_float2(s0 > 0.f && ja >= 0 ? dsa * ua[c] : 0.f, s1 > 0.f && ja >= 0 ? dsa * ua[c + 1] : 0.f);
+                    *reinterpret_cast<float2*>(sD2 + rb * LDA2 + c) =
+                        make_float2(s2 > 0.f && jb >= 0 ? dsb * ub[c] : 0.f, s3 > 0.f && jb >= 0 ? dsb * ub[c + 1] : 0.f);
+                    // dU_j[c] += ds relu(S)
+                    float v0 = dsa * fmaxf(s0, 0.f), v1 = dsa * fmaxf(s1, 0.f), v2 = dsb * fmaxf(s2, 0.f), v3 = dsb * fmaxf(s3, 0.f);
+                    if (one_j) {
+                        v0 += v2; v1 += v3;
+                        v0 += __shfl_xor_sync(0xffffffffu, v0, 4); v1 += __shfl_xor_sync(0xffffffffu, v1, 4);
+                        v0 += __shfl_xor_sync(0xffffffffu, v0, 8); v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
+                        v0 += __shfl_xor_sync(0xffffffffu, v0, 16); v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
+                        if (g8 == 0) { atomicAdd(dua + c, v0); atomicAdd(dua + c + 1, v1); }
+                    } else {
+                        if (ja >= 0) { if (v0 != 0.f) atomicAdd(dua + c, v0); if (v1 != 0.f) atomicAdd(dua + c + 1, v1); }
+                        if (jb >= 0) { if (v2 != 0.f) atomicAdd(dub + c, v2); if (v3 != 0.f) atomicAdd(dub + c + 1, v3); }
+                    }
+                }
+                {   // the s_j term: dU_j[F2] += ds
+                    float va = ja >= 0 ? dsa : 0.f, vb = jb >= 0 ? dsb : 0.f;
+                    if (one_j) {
+                        va += vb;
+                        va += __shfl_xor_sync(0xffffffffu, va, 4);
+                        va += __shfl_xor_sync(0xffffffffu, va, 8);
+                        va += __shfl_xor_sync(0xffffffffu, va, 16);
+                        if (lane == 0) atomicAdd(dua + F2, va);
+                    } else if (t4 == 0) {
+                        if (va != 0.f) atomicAdd(dua + F2, va);
+                        if (vb != 0.f) atomicAdd(dub + F2, vb);
+                    }
                 }
             }
-            __syncthreads();
-            {   // dA1 = (D2 W2) [A1 > 0]
+            __syncwarp();                        // D2 rows m0 .. m0 + 15 were written by this warp
+            {   // dA1 = (D2 W2) [A1 > 0]: warp = pairs m0 .. m0 + 15 x 32 inputs, K = 64 outputs;
+                // B (k t, n g) = W2[k0 + t][n0 + g] (banks 4 t + g: 2-way conflicts, the price of one copy of W2 for both products)
                 float acc[4][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
-                tile_dgrad<4, F2>(acc, sD2, LDA2, d_r0, 32, sW2, LDW2, d_kq * 4);
+                for (int j = 0; j < 4; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = d_r0 + 32 * i;
-                    const float4 a1 = ld4(sA1 + r * LDA1 + d_kq * 4);
-                    st4(sDA1 + r * LDA1 + d_kq * 4,
-                        make_float4(a1.x > 0.f ? acc[i][0] : 0.f, a1.y > 0.f ? acc[i][1] : 0.f,
-                                    a1.z > 0.f ? acc[i][2] : 0.f, a1.w > 0.f ? acc[i][3] : 0.f));
+                for (int k0 = 0; k0 < F2; k0 += 8) {
+                    const float* pa = sD2 + (m0 + g8) * LDA2 + k0 + t4;
+                    uint32_t ah[4], al[4];
+                    tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDA2], ah[1], al[1]);
+                    tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDA2 + 4], ah[3], al[3]);
+                    const int ob = (k0 + t4) * LDW2 + g8;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t bh0 = __float_as_uint(sW2[ob + 8 * j]), bh1 = __float_as_uint(sW2[ob + 4 * LDW2 + 8 * j]);
+                        const uint32_t bl0 = __float_as_uint(sW2l[ob + 8 * j]), bl1 = __float_as_uint(sW2l[ob + 4 * LDW2 + 8 * j]);
+                        mma_tf32_16x8x8(acc[j], ah, bh0, bh1);
+                        mma_tf32_16x8x8(acc[j], al, bh0, bh1);
+                        mma_tf32_16x8x8(acc[j], ah, bl0, bl1);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = 8 * j + 2 * t4;
+                    const float2 a1a = *reinterpret_cast<const float2*>(sA1 + (m0 + g8) * LDA1 + c);
+                    const float2 a1b = *reinterpret_cast<const float2*>(sA1 + (m0 + g8 + 8) * LDA1 + c);
+                    *reinterpret_cast<float2*>(sDA1 + (m0 + g8) * LDA1 + c) =
+                        make_float2(a1a.x > 0.f ? acc[j][0] : 0.f, a1a.y > 0.f ? acc[j][1] : 0.f);
+                    *reinterpret_cast<float2*>(sDA1 + (m0 + g8 + 8) * LDA1 + c) =
+                        make_float2(a1b.x > 0.f ? acc[j][2] : 0.f, a1b.y > 0.f ? acc[j][3] : 0.f);
                 }
             }
             __syncthreads();
-            tile_wgrad<PT / 2>(wacc, sD2 + whalf * (PT / 2) * LDA2, LDA2, w_oq * 4, sA1 + whalf * (PT / 2) * LDA1, LDA1,
-                               w_kq * 4);
+            {   // dW2 += D2^T A1: warp = outputs wm0 .. wm0 + 15 x inputs wn0 .. wn0 + 15, K = the tile's pairs;
+                // A (row g, k t) = sD2[(k0 + t) LDA2 + wm0 + g], B (k t, n g) = sA1[(k0 + t) LDA1 + n + g]
+#pragma unroll 4
+                for (int k0 = 0; k0 < PT; k0 += 8) {
+                    const float* pa = sD2 + (k0 + t4) * LDA2 + wm0 + g8;
+                    const float* pb = sA1 + (k0 + t4) * LDA1 + wn0 + g8;
+                    uint32_t ah[4], al[4];
+                    tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8], ah[1], al[1]);
+                    tf32_split(pa[4 * LDA2], ah[2], al[2]); tf32_split(pa[4 * LDA2 + 8], ah[3], al[3]);
+                    mma_3xtf32(wacc[0], ah, al, pb[0], pb[4 * LDA1]);
+                    mma_3xtf32(wacc[1], ah, al, pb[8], pb[4 * LDA1 + 8]);
+                }
+            }
             {
                 const int t = threadIdx.x;
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;      // four partial sums: a 128-long dependent chain otherwise
                 if (t < 64) {
-                    for (int r = 0; r < PT; ++r) acc_small += sD2[r * LDA2 + t];
+#pragma unroll 4
+                    for (int r = 0; r < PT; r += 4) {
+                        p0 += sD2[r * LDA2 + t]; p1 += sD2[(r + 1) * LDA2 + t]; p2 += sD2[(r + 2) * LDA2 + t]; p3 += sD2[(r + 3) * LDA2 + t];
+                    }
                 } else if (t < 160) {
                     int k = (t - 64) / 3, f = (t - 64) % 3;
-                    for (int r = 0; r < PT; ++r) acc_small = fmaf(sDA1[r * LDA1 + k], sF[r * 4 + f], acc_small);
+#pragma unroll 4
+                    for (int r = 0; r < PT; r += 4) {
+                        p0 = fmaf(sDA1[r * LDA1 + k], sF[r * 4 + f], p0); p1 = fmaf(sDA1[(r + 1) * LDA1 + k], sF[(r + 1) * 4 + f], p1);
+                        p2 = fmaf(sDA1[(r + 2) * LDA1 + k], sF[(r + 2) * 4 + f], p2); p3 = fmaf(sDA1[(r + 3) * LDA1 + k], sF[(r + 3) * 4 + f], p3);
+                    }
                 } else if (t < 192) {
                     int k = t - 160;
-                    for (int r = 0; r < PT; ++r) acc_small += sDA1[r * LDA1 + k];
+#pragma unroll 4
+                    for (int r = 0; r < PT; r += 4) {
+                        p0 += sDA1[r * LDA1 + k]; p1 += sDA1[(r + 1) * LDA1 + k]; p2 += sDA1[(r + 2) * LDA1 + k]; p3 += sDA1[(r + 3) * LDA1 + k];
+                    }
                 }
+                acc_small += (p0 + p1) + (p2 + p3);
             }
             __syncthreads();
         }
     }
-    atomic_block44(dW2, F1, w_oq * 4, w_kq * 4, wacc);
+    // dW2 C fragments: c0, c1 -> output wm0 + g, inputs n + 2t, n + 2t + 1; c2, c3 -> output wm0 + g + 8
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float* dst = dW2 + (size_t)(wm0 + g8) * F1 + wn0 + 8 * i + 2 * t4;
+        atomicAdd(dst, wacc[i][0]); atomicAdd(dst + 1, wacc[i][1]);
+        atomicAdd(dst + 8 * F1, wacc[i][2]); atomicAdd(dst + 8 * F1 + 1, wacc[i][3]);
+    }
     {
         const int t = threadIdx.x;
         if (t < 64) atomicAdd(db2 + t, acc_small);
@@ -364,7 +437,7 @@ size_t soc_fwd_smem() { return sizeof(float) * (F2 * LDW2 + F1 * 4 + F2 + NMAX *
 template <int HD>
 size_t soc_bwd_smem() {
     static_assert(2 * NMAX * (HD + 1) <= PT * LDA1 + PT * LDA2, "phase-1 buffers alias the pair tiles");
-    return sizeof(float) * (F2 * LDW2 + F1 * 4 + F2 + NMAX * 4 + ((NMAX * LDU + 3) & ~3) + 2 * PT * LDA1 + PT * LDA2 +
+    return sizeof(float) * (2 * F2 * LDW2 + F1 * 4 + F2 + NMAX * 4 + ((NMAX * LDU + 3) & ~3) + 2 * PT * LDA1 + PT * LDA2 +
                             PT * 4 + 2 * PT);
 }
 
