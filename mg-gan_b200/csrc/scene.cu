@@ -758,9 +758,7 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     for (int i = 0; i < 9; ++i) sacc[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < UPW; ++i) { wacc[i][0] = 0.f; wacc[i][1] = 0.f; wacc[i][2] = 0.f; wacc[i][3] = 0.f; }
-    float dbs[C], st[4 * NT];                            // st: BatchNorm-1 sums of channels 8 j + 2 t + e: [2j + e], [2NT + 2j + e]
-#pragma unroll
-    for (int c = 0; c < C; ++c) dbs[c] = 0.f;
+    float st[4 * NT];                                    // st: BatchNorm-1 sums of channels 8 j + 2 t + e: [2j + e], [2NT + 2j + e]
 #pragma unroll
     for (int c = 0; c < 4 * NT; ++c) st[c] = 0.f;
 
@@ -808,7 +806,6 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                     const float d = iv[cc] == loc ? dv[cc] : 0.f;
                     const float dx = sPar[4 * C + c] * (d - sPar[8 * C + c] - xh * sPar[9 * C + c]);
                     sDX[c * PPAD + (y + 1) * LDP + x + 1] = dx;
-                    dbs[c] += dx;
                 }
             }
             // e1 / idx1: 4 consecutive pooled pixels of one channel per thread and trip (float4 / 32-bit loads)
@@ -848,38 +845,78 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                 } else {
                     ah[1] = al[1] = ah[3] = al[3] = 0u;
                 }
+                // B fragments of the warp's units first, then the MMAs product-major over the units (three back-to-back
+                // MMAs on one accumulator wait for each other)
+                uint32_t bh[UPW][2], bl[UPW][2];
 #pragma unroll
                 for (int i = 0; i < UPW; ++i) {
                     const int unit = warp + 8 * i;
                     if (unit < UNITS) {
                         const int tap = unit / NT, j = unit - tap * NT;
                         const float* pb = sP + (8 * j + g8) * PPAD + (yy + tap / 3) * LDP + x0 + t4 + tap % 3;
-                        mma_3xtf32(wacc[i], ah, al, pb[0], pb[4]);
+                        tf32_split(pb[0], bh[i][0], bl[i][0]);
+                        tf32_split(pb[4], bh[i][1], bl[i][1]);
+                    } else {                       // unit UNITS: an all-ones B -> every column of the C fragment is sum_pix dx2 = dbias2
+                        bh[i][0] = bh[i][1] = 0x3F800000u;
+                        bl[i][0] = bl[i][1] = 0u;
                     }
                 }
+#pragma unroll
+                for (int i = 0; i < UPW; ++i) if (warp + 8 * i <= UNITS) mma_tf32_16x8x8(wacc[i], ah, bh[i][0], bh[i][1]);
+#pragma unroll
+                for (int i = 0; i < UPW; ++i) if (warp + 8 * i <= UNITS) mma_tf32_16x8x8(wacc[i], al, bh[i][0], bh[i][1]);
+#pragma unroll
+                for (int i = 0; i < UPW; ++i) if (warp + 8 * i < UNITS) mma_tf32_16x8x8(wacc[i], ah, bl[i][0], bl[i][1]);
             }
         }
         {   // conv2 input gradient as warp-level 3 x TF32 products: m-tile = one row of 16 pixels, N = 8 input channels,
-            // K = output channels of one tap (logical k = t, t + 4 <-> co = c0 + 2t, c0 + 2t + 1), then pool / ReLU / BN1 -> dy1
-#pragma unroll 1
-            for (int rr = 0; rr < 2; ++rr) {
-                const int yy = warp * 2 + rr;
-                float acc[NT][4];
+            // K = output channels of one tap (logical k = t, t + 4 <-> co = c0 + 2t, c0 + 2t + 1), then pool / ReLU / BN1 -> dy1.
+            // The warp's two rows run together and the MMAs are issued product-major over independent accumulators (three
+            // back-to-back MMAs on one accumulator wait for each other); C = 8: even / odd taps accumulate separately.
+            constexpr int NSET = NT == 1 ? 2 : 1;
+            const int y0 = warp * 2;
+            float acc[NSET][2][NT][4];
 #pragma unroll
-                for (int j = 0; j < NT; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+            for (int q = 0; q < NSET; ++q)
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-                    for (int ks = 0; ks < NT; ++ks) {
-                        const float* pa = sDX + (ks * 8 + 2 * t4) * PPAD + (yy + 2 - tap / 3) * LDP + g8 + 2 - tap % 3;
-                        uint32_t ah[4], al[4];
-                        tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8], ah[1], al[1]);
-                        tf32_split(pa[PPAD], ah[2], al[2]); tf32_split(pa[PPAD + 8], ah[3], al[3]);
-                        const float* pb = sWT + (tap * C + ks * 8 + 2 * t4) * LDWD + g8;
+                    for (int j = 0; j < NT; ++j) { acc[q][rr][j][0] = 0.f; acc[q][rr][j][1] = 0.f; acc[q][rr][j][2] = 0.f; acc[q][rr][j][3] = 0.f; }
 #pragma unroll
-                        for (int j = 0; j < NT; ++j) mma_3xtf32(acc[j], ah, al, pb[8 * j], pb[LDWD + 8 * j]);
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                for (int ks = 0; ks < NT; ++ks) {
+                    uint32_t ah[2][4], al[2][4], bh[NT][2], bl[NT][2];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const float* pa = sDX + (ks * 8 + 2 * t4) * PPAD + (y0 + rr + 2 - tap / 3) * LDP + g8 + 2 - tap % 3;
+                        tf32_split(pa[0], ah[rr][0], al[rr][0]); tf32_split(pa[8], ah[rr][1], al[rr][1]);
+                        tf32_split(pa[PPAD], ah[rr][2], al[rr][2]); tf32_split(pa[PPAD + 8], ah[rr][3], al[rr][3]);
                     }
+                    const float* pb = sWT + (tap * C + ks * 8 + 2 * t4) * LDWD + g8;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        tf32_split(pb[8 * j], bh[j][0], bl[j][0]);
+                        tf32_split(pb[LDWD + 8 * j], bh[j][1], bl[j][1]);
+                    }
+                    float (&ac)[2][NT][4] = acc[NSET == 2 ? (tap & 1) : 0];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) mma_tf32_16x8x8(ac[rr][j], ah[rr], bh[j][0], bh[j][1]);
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) mma_tf32_16x8x8(ac[rr][j], al[rr], bh[j][0], bh[j][1]);
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) mma_tf32_16x8x8(ac[rr][j], ah[rr], bl[j][0], bl[j][1]);
                 }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int yy = y0 + rr;
 #pragma unroll
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
@@ -890,7 +927,8 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                         for (int hx = 0; hx < 2; ++hx) {
                             const int pix = yy * P1 + g8 + 8 * hx;
                             const float ev = __ldg(e1 + ((size_t)n * C + ch) * P1SQ + pix);
-                            const float d = (sIdx[ch * P1SQ + pix] & 4) ? acc[j][2 * hx + e] : 0.f;
+                            const float av = NSET == 2 ? acc[0][rr][j][2 * hx + e] + acc[NSET - 1][rr][j][2 * hx + e] : acc[0][rr][j][2 * hx + e];
+                            const float d = (sIdx[ch * P1SQ + pix] & 4) ? av : 0.f;
                             st[2 * j + e] += d;
                             st[2 * NT + 2 * j + e] = fmaf(d, (ev - mu) * is, st[2 * NT + 2 * j + e]);
                             sDY[ch * LDY + pix] = d;
@@ -939,6 +977,10 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
 #pragma unroll
     for (int i = 0; i < UPW; ++i) {
         const int unit = warp + 8 * i;
+        if (unit == UNITS && t4 == 0) {          // the all-ones unit: column 0 of its C fragment
+            atomicAdd(dbias2 + g8, wacc[i][0]);
+            if (C == 16) atomicAdd(dbias2 + g8 + 8, wacc[i][2]);
+        }
         if (unit < UNITS) {
             const int tap = unit / NT, j = unit - tap * NT;
             float* dst = dW2 + ((size_t)g8 * C + 8 * j + 2 * t4) * 9 + tap;
@@ -952,7 +994,6 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     }
 #pragma unroll
     for (int t = 0; t < 9; ++t) atomicAdd(S1 + ((size_t)s_c * CIN + s_ci) * 9 + t, sacc[t]);
-    block_reduce_to_global_f<C>(dbs, dbias2, sred);
     {   // BatchNorm-1 sums: lanes that differ in g hold the same channels
         double* sd = reinterpret_cast<double*>(sred);
         __syncthreads();
