@@ -359,9 +359,20 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
         for (int i = 0; i < 8; ++i) dc[i] = 0.f;
 
         for (int t = T - 1; t >= 0; --t) {
-            // the tile's recurrent state of the previous step: 4 float4 per thread = (h, c) of two units, requested first so
-            // that the latency runs under the hidden2pos arithmetic (t = 0: h_0 from its own buffer, c_0 = 0)
+            // ---- phase 0: hidden2pos backward (thread = row x 4 mid units) on values requested one step ago.  They are consumed
+            // BEFORE this step's loads are issued: a register whose load shares a scoreboard with younger loads waits for those too
+            // (the gradient gather showed 8 % long-scoreboard stalls although it had been in flight for a whole step).
+            float dr0 = dn0, dr1 = dn1;
+            if (pcol >= 0) {
+                dxy0 += g_abs.x; dxy1 += g_abs.y;
+                dr0 += dxy0 + g_rel.x; dr1 += dxy1 + g_rel.y;
+            }
+            // this step's loads: the tile's recurrent state of the previous step (4 float4 per thread = (h, c) of two units;
+            // t = 0: h_0 from its own buffer, c_0 = 0), the row's hidden2pos pre-activations and step input, and the next
+            // step's output gradients
             float4 hc[4];
+            float2 xv = make_float2(0.f, 0.f);
+            float u1p[4] = {0.f, 0.f, 0.f, 0.f};
             {
                 const size_t ns = Rpad >> 7;
 #pragma unroll
@@ -370,45 +381,39 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                     if (t > 0) hc[q] = __ldg(reinterpret_cast<const float4*>(acts + dec_acts_off(ns, t - 1, row0 + r, 2 * j)));
                     else if (q < 2) hc[q] = __ldg(reinterpret_cast<const float4*>(h0save + dec_h0_off(row0 + r, 4 * j)));
                 }
-            }
-            // ---- phase 0: hidden2pos backward (thread = row x 4 mid units)
-            {
-                float dr0 = dn0, dr1 = dn1;
-                float du[4] = {0.f, 0.f, 0.f, 0.f};
-                float w2a[4], w2b[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { w2a[q] = sW2[mq + 4 * q]; w2b[q] = sW2[M1 + mq + 4 * q]; }
                 if (pcol >= 0) {
-                    dxy0 += g_abs.x; dxy1 += g_abs.y;
-                    dr0 += dxy0 + g_rel.x; dr1 += dxy1 + g_rel.y;
+                    const float* us = u1save + dec_u1_off(ns, t, row0 + prow, mq);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) u1p[j] = us[j * 512];                 // m = mq + 4 j
+                    if (mq == 0)
+                        xv = t > 0 ? __ldg(reinterpret_cast<const float2*>(out_rel + ((size_t)(t - 1) * n_cols + pcol) * 2))
+                                   : __ldg(reinterpret_cast<const float2*>(last_dxdy + (size_t)pag * 2));
                     if (t > 0) {
                         const size_t o = ((size_t)(t - 1) * n_cols + pcol) * 2;
                         if (d_abs != nullptr) g_abs = __ldg(reinterpret_cast<const float2*>(d_abs + o));
                         if (d_rel != nullptr) g_rel = __ldg(reinterpret_cast<const float2*>(d_rel + o));
                     }
-                    const float* us = u1save + dec_u1_off(Rpad >> 7, t, row0 + prow, mq);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float up = us[j * 512];                                       // m = mq + 4 j
-                        float a = lrelu_(up, 0.01f);
-                        aw2a[j] = fmaf(dr0, a, aw2a[j]);
-                        aw2b[j] = fmaf(dr1, a, aw2b[j]);
-                        du[j] = (w2a[j] * dr0 + w2b[j] * dr1) * (up > 0.f ? 1.f : 0.01f);
-                        dbs[j] += du[j];
-                    }
-                    if (mq == 0) { ab2a += dr0; ab2b += dr1; }
                 }
+            }
+            float du[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pcol >= 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float w2a = sW2[mq + 4 * j], w2b = sW2[M1 + mq + 4 * j];
+                    const float up = u1p[j];
+                    const float a = lrelu_(up, 0.01f);
+                    aw2a[j] = fmaf(dr0, a, aw2a[j]);
+                    aw2b[j] = fmaf(dr1, a, aw2b[j]);
+                    du[j] = (w2a * dr0 + w2b * dr1) * (up > 0.f ? 1.f : 0.01f);
+                    dbs[j] += du[j];
+                }
+                if (mq == 0) { ab2a += dr0; ab2b += dr1; }
+            }
+            {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sDu[prow * LDU + mq + 4 * j] = du[j];
                 // step input dxdy_{t-1} and the constant 1 go to the pad columns of the h_{t-1} tile
-                if (mq == 0) {
-                    float2 xv = make_float2(0.f, 0.f);
-                    if (pcol >= 0) {
-                        xv = t > 0 ? __ldg(reinterpret_cast<const float2*>(out_rel + ((size_t)(t - 1) * n_cols + pcol) * 2))
-                                   : __ldg(reinterpret_cast<const float2*>(last_dxdy + (size_t)pag * 2));
-                    }
-                    st4(sHp + prow * LDH + H, make_float4(xv.x, xv.y, pcol >= 0 ? 1.f : 0.f, 0.f));
-                }
+                if (mq == 0) st4(sHp + prow * LDH + H, make_float4(xv.x, xv.y, pcol >= 0 ? 1.f : 0.f, 0.f));
                 // h_{t-1}, c_{t-1} -> shared memory (padding rows: zeros)
                 if (t > 0) {
 #pragma unroll
@@ -477,8 +482,12 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                         tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDU], ah[1], al[1]);
                         tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDU + 4], ah[3], al[3]);
                         const float* pb = sW1h + (k0 + t4) * LDH + n0 + g8;
-                        mma_3xtf32(acc[0], ah, al, pb[0], pb[4 * LDH]);
-                        mma_3xtf32(acc[1], ah, al, pb[8], pb[4 * LDH + 8]);
+                        uint32_t bh[4], bl[4];
+                        tf32_split(pb[0], bh[0], bl[0]); tf32_split(pb[4 * LDH], bh[1], bl[1]);
+                        tf32_split(pb[8], bh[2], bl[2]); tf32_split(pb[4 * LDH + 8], bh[3], bl[3]);
+                        mma_tf32_16x8x8(acc[0], ah, bh[0], bh[1]); mma_tf32_16x8x8(acc[1], ah, bh[2], bh[3]);
+                        mma_tf32_16x8x8(acc[0], al, bh[0], bh[1]); mma_tf32_16x8x8(acc[1], al, bh[2], bh[3]);
+                        mma_tf32_16x8x8(acc[0], ah, bl[0], bl[1]); mma_tf32_16x8x8(acc[1], ah, bl[2], bl[3]);
                     }
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
@@ -532,11 +541,15 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                         const float2 x1 = *reinterpret_cast<const float2*>(pa1 + k0);
                         const float2 y0 = *reinterpret_cast<const float2*>(pb0 + k0);
                         const float2 y1 = *reinterpret_cast<const float2*>(pb1 + k0);
-                        uint32_t ah[4], al[4];
+                        uint32_t ah[4], al[4], bh[4], bl[4];
                         tf32_split(x0.x, ah[0], al[0]); tf32_split(x1.x, ah[1], al[1]);
                         tf32_split(x0.y, ah[2], al[2]); tf32_split(x1.y, ah[3], al[3]);
-                        mma_3xtf32(acc[0], ah, al, y0.x, y0.y);
-                        mma_3xtf32(acc[1], ah, al, y1.x, y1.y);
+                        tf32_split(y0.x, bh[0], bl[0]); tf32_split(y0.y, bh[1], bl[1]);
+                        tf32_split(y1.x, bh[2], bl[2]); tf32_split(y1.y, bh[3], bl[3]);
+                        // product-major over the two accumulators (back-to-back MMAs on one accumulator wait for each other)
+                        mma_tf32_16x8x8(acc[0], ah, bh[0], bh[1]); mma_tf32_16x8x8(acc[1], ah, bh[2], bh[3]);
+                        mma_tf32_16x8x8(acc[0], al, bh[0], bh[1]); mma_tf32_16x8x8(acc[1], al, bh[2], bh[3]);
+                        mma_tf32_16x8x8(acc[0], ah, bl[0], bl[1]); mma_tf32_16x8x8(acc[1], ah, bl[2], bl[3]);
                     }
                     // every read of sDh for step t happened before the barrier above
 #pragma unroll
@@ -562,12 +575,19 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                         uint32_t ah[4], al[4];
                         tf32_split(x0.x, ah[0], al[0]); tf32_split(x0.y, ah[1], al[1]);
                         tf32_split(x1.x, ah[2], al[2]); tf32_split(x1.y, ah[3], al[3]);
-                        mma_3xtf32(wacc[0], ah, al, y0.x, y1.x);
-                        mma_3xtf32(wacc[1], ah, al, y0.y, y1.y);
-                        mma_3xtf32(wacc[2], ah, al, y0.z, y1.z);
-                        mma_3xtf32(wacc[3], ah, al, y0.w, y1.w);
-                        // (dWx | db) += dG^T (x0 x1 1): a fifth n-tile over the pad columns of the h_{t-1} tile
-                        mma_3xtf32(wacc[4], ah, al, pb[k0 * LDH + H - 3 * g8], pb[(k0 + 4) * LDH + H - 3 * g8]);
+                        // five n-tiles (the fifth: (dWx | db) += dG^T (x0 x1 1) over the pad columns of the h_{t-1} tile), MMAs
+                        // product-major over the five accumulators
+                        const float b0[5] = {y0.x, y0.y, y0.z, y0.w, pb[k0 * LDH + H - 3 * g8]};
+                        const float b1[5] = {y1.x, y1.y, y1.z, y1.w, pb[(k0 + 4) * LDH + H - 3 * g8]};
+                        uint32_t bh[5][2], bl[5][2];
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) { tf32_split(b0[j], bh[j][0], bl[j][0]); tf32_split(b1[j], bh[j][1], bl[j][1]); }
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) mma_tf32_16x8x8(wacc[j], ah, bh[j][0], bh[j][1]);
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) mma_tf32_16x8x8(wacc[j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) mma_tf32_16x8x8(wacc[j], ah, bl[j][0], bl[j][1]);
                     }
                 }
             }

@@ -217,9 +217,19 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
         const float* pH = staged ? sHh : h + (size_t)a * HD;
         const float* pdS = staged ? sdS : dS + (size_t)a * HD;
         const int ldh = staged ? LDHS : HD;
+        // the scene's attention matrix (phase 1b reads it by columns: n dependent strided global loads per thread were
+        // 9 % of the kernel's samples) -> shared memory, row stride n + 1; sDA1 is free until phase 2
+        const float* pAtt = att + poff;
+        int lda_att = n;
+        if (staged) {
+            for (int i = threadIdx.x; i < n * n; i += MGGAN_THREADS) sDA1[(i / n) * (n + 1) + i % n] = __ldg(att + poff + i);
+            pAtt = sDA1;
+            lda_att = n + 1;
+            __syncthreads();
+        }
         // ---- phase 1a: d sigma_ij = att_ij (dS_i . h_j - sum_j' att_ij' dS_i . h_j'), zero on the diagonal
         for (int il = warp; il < n; il += MGGAN_THREADS / 32) {
-            const float* arow = att + poff + (size_t)il * n;
+            const float* arow = pAtt + (size_t)il * lda_att;
             float* drow = dsig + poff + (size_t)il * n;
             const float* dsi = pdS + (size_t)il * ldh;
             float r = 0.f;
@@ -237,9 +247,10 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
         // ---- phase 1b: dh_j[k] = sum_i att_ij dS_i[k]   (thread = (j, k))
         for (int o = threadIdx.x; o < n * HD; o += MGGAN_THREADS) {
             const int jl = o / HD, k = o - jl * HD;
-            const float* ac = att + poff + jl;
+            const float* ac = pAtt + jl;
             float acc = 0.f;
-            for (int il = 0; il < n; ++il) acc = fmaf(__ldg(ac + (size_t)il * n), pdS[(size_t)il * ldh + k], acc);
+#pragma unroll 4
+            for (int il = 0; il < n; ++il) acc = fmaf(ac[(size_t)il * lda_att], pdS[(size_t)il * ldh + k], acc);
             dh[(size_t)(a + jl) * HD + k] = acc;
         }
         __syncthreads();                     // dsig complete (written by this CTA only); phase-1 buffers are free
@@ -291,12 +302,20 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
                     tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDA1 + 4], ah[3], al[3]);
                     const int ob = g8 * LDW2 + k0 + t4;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t bh0 = __float_as_uint(sW2[ob + 8 * j * LDW2]), bh1 = __float_as_uint(sW2[ob + 8 * j * LDW2 + 4]);
-                        const uint32_t bl0 = __float_as_uint(sW2l[ob + 8 * j * LDW2]), bl1 = __float_as_uint(sW2l[ob + 8 * j * LDW2 + 4]);
-                        mma_tf32_16x8x8(acc[j], ah, bh0, bh1);
-                        mma_tf32_16x8x8(acc[j], al, bh0, bh1);
-                        mma_tf32_16x8x8(acc[j], ah, bl0, bl1);
+                    for (int j0 = 0; j0 < 8; j0 += 4) {      // MMAs product-major over four accumulators at a time
+                        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int o = ob + 8 * (j0 + j) * LDW2;
+                            bh[j][0] = __float_as_uint(sW2[o]); bh[j][1] = __float_as_uint(sW2[o + 4]);
+                            bl[j][0] = __float_as_uint(sW2l[o]); bl[j][1] = __float_as_uint(sW2l[o + 4]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j0 + j], ah, bh[j][0], bh[j][1]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j0 + j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j0 + j], ah, bl[j][0], bl[j][1]);
                     }
                 }
                 // the thread holds rows m0 + g, m0 + g + 8 and columns 8 j + 2 t + {0, 1}
@@ -356,14 +375,18 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
                     tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDA2], ah[1], al[1]);
                     tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDA2 + 4], ah[3], al[3]);
                     const int ob = (k0 + t4) * LDW2 + g8;
+                    uint32_t bh[4][2], bl[4][2];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t bh0 = __float_as_uint(sW2[ob + 8 * j]), bh1 = __float_as_uint(sW2[ob + 4 * LDW2 + 8 * j]);
-                        const uint32_t bl0 = __float_as_uint(sW2l[ob + 8 * j]), bl1 = __float_as_uint(sW2l[ob + 4 * LDW2 + 8 * j]);
-                        mma_tf32_16x8x8(acc[j], ah, bh0, bh1);
-                        mma_tf32_16x8x8(acc[j], al, bh0, bh1);
-                        mma_tf32_16x8x8(acc[j], ah, bl0, bl1);
+                        bh[j][0] = __float_as_uint(sW2[ob + 8 * j]); bh[j][1] = __float_as_uint(sW2[ob + 4 * LDW2 + 8 * j]);
+                        bl[j][0] = __float_as_uint(sW2l[ob + 8 * j]); bl[j][1] = __float_as_uint(sW2l[ob + 4 * LDW2 + 8 * j]);
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j], ah, bh[j][0], bh[j][1]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j], ah, bl[j][0], bl[j][1]);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -386,8 +409,12 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
                     uint32_t ah[4], al[4];
                     tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8], ah[1], al[1]);
                     tf32_split(pa[4 * LDA2], ah[2], al[2]); tf32_split(pa[4 * LDA2 + 8], ah[3], al[3]);
-                    mma_3xtf32(wacc[0], ah, al, pb[0], pb[4 * LDA1]);
-                    mma_3xtf32(wacc[1], ah, al, pb[8], pb[4 * LDA1 + 8]);
+                    uint32_t bh[4], bl[4];
+                    tf32_split(pb[0], bh[0], bl[0]); tf32_split(pb[4 * LDA1], bh[1], bl[1]);
+                    tf32_split(pb[8], bh[2], bl[2]); tf32_split(pb[4 * LDA1 + 8], bh[3], bl[3]);
+                    mma_tf32_16x8x8(wacc[0], ah, bh[0], bh[1]); mma_tf32_16x8x8(wacc[1], ah, bh[2], bh[3]);
+                    mma_tf32_16x8x8(wacc[0], al, bh[0], bh[1]); mma_tf32_16x8x8(wacc[1], al, bh[2], bh[3]);
+                    mma_tf32_16x8x8(wacc[0], ah, bl[0], bl[1]); mma_tf32_16x8x8(wacc[1], ah, bl[2], bl[3]);
                 }
             }
             {
