@@ -1142,138 +1142,269 @@ scene_attn_fwd_kernel(const float* __restrict__ x2, int N, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// backward of pass C: d(out) -> attention-MLP weight grads, sparse dy2 (+ arg index), BN2 sums
+// backward of pass C: d(out) -> attention-MLP weight grads, sparse dy2 (+ arg index), BN2 sums.
+// One trip = 2 agents = 128 positions.  The per-position MLP (C -> 32 -> C) and its gradients are warp-level 3 x TF32
+// tensor-pipe products over the 128 rows (warp w = rows 16 w .. 16 w + 15), with the operands handed over through shared
+// memory; pooling, the channel softmax and the sparse output stay thread-per-position (threads 0 .. 127).  The FP32 form
+// (thread = position, the whole MLP and its 4 x 4 weight-gradient blocks in registers) needed 255 registers and 114 KB:
+// one CTA of 8 warps per SM, every latency exposed (12 % occupancy, 0.36 ms per launch of 16,384 crops).
+//   S0  pool -> V                                S1  Hid = lrelu(V Wa1^T + ba1),  S = Hid Wa2^T + ba2
+//   S2  softmax, dS (in place of S)              S3  dHid = (dS Wa2) lrelu'(Hid)
+//   S4  dWa2 += dS^T Hid, dWa1 += dHid^T V, bias gradients from all-ones B tiles (C fragments kept across trips)
+//   S5  dV = dHid Wa1 (in place of dS)           S6  dy2 / idx2 / BatchNorm-2 sums
+constexpr int AT_ROWS = 128;
+constexpr int AT_LDH = AH + 4;                    // 36: row stride of Hid / dHid and of the [.][32] weight planes
+template <int C> struct AtLd { static constexpr int V = C + 4; };     // row stride of V / dS and of the [.][C] weight planes
+
+// acc (16 rows x 8 NTL columns) += A (rows m0 .. m0 + 15 of a row-major fp32 tile, split on the fly) . B^T with B given as
+// pre-split planes stored [n][k] (row stride ldb): B fragment (k = t, n = g) = B[(8 j + g) ldb + k0 + t]
+template <int KSTEPS, int NTL>
+__device__ __forceinline__ void rows_mma(float (&acc)[NTL][4], const float* __restrict__ A, int lda, const float* __restrict__ Bh,
+                                         const float* __restrict__ Bl, int ldb, int g8, int t4) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        const float* pa = A + g8 * lda + 8 * ks + t4;
+        uint32_t ah[4], al[4], bh[NTL][2], bl[NTL][2];
+        tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * lda], ah[1], al[1]);
+        tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * lda + 4], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) {
+            const int o = (8 * j + g8) * ldb + 8 * ks + t4;
+            bh[j][0] = __float_as_uint(Bh[o]); bh[j][1] = __float_as_uint(Bh[o + 4]);
+            bl[j][0] = __float_as_uint(Bl[o]); bl[j][1] = __float_as_uint(Bl[o + 4]);
+        }
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) mma_tf32_16x8x8(acc[j], ah, bh[j][0], bh[j][1]);
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) mma_tf32_16x8x8(acc[j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) mma_tf32_16x8x8(acc[j], ah, bl[j][0], bl[j][1]);
+    }
+}
+
+// acc (16 x 8) += A^T B over the AT_ROWS rows of a trip: A (m, k = row) = X[row ldx + m0 + m] (rows m >= MROWS are zero),
+// B (k = row, n) = Y[row ldy + n0 + n]; ONES: B = 1 (column sums of X)
+template <int MROWS, bool ONES>
+__device__ __forceinline__ void cols_mma(float (&acc)[4], const float* __restrict__ X, int ldx, const float* __restrict__ Y,
+                                         int ldy, int g8, int t4) {
+#pragma unroll 4
+    for (int k0 = 0; k0 < AT_ROWS; k0 += 8) {
+        const float* pa = X + (k0 + t4) * ldx + g8;
+        uint32_t ah[4], al[4], bh[2], bl[2];
+        tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[4 * ldx], ah[2], al[2]);
+        if (MROWS > 8) { tf32_split(pa[8], ah[1], al[1]); tf32_split(pa[4 * ldx + 8], ah[3], al[3]); }
+        else { ah[1] = al[1] = ah[3] = al[3] = 0u; }
+        if (ONES) { bh[0] = bh[1] = 0x3F800000u; bl[0] = bl[1] = 0u; }
+        else {
+            const float* pb = Y + (k0 + t4) * ldy + g8;
+            tf32_split(pb[0], bh[0], bl[0]); tf32_split(pb[4 * ldy], bh[1], bl[1]);
+        }
+        mma_tf32_16x8x8(acc, ah, bh[0], bh[1]);
+        mma_tf32_16x8x8(acc, al, bh[0], bh[1]);
+        if (!ONES) mma_tf32_16x8x8(acc, ah, bl[0], bl[1]);
+    }
+}
+
 template <int C>
-__global__ void __launch_bounds__(MGGAN_THREADS)
+__global__ void __launch_bounds__(MGGAN_THREADS, 2)
 scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restrict__ ab2,
                       const float* __restrict__ mean_istd2, const float* __restrict__ Wa1,
                       const float* __restrict__ ba1, const float* __restrict__ Wa2, const float* __restrict__ ba2,
                       const float* __restrict__ dout, float* __restrict__ dWa1, float* __restrict__ dba1,
                       float* __restrict__ dWa2, float* __restrict__ dba2, float* __restrict__ dy2,
                       unsigned char* __restrict__ idx2, double* __restrict__ sums2) {
-    constexpr int LDC = C + 4, LDA = AH + 4;
-    constexpr int NBLK = 4 * C;                   // 2 * (C/4) * (AH/4) weight-gradient blocks
-    constexpr int RG = MGGAN_THREADS / NBLK;      // row groups
-    constexpr int RPG = MGGAN_THREADS / RG;       // rows per group
+    constexpr int LDV = AtLd<C>::V, LDH = AT_LDH, NTC = C / 8;
     extern __shared__ __align__(16) float smem[];
-    AttnW<C> w = stage_attn_weights<C>(smem, Wa1, ba1, Wa2, ba2, ab2);
-    float* sDS = w.sAB + 2 * C;                   // [256][LDC]
-    float* sV = sDS + MGGAN_THREADS * LDC;        // [256][LDC]
-    float* sHid = sV + MGGAN_THREADS * LDC;       // [256][LDA]
-    float* sDH = sHid + MGGAN_THREADS * LDA;      // [256][LDA]
-    float* sMI = sDH + MGGAN_THREADS * LDA;       // [2C]
-    float* sred = sMI + 2 * C;                    // [8][2C]
-    if (threadIdx.x < 2 * C) sMI[threadIdx.x] = __ldg(mean_istd2 + threadIdx.x);
-    __syncthreads();
-    const int slot = threadIdx.x >> 6, pos = threadIdx.x & 63;
-    const int blk = threadIdx.x % NBLK, rg = threadIdx.x / NBLK;
-    float wacc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) wacc[i][j] = 0.f;
-    const int bcol = threadIdx.x & 63, bpart = threadIdx.x >> 6;
-    float bacc = 0.f;            // dba2[bcol] for bcol < C ; dba1[bcol - C] for C <= bcol < C + AH (rows of quarter bpart)
+    // pre-split weight planes, each stored [n][k] for the product that uses it as B
+    float* sW1h = smem;                            // [AH][LDV]   Wa1   (Hid = V Wa1^T)
+    float* sW1l = sW1h + AH * LDV;
+    float* sW2h = sW1l + AH * LDV;                 // [C][LDH]    Wa2   (S = Hid Wa2^T)
+    float* sW2l = sW2h + C * LDH;
+    float* sW2Th = sW2l + C * LDH;                 // [AH][LDV]   Wa2^T (dHid = dS Wa2)
+    float* sW2Tl = sW2Th + AH * LDV;
+    float* sW1Th = sW2Tl + AH * LDV;               // [C][LDH]    Wa1^T (dV = dHid Wa1)
+    float* sW1Tl = sW1Th + C * LDH;
+    float* sb1 = sW1Tl + C * LDH;                  // [AH]
+    float* sb2 = sb1 + AH;                         // [C]
+    float* sAB = sb2 + C;                          // [2C] BatchNorm-2 as an affine map
+    float* sMI = sAB + 2 * C;                      // [2C] mean, 1 / std
+    float* sV = sMI + 2 * C;                       // [AT_ROWS][LDV]
+    float* sDS = sV + AT_ROWS * LDV;               // [AT_ROWS][LDV]  S -> dS -> dV
+    float* sHid = sDS + AT_ROWS * LDV;             // [AT_ROWS][LDH]
+    float* sDH = sHid + AT_ROWS * LDH;             // [AT_ROWS][LDH]
+    float* sred = sDH + AT_ROWS * LDH;             // [8][2C]
+    for (int i = threadIdx.x; i < AH * C; i += MGGAN_THREADS) {
+        const int u = i / C, c = i - u * C;        // Wa1[u][c]
+        uint32_t hi, lo;
+        tf32_split(__ldg(Wa1 + i), hi, lo);
+        sW1h[u * LDV + c] = __uint_as_float(hi); sW1l[u * LDV + c] = __uint_as_float(lo);
+        sW1Th[c * LDH + u] = __uint_as_float(hi); sW1Tl[c * LDH + u] = __uint_as_float(lo);
+        const int c2 = i / AH, u2 = i - c2 * AH;   // Wa2[c2][u2]
+        tf32_split(__ldg(Wa2 + i), hi, lo);
+        sW2h[c2 * LDH + u2] = __uint_as_float(hi); sW2l[c2 * LDH + u2] = __uint_as_float(lo);
+        sW2Th[u2 * LDV + c2] = __uint_as_float(hi); sW2Tl[u2 * LDV + c2] = __uint_as_float(lo);
+    }
+    if (threadIdx.x < AH) sb1[threadIdx.x] = __ldg(ba1 + threadIdx.x);
+    if (threadIdx.x < C) sb2[threadIdx.x] = __ldg(ba2 + threadIdx.x);
+    if (threadIdx.x < 2 * C) { sAB[threadIdx.x] = __ldg(ab2 + threadIdx.x); sMI[threadIdx.x] = __ldg(mean_istd2 + threadIdx.x); }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g8 = lane >> 2, t4 = lane & 3;
+    const int m0 = warp * 16;
+    const int slot = threadIdx.x >> 6, pos = threadIdx.x & 63;       // threads 0 .. 127: (agent of the trip, position)
+    // weight-gradient tiles of the warp (S4): warps 0-3: dWa2 n-tile `warp` (+ warp 0: dba2); warps 4 ..: dWa1 tile
+    // (m-tile (warp - 4) / NTC, n-tile (warp - 4) % NTC) (+ n-tile 0: dba1 of that m-tile)
+    const int wt = warp - 4, wm = wt / NTC, wn = wt - wm * NTC;
+    const bool has_w1 = warp >= 4 && wt < 2 * NTC;
+    float wacc[4] = {0.f, 0.f, 0.f, 0.f}, bacc[4] = {0.f, 0.f, 0.f, 0.f};
     float st[2 * C];
 #pragma unroll
     for (int c = 0; c < 2 * C; ++c) st[c] = 0.f;
+    __syncthreads();
 
-    for (int n0 = blockIdx.x * 4; n0 < N; n0 += gridDim.x * 4) {
+    for (int n0 = blockIdx.x * 2; n0 < N; n0 += gridDim.x * 2) {
         const int n = n0 + slot;
-        float v[C], hp[AH], att[C], e[C], ds[C], dv[C]; int arg[C];
-        float dhid[AH];
-        __syncthreads();
-        if (threadIdx.x == 0) {               // the next trip's four agents -> L2 (8 warps per SM: every global latency is exposed)
-            const int nn = n0 + gridDim.x * 4;
-            if (nn < N) prefetch_l2_bulk(x2 + (size_t)nn * C * P1SQ, (uint32_t)min(4, N - nn) * C * P1SQ * 4);
+        const bool live = threadIdx.x < AT_ROWS && n < N;
+        float e[C], dvd[C], gout = 0.f;
+        int arg[C];
+        // ---- S0: pooled values of the position
+        if (threadIdx.x < AT_ROWS) {
+            float v[C];
+            if (live) {
+                pool_block2<C, true>(x2 + (size_t)n * C * P1SQ, sAB, pos, v, arg, e);
+                gout = __ldg(dout + (size_t)n * P2SQ + pos);
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) { v[c] = 0.f; e[c] = 0.f; arg[c] = 0; }
+            }
+#pragma unroll
+            for (int c = 0; c < C; c += 4) st4(sV + threadIdx.x * LDV + c, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
         }
-        if (n < N) {
-            pool_block2<C, true>(x2 + (size_t)n * C * P1SQ, w.sAB, pos, v, arg, e);
-            attn_mlp<C>(w, v, hp, att);
-            const float g = __ldg(dout + (size_t)n * P2SQ + pos);
+        __syncthreads();
+        // ---- S1: Hid = lrelu(V Wa1^T + ba1) -> S = Hid Wa2^T + ba2 (the warp's own 16 rows: warp-level hand-over)
+        {
+            float acc[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float b0 = sb1[8 * j + 2 * t4], b1 = sb1[8 * j + 2 * t4 + 1];
+                acc[j][0] = b0; acc[j][1] = b1; acc[j][2] = b0; acc[j][3] = b1;
+            }
+            rows_mma<NTC, 4>(acc, sV + m0 * LDV, LDV, sW1h, sW1l, LDV, g8, t4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float* o = sHid + (m0 + g8) * LDH + 8 * j + 2 * t4;
+                *reinterpret_cast<float2*>(o) = make_float2(lrelu_(acc[j][0], 0.01f), lrelu_(acc[j][1], 0.01f));
+                *reinterpret_cast<float2*>(o + 8 * LDH) = make_float2(lrelu_(acc[j][2], 0.01f), lrelu_(acc[j][3], 0.01f));
+            }
+            __syncwarp();
+            float sc[NTC][4];
+#pragma unroll
+            for (int j = 0; j < NTC; ++j) {
+                const float b0 = sb2[8 * j + 2 * t4], b1 = sb2[8 * j + 2 * t4 + 1];
+                sc[j][0] = b0; sc[j][1] = b1; sc[j][2] = b0; sc[j][3] = b1;
+            }
+            rows_mma<4, NTC>(sc, sHid + m0 * LDH, LDH, sW2h, sW2l, LDH, g8, t4);
+#pragma unroll
+            for (int j = 0; j < NTC; ++j) {
+                float* o = sDS + (m0 + g8) * LDV + 8 * j + 2 * t4;
+                *reinterpret_cast<float2*>(o) = make_float2(sc[j][0], sc[j][1]);
+                *reinterpret_cast<float2*>(o + 8 * LDV) = make_float2(sc[j][2], sc[j][3]);
+            }
+        }
+        __syncthreads();
+        // ---- S2: channel softmax and its backward: dS in place of S; the direct part of dV stays in registers
+        if (threadIdx.x < AT_ROWS) {
+            float att[C], v[C];
+            float mx = -3.4e38f;
+#pragma unroll
+            for (int c = 0; c < C; c += 4) {
+                const float4 q = ld4(sDS + threadIdx.x * LDV + c), w = ld4(sV + threadIdx.x * LDV + c);
+                att[c] = q.x; att[c + 1] = q.y; att[c + 2] = q.z; att[c + 3] = q.w;
+                v[c] = w.x; v[c + 1] = w.y; v[c + 2] = w.z; v[c + 3] = w.w;
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) mx = fmaxf(mx, att[c]);
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) { att[c] = __expf(att[c] - mx); sum += att[c]; }
+            const float inv = 1.f / sum;
             float dot = 0.f;
 #pragma unroll
-            for (int c = 0; c < C; ++c) dot = fmaf(att[c], g * v[c], dot);
+            for (int c = 0; c < C; ++c) { att[c] *= inv; dot = fmaf(att[c], gout * v[c], dot); }
+            float ds[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) { ds[c] = att[c] * (g * v[c] - dot); dv[c] = g * att[c]; }
+            for (int c = 0; c < C; ++c) { ds[c] = live ? att[c] * (gout * v[c] - dot) : 0.f; dvd[c] = gout * att[c]; }
 #pragma unroll
-            for (int k = 0; k < AH; ++k) dhid[k] = 0.f;
+            for (int c = 0; c < C; c += 4) st4(sDS + threadIdx.x * LDV + c, make_float4(ds[c], ds[c + 1], ds[c + 2], ds[c + 3]));
+        }
+        __syncthreads();
+        // ---- S3: dHid = (dS Wa2) lrelu'(Hid)
+        {
+            float acc[4][4];
 #pragma unroll
-            for (int c = 0; c < C; ++c)
+            for (int j = 0; j < 4; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+            rows_mma<NTC, 4>(acc, sDS + m0 * LDV, LDV, sW2Th, sW2Tl, LDV, g8, t4);
 #pragma unroll
-                for (int k = 0; k < AH; k += 4) {
-                    float4 q = ld4(w.sWa2 + c * AH + k);
-                    dhid[k] = fmaf(q.x, ds[c], dhid[k]); dhid[k + 1] = fmaf(q.y, ds[c], dhid[k + 1]);
-                    dhid[k + 2] = fmaf(q.z, ds[c], dhid[k + 2]); dhid[k + 3] = fmaf(q.w, ds[c], dhid[k + 3]);
-                }
-#pragma unroll
-            for (int k = 0; k < AH; ++k) {
-                dhid[k] *= hp[k] > 0.f ? 1.f : 0.01f;
-#pragma unroll
-                for (int c = 0; c < C; c += 4) {
-                    float4 q = ld4(w.sWa1 + k * C + c);
-                    dv[c] = fmaf(q.x, dhid[k], dv[c]); dv[c + 1] = fmaf(q.y, dhid[k], dv[c + 1]);
-                    dv[c + 2] = fmaf(q.z, dhid[k], dv[c + 2]); dv[c + 3] = fmaf(q.w, dhid[k], dv[c + 3]);
-                }
+            for (int j = 0; j < 4; ++j) {
+                const int o = (m0 + g8) * LDH + 8 * j + 2 * t4;
+                const float2 ha = *reinterpret_cast<const float2*>(sHid + o), hb = *reinterpret_cast<const float2*>(sHid + o + 8 * LDH);
+                *reinterpret_cast<float2*>(sDH + o) = make_float2(acc[j][0] * (ha.x > 0.f ? 1.f : 0.01f), acc[j][1] * (ha.y > 0.f ? 1.f : 0.01f));
+                *reinterpret_cast<float2*>(sDH + o + 8 * LDH) = make_float2(acc[j][2] * (hb.x > 0.f ? 1.f : 0.01f), acc[j][3] * (hb.y > 0.f ? 1.f : 0.01f));
             }
-            // sparse gradient at the pooled arg position + BatchNorm sums
+        }
+        __syncthreads();
+        // ---- S4: weight gradients over the trip's rows
+        if (warp < 4) {
+            cols_mma<C, false>(wacc, sDS, LDV, sHid + 8 * warp, LDH, g8, t4);              // dWa2[c][8 warp + .]
+            if (warp == 0) cols_mma<C, true>(bacc, sDS, LDV, nullptr, 0, g8, t4);           // dba2
+        } else if (has_w1) {
+            cols_mma<16, false>(wacc, sDH + 16 * wm, LDH, sV + 8 * wn, LDV, g8, t4);        // dWa1[16 wm + .][8 wn + .]
+            if (wn == 0) cols_mma<16, true>(bacc, sDH + 16 * wm, LDH, nullptr, 0, g8, t4);  // dba1[16 wm + .]
+        }
+        __syncthreads();
+        // ---- S5: dV (through the MLP) = dHid Wa1, in place of dS
+        {
+            float acc[NTC][4];
+#pragma unroll
+            for (int j = 0; j < NTC; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+            rows_mma<4, NTC>(acc, sDH + m0 * LDH, LDH, sW1Th, sW1Tl, LDH, g8, t4);
+#pragma unroll
+            for (int j = 0; j < NTC; ++j) {
+                float* o = sDS + (m0 + g8) * LDV + 8 * j + 2 * t4;
+                *reinterpret_cast<float2*>(o) = make_float2(acc[j][0], acc[j][1]);
+                *reinterpret_cast<float2*>(o + 8 * LDV) = make_float2(acc[j][2], acc[j][3]);
+            }
+        }
+        __syncthreads();
+        // ---- S6: sparse gradient at the pooled arg position + BatchNorm sums
+        if (live) {
             float* dyo = dy2 + (size_t)n * C * P2SQ + pos;
             unsigned char* ixo = idx2 + (size_t)n * C * P2SQ + pos;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                float d = (arg[c] & 4) ? dv[c] : 0.f;
+                const float dv = dvd[c] + sDS[threadIdx.x * LDV + c];
+                const float d = (arg[c] & 4) ? dv : 0.f;
                 dyo[c * P2SQ] = d;
                 ixo[c * P2SQ] = (unsigned char)(arg[c] & 3);
-                float xh = (e[c] - sMI[c]) * sMI[C + c];
+                const float xh = (e[c] - sMI[c]) * sMI[C + c];
                 st[c] += d;
                 st[C + c] = fmaf(d, xh, st[C + c]);
             }
-        } else {
-#pragma unroll
-            for (int c = 0; c < C; ++c) { ds[c] = 0.f; v[c] = 0.f; }
-#pragma unroll
-            for (int k = 0; k < AH; ++k) { dhid[k] = 0.f; hp[k] = 0.f; }
-        }
-#pragma unroll
-        for (int c = 0; c < C; c += 4) {
-            st4(sDS + threadIdx.x * LDC + c, make_float4(ds[c], ds[c + 1], ds[c + 2], ds[c + 3]));
-            st4(sV + threadIdx.x * LDC + c, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
-        }
-#pragma unroll
-        for (int k = 0; k < AH; k += 4) {
-            st4(sHid + threadIdx.x * LDA + k, make_float4(lrelu_(hp[k], 0.01f), lrelu_(hp[k + 1], 0.01f),
-                                                          lrelu_(hp[k + 2], 0.01f), lrelu_(hp[k + 3], 0.01f)));
-            st4(sDH + threadIdx.x * LDA + k, make_float4(dhid[k], dhid[k + 1], dhid[k + 2], dhid[k + 3]));
-        }
-        __syncthreads();
-        if (blk < NBLK / 2) {      // dWa2[c][k] += sum_r ds[r][c] hid[r][k]
-            int oq = blk % (C / 4), kq = blk / (C / 4);
-            tile_wgrad<RPG>(wacc, sDS + rg * RPG * LDC, LDC, oq * 4, sHid + rg * RPG * LDA, LDA, kq * 4);
-        } else {                   // dWa1[k][c] += sum_r dhid[r][k] v[r][c]
-            int b2 = blk - NBLK / 2;
-            int oq = b2 % (AH / 4), kq = b2 / (AH / 4);
-            tile_wgrad<RPG>(wacc, sDH + rg * RPG * LDA, LDA, oq * 4, sV + rg * RPG * LDC, LDC, kq * 4);
-        }
-        // bias gradients: column bcol over the 64 rows of quarter bpart (a 256-row chain in C + AH threads kept the other
-        // warps at the next barrier: 17 % of the kernel's stall samples)
-        if (bcol < C) {
-#pragma unroll 8
-            for (int r = bpart * 64; r < bpart * 64 + 64; ++r) bacc += sDS[r * LDC + bcol];
-        } else if (bcol < C + AH) {
-#pragma unroll 8
-            for (int r = bpart * 64; r < bpart * 64 + 64; ++r) bacc += sDH[r * LDA + bcol - C];
         }
     }
-    if (blk < NBLK / 2) {
-        int oq = blk % (C / 4), kq = blk / (C / 4);
-        atomic_block44(dWa2, AH, oq * 4, kq * 4, wacc);
-    } else {
-        int b2 = blk - NBLK / 2;
-        int oq = b2 % (AH / 4), kq = b2 / (AH / 4);
-        atomic_block44(dWa1, C, oq * 4, kq * 4, wacc);
+    // C fragments: c0, c1 -> row g, columns 2t, 2t + 1; c2, c3 -> row g + 8
+    if (warp < 4) {
+        float* dst = dWa2 + (size_t)g8 * AH + 8 * warp + 2 * t4;
+        atomicAdd(dst, wacc[0]); atomicAdd(dst + 1, wacc[1]);
+        if (C > 8) { atomicAdd(dst + 8 * AH, wacc[2]); atomicAdd(dst + 8 * AH + 1, wacc[3]); }
+        if (warp == 0 && t4 == 0) {
+            atomicAdd(dba2 + g8, bacc[0]);
+            if (C > 8) atomicAdd(dba2 + g8 + 8, bacc[2]);
+        }
+    } else if (has_w1) {
+        float* dst = dWa1 + (size_t)(16 * wm + g8) * C + 8 * wn + 2 * t4;
+        atomicAdd(dst, wacc[0]); atomicAdd(dst + 1, wacc[1]);
+        atomicAdd(dst + 8 * C, wacc[2]); atomicAdd(dst + 8 * C + 1, wacc[3]);
+        if (wn == 0 && t4 == 0) { atomicAdd(dba1 + 16 * wm + g8, bacc[0]); atomicAdd(dba1 + 16 * wm + g8 + 8, bacc[2]); }
     }
-    if (bcol < C) atomicAdd(dba2 + bcol, bacc);
-    else if (bcol < C + AH) atomicAdd(dba1 + bcol - C, bacc);
     block_reduce_to_global<2 * C>(st, sums2, sred);
 }
 
@@ -1291,7 +1422,7 @@ template <int C>
 size_t attn_fwd_smem() { return sizeof(float) * attn_w_floats<C>(); }
 template <int C>
 size_t attn_bwd_smem() {
-    return sizeof(float) * (attn_w_floats<C>() + 2 * MGGAN_THREADS * (C + 4) + 2 * MGGAN_THREADS * (AH + 4) + 2 * C + 8 * 2 * C);
+    return sizeof(float) * (4 * AH * AtLd<C>::V + 4 * C * AT_LDH + AH + C + 4 * C + 2 * AT_ROWS * AtLd<C>::V + 2 * AT_ROWS * AT_LDH + 8 * 2 * C);
 }
 
 int agent_grid(int N, int per_sm) {
@@ -1338,7 +1469,7 @@ int attn_bwd(const float* x2, int N, const float* ab2, const float* mi2, const f
              unsigned char* idx2, double* sums2, cudaStream_t s) {
     size_t sm = attn_bwd_smem<C>();
     cudaFuncSetAttribute(scene_attn_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    int g = (N + 3) / 4;
+    int g = (N + 1) / 2;
     int cap = sm_count() * 2;
     scene_attn_bwd_kernel<C><<<g < cap ? g : cap, MGGAN_THREADS, sm, s>>>(x2, N, ab2, mi2, Wa1, ba1, Wa2, ba2, dout, dWa1,
                                                                           dba1, dWa2, dba2, dy2, idx2, sums2);
