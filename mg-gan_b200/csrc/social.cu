@@ -66,22 +66,37 @@ __device__ __forceinline__ void stage_pair_weights(float* sW1, float* sW2, float
     for (int i = threadIdx.x; i < F2; i += blockDim.x) sb2[i] = __ldg(b2 + i);
 }
 
+// Forward.  Per scene: (1) sigma for the n^2 ordered pairs in tiles of PT pairs (pair p = i n + j, so a tile is a
+// contiguous piece of the scene's attention matrix): features + layer 1 thread-per-(pair, half), layer 2 as a warp-level
+// 3 x TF32 tensor-pipe product (warp = 16 pairs x 64 units, W2 pre-split), sigma = relu(S) . u_j + s_j reduced over the four
+// lanes that share a row; (2) per agent (warp): softmax over its row and S_i = sum_j att_ij h_j.
+// (The lane-per-pair FP32 form spent 2,048 FMAs and 512 LDS.128 per pair-lane on layer 2: 0.12 ms per launch.)
 template <int HD>
-__global__ void __launch_bounds__(MGGAN_THREADS)
+__global__ void __launch_bounds__(MGGAN_THREADS, 2)
 social_fwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, const float* __restrict__ Us,
                   const int* __restrict__ scene_off, const int* __restrict__ pair_off, int n_scenes,
                   const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                   const float* __restrict__ b2, float* __restrict__ S, float* __restrict__ att) {
     constexpr int LDHS = HD + 1;
     extern __shared__ __align__(16) float smem[];
-    float* sW2 = smem;                       // [F2][LDW2]
-    float* sW1 = sW2 + F2 * LDW2;            // [F1][4]
+    float* sW2 = smem;                       // [F2][LDW2]  TF32 hi plane of W2
+    float* sW2l = sW2 + F2 * LDW2;           // [F2][LDW2]  lo plane
+    float* sW1 = sW2l + F2 * LDW2;           // [F1][4]
     float* sb2 = sW1 + F1 * 4;               // [F2]
     float* sX = sb2 + F2;                    // [NMAX][4]
     float* sU = sX + NMAX * 4;               // [NMAX][LDU]
-    float* sHh = sU + NMAX * LDU;            // [NMAX][LDHS]
+    float* sHh = sU + ((NMAX * LDU + 3) & ~3);   // [NMAX][LDHS]
+    float* sA1 = sHh + ((NMAX * LDHS + 3) & ~3); // [PT][LDA1]
     stage_pair_weights(sW1, sW2, sb2, W1, b1, W2, b2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    for (int i = threadIdx.x; i < F2 * LDW2; i += MGGAN_THREADS) {
+        uint32_t hi, lo;
+        tf32_split(sW2[i], hi, lo);
+        sW2[i] = __uint_as_float(hi);
+        sW2l[i] = __uint_as_float(lo);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g8 = lane >> 2, t4 = lane & 3;
+    const int m0 = warp * 16;
 
     for (int sc = blockIdx.x; sc < n_scenes; sc += gridDim.x) {
         const int a = scene_off[sc], n = scene_off[sc + 1] - a;
@@ -103,27 +118,89 @@ social_fwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
         const float* pH = staged ? sHh : h + (size_t)a * HD;
         const int ldh = staged ? LDHS : HD;
         const size_t poff = (size_t)pair_off[sc];
-        for (int il = warp; il < n; il += MGGAN_THREADS / 32) {
-            const float4 xi = ld4(pX + 4 * il);
-            float* arow = att + poff + (size_t)il * n;
-            float mx = -INFINITY;
-            for (int jl = lane; jl < n; jl += 32) {
-                float sigma = -1000.f;
-                if (jl != il) {
-                    float f1, f2, f3, a1[F1];
-                    pair_features(xi, ld4(pX + 4 * jl), f1, f2, f3);
-                    pair_layer1(sW1, f1, f2, f3, a1);
-                    const float* uj = pU + (size_t)jl * LDU;
-                    sigma = uj[F2];
-#pragma unroll 4
-                    for (int c = 0; c < F2; ++c) {
-                        float s = pair_layer2_unit(sW2, sb2, c, a1);
-                        sigma = fmaf(fmaxf(s, 0.f), uj[c], sigma);
+        // ---- (1) sigma of every ordered pair, PT pairs at a time; every stage of a tile is local to the warp's 16 pairs
+        const int npairs = n * n;
+        for (int p0 = 0; p0 < npairs; p0 += PT) {
+            {   // features + layer 1: thread = (pair, half of the 32 units)
+                const int pl = threadIdx.x >> 1, half = threadIdx.x & 1;
+                const int p = p0 + pl;
+                float f1 = 0.f, f2 = 0.f, f3 = 0.f;
+                if (p < npairs) {
+                    const int il = p / n, jl = p - il * n;
+                    pair_features(ld4(pX + 4 * il), ld4(pX + 4 * jl), f1, f2, f3);
+                }
+                float* arow = sA1 + pl * LDA1 + half * (F1 / 2);
+#pragma unroll
+                for (int k = 0; k < F1 / 2; k += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 w = ld4(sW1 + 4 * (half * (F1 / 2) + k + q));
+                        v[q] = fmaxf(fmaf(w.x, f1, fmaf(w.y, f2, fmaf(w.z, f3, w.w))), 0.f);
+                    }
+                    st4(arow + k, make_float4(v[0], v[1], v[2], v[3]));
+                }
+            }
+            __syncwarp();
+            {   // S = A1 W2^T + b2 (warp = pairs m0 .. m0 + 15), then sigma = relu(S) . u_j + s_j
+                float acc[8][4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float ba = sb2[8 * j + 2 * t4], bb = sb2[8 * j + 2 * t4 + 1];
+                    acc[j][0] = ba; acc[j][1] = bb; acc[j][2] = ba; acc[j][3] = bb;
+                }
+#pragma unroll
+                for (int k0 = 0; k0 < F1; k0 += 8) {
+                    const float* pa = sA1 + (m0 + g8) * LDA1 + k0 + t4;
+                    uint32_t ah[4], al[4];
+                    tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDA1], ah[1], al[1]);
+                    tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDA1 + 4], ah[3], al[3]);
+                    const int ob = g8 * LDW2 + k0 + t4;
+#pragma unroll
+                    for (int j0 = 0; j0 < 8; j0 += 4) {
+                        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int o = ob + 8 * (j0 + j) * LDW2;
+                            bh[j][0] = __float_as_uint(sW2[o]); bh[j][1] = __float_as_uint(sW2[o + 4]);
+                            bl[j][0] = __float_as_uint(sW2l[o]); bl[j][1] = __float_as_uint(sW2l[o + 4]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j0 + j], ah, bh[j][0], bh[j][1]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j0 + j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j0 + j], ah, bl[j][0], bl[j][1]);
                     }
                 }
-                arow[jl] = sigma;
-                mx = fmaxf(mx, sigma);
+                // rows m0 + g (c0, c1) and m0 + g + 8 (c2, c3), columns 8 j + 2 t + {0, 1}
+                const int pa_ = p0 + m0 + g8, pb_ = pa_ + 8;
+                const int ia = pa_ < npairs ? pa_ / n : 0, ja = pa_ < npairs ? pa_ - ia * n : 0;
+                const int ib = pb_ < npairs ? pb_ / n : 0, jb = pb_ < npairs ? pb_ - ib * n : 0;
+                const float* ua = pU + (size_t)ja * LDU;
+                const float* ub = pU + (size_t)jb * LDU;
+                float sa = 0.f, sb = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = 8 * j + 2 * t4;
+                    sa = fmaf(fmaxf(acc[j][0], 0.f), ua[c], fmaf(fmaxf(acc[j][1], 0.f), ua[c + 1], sa));
+                    sb = fmaf(fmaxf(acc[j][2], 0.f), ub[c], fmaf(fmaxf(acc[j][3], 0.f), ub[c + 1], sb));
+                }
+                sa += __shfl_xor_sync(0xffffffffu, sa, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+                sa += __shfl_xor_sync(0xffffffffu, sa, 2); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+                if (t4 == 0) {
+                    if (pa_ < npairs) att[poff + pa_] = ia == ja ? -1000.f : sa + ua[F2];
+                    if (pb_ < npairs) att[poff + pb_] = ib == jb ? -1000.f : sb + ub[F2];
+                }
             }
+            __syncwarp();                    // the warp's rows of sA1 are rewritten by the next tile's layer 1
+        }
+        __syncthreads();                     // sigma of the whole scene is in `att` (written by this CTA only)
+        // ---- (2) softmax over each agent's row and the weighted sum of the neighbours' hidden states
+        for (int il = warp; il < n; il += MGGAN_THREADS / 32) {
+            float* arow = att + poff + (size_t)il * n;
+            float mx = -INFINITY;
+            for (int jl = lane; jl < n; jl += 32) mx = fmaxf(mx, arow[jl]);
             mx = warp_max(mx);
             float sum = 0.f;
             for (int jl = lane; jl < n; jl += 32) {
@@ -460,7 +537,7 @@ social_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ h, con
 }
 
 template <int HD>
-size_t soc_fwd_smem() { return sizeof(float) * (F2 * LDW2 + F1 * 4 + F2 + NMAX * 4 + NMAX * LDU + NMAX * (HD + 1)); }
+size_t soc_fwd_smem() { return sizeof(float) * (2 * F2 * LDW2 + F1 * 4 + F2 + NMAX * 4 + ((NMAX * LDU + 3) & ~3) + ((NMAX * (HD + 1) + 3) & ~3) + PT * LDA1); }
 template <int HD>
 size_t soc_bwd_smem() {
     static_assert(2 * NMAX * (HD + 1) <= PT * LDA1 + PT * LDA2, "phase-1 buffers alias the pair tiles");
@@ -484,7 +561,7 @@ int launch_fwd(const float* x4, const float* h, const float* Us, const int* so, 
                const float* b1, const float* W2, const float* b2, float* S, float* att, cudaStream_t st) {
     size_t sm = soc_fwd_smem<HD>();
     cudaFuncSetAttribute(social_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    int grid = ns < sm_count() * 4 ? ns : sm_count() * 4;
+    int grid = ns < sm_count() * 2 ? ns : sm_count() * 2;
     social_fwd_kernel<HD><<<grid, MGGAN_THREADS, sm, st>>>(x4, h, Us, so, po, ns, W1, b1, W2, b2, S, att);
     return mggan_check_launch("social_attn_fwd");
 }
