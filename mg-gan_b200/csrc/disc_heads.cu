@@ -71,6 +71,48 @@ __device__ __forceinline__ void stage_tile(float* sA, float* sPe, const float* _
     }
 }
 
+// Backward tiling: a tile holds ALL k samples of ROWS / k consecutive agents (tile row r = a k + s -> global row s n + agent),
+// so that d base[agent] = sum_s dz[s, agent] is a sum over rows of the same tile: round 1 added every (row, column) of dz to
+// d_base with its own atomicAdd (63 M atomics per generator step at k = 20, n = 16,384).
+struct RowMap {
+    int k, n, apt;                 // apt = agents per tile
+    long long agent0;              // first agent of the tile
+    __device__ __forceinline__ bool map(int r, long long& row, int& ag, int& smp) const {
+        const int a = r / k;
+        smp = r - a * k;
+        ag = (int)(agent0 + a);
+        row = (long long)smp * n + ag;
+        return a < apt && ag < n;
+    }
+};
+
+template <int TOD, bool HASG>
+__device__ __forceinline__ void stage_tile_grouped(float* sA, float* sPe, const float* __restrict__ pe,
+                                                   const float* __restrict__ base, const float* __restrict__ soc0,
+                                                   const RowMap& rm) {
+    using C = Cfg<TOD, HASG>;
+    constexpr int Q = C::NZ / 4;
+    for (int idx = threadIdx.x; idx < ROWS * Q; idx += MGGAN_THREADS) {
+        int r = idx / Q, c = (idx - r * Q) * 4;
+        long long row; int ag, smp;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rm.map(r, row, ag, smp)) {
+            v = __ldg(reinterpret_cast<const float4*>(base + (size_t)ag * C::NZ + c));
+            if (smp == 0) {
+                float4 q = __ldg(reinterpret_cast<const float4*>(soc0 + (size_t)ag * C::NZ + c));
+                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            }
+        }
+        st4(sA + r * C::LDA + c, v);
+    }
+    for (int idx = threadIdx.x; idx < ROWS * (KP / 4); idx += MGGAN_THREADS) {
+        int r = idx / (KP / 4), c = (idx - r * (KP / 4)) * 4;
+        long long row; int ag, smp;
+        float4 v = rm.map(r, row, ag, smp) ? __ldg(reinterpret_cast<const float4*>(pe + (size_t)row * KP + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        st4(sPe + r * LDK + c, v);
+    }
+}
+
 template <int TOD, bool HASG>
 __global__ void __launch_bounds__(MGGAN_THREADS, 2)
 disc_heads_fwd_kernel(const float* __restrict__ pe, int n, int k, const float* __restrict__ base,
@@ -170,18 +212,19 @@ disc_heads_bwd_kernel(const float* __restrict__ pe, int n, int k, const float* _
     const int u = (warp & 3) * 8 + (lane & 7);
     const int rl = (warp >> 2) * 32 + (lane >> 3);
     const int d_kq = threadIdx.x & 7, d_r0 = threadIdx.x >> 3;
-    const long long R = (long long)n * k;
-    const long long n_tiles = (R + ROWS - 1) / ROWS;
+    RowMap rm;
+    rm.k = k; rm.n = n; rm.apt = ROWS / k;                 // k <= ROWS (checked by the caller)
+    const long long n_tiles = ((long long)n + rm.apt - 1) / rm.apt;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long row0 = tile * ROWS;
+        rm.agent0 = tile * rm.apt;
         __syncthreads();
-        stage_tile<TOD, HASG>(sA, sPe, pe, base, soc0, row0, R, n);
+        stage_tile_grouped<TOD, HASG>(sA, sPe, pe, base, soc0, rm);
         for (int idx = threadIdx.x; idx < ROWS * LDO; idx += MGGAN_THREADS) {
             int r = idx / LDO, c = idx - r * LDO;
-            long long row = row0 + r;
+            long long row; int ag_, smp_;
             float v = 0.f;
-            if (row < R) {
+            if (rm.map(r, row, ag_, smp_)) {
                 if (c == 0) {
                     if (dp != nullptr) {
                         float s = (__ldg(p + row) - D_EPS) / (1.f - 2.f * D_EPS);
@@ -232,16 +275,13 @@ disc_heads_bwd_kernel(const float* __restrict__ pe, int n, int k, const float* _
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = rl + 4 * i;
-                const long long row = row0 + r;
+                long long row; int ag, smp;
+                const bool ok = rm.map(r, row, ag, smp);
 #pragma unroll
                 for (int j = 0; j < C::TO; ++j) {
-                    const float dz = t[i][j] * (acc[i][j] > 0.f ? 1.f : SLOPE);
+                    const float dz = ok ? t[i][j] * (acc[i][j] > 0.f ? 1.f : SLOPE) : 0.f;
                     sA[r * C::LDA + u + 32 * j] = dz;
-                    if (row < R) {
-                        const int ag = (int)(row % n);
-                        if (row < n) d_soc0[(size_t)ag * C::NZ + u + 32 * j] = dz;
-                        if (d_base != nullptr) atomicAdd(d_base + (size_t)ag * C::NZ + u + 32 * j, dz);
-                    }
+                    if (ok && smp == 0) d_soc0[(size_t)ag * C::NZ + u + 32 * j] = dz;
                 }
             }
         }
@@ -251,9 +291,20 @@ disc_heads_bwd_kernel(const float* __restrict__ pe, int n, int k, const float* _
             tile_dgrad<2, C::NZ>(acc, sA, C::LDA, d_r0, 32, sW1, LDK, d_kq * 4);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const long long row = row0 + d_r0 + 32 * h;
-                if (row < R)
+                long long row; int ag, smp;
+                if (rm.map(d_r0 + 32 * h, row, ag, smp))
                     *reinterpret_cast<float4*>(d_pe + (size_t)row * KP + d_kq * 4) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+            }
+        }
+        if (d_base != nullptr) {     // d base[agent] = sum over the agent's k rows of the tile (plain stores: each agent is in one tile)
+            for (int idx = threadIdx.x; idx < rm.apt * C::NZ; idx += MGGAN_THREADS) {
+                const int a = idx / C::NZ, c = idx - a * C::NZ;
+                const long long ag = rm.agent0 + a;
+                if (ag < n) {
+                    float sum = 0.f;
+                    for (int q = 0; q < k; ++q) sum += sA[(a * k + q) * C::LDA + c];
+                    d_base[(size_t)ag * C::NZ + c] = sum;
+                }
             }
         }
     }
@@ -302,7 +353,8 @@ int launch_bwd(const float* pe, int n, int k, const float* base, const float* so
                float* d_base, cudaStream_t s) {
     size_t sm = bwd_smem<TOD, HASG>();
     cudaFuncSetAttribute(disc_heads_bwd_kernel<TOD, HASG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    disc_heads_bwd_kernel<TOD, HASG><<<grid_for((long long)n * k), MGGAN_THREADS, sm, s>>>(pe, n, k, base, soc0, W1p, Wd2, Wg2, G, p,
+    const long long tiles = ((long long)n + ROWS / k - 1) / (ROWS / k), cap = (long long)sm_count() * 2;
+    disc_heads_bwd_kernel<TOD, HASG><<<(int)(tiles < cap ? tiles : cap), MGGAN_THREADS, sm, s>>>(pe, n, k, base, soc0, W1p, Wd2, Wg2, G, p,
                                                                                           dp, dbranch, d_pe, d_soc0, d_base);
     return mggan_check_launch("disc_heads_bwd");
 }
@@ -331,6 +383,7 @@ extern "C" int mggan_disc_heads_bwd(const float* pe, int n, int k, int HH, const
     MGGAN_REQUIRE(n >= 0 && k >= 1 && (HH == 64 || HH == 96), "mggan_disc_heads_bwd: n=%d k=%d HH=%d (HH must be 64 or 96)", n, k, HH);
     MGGAN_REQUIRE(G >= 0 && G <= GMAX, "mggan_disc_heads_bwd: %d generators (max %d)", G, GMAX);
     MGGAN_REQUIRE(d_pe != nullptr && d_soc0 != nullptr, "mggan_disc_heads_bwd: d_pe and d_soc0 are required");
+    MGGAN_REQUIRE(k <= ROWS, "mggan_disc_heads_bwd: %d samples per agent (the backward tiles hold at most %d)", k, ROWS);
     if (n == 0) return MGGAN_OK;
     if (HH == 96) {
         if (G > 0) return launch_bwd<3, true>(pe, n, k, base, soc0, W1p, Wd2, Wg2, G, p, dp, dbranch, d_pe, d_soc0, d_base, stream);
