@@ -262,14 +262,14 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
     const int z_u = threadIdx.x & 31, z_g = threadIdx.x >> 5;       // dWz: unit, noise-column group (z_g, z_g + 8)
     const size_t Rpad = (size_t)n_tiles * ROWS;
 
-    float wacc[5][4], w1acc[4][4];      // wacc[0..3]: dW_hh n-tiles; wacc[4]: the pad columns (x0, x1, 1) = (dWx | db)
+    float wacc[5][4], w1acc[4];         // wacc[0..3]: dW_hh n-tiles; wacc[4]: the pad columns (x0, x1, 1) = (dWx | db); w1acc: dW1h (warps 0-3)
     float aw2a[4], aw2b[4], ab2a, ab2b, ab1[4], awz0, awz1;
     auto zero_acc = [&]() {
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) { wacc[a][b] = 0.f; w1acc[a][b] = 0.f; }
-            wacc[4][a] = 0.f;
+            for (int b = 0; b < 4; ++b) wacc[a][b] = 0.f;
+            wacc[4][a] = 0.f; w1acc[a] = 0.f;
             aw2a[a] = aw2b[a] = ab1[a] = 0.f;
         }
         ab2a = ab2b = awz0 = awz1 = 0.f;
@@ -293,7 +293,11 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 atomicAdd(gr.db + o, wacc[4][0]); atomicAdd(gr.db + o + 1, wacc[4][2]);
             }
         }
-        atomic_block44(gr.dW1h + (size_t)g * M1 * H, H, e_mq * 4, e_kq * 4, w1acc);
+        if (warp < 4) {   // w1acc: c0, c1 -> mid unit g, hidden units 8 warp + 2t, + 1; c2, c3 -> mid unit g + 8
+            float* dst = gr.dW1h + (size_t)g * M1 * H + (size_t)(lane >> 2) * H + 8 * warp + 2 * (lane & 3);
+            atomicAdd(dst, w1acc[0]); atomicAdd(dst + 1, w1acc[1]);
+            atomicAdd(dst + 8 * H, w1acc[2]); atomicAdd(dst + 8 * H + 1, w1acc[3]);
+        }
         for (int i = threadIdx.x; i < M1 * H; i += MGGAN_THREADS) atomicAdd(gr.dW1s + (size_t)g * M1 * H + i, sW1sAcc[i]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -332,8 +336,7 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
         }
         const int row0 = tile * ROWS;
         if (threadIdx.x < ROWS) sAgent[threadIdx.x] = sq.seq_agent[row0 + threadIdx.x];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sDh[(rl + 4 * i) * LDH + u] = 0.f;
+        float dhreg[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};     // dL/dh of the warp's block from the later step
         __syncthreads();
         const int pag = sAgent[prow];
         const int pcol = pag >= 0 ? sq.seq_out[row0 + prow] : -1;
@@ -433,94 +436,85 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 }
             }
             __syncthreads();
-            // ---- phase G: gate pre-activations Z = [h_{t-1} | x | 1] [W_hh | Wx | b]^T as warp-level 3 x TF32 products:
-            // warp = 16 rows x 64 gates (4 n-tiles at a time: register budget), K = 40; B fragment (k = t, n = g) =
-            // sWT[(k0 + t) LDG + n0 + g] (row stride = 8 mod 32: 32 distinct banks); MMAs product-major over the n-tiles
+            // ---- phase G + 1: the warp owns rows m0 .. m0 + 15 x units n0 .. n0 + 15 (the same block whose dh it produced in
+            // phase 2 of the later step, kept in registers).  Gate pre-activations Z = [h_{t-1} | x | 1] [W_hh | Wx | b]^T as
+            // warp-level 3 x TF32 products: K = 40, B fragment (k = t, n = g) = sWT[(k0 + t) LDG + col + g] (row stride = 8 mod
+            // 32: 32 distinct banks); the four n-tiles of a pass are the gates (i, f, g, o) of 8 units, so every lane ends up with
+            // the complete gates of its (2 rows x 2 units) and the cell backward runs on the accumulators: no round trip of Z
+            // through shared memory and no barrier between the product and the cell.
             {
                 const int g8 = lane >> 2, t4 = lane & 3;
-                const int m0 = (warp & 3) * 16;
-#pragma unroll 1
-                for (int nh = 0; nh < 2; ++nh) {
-                    const int nb = (warp >> 2) * 64 + nh * 32;
-                    float acc[4][4];
+                const int m0 = (warp & 3) * 16, n0 = (warp >> 2) * 16;
+                float hacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // dU_t W1h: the hidden2pos path into h_t
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+                for (int k0 = 0; k0 < M1; k0 += 8) {
+                    const float* pa = sDu + (m0 + g8) * LDU + k0 + t4;
+                    uint32_t ah[4], al[4], bh[4], bl[4];
+                    tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDU], ah[1], al[1]);
+                    tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDU + 4], ah[3], al[3]);
+                    const float* pb = sW1h + (k0 + t4) * LDH + n0 + g8;
+                    tf32_split(pb[0], bh[0], bl[0]); tf32_split(pb[4 * LDH], bh[1], bl[1]);
+                    tf32_split(pb[8], bh[2], bl[2]); tf32_split(pb[4 * LDH + 8], bh[3], bl[3]);
+                    mma_tf32_16x8x8(hacc[0], ah, bh[0], bh[1]); mma_tf32_16x8x8(hacc[1], ah, bh[2], bh[3]);
+                    mma_tf32_16x8x8(hacc[0], al, bh[0], bh[1]); mma_tf32_16x8x8(hacc[1], al, bh[2], bh[3]);
+                    mma_tf32_16x8x8(hacc[0], ah, bl[0], bl[1]); mma_tf32_16x8x8(hacc[1], ah, bl[2], bl[3]);
+                }
+#pragma unroll
+                for (int jp = 0; jp < 2; ++jp) {
+                    const int u0 = n0 + 8 * jp;                 // units u0 .. u0 + 7 of this pass
+                    float acc[4][4];                            // [gate][row g: units 2t, 2t + 1 | row g + 8: units 2t, 2t + 1]
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { acc[q][0] = 0.f; acc[q][1] = 0.f; acc[q][2] = 0.f; acc[q][3] = 0.f; }
 #pragma unroll
                     for (int k0 = 0; k0 < KG; k0 += 8) {
                         const float* pa = sHp + (m0 + g8) * LDH + k0 + t4;
                         uint32_t ah[4], al[4], bh[4][2], bl[4][2];
                         tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDH], ah[1], al[1]);
                         tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDH + 4], ah[3], al[3]);
-                        const float* pb = sWT + (k0 + t4) * LDG + nb + g8;
+                        const float* pb = sWT + (k0 + t4) * LDG + u0 + g8;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            tf32_split(pb[8 * j], bh[j][0], bl[j][0]);
-                            tf32_split(pb[4 * LDG + 8 * j], bh[j][1], bl[j][1]);
+                        for (int q = 0; q < 4; ++q) {
+                            tf32_split(pb[H * q], bh[q][0], bl[q][0]);
+                            tf32_split(pb[4 * LDG + H * q], bh[q][1], bl[q][1]);
                         }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j], ah, bh[j][0], bh[j][1]);
+                        for (int q = 0; q < 4; ++q) mma_tf32_16x8x8(acc[q], ah, bh[q][0], bh[q][1]);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j], al, bh[j][0], bh[j][1]);
+                        for (int q = 0; q < 4; ++q) mma_tf32_16x8x8(acc[q], al, bh[q][0], bh[q][1]);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[j], ah, bl[j][0], bl[j][1]);
+                        for (int q = 0; q < 4; ++q) mma_tf32_16x8x8(acc[q], ah, bl[q][0], bl[q][1]);
                     }
+                    // LSTM cell backward on the accumulators: c_t = f c_{t-1} + i g; gate gradients -> sG, h_t -> sHt
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float* o = sG + (m0 + g8) * LDG + nb + 8 * j + 2 * t4;
-                        *reinterpret_cast<float2*>(o) = make_float2(acc[j][0], acc[j][1]);
-                        *reinterpret_cast<float2*>(o + 8 * LDG) = make_float2(acc[j][2], acc[j][3]);
-                    }
-                }
-                {   // dh_t += dU_t W1h (64 x 32, K = 16), the hidden2pos path into h_t: warp = 16 rows x 16 units.  As FP32
-                    // (8 rows x 16 FMAs behind 32 LDS.128 per thread in phase 1) it was 10 % of the kernel's stall samples.
-                    const int n0 = (warp >> 2) * 16;
-                    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int r = m0 + g8 + 8 * hf;
+                        const bool valid = sAgent[r] >= 0;
+                        const float2 cpv = *reinterpret_cast<const float2*>(sCp + r * LDH + u0 + 2 * t4);
+                        float dgi[2], dgf[2], dgg[2], dgo[2], htv[2];
 #pragma unroll
-                    for (int k0 = 0; k0 < M1; k0 += 8) {
-                        const float* pa = sDu + (m0 + g8) * LDU + k0 + t4;
-                        uint32_t ah[4], al[4];
-                        tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8 * LDU], ah[1], al[1]);
-                        tf32_split(pa[4], ah[2], al[2]); tf32_split(pa[8 * LDU + 4], ah[3], al[3]);
-                        const float* pb = sW1h + (k0 + t4) * LDH + n0 + g8;
-                        uint32_t bh[4], bl[4];
-                        tf32_split(pb[0], bh[0], bl[0]); tf32_split(pb[4 * LDH], bh[1], bl[1]);
-                        tf32_split(pb[8], bh[2], bl[2]); tf32_split(pb[4 * LDH + 8], bh[3], bl[3]);
-                        mma_tf32_16x8x8(acc[0], ah, bh[0], bh[1]); mma_tf32_16x8x8(acc[1], ah, bh[2], bh[3]);
-                        mma_tf32_16x8x8(acc[0], al, bh[0], bh[1]); mma_tf32_16x8x8(acc[1], al, bh[2], bh[3]);
-                        mma_tf32_16x8x8(acc[0], ah, bl[0], bl[1]); mma_tf32_16x8x8(acc[1], ah, bl[2], bl[3]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        float2* o0 = reinterpret_cast<float2*>(sDh + (m0 + g8) * LDH + n0 + 8 * j + 2 * t4);
-                        float2* o1 = reinterpret_cast<float2*>(sDh + (m0 + g8 + 8) * LDH + n0 + 8 * j + 2 * t4);
-                        float2 v0 = *o0, v1 = *o1;
-                        *o0 = make_float2(v0.x + acc[j][0], v0.y + acc[j][1]);
-                        *o1 = make_float2(v1.x + acc[j][2], v1.y + acc[j][3]);
+                        for (int e = 0; e < 2; ++e) {
+                            const int ci = 2 * hf + e;
+                            const float ig = sigmoidf_(acc[0][ci]), fg = sigmoidf_(acc[1][ci]);
+                            const float gg = tanhf_(acc[2][ci]), og = sigmoidf_(acc[3][ci]);
+                            const float cp = e ? cpv.y : cpv.x;
+                            const float tc = tanhf_(fmaf(fg, cp, ig * gg));
+                            const float dh = dhreg[jp][ci] + hacc[jp][ci];
+                            const float dcc = fmaf(dh * og, 1.f - tc * tc, dc[4 * jp + ci]);
+                            dc[4 * jp + ci] = valid ? dcc * fg : 0.f;
+                            dgo[e] = valid ? dh * tc * og * (1.f - og) : 0.f;
+                            dgi[e] = valid ? dcc * gg * ig * (1.f - ig) : 0.f;
+                            dgg[e] = valid ? dcc * ig * (1.f - gg * gg) : 0.f;
+                            dgf[e] = valid ? dcc * cp * fg * (1.f - fg) : 0.f;
+                            htv[e] = valid ? og * tc : 0.f;
+                        }
+                        float* og_ = sG + r * LDG + u0 + 2 * t4;
+                        *reinterpret_cast<float2*>(og_) = make_float2(dgi[0], dgi[1]);
+                        *reinterpret_cast<float2*>(og_ + H) = make_float2(dgf[0], dgf[1]);
+                        *reinterpret_cast<float2*>(og_ + 2 * H) = make_float2(dgg[0], dgg[1]);
+                        *reinterpret_cast<float2*>(og_ + 3 * H) = make_float2(dgo[0], dgo[1]);
+                        *reinterpret_cast<float2*>(sHt + r * LDH + u0 + 2 * t4) = make_float2(htv[0], htv[1]);
                     }
                 }
-            }
-            __syncthreads();
-            // ---- phase 1: dh_t, LSTM cell backward (thread = 8 rows x 1 unit): gates from the recomputed pre-activations,
-            // c_t = f c_{t-1} + i g, gate gradients written in place of the pre-activations
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rl + 4 * i;
-                const bool valid = sAgent[r] >= 0;
-                const float ig = sigmoidf_(sG[r * LDG + u]), fg = sigmoidf_(sG[r * LDG + H + u]);
-                const float gg = tanhf_(sG[r * LDG + 2 * H + u]), og = sigmoidf_(sG[r * LDG + 3 * H + u]);
-                const float cp = sCp[r * LDH + u];
-                const float tc = tanhf_(fmaf(fg, cp, ig * gg));
-                const float ht = og * tc;
-                const float dh = sDh[r * LDH + u];
-                const float dcc = fmaf(dh * og, 1.f - tc * tc, dc[i]);
-                const float dao = dh * tc * og * (1.f - og);
-                const float dai = dcc * gg * ig * (1.f - ig);
-                const float dag = dcc * ig * (1.f - gg * gg);
-                const float daf = dcc * cp * fg * (1.f - fg);
-                dc[i] = valid ? dcc * fg : 0.f;
-                sG[r * LDG + u] = valid ? dai : 0.f; sG[r * LDG + H + u] = valid ? daf : 0.f;
-                sG[r * LDG + 2 * H + u] = valid ? dag : 0.f; sG[r * LDG + 3 * H + u] = valid ? dao : 0.f;
-                sHt[r * LDH + u] = valid ? ht : 0.f;
             }
             __syncthreads();
             // ---- phase 2: tile products
@@ -551,13 +545,9 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                         mma_tf32_16x8x8(acc[0], al, bh[0], bh[1]); mma_tf32_16x8x8(acc[1], al, bh[2], bh[3]);
                         mma_tf32_16x8x8(acc[0], ah, bl[0], bl[1]); mma_tf32_16x8x8(acc[1], ah, bl[2], bl[3]);
                     }
-                    // every read of sDh for step t happened before the barrier above
+                    // dh_{t-1} of the warp's (rows, units) block stays in registers for the next step's cell backward
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        float* o = sDh + (m0 + g8) * LDH + n0 + 8 * j + 2 * t4;
-                        *reinterpret_cast<float2*>(o) = make_float2(acc[j][0], acc[j][1]);
-                        *reinterpret_cast<float2*>(o + 8 * LDH) = make_float2(acc[j][2], acc[j][3]);
-                    }
+                    for (int j = 0; j < 2; ++j) { dhreg[j][0] = acc[j][0]; dhreg[j][1] = acc[j][1]; dhreg[j][2] = acc[j][2]; dhreg[j][3] = acc[j][3]; }
                 }
                 // dW_hh += dG^T h_{t-1}: warp = 16 gates x 32 units, K = 64 rows.  Rows of the A fragment are permuted
                 // (logical g, g+8 <-> gates m0 + 2g, m0 + 2g + 1: one LDS.64) and so are the columns of B (n-tile j, logical
@@ -592,7 +582,21 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
                 }
             }
             // dW1h: rows [8 warp, 8 warp + 8) of dU^T h_t
-            tile_wgrad<8>(w1acc, sDu + warp * 8 * LDU, LDU, e_mq * 4, sHt + warp * 8 * LDH, LDH, e_kq * 4);
+            if (warp < 4) {   // dW1h += dU^T h_t (16 x 32, K = 64 rows): warp = hidden units 8 warp .. + 7; A (m, k = row) = sDu[row LDU + m]
+                const int g8 = lane >> 2, t4 = lane & 3;
+#pragma unroll 2
+                for (int k0 = 0; k0 < ROWS; k0 += 8) {
+                    const float* pa = sDu + (k0 + t4) * LDU + g8;
+                    const float* pb = sHt + (k0 + t4) * LDH + 8 * warp + g8;
+                    uint32_t ah[4], al[4], bh[2], bl[2];
+                    tf32_split(pa[0], ah[0], al[0]); tf32_split(pa[8], ah[1], al[1]);
+                    tf32_split(pa[4 * LDU], ah[2], al[2]); tf32_split(pa[4 * LDU + 8], ah[3], al[3]);
+                    tf32_split(pb[0], bh[0], bl[0]); tf32_split(pb[4 * LDH], bh[1], bl[1]);
+                    mma_tf32_16x8x8(w1acc, ah, bh[0], bh[1]);
+                    mma_tf32_16x8x8(w1acc, al, bh[0], bh[1]);
+                    mma_tf32_16x8x8(w1acc, ah, bl[0], bl[1]);
+                }
+            }
             {   // gradient wrt this step's input dxdy_{t-1}: dG Wx (row = prow; the 4 lanes of a row take interleaved gate
                 // quads, so each load instruction of the quad is 64 contiguous bytes -- a contiguous quarter per lane put
                 // all four on one bank: 4-way conflicts on 24 LDS.128 per step, 16 % of the kernel's shared wavefronts)
@@ -611,7 +615,17 @@ decoder_bwd_kernel(DecSeq sq, int n_tiles, const float* __restrict__ social, con
             }
             __syncthreads();
         }
-        // ---- epilogue: h0 and the hoisted social / b1 terms
+        // ---- epilogue: h0 and the hoisted social / b1 terms (dh_0 -> shared memory for the row-wise passes below)
+        {
+            const int g8 = lane >> 2, t4 = lane & 3, m0 = (warp & 3) * 16, n0 = (warp >> 2) * 16;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float* o = sDh + (m0 + g8) * LDH + n0 + 8 * j + 2 * t4;
+                *reinterpret_cast<float2*>(o) = make_float2(dhreg[j][0], dhreg[j][1]);
+                *reinterpret_cast<float2*>(o + 8 * LDH) = make_float2(dhreg[j][2], dhreg[j][3]);
+            }
+        }
+        __syncthreads();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             int r = rl + 4 * i, ag = sAgent[r];
