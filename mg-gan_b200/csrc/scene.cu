@@ -736,7 +736,7 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     float* sPar = sImg + CIN * IMGPAD_BWD;                   // ab1[2C] mi1[2C] ab2[2C] mi2[2C] m12_2[2C]
     float* sred = sPar + 10 * C;                         // [8][2C]
     unsigned char* sIdx = reinterpret_cast<unsigned char*>(sred + 8 * 2 * C);    // [C][256]
-    unsigned char* sList = sIdx + C * P1SQ;                                      // [C][256] pooled pixels with a non-zero dy1
+    unsigned short* sOff = reinterpret_cast<unsigned short*>(sIdx + C * P1SQ);   // [C][256] crop offsets of the non-zero dy1 (compacted)
     for (int i = threadIdx.x; i < 9 * C * C; i += MGGAN_THREADS) {
         int co = i / (9 * C), r = i - co * 9 * C, ci = r / 9, tap = r - ci * 9;
         sWT[(tap * C + co) * LDWD + ci] = __ldg(W2 + i);
@@ -939,9 +939,10 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
         cp_async_wait<0>();
         __syncthreads();
         {   // sparse half of the conv1 weight gradient: thread = (c, ci, lane group).  dy1 is zero wherever the ReLU was
-            // inactive (about half of the pooled pixels), so every warp first compacts the non-zero pixels of the channels
-            // it owns (C = 16: channels 2 warp, 2 warp + 1; C = 8: channel warp) into a list with warp ballots, and the lane
-            // groups then walk the list: every lane of every trip does useful work
+            // inactive (about half of the pooled pixels), so every warp first compacts the non-zero entries of the channels
+            // it owns (C = 16: channels 2 warp, 2 warp + 1; C = 8: channel warp) with warp ballots -- the value in place, the
+            // offset of its window corner in the padded crop (from the pooled pixel and the pool arg) as 16 bits -- and the
+            // lane groups then walk the list: 2 loads + 9 (load, FMA) per entry, every lane of every trip does useful work
             constexpr int CPW = C / 8;                       // channels per warp
             const int lane = threadIdx.x & 31;
             int nnz = 0;
@@ -951,9 +952,16 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                 int count = 0;
 #pragma unroll 2
                 for (int base = 0; base < P1SQ; base += 32) {
-                    const bool on = sDY[ch * LDY + base + lane] != 0.f;
+                    const int q = base + lane;
+                    const float v = sDY[ch * LDY + q];
+                    const int code = sIdx[ch * P1SQ + q] & 3;
+                    const bool on = v != 0.f;
                     const unsigned m = __ballot_sync(0xffffffffu, on);
-                    if (on) sList[ch * P1SQ + count + __popc(m & ((1u << lane) - 1u))] = (unsigned char)(base + lane);
+                    if (on) {                                // slot <= q: the compaction never overtakes its own reads
+                        const int slot = count + __popc(m & ((1u << lane) - 1u));
+                        sDY[ch * LDY + slot] = v;
+                        sOff[ch * P1SQ + slot] = (unsigned short)((2 * (q >> 4) + (code >> 1)) * LDI + 2 * (q & 15) + (code & 1));
+                    }
                     count += __popc(m);
                 }
                 if (ch == s_c) nnz = count;
@@ -962,10 +970,8 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
             const float* ipc = sImg + s_ci * IMGPAD_BWD;
 #pragma unroll 2
             for (int e = s_qg; e < nnz; e += QG) {
-                const int q = sList[s_c * P1SQ + e];
-                const float d = sDY[s_c * LDY + q];
-                const int code = sIdx[s_c * P1SQ + q] & 3;
-                const float* bp = ipc + (2 * (q >> 4) + (code >> 1)) * LDI + 2 * (q & 15) + (code & 1);
+                const float d = sDY[s_c * LDY + e];
+                const float* bp = ipc + sOff[s_c * P1SQ + e];
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -1414,7 +1420,7 @@ size_t fused_fwd_smem() { constexpr int PPAD = FwdPad::PPAD; return sizeof(float
 template <int C>
 size_t fused_bwd_smem() {
     constexpr int PPAD = BwdPad::PPAD;
-    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * BwdPad::LDWD + C * (P1SQ + 4) + CIN * IMGPAD_BWD + 10 * C + 8 * 2 * C) + 2 * C * P1SQ;
+    return sizeof(float) * (C * PPAD + ((C * PPAD + 3) & ~3) + 9 * C * BwdPad::LDWD + C * (P1SQ + 4) + CIN * IMGPAD_BWD + 10 * C + 8 * 2 * C) + 3 * C * P1SQ;
 }
 template <int C>
 size_t attn_w_floats() { return 2 * AH * C + AH + C + 2 * C; }

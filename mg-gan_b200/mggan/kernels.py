@@ -153,7 +153,7 @@ class _DiscHeads(torch.autograd.Function):
             return (None,) * 11
         d_pe = torch.empty_like(pe)
         d_soc0 = torch.empty_like(soc0)
-        d_base = torch.zeros_like(base) if ctx.needs_input_grad[1] else None
+        d_base = torch.empty_like(base) if ctx.needs_input_grad[1] else None     # written in full by the kernel (plain stores)
         dp = _f32(dp) if dp is not None else None
         dbranch = _f32(dbranch) if (G and dbranch is not None) else None
         call("mggan_disc_heads_bwd", ptr(pe), n, k, HH, ptr(base), ptr(soc0), ptr(w1p), ptr(wd2), ptr(wg2), G, ptr(p),
