@@ -26,7 +26,6 @@ constexpr int P2 = 8, P2SQ = 64;               // after second pool
 constexpr int CIN = 4;
 constexpr int AH = 32;                         // attention MLP hidden width (cnn.py mlp_dim)
 constexpr int LDI = 36;                        // padded image row (35 used)
-constexpr int IMGPAD = 35 * LDI;               // one padded channel
 // Channel stride of the crop in the backward kernel: = 8 mod 32.  In the sparse conv1 weight-gradient stage the lanes of a
 // warp that differ only in the input channel read the same (data-dependent) pixel of 4 channels; with the dense stride
 // (1260 = 12 mod 32) channels 0 and 3 sit 4 banks apart and collide with the neighbouring pooled pixels of the other
@@ -46,12 +45,13 @@ struct BwdPad {
 template <int C>
 struct FwdLdw2 { static constexpr int value = C == 16 ? 24 : 8; };            // 24 t + g / 8 t + g: 32 distinct banks
 
-// ---- bulk (TMA-engine) staging of one agent's crop --------------------------------------------------------------
-// A crop is 4 x 33 x 33 fp32 = 17,424 contiguous bytes (16-byte multiple, 16-byte aligned for every agent of a 16-byte
-// aligned batch), so one `cp.async.bulk` (SASS UBLKCP) moves it global -> shared without touching registers and signals an
-// mbarrier when the bytes have landed.  The fused conv kernels double-buffer it: agent n+1's crop streams in while agent n
-// is convolved, and the kernels read the UNPADDED [4][33][33] layout directly (only row / column -1 of a 3 x 3 window can
-// fall outside; it is predicated to zero).
+// ---- bulk (TMA-engine) copies ---------------------------------------------------------------------------------------
+// `cp.async.bulk` (SASS UBLKCP) moves a contiguous, 16-byte aligned chunk global -> shared without touching registers and
+// signals an mbarrier when the bytes have landed; `cp.async.bulk.prefetch.L2` requests a chunk into the L2.  Used where a
+// kernel consumes a contiguous per-agent block as it is: the conv2 outputs of the next trip in the attention backward
+// (staged while the current trip is processed) and the L2 prefetch of the next crop's inputs in the fused backward.  The
+// crops themselves are staged with 4-byte cp.async into zero-padded layouts (their 132-byte rows rule out both wider
+// copies and tensor-map boxes).
 constexpr int RAW = CIN * IMG2;                // floats per crop
 constexpr uint32_t RAW_BYTES = RAW * 4;
 
@@ -80,13 +80,6 @@ __device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {
         if (spins > (1u << 24)) __trap();       // a lost copy traps (reported by the C ABI) instead of hanging the device
     }
 }
-// One thread: arm the barrier and start the copy of agent `src`'s crop into `dst`.
-__device__ __forceinline__ void stage_crop(const float* __restrict__ img, int src, float* dst, uint64_t* bar) {
-    const uint32_t b = smem_addr(bar);
-    sbar_expect_tx(b, RAW_BYTES);
-    bulk_g2s(smem_addr(dst), img + (size_t)src * RAW, RAW_BYTES, b);
-}
-
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -723,7 +716,6 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
     constexpr int UNITS = 9 * NT;                        // (tap, input-channel tile) units of the conv2 weight gradient
     constexpr int UPW = (UNITS + 7) / 8;                 // units per warp (3 or 2)
     constexpr int QG = MGGAN_THREADS / (C * CIN);        // pooled-pixel groups for the sparse conv1 term (4 or 8)
-    constexpr int Q_PER = P1SQ / QG;
     constexpr int LDY = P1SQ + 4;                        // channel stride of sDY: neighbouring channels on different banks
     constexpr int PPAD = BwdPad::PPAD;                   // 324 = 4 mod 32: bank 4 g + t (weight gradient) / 8 t + g (input gradient)
     constexpr int LDWD = BwdPad::LDWD;                   // 20: rows co = c0 + 2t of the input-gradient B fragment 8 banks apart
@@ -1073,7 +1065,7 @@ __device__ __forceinline__ AttnW<C> stage_attn_weights(float* base, const float*
 }
 
 // v[c] = maxpool(relu(BN2(x2))) at one position; optionally the arg index / pre-BN value at the arg.
-template <int C, bool WITH_ARG>
+template <int C, bool WITH_ARG, bool SHARED = false>
 __device__ __forceinline__ void pool_block2(const float* __restrict__ x2n, const float* sAB, int pos, float (&v)[C],
                                             int (&arg)[C], float (&e)[C]) {
     const int py = pos >> 3, px = pos & 7;
@@ -1081,7 +1073,8 @@ __device__ __forceinline__ void pool_block2(const float* __restrict__ x2n, const
     for (int c = 0; c < C; ++c) {
         const float a = sAB[c], b = sAB[C + c];
         const float2* s = reinterpret_cast<const float2*>(x2n + c * P1SQ + (2 * py) * P1 + 2 * px);
-        float2 t0 = __ldg(s), t1 = __ldg(s + P1 / 2);
+        float2 t0, t1;
+        if (SHARED) { t0 = s[0]; t1 = s[P1 / 2]; } else { t0 = __ldg(s); t1 = __ldg(s + P1 / 2); }
         float v0 = fmaf(a, t0.x, b), v1 = fmaf(a, t0.y, b), v2 = fmaf(a, t1.x, b), v3 = fmaf(a, t1.y, b);
         float m = v0, ee = t0.x; int ag = 0;
         if (v1 > m) { m = v1; ee = t0.y; ag = 1; }
@@ -1239,6 +1232,12 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
     float* sHid = sDS + AT_ROWS * LDV;             // [AT_ROWS][LDH]
     float* sDH = sHid + AT_ROWS * LDH;             // [AT_ROWS][LDH]
     float* sred = sDH + AT_ROWS * LDH;             // [8][2C]
+    float* sX2 = sred + 8 * 2 * C;                 // [2][C][256] the trip's conv2 outputs, bulk-copied one trip ahead
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sX2 + 2 * C * P1SQ);
+    if (threadIdx.x == 0) {
+        sbar_init(smem_addr(sBar), 1);
+        sbar_fence_init();
+    }
     for (int i = threadIdx.x; i < AH * C; i += MGGAN_THREADS) {
         const int u = i / C, c = i - u * C;        // Wa1[u][c]
         uint32_t hi, lo;
@@ -1265,18 +1264,27 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
 #pragma unroll
     for (int c = 0; c < 2 * C; ++c) st[c] = 0.f;
     __syncthreads();
+    // one thread arms the barrier and starts the bulk copy of a trip's conv2 outputs (its 1 or 2 agents are contiguous)
+    auto stage_x2 = [&](int n0) {
+        const uint32_t bytes = (uint32_t)min(2, N - n0) * C * P1SQ * 4;
+        sbar_expect_tx(smem_addr(sBar), bytes);
+        bulk_g2s(smem_addr(sX2), x2 + (size_t)n0 * C * P1SQ, bytes, smem_addr(sBar));
+    };
+    if (threadIdx.x == 0 && (int)blockIdx.x * 2 < N) stage_x2(blockIdx.x * 2);
+    uint32_t phase = 0;
 
-    for (int n0 = blockIdx.x * 2; n0 < N; n0 += gridDim.x * 2) {
+    for (int n0 = blockIdx.x * 2; n0 < N; n0 += gridDim.x * 2, phase ^= 1u) {
         const int n = n0 + slot;
         const bool live = threadIdx.x < AT_ROWS && n < N;
         float e[C], dvd[C], gout = 0.f;
         int arg[C];
-        // ---- S0: pooled values of the position
+        // ---- S0: pooled values of the position (from the staged copy)
         if (threadIdx.x < AT_ROWS) {
             float v[C];
+            if (live) gout = __ldg(dout + (size_t)n * P2SQ + pos);
+            sbar_wait(smem_addr(sBar), phase);
             if (live) {
-                pool_block2<C, true>(x2 + (size_t)n * C * P1SQ, sAB, pos, v, arg, e);
-                gout = __ldg(dout + (size_t)n * P2SQ + pos);
+                pool_block2<C, true, true>(sX2 + slot * C * P1SQ, sAB, pos, v, arg, e);
             } else {
 #pragma unroll
                 for (int c = 0; c < C; ++c) { v[c] = 0.f; e[c] = 0.f; arg[c] = 0; }
@@ -1285,6 +1293,8 @@ scene_attn_bwd_kernel(const float* __restrict__ x2, int N, const float* __restri
             for (int c = 0; c < C; c += 4) st4(sV + threadIdx.x * LDV + c, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
         }
         __syncthreads();
+        // the staged block has been consumed: the next trip's copy runs behind the six stages below
+        if (threadIdx.x == 0 && n0 + (int)gridDim.x * 2 < N) stage_x2(n0 + gridDim.x * 2);
         // ---- S1: Hid = lrelu(V Wa1^T + ba1) -> S = Hid Wa2^T + ba2 (the warp's own 16 rows: warp-level hand-over)
         {
             float acc[4][4];
@@ -1428,7 +1438,7 @@ template <int C>
 size_t attn_fwd_smem() { return sizeof(float) * attn_w_floats<C>(); }
 template <int C>
 size_t attn_bwd_smem() {
-    return sizeof(float) * (4 * AH * AtLd<C>::V + 4 * C * AT_LDH + AH + C + 4 * C + 2 * AT_ROWS * AtLd<C>::V + 2 * AT_ROWS * AT_LDH + 8 * 2 * C);
+    return sizeof(float) * (4 * AH * AtLd<C>::V + 4 * C * AT_LDH + AH + C + 4 * C + 2 * AT_ROWS * AtLd<C>::V + 2 * AT_ROWS * AT_LDH + 8 * 2 * C + 2 * C * P1SQ) + 16;
 }
 
 int agent_grid(int N, int per_sm) {
