@@ -102,7 +102,7 @@ KERNEL_UNIT_BYTES = {
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` summary (profiles/ncu_traffic.json)."""
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json names the call and the table it came from)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         return json.load(open(path)).get(kernel, {}).get("dram_bytes_per_launch")
