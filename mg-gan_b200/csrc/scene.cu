@@ -949,6 +949,7 @@ scene_fused12_bwd_kernel(const float* __restrict__ img, const int* __restrict__ 
                     const int code = sIdx[ch * P1SQ + q] & 3;
                     const bool on = v != 0.f;
                     const unsigned m = __ballot_sync(0xffffffffu, on);
+                    __syncwarp();                            // every lane's read of this trip is ordered before the in-place writes
                     if (on) {                                // slot <= q: the compaction never overtakes its own reads
                         const int slot = count + __popc(m & ((1u << lane) - 1u));
                         sDY[ch * LDY + slot] = v;
