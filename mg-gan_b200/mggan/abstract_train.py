@@ -109,12 +109,15 @@ class MultiGeneratorGAN(abc.ABC):
             if self.scene_images is None:
                 raise RuntimeError("the batch carries image_ids but no SceneImageStore is attached "
                                    "(trainer.attach_scene_images(dataset.scene_image_store()))")
-            out = None
             if ring is not None:
-                out = ring.get("crop")
-                if out is None or out.shape[0] != b:
-                    out = ring["crop"] = torch.empty(b, 4, 33, 33, device=self.device, dtype=torch.float32)
-            img = self.scene_images.crop(batch["image_ids"], in_xy[-1], out=out)
+                # the loop's prefetch stages the ids only; the iteration cuts the crops on the main stream, straight into
+                # the buffer it reads (scene_images.DeferredCrop)
+                from mggan.data_utils.scene_images import DeferredCrop
+                ids = torch.as_tensor(batch["image_ids"])
+                img = DeferredCrop(self.scene_images, put("image_ids", ids if ids.dtype == torch.int32 else ids.to(torch.int32)),
+                                   in_xy)
+            else:
+                img = self.scene_images.crop(batch["image_ids"], in_xy[-1])
         return in_xy, in_dxdy, gt_xy, gt_dxdy, sub_batches, img
 
     def attach_scene_images(self, store):
@@ -209,6 +212,9 @@ class MultiGeneratorGAN(abc.ABC):
                 metrics[k].extend(t.clone() for t in v_)           # the graph's own tensors are overwritten by the next replay
             return
         self.graph_misses += 1
+        if prepared[5] is not None and not torch.is_tensor(prepared[5]):
+            # deferred crops (train_iterations): an eager iteration cuts them now; a replay cuts them into its own input
+            prepared = prepared[:5] + (prepared[5].materialize(),) + prepared[6:]
         if eligible:
             if len(self._graph_seen) > 4096:
                 self._graph_seen.clear()

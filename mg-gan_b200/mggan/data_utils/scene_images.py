@@ -49,3 +49,18 @@ class SceneImageStore:
             ids = ids.to(torch.int32)
         ids = ids.to(self.device, non_blocking=True)
         return K.scene_crop(self.atlas, self.img_off, self.img_wh, self.img_scale, ids, last_xy, out=out)
+
+
+class DeferredCrop:
+    """Crop features of a staged batch that have not been cut yet.  The training loop stages batch i + 1 on a copy stream
+    while batch i computes; cutting its crops there would write 17,424 B per agent into a staging buffer that the main
+    stream then copies once more into the captured iteration's input.  The loop stages only the image ids and the
+    trajectories, and the iteration cuts the crops itself on the main stream, straight into the buffer it reads
+    (`materialize(out=...)`): one write of the crops per step instead of a write, a read and a write."""
+
+    def __init__(self, store, ids, in_xy):
+        self.store, self.ids, self.in_xy = store, ids, in_xy          # ids (N) int32 device, in_xy (obs_len, N, 2) device
+        self.shape = (int(ids.numel()), 4, 33, 33)
+
+    def materialize(self, out=None):
+        return self.store.crop(self.ids, self.in_xy[-1], out=out)

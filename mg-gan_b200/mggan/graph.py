@@ -173,7 +173,11 @@ class GraphedIteration:
         dict of the captured iteration (its tensors are overwritten by the next replay)."""
         in_xy, in_dxdy, gt_xy, gt_dxdy, _, img, _ = prepared
         for dst, src in zip(self.static, (in_xy, in_dxdy, gt_xy, gt_dxdy, img)):
-            if dst is not None and dst.data_ptr() != src.data_ptr():
+            if dst is None:
+                continue
+            if not torch.is_tensor(src):
+                src.materialize(out=dst)           # deferred crops: cut from the resident images straight into the input
+            elif dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._stage_scalars()
         self.feed.upload()

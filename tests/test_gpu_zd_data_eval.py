@@ -217,3 +217,46 @@ def test_training_iteration_resident_images_equals_host_features():
         assert v == pytest.approx(results[1][1][k], rel=1e-4, abs=1e-6), k
     for p, q in zip(results[0][2], results[1][2]):
         assert torch.allclose(p, q, rtol=1e-4, atol=1e-6)
+
+
+def test_training_loop_deferred_crops_equal_host_features():
+    """`train_iterations` stages only the image ids of a resident-image batch and the iteration cuts the crops itself --
+    eagerly the first two times, then straight into the captured iteration's input on every replay.  Four iterations of
+    the loop on host-cut `features` and on `image_ids` give the same losses, and the loop did replay."""
+    import tempfile
+    from collections import defaultdict
+    from mggan.data_utils.scene_images import DeferredCrop, SceneImageStore
+    from mggan.logging import Experiment
+    from mggan.model.config import get_parser
+    from mggan.model.model_factory import construct_model
+    from mggan.model.train import PiNetMultiGeneratorGAN
+    from mggan.synthetic import SCALING_SMALL, make_image_batch
+    sizes = [3, 1, 4, 2]
+    host, images = make_image_batch(sizes, seed=11)
+    res, _ = make_image_batch(sizes, seed=11, resident=True)
+    results = []
+    from mggan.graph import GraphedIteration
+    for b in (host, res):
+        torch.manual_seed(5)
+        np.random.seed(5)
+        GraphedIteration._uid = 0          # the replayed sampler's Philox offsets are keyed on the capture's uid: same draws in both runs
+        cfg = get_parser().parse_args(["--num_gens", "2", "--num_samples", "4", "--cuda_graph", "1"])
+        cfg.gpus = True
+        G, D = construct_model(cfg)
+        tr = PiNetMultiGeneratorGAN(G, D, cfg, Experiment(tempfile.mkdtemp(prefix="mggan_dc_"), "dc", version=0))
+        tr.attach_scene_images(SceneImageStore(images, SCALING_SMALL, DEV))
+        tr.G.train(); tr.D.train()
+        tr.epoch = 1
+        batch = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in b.items()}
+        batch = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        if "image_ids" in batch:
+            assert isinstance(tr._prepare(batch, 0)[5], DeferredCrop)
+        metrics = defaultdict(list)
+        assert tr.train_iterations((batch for _ in range(4)), metrics) == 4
+        torch.cuda.synchronize()
+        assert tr.graph_hits == 2, (tr.graph_hits, tr.graph_misses)
+        results.append({k: [float(x) for x in v] for k, v in metrics.items()})
+    assert set(results[0]) == set(results[1])
+    for k, v in results[0].items():
+        assert len(v) == 4
+        assert v == pytest.approx(results[1][k], rel=2e-3, abs=1e-5), k
