@@ -6,8 +6,9 @@
 // PyTorch gate order [i; f; g; o].  One persistent CTA owns a tile of rows (agents) for the
 // whole sequence: W_hh stays in shared memory, h ping-pongs through shared memory, c lives in
 // registers.  Forward optionally saves (i, f, g, o, c, tanh c) per step for the backward,
-// which walks the sequence in reverse and keeps the weight-gradient tiles in registers until
-// the end (one atomicAdd per element per CTA).
+// which walks the sequence in reverse, runs its two contractions per step on the tensor pipe
+// (3 x TF32) and keeps the weight-gradient fragments in registers until the end (one atomicAdd
+// per element per CTA).
 #include "common.cuh"
 
 namespace {
@@ -85,144 +86,201 @@ lstm_enc_fwd_kernel(const float* __restrict__ x, int T, int N, const float* __re
     }
 }
 
+// Backward.  Per step the two contractions -- dh_{t-1} = dgates . W_hh (rows x 4H x H) and
+// dW_hh += dgates^T . h_{t-1} (4H x rows x H) -- run as warp-level 3 x TF32 products (common.cuh) over a 64-row tile:
+// the FP32 register tiles they replace re-read every operand once per 4 x 4 outputs and kept the FMA pipe 31 % busy at
+// 177 registers (one CTA of 8 warps per SM).  The h_{t-1} tile carries three more columns (x0, x1, 1), so the same
+// weight-gradient product also yields dWx and db (one more n-tile instead of a 64-row scalar loop per gate).
+// Shared-memory strides are chosen per fragment pattern: the dgates tile is read as A[row g][gate t] by the input
+// gradient (stride = 4 mod 32: banks 4 g + t) and as A[gate g][row 2 t] by the weight gradient, whose contraction index
+// is permuted (fragment k = t <-> row 2 t, k = t + 4 <-> row 2 t + 1: banks 8 t + g); W_hh rows are 8 mod 32 apart
+// (B[gate t][unit g]: 8 t + g) and the h tile's 12 mod 32 (B[row 2 t][unit g]: 24 t + g).
 template <int H>
-__global__ void __launch_bounds__(MGGAN_THREADS)
+struct EncBwd {
+    static constexpr int ROWS = 64;
+    static constexpr int G4 = 4 * H;
+    static constexpr int LDW = H + 8;
+    static constexpr int LDG = G4 + 4;
+    static constexpr int LDH = H + 12;               // columns H .. H + 7: x0, x1, 1, 0, 0, 0, 0, 0
+    static constexpr int LDD = H + 8;                // dh tile: float2 stores of the C fragments on 8 g + 2 t
+    static constexpr int NTW = H / 8 + 1;            // n-tiles of the weight gradient (the last one: dWx | db)
+    static constexpr int MTW = G4 / 16 / 8;          // its m-tiles (16 gates each) per warp: 1 or 2
+    static constexpr int NTD = H / 16;               // n-tiles of the input gradient per warp: 2 or 4
+    static constexpr int UH = H / 32;                // 32-unit groups
+    static constexpr int ITEMS = ROWS * H / MGGAN_THREADS;     // (row, unit) pairs per thread in the cell backward
+    static constexpr size_t SMEM = sizeof(float) * (G4 * LDW + ROWS * LDG + ROWS * LDH + ROWS * LDD);
+};
+
+template <int H>
+__global__ void __launch_bounds__(MGGAN_THREADS, H == 32 ? 2 : 1)
 lstm_enc_bwd_kernel(const float* __restrict__ x, int T, int N, const float* __restrict__ Whh,
                     const float* __restrict__ acts, const float* __restrict__ dhT, float* __restrict__ dWx,
                     float* __restrict__ db, float* __restrict__ dWhh) {
-    using C = EncCfg<H>;
-    constexpr int ROWS = C::ROWS, LDH = C::LDH, LDG = C::LDG;
+    using C = EncBwd<H>;
+    constexpr int ROWS = C::ROWS, G4 = C::G4, LDW = C::LDW, LDG = C::LDG, LDH = C::LDH, LDD = C::LDD;
+    constexpr int NTW = C::NTW, MTW = C::MTW, NTD = C::NTD, UH = C::UH, ITEMS = C::ITEMS;
     extern __shared__ __align__(16) float smem[];
-    float* sW = smem;                      // [4H][LDH]
-    float* sG = sW + 4 * H * LDH;          // [ROWS][LDG]   gate pre-activation gradients
-    float* sHp = sG + ROWS * LDG;          // [ROWS][LDH]   h_{t-1}
-    float* sDh = sHp + ROWS * LDH;         // [ROWS][LDH]   dL/dh_t
-    float* sX = sDh + ROWS * LDH;          // [ROWS][2]
-    stage_matrix(sW, LDH, Whh, 4 * H, H);
-
+    float* sW = smem;                      // [4H][LDW]
+    float* sG = sW + G4 * LDW;             // [ROWS][LDG]   gate pre-activation gradients
+    float* sHp = sG + ROWS * LDG;          // [ROWS][LDH]   h_{t-1} | x_t | 1
+    float* sDh = sHp + ROWS * LDH;         // [ROWS][LDD]   dL/dh_t
+    for (int i = threadIdx.x; i < G4 * H; i += MGGAN_THREADS) sW[(i / H) * LDW + (i % H)] = __ldg(Whh + i);
+    if (threadIdx.x < ROWS) {
+        float* e = sHp + threadIdx.x * LDH + H;
+        e[0] = 0.f; e[1] = 0.f; e[2] = 1.f; e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; e[6] = 0.f; e[7] = 0.f;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int u = (warp % C::UG) * 8 + (lane & 7);
-    const int rl = (warp / C::UG) * 32 + (lane >> 3);
-    // dgrad mapping: thread -> (k-quad, 2 rows)
-    constexpr int KQ = H / 4;
-    const int d_kq = threadIdx.x % KQ, d_r0 = threadIdx.x / KQ;
-    constexpr int D_RS = MGGAN_THREADS / KQ;   // ROWS == 2 * D_RS
-    static_assert(ROWS == 2 * D_RS, "dgrad mapping");
-    // wgrad mapping: thread -> NB 4x4 blocks of dWhh
-    constexpr int NB = (4 * H * H / 16) / MGGAN_THREADS;
-    float wacc[NB][4][4];
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int md = warp & 3, nd0 = (warp >> 2) * NTD;          // input gradient: m-tile, first n-tile of this warp
+    float wacc[MTW][NTW][4];
 #pragma unroll
-    for (int j = 0; j < NB; ++j)
+    for (int i = 0; i < MTW; ++i)
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int j = 0; j < NTW; ++j)
 #pragma unroll
-            for (int bq = 0; bq < 4; ++bq) wacc[j][a][bq] = 0.f;
-    float ax0 = 0.f, ax1 = 0.f, ab = 0.f;          // dWx[o][0..1], db[o] for o = threadIdx.x < 4H
+            for (int e = 0; e < 4; ++e) wacc[i][j][e] = 0.f;
 
     const int n_tiles = (N + ROWS - 1) / ROWS;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int row0 = tile * ROWS;
-        float dc[8];
+        float dc[ITEMS];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dc[i] = 0.f;
-        __syncthreads();
+        for (int j = 0; j < ITEMS; ++j) dc[j] = 0.f;
+        __syncthreads();                   // weights staged / the previous tile's products are done with the tiles
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int r = rl + 4 * i, row = row0 + r;
-            sDh[r * LDH + u] = row < N ? __ldg(dhT + (size_t)row * H + u) : 0.f;
+        for (int j = 0; j < ITEMS; ++j) {
+            const int u = lane + 32 * (j % UH), r = warp + 8 * (j / UH), row = row0 + r;
+            sDh[r * LDD + u] = row < N ? __ldg(dhT + (size_t)row * H + u) : 0.f;
         }
         __syncthreads();
         for (int t = T - 1; t >= 0; --t) {
-            // ---- phase 1: cell backward.  Activation loads are unconditional (row clamped, result masked) and issued
-            // for 4 rows at a time so that their latencies overlap instead of adding up.
+            // ---- phase 1: cell backward, thread = (unit lane + 32 ., rows warp + 8 .): every load is a full line.
+            // Loads are unconditional (row clamped, result masked) and issued for 4 pairs at a time.
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int b4 = 0; b4 < ITEMS; b4 += 4) {
                 float v[4][5], pv[4][3];
 #pragma unroll
-                for (int ii = 0; ii < 4; ++ii) {
-                    const int row = min(row0 + rl + 4 * (half * 4 + ii), N - 1);
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = b4 + jj;
+                    const int u = lane + 32 * (j % UH), row = min(row0 + warp + 8 * (j / UH), N - 1);
                     const float* a = acts + ((size_t)t * N + row) * (6 * H) + u;
-                    v[ii][0] = __ldg(a); v[ii][1] = __ldg(a + H); v[ii][2] = __ldg(a + 2 * H); v[ii][3] = __ldg(a + 3 * H);
-                    v[ii][4] = __ldg(a + 5 * H);
+                    v[jj][0] = __ldg(a); v[jj][1] = __ldg(a + H); v[jj][2] = __ldg(a + 2 * H); v[jj][3] = __ldg(a + 3 * H);
+                    v[jj][4] = __ldg(a + 5 * H);
                     if (t > 0) {
                         const float* ap = a - (size_t)N * (6 * H);
-                        pv[ii][0] = __ldg(ap + 4 * H); pv[ii][1] = __ldg(ap + 3 * H); pv[ii][2] = __ldg(ap + 5 * H);
+                        pv[jj][0] = __ldg(ap + 4 * H); pv[jj][1] = __ldg(ap + 3 * H); pv[jj][2] = __ldg(ap + 5 * H);
                     }
                 }
 #pragma unroll
-                for (int ii = 0; ii < 4; ++ii) {
-                    const int i = half * 4 + ii;
-                    const int r = rl + 4 * i;
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = b4 + jj;
+                    const int u = lane + 32 * (j % UH), r = warp + 8 * (j / UH);
                     const bool valid = row0 + r < N;
-                    const float ig = v[ii][0], fg = v[ii][1], gg = v[ii][2], og = v[ii][3], tc = v[ii][4];
-                    const float cp = t > 0 ? pv[ii][0] : 0.f;
-                    const float hp = t > 0 ? pv[ii][1] * pv[ii][2] : 0.f;
-                    const float dh = sDh[r * LDH + u];
-                    const float dcc = fmaf(dh * og, 1.f - tc * tc, dc[i]);
+                    const float ig = v[jj][0], fg = v[jj][1], gg = v[jj][2], og = v[jj][3], tc = v[jj][4];
+                    const float cp = t > 0 ? pv[jj][0] : 0.f;
+                    const float hp = t > 0 ? pv[jj][1] * pv[jj][2] : 0.f;
+                    const float dh = sDh[r * LDD + u];
+                    const float dcc = fmaf(dh * og, 1.f - tc * tc, dc[j]);
                     const float dao = dh * tc * og * (1.f - og);
                     const float dai = dcc * gg * ig * (1.f - ig);
                     const float dag = dcc * ig * (1.f - gg * gg);
                     const float daf = dcc * cp * fg * (1.f - fg);
-                    dc[i] = valid ? dcc * fg : 0.f;
-                    sG[r * LDG + u] = valid ? dai : 0.f; sG[r * LDG + H + u] = valid ? daf : 0.f;
-                    sG[r * LDG + 2 * H + u] = valid ? dag : 0.f; sG[r * LDG + 3 * H + u] = valid ? dao : 0.f;
+                    dc[j] = valid ? dcc * fg : 0.f;
+                    float* gr = sG + r * LDG + u;
+                    gr[0] = valid ? dai : 0.f; gr[H] = valid ? daf : 0.f; gr[2 * H] = valid ? dag : 0.f; gr[3 * H] = valid ? dao : 0.f;
                     sHp[r * LDH + u] = valid ? hp : 0.f;
                 }
             }
-            for (int i = threadIdx.x; i < ROWS; i += MGGAN_THREADS) {
-                int row = row0 + i;
-                float2 xv = row < N ? __ldg(reinterpret_cast<const float2*>(x) + (size_t)t * N + row) : make_float2(0.f, 0.f);
-                sX[2 * i] = xv.x; sX[2 * i + 1] = xv.y;
+            if (threadIdx.x < ROWS) {
+                const int row = row0 + threadIdx.x;
+                const float2 xv = row < N ? __ldg(reinterpret_cast<const float2*>(x) + (size_t)t * N + row) : make_float2(0.f, 0.f);
+                *reinterpret_cast<float2*>(sHp + threadIdx.x * LDH + H) = xv;
             }
             __syncthreads();
-            // ---- phase 2: dh_{t-1} = W_hh^T dgates ; weight-gradient tiles
+            // ---- phase 2a: dh_{t-1}[row][n] = sum_gate dgates[row][gate] W_hh[gate][n]
             if (t > 0) {
-                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                tile_dgrad<2, 4 * H>(acc, sG, LDG, d_r0, D_RS, sW, LDH, d_kq * 4);
+                float dacc[NTD][4];
 #pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    int oq = (H == 32) ? (warp & 3) * 8 + (lane & 7) : warp * 8 + (lane & 7);
-                    int kq = (H == 32) ? (warp >> 2) * 4 + (lane >> 3) : (lane >> 3) + 4 * j;
-                    tile_wgrad<ROWS>(wacc[j], sG, LDG, oq * 4, sHp, LDH, kq * 4);
+                for (int j = 0; j < NTD; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dacc[j][e] = 0.f;
+                const float* ga = sG + (md * 16 + g8) * LDG + t4;
+#pragma unroll 2
+                for (int k0 = 0; k0 < G4; k0 += 8) {
+                    uint32_t ah[4], al[4];
+                    tf32_split(ga[k0], ah[0], al[0]);
+                    tf32_split(ga[k0 + 8 * LDG], ah[1], al[1]);
+                    tf32_split(ga[k0 + 4], ah[2], al[2]);
+                    tf32_split(ga[k0 + 8 * LDG + 4], ah[3], al[3]);
+                    const float* wb = sW + (k0 + t4) * LDW + nd0 * 8 + g8;
+#pragma unroll
+                    for (int j = 0; j < NTD; ++j) mma_3xtf32(dacc[j], ah, al, wb[8 * j], wb[8 * j + 4 * LDW]);
                 }
-                // sDh of step t was consumed in phase 1 (before the barrier above): safe to overwrite
+                // dh of step t was consumed in phase 1 (before the barrier above): safe to overwrite
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
-                    st4(sDh + (d_r0 + i * D_RS) * LDH + d_kq * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+                for (int j = 0; j < NTD; ++j) {
+                    float* d = sDh + (md * 16 + g8) * LDD + (nd0 + j) * 8 + 2 * t4;
+                    *reinterpret_cast<float2*>(d) = make_float2(dacc[j][0], dacc[j][1]);
+                    *reinterpret_cast<float2*>(d + 8 * LDD) = make_float2(dacc[j][2], dacc[j][3]);
+                }
             }
-            if (threadIdx.x < 4 * H) {
-                int o = threadIdx.x;
-#pragma unroll 4
-                for (int r = 0; r < ROWS; ++r) {
-                    float g = sG[r * LDG + o];
-                    ax0 = fmaf(g, sX[2 * r], ax0);
-                    ax1 = fmaf(g, sX[2 * r + 1], ax1);
-                    ab += g;
+            // ---- phase 2b: dW[gate][n] += sum_row dgates[row][gate] (h_{t-1} | x | 1)[row][n]
+#pragma unroll 1
+            for (int r0 = 2 * t4; r0 < ROWS; r0 += 8) {
+                uint32_t ah[MTW][4], al[MTW][4];
+#pragma unroll
+                for (int i = 0; i < MTW; ++i) {
+                    const float* ga = sG + r0 * LDG + (warp * MTW + i) * 16 + g8;
+                    tf32_split(ga[0], ah[i][0], al[i][0]);
+                    tf32_split(ga[8], ah[i][1], al[i][1]);
+                    tf32_split(ga[LDG], ah[i][2], al[i][2]);
+                    tf32_split(ga[LDG + 8], ah[i][3], al[i][3]);
+                }
+                const float* hb = sHp + r0 * LDH + g8;
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) {
+                    uint32_t b0h, b0l, b1h, b1l;
+                    tf32_split(hb[8 * j], b0h, b0l);
+                    tf32_split(hb[8 * j + LDH], b1h, b1l);
+#pragma unroll
+                    for (int i = 0; i < MTW; ++i) {
+                        mma_tf32_16x8x8(wacc[i][j], ah[i], b0h, b1h);
+                        mma_tf32_16x8x8(wacc[i][j], al[i], b0h, b1h);
+                        mma_tf32_16x8x8(wacc[i][j], ah[i], b0l, b1l);
+                    }
                 }
             }
             __syncthreads();
         }
     }
+    // C fragments -> global: c0 (gate m0 + g, col n0 + 2t), c1 (., + 1), c2 / c3: gate + 8
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        int oq = (H == 32) ? (warp & 3) * 8 + (lane & 7) : warp * 8 + (lane & 7);
-        int kq = (H == 32) ? (warp >> 2) * 4 + (lane >> 3) : (lane >> 3) + 4 * j;
-        atomic_block44(dWhh, H, oq * 4, kq * 4, wacc[j]);
-    }
-    if (threadIdx.x < 4 * H) {
-        atomicAdd(dWx + threadIdx.x * 2, ax0);
-        atomicAdd(dWx + threadIdx.x * 2 + 1, ax1);
-        atomicAdd(db + threadIdx.x, ab);
+    for (int i = 0; i < MTW; ++i) {
+        const int m = (warp * MTW + i) * 16 + g8;
+#pragma unroll
+        for (int j = 0; j < NTW - 1; ++j) {
+            float* d = dWhh + (size_t)m * H + 8 * j + 2 * t4;
+            atomicAdd(d, wacc[i][j][0]);
+            atomicAdd(d + 1, wacc[i][j][1]);
+            atomicAdd(d + 8 * H, wacc[i][j][2]);
+            atomicAdd(d + 8 * H + 1, wacc[i][j][3]);
+        }
+        if (t4 == 0) {                                   // columns 0, 1 of the last n-tile: dWx
+            atomicAdd(dWx + 2 * m, wacc[i][NTW - 1][0]);
+            atomicAdd(dWx + 2 * m + 1, wacc[i][NTW - 1][1]);
+            atomicAdd(dWx + 2 * (m + 8), wacc[i][NTW - 1][2]);
+            atomicAdd(dWx + 2 * (m + 8) + 1, wacc[i][NTW - 1][3]);
+        } else if (t4 == 1) {                            // column 2: db
+            atomicAdd(db + m, wacc[i][NTW - 1][0]);
+            atomicAdd(db + m + 8, wacc[i][NTW - 1][2]);
+        }
     }
 }
 
 template <int H>
 size_t enc_fwd_smem() { using C = EncCfg<H>; return sizeof(float) * (4 * H * C::LDH + 2 * C::ROWS * C::LDH); }
 template <int H>
-size_t enc_bwd_smem() {
-    using C = EncCfg<H>;
-    return sizeof(float) * (4 * H * C::LDH + C::ROWS * C::LDG + 2 * C::ROWS * C::LDH + 2 * C::ROWS);
-}
+size_t enc_bwd_smem() { return EncBwd<H>::SMEM; }
 
 int sm_count() {
     static int n = 0;
@@ -249,11 +307,10 @@ int launch_fwd(const float* x, int T, int N, const float* Wx, const float* b, co
 template <int H>
 int launch_bwd(const float* x, int T, int N, const float* Whh, const float* acts, const float* dhT, float* dWx, float* db,
                float* dWhh, cudaStream_t s) {
-    using C = EncCfg<H>;
     size_t sm = enc_bwd_smem<H>();
     cudaFuncSetAttribute(lstm_enc_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    int tiles = (N + C::ROWS - 1) / C::ROWS;
-    int per_sm = sm <= 110 * 1024 ? 2 : 1;
+    int tiles = (N + EncBwd<H>::ROWS - 1) / EncBwd<H>::ROWS;
+    int per_sm = H == 32 ? 2 : 1;
     int grid = tiles < sm_count() * per_sm ? tiles : sm_count() * per_sm;
     lstm_enc_bwd_kernel<H><<<grid, MGGAN_THREADS, sm, s>>>(x, T, N, Whh, acts, dhT, dWx, db, dWhh);
     return mggan_check_launch("lstm_enc_bwd");
