@@ -5,10 +5,10 @@
 // b = W_ih b_e + b_ih + b_hh), so one step is  gates = Wx x_t + b + W_hh h_{t-1}  with the
 // PyTorch gate order [i; f; g; o].  One persistent CTA owns a tile of rows (agents) for the
 // whole sequence: W_hh stays in shared memory, h ping-pongs through shared memory, c lives in
-// registers.  Forward optionally saves (i, f, g, o, c, tanh c) per step for the backward,
-// which walks the sequence in reverse, runs its two contractions per step on the tensor pipe
-// (3 x TF32) and keeps the weight-gradient fragments in registers until the end (one atomicAdd
-// per element per CTA).
+// registers.  Forward and backward both run their per-step contractions on the tensor pipe
+// (warp-level 3 x TF32 products, common.cuh).  Forward optionally saves (i, f, g, o, c, tanh c)
+// per step for the backward, which walks the sequence in reverse and keeps the weight-gradient
+// fragments in registers until the end (one atomicAdd per element per CTA).
 #include "common.cuh"
 
 namespace {
@@ -18,70 +18,139 @@ struct EncCfg {
     static constexpr int UG = H / 8;          // warps along hidden units
     static constexpr int RG = 8 / UG;         // warps along rows
     static constexpr int ROWS = RG * 32;      // rows per CTA tile
-    static constexpr int LDH = H + 4;
-    static constexpr int LDG = 4 * H + 4;
+};
+
+// Forward.  gates[row][4H] = (h_{t-1} | x_t | 1) . (W_hh | Wx | b)^T is one warp-level 3 x TF32 product per step
+// (contraction H + 8: the input projection and the bias ride in three extra columns).  A warp owns 8 hidden units --
+// the n-tiles of their four gates -- for two 16-row m-tiles, so the cell update is local to the thread that holds the
+// C fragments: c stays in registers, h goes to the other half of the ping-pong tile as float2.  Both operand tiles
+// have row stride 12 mod 32 (A[row g][k t] and B[gate g][k t] on banks 12 g + t).
+template <int H>
+struct EncFwd {
+    static constexpr int ROWS = EncCfg<H>::ROWS;     // 32 (H = 64) or 64 (H = 32): two m-tiles per warp either way
+    static constexpr int G4 = 4 * H;
+    static constexpr int UG = H / 8;                 // unit groups
+    static constexpr int LDW = H + 12;               // (W_hh | Wx0 Wx1 b 0 0 0 0 0) per gate row
+    static constexpr int LDH = H + 12;               // (h | x0 x1 1 0 0 0 0 0) per row
+    static constexpr size_t SMEM = sizeof(float) * (G4 * LDW + 2 * ROWS * LDH);
 };
 
 template <int H>
-__global__ void __launch_bounds__(MGGAN_THREADS)
+__global__ void __launch_bounds__(MGGAN_THREADS, 2)
 lstm_enc_fwd_kernel(const float* __restrict__ x, int T, int N, const float* __restrict__ Wx,
                     const float* __restrict__ b, const float* __restrict__ Whh, float* __restrict__ hT,
                     float* __restrict__ acts) {
-    using C = EncCfg<H>;
+    using C = EncFwd<H>;
+    constexpr int ROWS = C::ROWS, G4 = C::G4, UG = C::UG, LDW = C::LDW, LDH = C::LDH;
     extern __shared__ __align__(16) float smem[];
-    float* sW = smem;                              // [4H][LDH]
-    float* sH = sW + 4 * H * C::LDH;               // [2][ROWS][LDH]
-    stage_matrix(sW, C::LDH, Whh, 4 * H, H);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int u = (warp % C::UG) * 8 + (lane & 7);
-    const int rl = (warp / C::UG) * 32 + (lane >> 3);
-    float wx0[4], wx1[4], bb[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        wx0[g] = __ldg(Wx + (g * H + u) * 2);
-        wx1[g] = __ldg(Wx + (g * H + u) * 2 + 1);
-        bb[g] = __ldg(b + g * H + u);
+    float* sW = smem;                              // [4H][LDW]
+    float* sH = sW + G4 * LDW;                     // [2][ROWS][LDH]
+    for (int i = threadIdx.x; i < G4 * H; i += MGGAN_THREADS) sW[(i / H) * LDW + (i % H)] = __ldg(Whh + i);
+    for (int o = threadIdx.x; o < G4; o += MGGAN_THREADS) {
+        float* e = sW + o * LDW + H;
+        e[0] = __ldg(Wx + 2 * o); e[1] = __ldg(Wx + 2 * o + 1); e[2] = __ldg(b + o);
+        e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; e[6] = 0.f; e[7] = 0.f;
     }
-    const int n_tiles = (N + C::ROWS - 1) / C::ROWS;
+    for (int r = threadIdx.x; r < 2 * ROWS; r += MGGAN_THREADS) {
+        float* e = sH + r * LDH + H;
+        e[2] = 1.f; e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; e[6] = 0.f; e[7] = 0.f;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int ug = warp % UG, m0 = (warp / UG) * 32;           // this warp's units 8 ug .. + 7, rows m0 .. m0 + 31
+    const int u = ug * 8 + 2 * t4;                             // the C fragments hold units u, u + 1
+
+    const int n_tiles = (N + ROWS - 1) / ROWS;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row0 = tile * C::ROWS;
-        float c[8], h[8];
+        const int row0 = tile * ROWS;
+        float c[2][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) c[i] = 0.f, h[i] = 0.f;
-        __syncthreads();                           // previous tile done with sH / weights staged
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c[i][e] = 0.f;
+        __syncthreads();                           // weights staged / previous tile done with sH
+        if (threadIdx.x < ROWS) {
+            const int row = row0 + threadIdx.x;
+            const float2 xv = row < N ? __ldg(reinterpret_cast<const float2*>(x) + row) : make_float2(0.f, 0.f);
+            *reinterpret_cast<float2*>(sH + threadIdx.x * LDH + H) = xv;
+        }
+        __syncthreads();
         for (int t = 0; t < T; ++t) {
-            const float* hcur = sH + (t & 1) * C::ROWS * C::LDH;
-            float* hnext = sH + ((t + 1) & 1) * C::ROWS * C::LDH;
-            float acc[8][4];
+            const float* hcur = sH + (t & 1) * ROWS * LDH;
+            float* hnext = sH + ((t + 1) & 1) * ROWS * LDH;
+            float acc[2][4][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int row = row0 + rl + 4 * i;
-                float2 xv = row < N ? __ldg(reinterpret_cast<const float2*>(x) + (size_t)t * N + row) : make_float2(0.f, 0.f);
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int g = 0; g < 4; ++g) acc[i][g] = fmaf(wx0[g], xv.x, fmaf(wx1[g], xv.y, bb[g]));
-            }
-            if (t > 0) tile_rowdot<8, 4, H>(acc, hcur, C::LDH, rl, 4, sW, C::LDH, u, H);
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float ig = sigmoidf_(acc[i][0]), fg = sigmoidf_(acc[i][1]);
-                float gg = tanhf_(acc[i][2]), og = sigmoidf_(acc[i][3]);
-                c[i] = fmaf(fg, c[i], ig * gg);
-                float tc = tanhf_(c[i]);
-                h[i] = og * tc;
-                hnext[(rl + 4 * i) * C::LDH + u] = h[i];
-                int row = row0 + rl + 4 * i;
-                if (acts != nullptr && row < N) {
-                    float* a = acts + ((size_t)t * N + row) * (6 * H) + u;
-                    a[0] = ig; a[H] = fg; a[2 * H] = gg; a[3 * H] = og; a[4 * H] = c[i]; a[5 * H] = tc;
+                    for (int e = 0; e < 4; ++e) acc[i][q][e] = 0.f;
+            auto kstep = [&](int k0) {
+                uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float* ha = hcur + (m0 + 16 * i + g8) * LDH + k0 + t4;
+                    tf32_split(ha[0], ah[i][0], al[i][0]);
+                    tf32_split(ha[8 * LDH], ah[i][1], al[i][1]);
+                    tf32_split(ha[4], ah[i][2], al[i][2]);
+                    tf32_split(ha[8 * LDH + 4], ah[i][3], al[i][3]);
                 }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float* wb = sW + (q * H + ug * 8 + g8) * LDW + k0 + t4;
+                    uint32_t b0h, b0l, b1h, b1l;
+                    tf32_split(wb[0], b0h, b0l);
+                    tf32_split(wb[4], b1h, b1l);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        mma_tf32_16x8x8(acc[i][q], ah[i], b0h, b1h);
+                        mma_tf32_16x8x8(acc[i][q], al[i], b0h, b1h);
+                        mma_tf32_16x8x8(acc[i][q], ah[i], b0l, b1l);
+                    }
+                }
+            };
+            kstep(H);                              // the (x | 1) columns; h_{-1} = 0: the first step has nothing else
+            if (t > 0) {
+#pragma unroll 2
+                for (int k0 = 0; k0 < H; k0 += 8) kstep(k0);
+            }
+            // cell update on the C fragments: element e = 2 half + unit (rows g8 + 8 half, units u + {0, 1})
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int r = m0 + 16 * i + g8 + 8 * half, row = row0 + r;
+                    float ig[2], fg[2], gg[2], og[2], tc[2], hh[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        ig[e] = sigmoidf_(acc[i][0][2 * half + e]);
+                        fg[e] = sigmoidf_(acc[i][1][2 * half + e]);
+                        gg[e] = tanhf_(acc[i][2][2 * half + e]);
+                        og[e] = sigmoidf_(acc[i][3][2 * half + e]);
+                        c[i][2 * half + e] = fmaf(fg[e], c[i][2 * half + e], ig[e] * gg[e]);
+                        tc[e] = tanhf_(c[i][2 * half + e]);
+                        hh[e] = og[e] * tc[e];
+                    }
+                    *reinterpret_cast<float2*>(hnext + r * LDH + u) = make_float2(hh[0], hh[1]);
+                    if (row < N) {
+                        if (acts != nullptr) {
+                            float* a = acts + ((size_t)t * N + row) * (6 * H) + u;
+                            *reinterpret_cast<float2*>(a) = make_float2(ig[0], ig[1]);
+                            *reinterpret_cast<float2*>(a + H) = make_float2(fg[0], fg[1]);
+                            *reinterpret_cast<float2*>(a + 2 * H) = make_float2(gg[0], gg[1]);
+                            *reinterpret_cast<float2*>(a + 3 * H) = make_float2(og[0], og[1]);
+                            *reinterpret_cast<float2*>(a + 4 * H) = make_float2(c[i][2 * half], c[i][2 * half + 1]);
+                            *reinterpret_cast<float2*>(a + 5 * H) = make_float2(tc[0], tc[1]);
+                        }
+                        if (t == T - 1) *reinterpret_cast<float2*>(hT + (size_t)row * H + u) = make_float2(hh[0], hh[1]);
+                    }
+                }
+            if (t + 1 < T && threadIdx.x < ROWS) {           // x_{t+1} next to h_t
+                const int row = row0 + threadIdx.x;
+                const float2 xv = row < N ? __ldg(reinterpret_cast<const float2*>(x) + (size_t)(t + 1) * N + row) : make_float2(0.f, 0.f);
+                *reinterpret_cast<float2*>(hnext + threadIdx.x * LDH + H) = xv;
             }
             __syncthreads();
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int row = row0 + rl + 4 * i;
-            if (row < N) hT[(size_t)row * H + u] = h[i];
         }
     }
 }
@@ -278,7 +347,7 @@ lstm_enc_bwd_kernel(const float* __restrict__ x, int T, int N, const float* __re
 }
 
 template <int H>
-size_t enc_fwd_smem() { using C = EncCfg<H>; return sizeof(float) * (4 * H * C::LDH + 2 * C::ROWS * C::LDH); }
+size_t enc_fwd_smem() { return EncFwd<H>::SMEM; }
 template <int H>
 size_t enc_bwd_smem() { return EncBwd<H>::SMEM; }
 
